@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""
+bench.py — TR loci/sec of the hot path on a synthetic 100k-locus x 50k-sample HipSTR block.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--loci L] [--samples S]
+
+A "step" is one pass of the hot path (harmonize kernel + GT scan + FP64 epilogue, results copied to
+the host) over the whole synthetic block, which is generated directly in HBM by ``trt_synth_fill``
+(30 GB of GT never crosses PCIe).  ``value`` = loci/s with the GT rows resident in HBM; ``e2e`` =
+the same pass through the C-ABI with HOST buffers (pinned staging block -> H2D -> kernels -> D2H).
+``--impl reference`` times the CPU restatement of the reference's algorithm (oracle port; the
+reference itself is pure Python and cannot travel to the GPU box) on a bounded locus sample.
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+SEED = 20261017
+STATS6 = ("afreq", "het", "hwep", "mean", "var", "entropy")      # BASELINE.json configs[1]
+METRIC = "TR loci/sec (statSTR all; associaTR OLS) 100k×50k samp, 1/2/4/8 GPU"
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's statSTR path on a bounded locus sample
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    lo, hi, S, seed = args
+    from oracle import stats as ostats, trh as otrh
+    from oracle.records import synth_to_loci
+    from trtools_b200 import synth
+    sl = synth.make_loci(hi, seed=seed)
+    calls = synth.fill_calls(sl, S, slice(lo, hi))
+    sub = synth.SynthLoci(seed=sl.seed, n_loci=hi - lo, chrom=sl.chrom[lo:hi], pos=sl.pos[lo:hi], start=sl.start[lo:hi],
+                          end=sl.end[lo:hi], period=sl.period[lo:hi], ref=sl.ref[lo:hi], alts=sl.alts[lo:hi],
+                          n_alleles=sl.n_alleles[lo:hi], cum_freq=sl.cum_freq[lo:hi], locus_offset=lo)
+    loci = synth_to_loci(sub, calls, with_fmt=False)
+    t0 = time.perf_counter()
+    rows = []
+    for l in loci:
+        h = otrh.harmonize(l)                                           # HarmonizeRecord
+        vals = ostats.locus_stats(h, l.gt, STATS6, [None], uselength=False)   # statSTR stat wrappers
+        rows.append(ostats.format_row(l.chrom, l.pos, h, vals))          # .tab row
+    return time.perf_counter() - t0, len(rows)
+
+
+def cpu_statstr(n_loci, S, cores, seed=SEED):
+    """loci/s of the oracle port with one process per core on disjoint loci (wall clock of the
+    timed sections, data generation excluded)."""
+    import multiprocessing as mp
+    per = max(1, n_loci // cores)
+    jobs = [(i * per, (i + 1) * per, S, seed) for i in range(cores)]
+    ctxmp = mp.get_context("fork")
+    with ctxmp.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = max(r[0] for r in res)
+    done = sum(r[1] for r in res)
+    return done / wall, done, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    L, S = args.loci, args.samples
+    n_sub = max(cores, min(4 * cores, 64))
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_statstr(cores, S, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, done, wall = cpu_statstr(n_sub, S, cores)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = "{} loci x {} samples per step (of the {}-locus workload), {} processes".format(n_sub, S, L, cores)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "statSTR --afreq --het --hwep --mean --var --entropy, synthetic HipSTR {}x{}".format(L, S),
+                   "loci": L, "samples": S, "note": "oracle port of the reference's Python/numpy path; loci/s extrapolates "
+                   "linearly (loci are independent)"},
+        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from trtools_b200 import _lib, synth
+
+    ctx = _lib.Context(local_rank)
+    info = ctx.device_info()
+    L, S = args.loci, args.samples
+    # weak scaling: every rank owns its own L loci (global locus ids rank*L .. rank*L+L-1)
+    loci = synth.make_loci(L, seed=SEED, locus_offset=rank * L)
+    tables = synth.allele_tables(loci)
+    ctx.block_begin(L, S, 2, "hipstr")
+    ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=False)
+    ctx.block_set_alleles(*tables)
+
+    def step():
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        return ctx.locus_stats(False, None, 0.01)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+
+    def gather_rows(st):
+        """NCCL gather of the fixed-width per-locus result rows (north_star: the only collective)."""
+        if dist is None:
+            return
+        import torch
+        rows = np.stack([st[k][0] for k in ("thresh", "het", "entropy", "mean", "mode", "var", "hwep")], axis=1)
+        t = torch.from_numpy(rows).cuda(non_blocking=True)
+        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, out, dst=0)
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        gather_rows(step())
+    sampler = ClockSampler(local_rank)
+    scan_ms = []
+    barrier()
+    sampler.start()
+    launches0 = ctx.launch_count()
+    t_wall0 = time.perf_counter()
+    ctx.stopwatch_start()
+    for _ in range(args.steps):
+        st = step()
+        scan_ms.append(ctx.last_scan_ms())
+        gather_rows(st)
+    ms = ctx.stopwatch_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1000.0
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    # the device stopwatch only spans this rank's stream; use the larger of device and wall time,
+    # then the max over ranks
+    ms = max(ms, 0.0)
+    step_ms = max(ms, wall_ms) / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    value = world * L / (step_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel (GT scan): 6 algorithmic bytes per call ----------------
+    peak, peak_src = load_peaks()
+    scan = float(np.mean(scan_ms)) if scan_ms else float("nan")
+    algo_bytes = 6.0 * L * S
+    achieved = algo_bytes / (scan / 1000.0) / 1e9 if scan > 0 else float("nan")
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "scan_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "scan_diploid_tma_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": scan, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_share_of_step": scan / step_ms if step_ms > 0 else None}
+
+    # ---- e2e through the C-ABI with HOST buffers (rank-local; max over ranks) -------------------
+    Lb = min(L, args.e2e_block)
+    nblk = (L + Lb - 1) // Lb
+    host_gt = ctx.pinned_empty((Lb, S, 3), np.int16)
+    host_gt[...] = ctx.block_get_gt(0, Lb)                     # untimed: fill the pinned staging block
+    blk_tables = [synth.allele_tables(loci, b * Lb, min(L, (b + 1) * Lb)) for b in range(nblk)]
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for b in range(nblk):
+            n = blk_tables[b][2].shape[0] - 1
+            ctx.block_begin(n, S, 2, "hipstr")
+            ctx.block_set_gt(host_gt[:n])
+            ctx.block_set_alleles(*blk_tables[b])
+            ctx.check(ctx.lib.trt_harmonize(ctx.h))
+            st = ctx.locus_stats(False, None, 0.01)
+            h2d += host_gt[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
+            d2h += sum(v.nbytes for v in st.values())
+        return st
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()                                                 # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * L / (e2e_ms / 1000.0)
+    ctx.free_pinned(host_gt)
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_sub = max(cores, min(4 * cores, 64))
+            v, done, wall = cpu_statstr(n_sub, S, cores)
+            cpu = {"value": v, "unit": "loci/s", "cores": cores, "kind": "port",
+                   "sample": "{} loci x {} samples, statSTR 6 stats (sequence grouping), {} processes, {:.1f} s".format(
+                       done, S, cores, wall)}
+        out = {
+            "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "statSTR all 11 stats (sequence grouping) on synthetic HipSTR, {} loci x {} samples per GPU, "
+                                   "GT int16 [L][S][3] generated in HBM".format(L, S),
+                       "loci_per_gpu": L, "samples": S, "seed": SEED, "parallelism": "loci sharded x{}".format(world),
+                       "l2": "inputs ({:.1f} GB) far larger than L2; no flush needed".format(algo_bytes / 1e9),
+                       "e2e": "one pinned {}-locus host block streamed {}x per step".format(Lb, nblk),
+                       "device": info["name"], "sm_count": info["sm_count"]},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "timing": {"device_ms_total": ms, "wall_ms_total": wall_ms},
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--loci", type=int, default=100000)
+    ap.add_argument("--samples", type=int, default=50000)
+    ap.add_argument("--e2e-block", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

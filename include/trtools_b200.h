@@ -1,0 +1,302 @@
+/*
+ * trtools_b200 — C-ABI of the B200-native TRTools hot path.
+ *
+ * The reference (gymrek-lab/TRTools v6.1.0) is pure Python and has no FFI; its seams for this
+ * path are Python protocols.  This header is what a ctypes binding on the
+ * reference side would bind (INTEGRATION.md shows the stub): one shared object,
+ * libtrtools_b200.so, built with nvcc for sm_100a.  Every entry point cites the reference
+ * function(s) it replaces as  file:line  relative to the reference tree.
+ *
+ * Conventions
+ *   - every function returns TRT_OK (0) or a negative TRT_E* code; the message is available from
+ *     trt_last_error(ctx) (or trt_last_error(NULL) for failures of trt_init itself);
+ *   - no exceptions cross the ABI; no torch types; plain pointers and sizes only;
+ *   - the caller owns all host buffers (the library never retains them past the call unless
+ *     they came from trt_host_alloc); the context owns device buffers and streams;
+ *   - a context is bound to one CUDA device and is not thread-safe: one context per GPU,
+ *     driven by one host thread/process;
+ *   - there is NO CPU fallback: without a CUDA device trt_init fails with TRT_ENODEV.
+ */
+#ifndef TRTOOLS_B200_H
+#define TRTOOLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRT_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define TRT_OK          0
+#define TRT_ENODEV     -1   /* no usable CUDA device                                             */
+#define TRT_ECUDA      -2   /* CUDA runtime error (message has the cudaError string)             */
+#define TRT_EINVAL     -3   /* bad argument                                                      */
+#define TRT_ESTATE     -4   /* call out of order (e.g. stats before trt_harmonize)               */
+#define TRT_ENOMEM     -5
+#define TRT_ERECORD    -6   /* malformed record -> reference raises ValueError/TypeError         */
+#define TRT_ENCCL      -7
+
+/* ---- VCF caller types: trtools/utils/tr_harmonizer.py:23-38 (VcfTypes) ---------------------- */
+#define TRT_VCF_GANGSTR 0
+#define TRT_VCF_ADVNTR  1
+#define TRT_VCF_HIPSTR  2
+#define TRT_VCF_EH      3
+#define TRT_VCF_POPSTR  4
+#define TRT_VCF_LONGTR  5
+
+/* ---- numeric FORMAT fields a block can carry (cyvcf2 Variant.format(key) arrays) ---------- */
+#define TRT_FMT_DP           0   /* int32 [L][S]                                                  */
+#define TRT_FMT_DSTUTTER     1   /* int32 [L][S]                                                  */
+#define TRT_FMT_DFLANKINDEL  2   /* int32 [L][S]                                                  */
+#define TRT_FMT_Q            3   /* float32 [L][S]                                                */
+#define TRT_FMT_AUX_I32      4   /* any other Integer field used by a min/max call filter         */
+#define TRT_FMT_AUX_F32      5   /* any other Float field used by a min/max call filter           */
+#define TRT_FMT_QEXP         6   /* float32 [L][S][3]  (GangSTR)                                  */
+#define TRT_FMT_NFIELDS      7
+
+typedef struct trt_ctx trt_ctx;
+
+typedef struct {
+    char     name[128];
+    int32_t  cc_major, cc_minor;
+    int32_t  sm_count;
+    int64_t  total_mem_bytes;
+    int64_t  free_mem_bytes;
+    int32_t  l2_bytes;
+    int32_t  abi_version;
+} trt_devinfo;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int         trt_device_count(void);
+int         trt_init(int device_ordinal, trt_ctx** out);
+void        trt_destroy(trt_ctx* ctx);
+const char* trt_last_error(const trt_ctx* ctx);
+int         trt_device_info(trt_ctx* ctx, trt_devinfo* out);
+int         trt_synchronize(trt_ctx* ctx);
+/* pinned host staging memory for the ingest ring (cudaHostAlloc)                              */
+void*       trt_host_alloc(trt_ctx* ctx, size_t bytes);
+int         trt_host_free(trt_ctx* ctx, void* p);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches)        */
+int64_t     trt_launch_count(const trt_ctx* ctx);
+/* device milliseconds of the most recent call's kernels, measured with CUDA events on the
+ * context's stream (0 if the call launched nothing)                                           */
+double      trt_last_kernel_ms(const trt_ctx* ctx);
+/* device milliseconds of the dominant sample-axis kernel(s) (GT scan / call filter / OLS moments)
+ * inside the most recent call — the numerator of bench.py's roofline figure                       */
+double      trt_last_scan_ms(const trt_ctx* ctx);
+/* user-level CUDA-event stopwatch on the context's stream (bench.py times K steps with it)       */
+int         trt_stopwatch_start(trt_ctx* ctx);
+int         trt_stopwatch_stop(trt_ctx* ctx, double* ms_out);
+
+/* ---- block ingest ------------------------------------------------------------------------
+ * A block is L consecutive VCF records ("loci") over the same S samples, in exactly the arrays
+ * cyvcf2 hands the reference per record, stacked over loci.
+ * Replaces the per-record pulls  vcfrecord.genotype.array()  (tr_harmonizer.py:829-862) and
+ * vcfrecord.format(key)  (tr_harmonizer.py:561-588).                                           */
+int trt_block_begin(trt_ctx* ctx, int64_t n_loci, int64_t n_samples, int ploidy, int vcftype);
+
+/* GT in cyvcf2 layout: int16 [L][S][P+1]; allele index, -1 = '.', -2 = ploidy pad, last col phased */
+int trt_block_set_gt(trt_ctx* ctx, const int16_t* gt_host);
+/* same, but the array already lives in device memory (row pitch in bytes, multiple of 16; the
+ * buffer must stay valid until the next trt_block_begin).  Used for device-generated blocks.     */
+int trt_block_set_gt_device(trt_ctx* ctx, const int16_t* gt_dev, size_t row_pitch_bytes);
+
+int trt_block_set_format_i32(trt_ctx* ctx, int field_id, const int32_t* v_host /*[L][S]*/);
+int trt_block_set_format_f32(trt_ctx* ctx, int field_id, const float* v_host /*[L][S][ncol]*/, int ncol);
+int trt_block_set_format_device(trt_ctx* ctx, int field_id, const void* v_dev, int ncol);
+
+/* Allele table of the block.  seqs: concatenated REF/ALT strings exactly as in the VCF (any
+ * case); allele_off[nA+1] byte offsets; locus_off[L+1] allele index ranges (first allele of a
+ * locus = REF).  pos = VCF POS; start/end = INFO START/END (HipSTR/LongTR; pass pos and
+ * pos+len(REF)-1 for callers without flanks); period = INFO PERIOD or len(RU/Motif).
+ * given_len (may be NULL): per-allele repeat-unit length for callers that report lengths
+ * (EH <STRn>, popSTR <n>; NaN = derive from the sequence).
+ * motifs (may be NULL): concatenated INFO RU / Motif strings, period[l] bytes per locus, for the
+ * callers that state the motif (GangSTR, adVNTR, EH, popSTR); HipSTR/LongTR motifs are inferred.
+ * Replaces the string work of  _HarmonizeHipSTRRecord  tr_harmonizer.py:336-408,
+ * _HarmonizeGangSTRRecord :303-333, _HarmonizeAdVNTRRecord :411-436, _HarmonizePopSTRRecord
+ * :473-512, _HarmonizeEHRecord :515-550 and  TRRecord.__init__ :693-773.                        */
+int trt_block_set_alleles(trt_ctx* ctx, const char* seqs, const int64_t* allele_off, const int32_t* locus_off,
+                          const int32_t* pos, const int32_t* start, const int32_t* end, const int32_t* period,
+                          const double* given_len, const char* motifs);
+
+/* ---- harmonize ---------------------------------------------------------------------------
+ * Warp-per-locus kernel: trims flanks (python slice semantics), upper-cases, derives
+ * repeat-unit lengths (float64), length/sequence equivalence classes and their sort order,
+ * infers the HipSTR motif (utils.InferRepeatSequence utils.py:465-508 + GetCanonicalOneStrand
+ * :396-427) and the homopolymer run of the full REF (utils.GetHomopolymerRun :340-360).          */
+int trt_harmonize(trt_ctx* ctx);
+
+typedef struct {
+    /* per allele (nA entries, locus-major) */
+    double*  allele_len;   /* repeat units: [ref_len, *alt_lens]  tr_harmonizer.py:740,757-759   */
+    int32_t* trim_off;     /* trimmed allele = seqs[allele_off[a]+trim_off[a] ...+trim_len[a])   */
+    int32_t* trim_len;
+    int32_t* len_class;    /* first allele index (within locus) with the same length             */
+    int32_t* seq_class;    /* first allele index (within locus) with the same trimmed sequence   */
+    int32_t* len_order;    /* allele indices of the locus sorted by (length, index)              */
+    int32_t* seq_order;    /* allele indices of the locus sorted by (trimmed sequence, index)    */
+    /* per locus (L entries) */
+    int32_t* hrun;         /* GetHomopolymerRun(full REF)                                        */
+    int32_t* flags;        /* TRT_HF_* bits                                                      */
+    char*    motif;        /* [sum(period)] inferred motif bytes, locus l at motif_off[l]        */
+    int64_t* motif_off;    /* [L+1] (exclusive prefix sum of period)                             */
+} trt_harmonize_out;
+#define TRT_HF_HAS_FULL     1   /* start/end offsets non-zero -> full_alleles kept (:360-369)      */
+#define TRT_HF_MOTIF_N      2   /* period > len(seq): motif is 'N'*period (utils.py:488-489)       */
+#define TRT_HF_MOTIF_NONACGT 4  /* GetCanonicalOneStrand would raise KeyError                       */
+#define TRT_HF_LEN_DUPS     8   /* some alleles share a length                                     */
+#define TRT_HF_SEQ_DUPS    16   /* some alleles share a trimmed sequence                           */
+#define TRT_HF_BAD_PERIOD  32   /* period <= 0                                                     */
+int trt_get_harmonized(trt_ctx* ctx, trt_harmonize_out* out /* any member may be NULL */);
+
+/* Packed length-genotype tensor: int16 [L][S][P]; entry = rank of the haplotype's length among
+ * the locus' sorted distinct lengths (table via trt_get_len_table), -1 no-call, -2 ploidy pad.
+ * Device-side equivalent of TRRecord.GetLengthGenotypes (tr_harmonizer.py:1210-1245) — the
+ * float64 [S][P+1] array is only materialised at the Python API edge.                            */
+int trt_pack_length_genotypes(trt_ctx* ctx);
+int trt_get_packed_gt(trt_ctx* ctx, int16_t* out_host /*[L][S][P]*/);
+
+/* ---- per-locus statistics (statSTR) ---------------------------------------------------------
+ * One pass over the native GT array per sample group.  Replaces, per locus and per group,
+ *   GetAlleleCounts tr_harmonizer.py:1420-1499, GetGenotypeCounts :1326-1418,
+ *   GetAlleleFreqs :1501-1540, GetMaxAllele :1542-1575, GetCalledSamples :864-897,
+ *   utils.GetHeterozygosity/GetEntropy/GetMean/GetMode/GetVariance/
+ *   GetHardyWeinbergBinomialTest utils.py:142-338 and the statSTR wrappers statSTR.py:104-426.  */
+typedef struct {
+    /* [G][nA]: allele counts keyed by allele INDEX (partial calls contribute their called hap) */
+    int32_t* ac;
+    /* [G][L] each; NULL = not wanted */
+    int64_t* n_called;           /* samples with no '.' haplotype  (= sum of genotype counts)    */
+    int64_t* n_called_nonstrict; /* samples with at least one called haplotype                   */
+    int64_t* n_hom;              /* fully-called samples whose two smallest alleles are equal
+                                    under the selected equivalence (length or sequence)          */
+    int64_t* n_padded;           /* fully-called samples carrying a -2 ploidy pad                */
+    double*  thresh;             /* GetMaxAllele                                                 */
+    double*  het;
+    double*  entropy;
+    double*  mean;
+    double*  mode;
+    double*  var;
+    double*  hwep;
+    int32_t* nalleles;           /* classes with freq >= nalleles_thresh                         */
+} trt_locus_stats_out;
+
+/* group_masks: [G][S] bytes (0/1) or NULL with G = 1 for "all samples" (statSTR.py:520-542).
+ * use_length: collapse alleles by length (1) or by trimmed sequence (0) for
+ * het/entropy/hwep/nalleles — mean/mode/var/thresh always use lengths (statSTR.py:347,375,402). */
+int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* group_masks, int n_groups,
+                    double nalleles_thresh, trt_locus_stats_out* out);
+
+/* TRRecord.GetGenotypeCounts tr_harmonizer.py:1326-1418 for ONE locus (API edge, optional sample
+ * mask [S] bytes): counts of index genotypes with haplotypes sorted, as a dense base-(A+2) table of
+ * (A+2)^P entries where digit = allele + 2 (-2 pad -> 0, -1 no-call -> 1).                         */
+int trt_genotype_counts(trt_ctx* ctx, int64_t locus, const uint8_t* mask, int64_t* table, int64_t table_len);
+
+/* ---- dumpSTR ---------------------------------------------------------------------------------
+ * Call-level filter operators (filters.py:327-484, 573-674) evaluated in the order given,
+ * followed by ApplyCallFilters' bookkeeping (dumpSTR.py:613-774).                                 */
+#define TRT_CF_MIN       0   /* value <  threshold filtered   (CallFilterMinValue)                */
+#define TRT_CF_MAX       1   /* value >  threshold filtered   (CallFilterMaxValue)                */
+#define TRT_CF_RATIO_GT  2   /* field/DP > threshold filtered (HipSTRCallFlankIndels/Stutter)     */
+#define TRT_CF_QEXP_HET  3   /* QEXP[1] < thr on called samples                                   */
+#define TRT_CF_QEXP_HOM  4   /* QEXP[2] < thr                                                     */
+#define TRT_CF_QEXP_TOT  5   /* QEXP[1]+QEXP[2] < thr                                             */
+typedef struct {
+    int32_t kind;        /* TRT_CF_*                                                              */
+    int32_t field_id;    /* TRT_FMT_* the operator reads (numerator for RATIO_GT)                 */
+    double  threshold;
+} trt_call_filter_spec;
+
+#define TRT_MAX_CALL_FILTERS 16
+typedef struct {
+    /* per call, [L][S]: bit f set = filter f fired (value non-NaN); bit 31 = no-call before
+     * filtering.  May be NULL.                                                                   */
+    uint32_t* call_mask;
+    /* [n_specs][L][S] float64 triggering values (NaN = not filtered) — only what the host needs
+     * to print FORMAT:FILTER ('%g');  may be NULL                                                */
+    double*   trigger_values;
+    /* masked genotypes int16 [L][S][P+1] (filtered calls -> all -1, phase 0); may be NULL        */
+    int16_t*  gt_masked;
+    /* per-sample accumulators, ADDED to the caller's arrays (they persist across blocks):
+     * filter_counts [n_specs][S]; numcalls [S]; totaldp [S] (NaN-poisoned like dumpSTR.py:710)    */
+    int64_t*  filter_counts;
+    int64_t*  numcalls;
+    double*   totaldp;
+    int32_t*  negative_dp_locus; /* out: first locus with a PASS call of negative DP, or -1       */
+} trt_call_filter_out;
+int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_specs, int dp_field_id /* TRT_FMT_DP or -1 */,
+                     trt_call_filter_out* out);
+/* after trt_call_filters: subsequent trt_locus_stats / trt_locus_filters / trt_assoc_* read the
+ * MASKED genotypes (the rebuilt TRRecord of dumpSTR.py:748-774) until the next trt_block_begin.  */
+
+/* Locus-level filters (filters.py:35-217) + ApplyLocusFilters (dumpSTR.py:917-973) + INFO
+ * recompute (dumpSTR.py:1307-1336).                                                               */
+#define TRT_LF_CALLRATE 0
+#define TRT_LF_HWE      1
+#define TRT_LF_HETLOW   2
+#define TRT_LF_HETHIGH  3
+#define TRT_LF_HRUN     4
+typedef struct { int32_t kind; double threshold; } trt_locus_filter_spec;
+typedef struct {
+    uint32_t* flags;      /* [L] bit i = locus filter i fired; bit 31 = NO_CALLS_REMAINING        */
+    int64_t*  n_called;   /* [L]                                                                  */
+    double*   het;        /* [L] INFO HET  (-1 when nothing is called)                            */
+    double*   hwep;       /* [L] INFO HWEP (-1 when nothing is called)                            */
+    int32_t*  ac;         /* [nA] index allele counts (INFO AC / REFAC)                           */
+    int32_t*  hrun;       /* [L]                                                                  */
+} trt_locus_filter_out;
+int trt_locus_filters(trt_ctx* ctx, const trt_locus_filter_spec* specs, int n_specs, int use_length,
+                      trt_locus_filter_out* out);
+
+/* ---- associaTR ---------------------------------------------------------------------------------
+ * Design = standardised covariates with column 0 reserved for the genotype and column 1 the
+ * intercept (associaTR.py:190-194), restricted to the samples kept by the sample filter.
+ * sample_index[n_design]: VCF sample index of each design row (ascending).                        */
+int trt_assoc_set_design(trt_ctx* ctx, const double* covars /*[n_design][K] row-major, col 0 ignored*/,
+                         const double* outcome /*[n_design]*/, const int32_t* sample_index, int64_t n_design, int K);
+#define TRT_AF_OK              0
+#define TRT_AF_NO_CALLED       1   /* 'No called samples'          lafg.py:228-229                */
+#define TRT_AF_ONE_ALLELE      2   /* 'Only one called allele'     lafg.py:230-231                */
+#define TRT_AF_NON_MAJOR       3   /* 'non-major allele count<c'   lafg.py:232-236                */
+#define TRT_AF_NCOVARS         4   /* 'n covars >= n samples'      associaTR.py:257-258           */
+typedef struct {
+    int32_t* filter_code;   /* [L] TRT_AF_*                                                       */
+    int64_t* n_tested;      /* [L] called samples among the design rows                           */
+    double*  p;             /* [L] two-sided t-test p of the genotype coefficient                 */
+    double*  coef;          /* [L] coefficient on the standardised scale / std(g)  (x pheno_std by caller) */
+    double*  se;            /* [L]                                                                */
+    double*  r2;            /* [L]                                                                */
+    double*  std_g;         /* [L] population std of the summed length genotype                   */
+    int32_t* ac_len;        /* [nA] allele counts among tested samples keyed by allele index      */
+} trt_assoc_out;
+/* load_and_filter_genotypes.load_trs lafg.py:157-259 (non-dosage branch) + per-locus regression
+ * associaTR.py:246-291 (statsmodels OLS on called rows: params, bse, pvalues, rsquared).          */
+int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out);
+
+/* ---- synthetic blocks (bench / parity at sizes that do not fit through PCIe) ------------------
+ * Device twin of trtools_b200/synth.py::fill_calls — bit-identical arrays.                        */
+int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset, int64_t n_loci, int64_t n_samples,
+                   const uint32_t* cum_freq_host /*[n_loci][16]*/, uint32_t miss_thresh, uint32_t half_thresh,
+                   int with_format /* also DP/DSTUTTER/DFLANKINDEL/Q */);
+/* after trt_synth_fill the block's GT (and FORMAT) arrays are the generated ones; these copy
+ * a locus range back for parity checks                                                          */
+int trt_block_get_gt(trt_ctx* ctx, int64_t locus0, int64_t n, int16_t* out_host /*[n][S][P+1]*/);
+int trt_block_get_format(trt_ctx* ctx, int field_id, int64_t locus0, int64_t n, void* out_host);
+
+/* ---- multi-GPU: loci shard by contiguous ranges, one context per rank --------------------------
+ * NCCL is used only to gather fixed-width per-locus result rows and to sum per-sample counters.  */
+int trt_dist_unique_id(void* out_128_bytes);
+int trt_dist_init(trt_ctx* ctx, int rank, int world, const void* unique_id_128_bytes);
+int trt_dist_allgather_f64(trt_ctx* ctx, const double* send_host, int64_t count, double* recv_host /*[world*count]*/);
+int trt_dist_allreduce_sum_i64(trt_ctx* ctx, int64_t* inout_host, int64_t count);
+int trt_dist_allreduce_sum_f64(trt_ctx* ctx, double* inout_host, int64_t count);
+int trt_dist_barrier(trt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRTOOLS_B200_H */

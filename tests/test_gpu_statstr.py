@@ -1,0 +1,355 @@
+"""
+GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI /
+the drop-in Python API, against (a) golden vectors produced by the unmodified reference and
+(b) the oracle on seeded synthetic inputs.  Integer counts bit-exact; floating-point statistics
+within 1e-6 relative (BASELINE.json north_star), NaN == NaN.
+"""
+import argparse
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, assert_close_list, REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["hipstr_many", "hipstr_trio", "gangstr", "popstr", "eh", "advntr", "longtr", "synth_small",
+            "synth_wide", "edge"]
+_cache = {}
+
+
+def fixture(golden_dir, name):
+    from oracle.records import load_loci
+    if name not in _cache:
+        _cache[name] = load_loci(os.path.join(golden_dir, name + ".npz"))
+    return _cache[name]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from trtools_b200 import _lib
+    return _lib.default_context()
+
+
+def _blocks_from_loci(ctx, loci):
+    """Group fixture loci into GPU blocks (same vcftype / sample count / ploidy)."""
+    from oracle.records import LocusAsVariant
+    from trtools_b200 import block
+    runs, cur, key = [], [], None
+    for i, l in enumerate(loci):
+        k = (l.vcftype, None if l.gt is None else l.gt.shape)
+        if cur and k != key:
+            runs.append(cur)
+            cur = []
+        key = k
+        cur.append(i)
+    if cur:
+        runs.append(cur)
+    for run in runs:
+        recs = [LocusAsVariant(loci[i]) for i in run]
+        yield run, recs, loci[run[0]].vcftype
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_harmonize_kernel_matches_reference(golden_dir, ctx, name):
+    from trtools_b200 import block, tr_harmonizer as trh
+    loci, extra, _ = fixture(golden_dir, name)
+    n_checked = 0
+    for run, recs, vt in _blocks_from_loci(ctx, loci):
+        refs = [extra["ref"][i] for i in run]
+        if any("error" in r for r in refs):
+            for rec, r in zip(recs, refs):
+                if "error" in r:
+                    with pytest.raises((TypeError, ValueError)) as e:
+                        trh.HarmonizeRecord(vt, rec)
+                    assert type(e.value).__name__ == r["error"]
+            continue
+        blk = block.build_block(ctx, vt, recs)
+        for j, (rec, r) in enumerate(zip(recs, refs)):
+            tr = trh.TRRecord._from_block(blk, j, rec)
+            h = r["harm"]
+            assert tr.ref_allele == h["ref_allele"], (name, run[j])
+            assert tr.alt_alleles == h["alt_alleles"], (name, run[j])
+            assert tr.motif == h["motif"], (name, run[j])
+            assert tr.record_id == h["record_id"]
+            assert tr.pos == h["pos"] and tr.end_pos == h["end_pos"]
+            assert tr.ref_allele_length == h["ref_len"]          # float64 bit-exact
+            assert tr.alt_allele_lengths == h["alt_lens"]
+            assert tr.HasFullStringGenotypes() == h["has_full"]
+            assert tr.quality_field == h["quality_field"]
+            n_checked += 1
+    assert n_checked > 0 or name == "edge"
+
+
+def _afreq_from_ac(keys, ac, count):
+    from trtools_b200.statSTR import _afreq_string
+    return _afreq_string(keys, ac, count)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_locus_stats_kernel_matches_reference(golden_dir, ctx, name):
+    from trtools_b200 import block
+    from trtools_b200.statSTR import _locus_keys
+    loci, extra, _ = fixture(golden_dir, name)
+    masks = [np.array(m, dtype=np.uint8) for m in extra.get("group_masks", [])]
+    for run, recs, vt in _blocks_from_loci(ctx, loci):
+        refs = [extra["ref"][i] for i in run]
+        if any("error" in r for r in refs) or loci[run[0]].gt is None:
+            continue
+        blk = block.build_block(ctx, vt, recs)
+        S = blk.S
+        gm = None
+        if masks and masks[0].shape[0] == S:
+            gm = np.stack([np.ones(S, np.uint8)] + masks)
+        for key, uselength in (("stats_len", True), ("stats_seq", False)):
+            st = blk.stats(uselength, 0.01, gm)
+            G = 1 if gm is None else gm.shape[0]
+            for j, r in enumerate(refs):
+                c = r["counts"]
+                sl = blk.allele_slice(j)
+                ac = st["ac"][0, sl]
+                assert {str(k): int(v) for k, v in enumerate(ac) if v > 0} == c["ac_idx"], (name, run[j])
+                assert int(st["n_called"][0, j]) == c["n_called"]
+                assert int(st["n_called_nonstrict"][0, j]) == c["n_called_nonstrict"]
+                if key not in r:
+                    continue
+                ref = r[key]
+                keys = _locus_keys(blk, j, uselength)
+                for g in range(G):
+                    what = "{} locus {} {} group {}".format(name, run[j], key, g)
+                    assert _afreq_from_ac(keys, st["ac"][g, sl], False) == ref["afreq"][g], what
+                    assert _afreq_from_ac(keys, st["ac"][g, sl], True) == ref["acount"][g], what
+                    assert int(st["nalleles"][g, j]) == ref["nalleles"][g], what
+                    assert int(st["n_called"][g, j]) == ref["numcalled"][g], what
+                    for stat in ("thresh", "hwep", "het", "entropy", "mean", "mode", "var"):
+                        assert_close(st[stat][g, j], ref[stat][g], what + " " + stat, rel=REL_TOL, abs_tol=1e-300)
+
+
+def _statstr_args(vcf, out, **kw):
+    ns = argparse.Namespace(vcf=vcf, out=out, vcftype="auto", samples=None, sample_prefixes=None, region=None,
+                            precision=3, nalleles_thresh=0.01, plot_afreq=False, use_length=False,
+                            only_passing=False, block_size=512)
+    for s in ("thresh", "afreq", "acount", "nalleles", "hwep", "het", "entropy", "mean", "mode", "var", "numcalled"):
+        setattr(ns, s, True)
+    for k, v in kw.items():
+        setattr(ns, k, v)
+    return ns
+
+
+def _same_tab(got: str, want: str, float_cols_rel=2e-4):
+    """Text equality; numeric cells may differ in the last printed digit (the reference's own
+    comparator, test_statSTR.py:111-131, allows the same)."""
+    g, w = got.splitlines(), want.splitlines()
+    assert len(g) == len(w)
+    assert g[0] == w[0]
+    n_diff = 0
+    for i, (a, b) in enumerate(zip(g, w)):
+        if a == b:
+            continue
+        ca, cb = a.split("\t"), b.split("\t")
+        assert len(ca) == len(cb), i
+        for x, y in zip(ca, cb):
+            if x == y:
+                continue
+            fx, fy = float(x), float(y)
+            assert abs(fx - fy) <= float_cols_rel * max(abs(fx), abs(fy)), (i, x, y)
+            n_diff += 1
+    return n_diff
+
+
+def test_statstr_cli_matches_reference_output(golden_dir, data_dir, tmp_path):
+    from trtools_b200 import statSTR
+    loci, extra, _ = fixture(golden_dir, "hipstr_many")
+    vcf = os.path.join(data_dir, "many_samples.vcf.gz")
+    cases = [("tab_all", {}), ("tab_all_uselength", {"use_length": True}),
+             ("tab_strat", {"samples": os.path.join(data_dir, "many_samples_subsample1.txt") + "," +
+                            os.path.join(data_dir, "many_samples_subsample2.txt"), "sample_prefixes": "1,2"})]
+    for key, kw in cases:
+        out = str(tmp_path / key)
+        assert statSTR.main(_statstr_args(vcf, out, precision=4, **kw)) == 0
+        n_diff = _same_tab(open(out + ".tab").read(), extra[key])
+        assert n_diff <= 20, (key, n_diff)      # last-digit rounding of printed floats only
+
+
+def test_statstr_config1_trio(golden_dir, data_dir, tmp_path):
+    """BASELINE config 1: statSTR --afreq --mean --vcftype hipstr on trio_chr21_hipstr."""
+    from trtools_b200 import statSTR
+    _, extra, _ = fixture(golden_dir, "hipstr_trio")
+    out = str(tmp_path / "c1")
+    args = _statstr_args(os.path.join(data_dir, "trio_chr21_hipstr.sorted.vcf.gz"), out, vcftype="hipstr")
+    for s in ("thresh", "acount", "nalleles", "hwep", "het", "entropy", "mode", "var", "numcalled"):
+        setattr(args, s, False)
+    assert statSTR.main(args) == 0
+    assert _same_tab(open(out + ".tab").read(), extra["tab_c1"]) <= 5
+
+
+def test_other_callers_cli(golden_dir, data_dir, tmp_path):
+    from trtools_b200 import statSTR
+    for name, fn, vt in [("gangstr", "test_gangstr_head.vcf", "gangstr"), ("popstr", "test_popstr.vcf", "popstr"),
+                         ("eh", "test_ExpansionHunter.vcf", "eh"), ("advntr", "test_advntr.vcf", "advntr"),
+                         ("longtr", "test_longtr.vcf", "longtr")]:
+        _, extra, _ = fixture(golden_dir, name)
+        for key, ul in (("tab", False), ("tab_uselength", True)):
+            out = str(tmp_path / (name + key))
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                assert statSTR.main(_statstr_args(os.path.join(data_dir, fn), out, vcftype=vt, precision=4,
+                                                  use_length=ul)) == 0
+            assert _same_tab(open(out + ".tab").read(), extra[key]) <= 10, (name, key)
+
+
+def test_synthetic_generator_twins_agree(ctx):
+    """trt_synth_fill (CUDA) == trtools_b200.synth.fill_calls (numpy), bit for bit."""
+    from trtools_b200 import synth, _lib
+    for L, S, seed, off in [(37, 1000, 20261017, 0), (5, 4099, 3, 1000)]:
+        sl = synth.make_loci(L, seed=seed, locus_offset=off)
+        want = synth.fill_calls(sl, S)
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.synth_fill(seed, off, sl.cum_freq, sl.miss_thresh, sl.half_thresh, True)
+        assert np.array_equal(ctx.block_get_gt(0, L), want.gt)
+        assert np.array_equal(ctx.block_get_format(_lib.FMT_DP, 0, L, np.int32), want.dp)
+        assert np.array_equal(ctx.block_get_format(_lib.FMT_DSTUTTER, 0, L, np.int32), want.dstutter)
+        assert np.array_equal(ctx.block_get_format(_lib.FMT_DFLANKINDEL, 0, L, np.int32), want.dflankindel)
+        q = ctx.block_get_format(_lib.FMT_Q, 0, L, np.float32)
+        assert np.array_equal(np.isnan(q), np.isnan(want.q)) and np.array_equal(q[~np.isnan(q)], want.q[~np.isnan(want.q)])
+
+
+@pytest.mark.parametrize("L,S", [(64, 10000), (24, 50000), (40, 2055), (16, 16385)])
+def test_stats_vs_oracle_on_synthetic(ctx, L, S):
+    """Fast TMA path (S >= 2048) vs the oracle on seeded synthetic blocks, both relations."""
+    from oracle import stats as ostats, trh as otrh
+    from oracle.records import synth_to_loci, LocusAsVariant
+    from trtools_b200 import synth, block
+    from trtools_b200.statSTR import _locus_keys, _afreq_string
+    sl = synth.make_loci(L, seed=S)
+    calls = synth.fill_calls(sl, S)
+    loci = synth_to_loci(sl, calls, with_fmt=False)
+    blk = block.build_block(ctx, "hipstr", [LocusAsVariant(l) for l in loci])
+    rng = np.random.default_rng(S)
+    gm = np.stack([np.ones(S, np.uint8), (rng.random(S) < 0.3).astype(np.uint8)])
+    groups = [None, gm[1].astype(bool)]
+    step = max(1, L // 8)
+    for uselength in (True, False):
+        st = blk.stats(uselength, 0.01, gm)
+        for j in range(0, L, step):
+            h = otrh.harmonize(loci[j])
+            want = ostats.locus_stats(h, loci[j].gt, ostats.STAT_ORDER, groups, uselength=uselength)
+            keys = _locus_keys(blk, j, uselength)
+            sl_ = blk.allele_slice(j)
+            for g in range(2):
+                what = "L{} S{} locus {} ul {} g {}".format(L, S, j, uselength, g)
+                assert _afreq_string(keys, st["ac"][g, sl_], True) == want["acount"][g], what
+                assert int(st["n_called"][g, j]) == want["numcalled"][g], what
+                assert int(st["nalleles"][g, j]) == want["nalleles"][g], what
+                for stat in ("thresh", "hwep", "het", "entropy", "mean", "mode", "var"):
+                    assert_close(st[stat][g, j], want[stat][g], what + " " + stat, abs_tol=1e-300)
+
+
+def test_many_alleles_and_odd_shapes(ctx):
+    """Loci beyond the fast path's allele budget (generic kernel), haploid and triploid blocks."""
+    from oracle import stats as ostats, trh as otrh
+    from oracle.records import Locus, LocusAsVariant
+    from trtools_b200 import block
+    rng = np.random.default_rng(5)
+    S = 3000
+    # 150 alleles (> 96): falls back to the generic kernel inside a fast-path launch
+    ref = "AC" * 20
+    alts = ["AC" * k for k in range(1, 151) if k != 20][:149]
+    gt = np.stack([rng.integers(0, 150, S), rng.integers(0, 150, S), np.ones(S, int)], axis=1).astype(np.int16)
+    gt[rng.random(S) < 0.05, :2] = (-1, -2)
+    big = Locus("hipstr", "1", 100, ref, alts, {"START": 100, "END": 139, "PERIOD": 2}, gt)
+    small = Locus("hipstr", "1", 500, "ACAC", ["AC"], {"START": 500, "END": 503, "PERIOD": 2},
+                  np.stack([rng.integers(0, 2, S), rng.integers(0, 2, S), np.zeros(S, int)], axis=1).astype(np.int16))
+    blk = block.build_block(ctx, "hipstr", [LocusAsVariant(big), LocusAsVariant(small)])
+    for ul in (True, False):
+        st = blk.stats(ul)
+        for j, l in enumerate((big, small)):
+            h = otrh.harmonize(l)
+            want = ostats.locus_stats(h, l.gt, ostats.STAT_ORDER, [None], uselength=ul)
+            ac = otrh.allele_counts(h, l.gt, index=True)
+            got = st["ac"][0, blk.allele_slice(j)]
+            assert {int(k): int(v) for k, v in ac.items()} == {i: int(v) for i, v in enumerate(got) if v > 0}
+            for stat in ("thresh", "hwep", "het", "entropy", "mean", "mode", "var"):
+                assert_close(st[stat][0, j], want[stat][0], "{} {}".format(j, stat), abs_tol=1e-300)
+    # triploid / haploid rows
+    for P in (1, 3):
+        g = rng.integers(-2, 3, size=(200, P)).astype(np.int16)
+        g = np.concatenate([g, np.zeros((200, 1), np.int16)], axis=1)
+        l = Locus("hipstr", "1", 100, "ACACAC", ["ACAC", "ACACACAC"], {"START": 100, "END": 105, "PERIOD": 2}, g)
+        blk = block.build_block(ctx, "hipstr", [LocusAsVariant(l)])
+        st = blk.stats(True)
+        h = otrh.harmonize(l)
+        ac = otrh.allele_counts(h, l.gt, index=True)
+        assert {int(k): int(v) for k, v in ac.items()} == {i: int(v) for i, v in enumerate(st["ac"][0]) if v > 0}
+        assert int(st["n_called"][0, 0]) == int(np.sum(otrh.called_samples(l.gt)))
+        if P == 3:
+            want = ostats.stat_hwep(h, l.gt, [None], True)[0]
+            assert_close(st["hwep"][0, 0], want, "triploid hwep")
+
+
+def test_trrecord_api_known_answers(ctx):
+    """Known answers of the reference's own unit tests (trtools/utils/tests/test_trharmonizer.py:
+    312-715) through the drop-in TRRecord constructor and accessors."""
+    import types
+    from trtools_b200 import tr_harmonizer as trh
+
+    class DummyCyvcf2Record:      # same surface as the reference's test double (:18-50)
+        def __init__(self, gts, ref, alt):
+            self.POS, self.CHROM, self.FORMAT, self.INFO = 42, '1984', {}, {}
+            self.ALT, self.REF = list(alt), ref
+            if gts is not None:
+                self.genotype = types.SimpleNamespace()
+                self._gts = np.array(gts)
+                if len(self._gts) > 0:
+                    self._gts = np.concatenate((self._gts, np.zeros((self._gts.shape[0], 1))), axis=1)
+                self.genotype.array = lambda: self._gts
+                self.genotype.n_samples = len(gts)
+                self.ploidy = self._gts.shape[1] - 1 if len(self._gts) else 2
+            else:
+                self.genotype = None
+
+        def format(self, key):
+            return self.FORMAT.get(key, None)
+
+    gts = [[0, 1], [1, 1], [1, 1], [1, 2], [2, 2], [0, -1]]
+    rec = DummyCyvcf2Record(gts, "CAGCAGCAG", ["CAGCAGCAGCAG", "CAGCAGCAGCAGCAGCAG"])
+    tr = trh.TRRecord(rec, "CAGCAGCAG", ["CAGCAGCAGCAG", "CAGCAGCAGCAGCAGCAG"], "CAG", "STR1", None)
+    assert tr.ref_allele_length == 3 and tr.alt_allele_lengths == [4, 6]
+    # test_GetGenotypeCounts :441-508
+    assert tr.GetGenotypeCounts() == {(3, 4): 1, (4, 4): 2, (4, 6): 1, (6, 6): 1}
+    assert tr.GetGenotypeCounts(index=True) == {(0, 1): 1, (1, 1): 2, (1, 2): 1, (2, 2): 1}
+    assert tr.GetGenotypeCounts(uselength=False) == {
+        ("CAGCAGCAG", "CAGCAGCAGCAG"): 1, ("CAGCAGCAGCAG", "CAGCAGCAGCAG"): 2,
+        ("CAGCAGCAGCAG", "CAGCAGCAGCAGCAGCAG"): 1, ("CAGCAGCAGCAGCAGCAG", "CAGCAGCAGCAGCAGCAG"): 1}
+    assert tr.GetGenotypeCounts(include_nocalls=True)[(-1, 3)] == 1
+    assert tr.GetGenotypeCounts(sample_index=[0, 1, 3]) == {(3, 4): 1, (4, 4): 1, (4, 6): 1}
+    # test_GetAlleleCounts :511-558 / GetAlleleFreqs :561-633
+    assert tr.GetAlleleCounts() == {3: 2, 4: 6, 6: 3}
+    assert tr.GetAlleleCounts(index=True) == {0: 2, 1: 6, 2: 3}
+    assert tr.GetAlleleCounts(uselength=False) == {"CAGCAGCAG": 2, "CAGCAGCAGCAG": 6, "CAGCAGCAGCAGCAGCAG": 3}
+    assert tr.GetAlleleCounts(sample_index=[0, 5]) == {3: 2, 4: 1}
+    fr = tr.GetAlleleFreqs()
+    assert fr[3] == pytest.approx(2 / 11) and fr[4] == pytest.approx(6 / 11) and fr[6] == pytest.approx(3 / 11)
+    assert tr.GetMaxAllele() == 6 and tr.GetMaxAllele(sample_index=[0, 5]) == 4
+    # called samples / call rate / ploidies :666-715
+    assert np.array_equal(tr.GetCalledSamples(), [True] * 5 + [False])
+    assert np.array_equal(tr.GetCalledSamples(strict=False), [True] * 6)
+    assert tr.GetCallRate() == pytest.approx(5 / 6) and tr.GetCallRate(strict=False) == 1
+    lg = tr.GetLengthGenotypes()
+    assert lg.dtype == np.float64 and np.array_equal(lg[:, :-1], [[3, 4], [4, 4], [4, 4], [4, 6], [6, 6], [3, -1]])
+    assert np.array_equal(tr.GetDosages(), np.array([7, 8, 8, 10, 12, 3], dtype=np.float32))
+    # fabricated alleles (length-only callers)
+    rec2 = DummyCyvcf2Record(gts, "A", ["<STR4>", "<STR5.5>"])
+    tr2 = trh.TRRecord(rec2, None, None, "CAG", "x", None, ref_allele_length=3, alt_allele_lengths=[4, 5.5])
+    assert tr2.ref_allele == "CAGCAGCAG" and tr2.alt_alleles == ["CAGCAGCAGCAG", "CAGCAGCAGCAGCAGC"]
+    assert tr2.GetAlleleCounts() == {3: 2, 4: 6, 5.5: 3}
+    # no samples
+    tr3 = trh.TRRecord(DummyCyvcf2Record(None, "CAGCAG", []), "CAGCAG", [], "CAG", "y", None)
+    assert tr3.GetAlleleCounts() == {} and tr3.GetGenotypeCounts() == {} and tr3.GetGenotypeIndicies() is None
+    # argument validation errors of the constructor (:720-731)
+    with pytest.raises(ValueError):
+        trh.TRRecord(rec, "CAG", ["CAG"], "CAG", "", None, alt_allele_lengths=[1])
+    with pytest.raises(ValueError):
+        trh.TRRecord(rec, "CAGCAGCAG", ["CAG"], "CAG", "", None)      # wrong number of alts

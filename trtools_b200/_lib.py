@@ -1,0 +1,354 @@
+"""
+ctypes binding of libtrtools_b200.so (include/trtools_b200.h).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present, every
+compute entry point raises.  ``load()`` only dlopens the library (no CUDA call), so the
+symbol-export test can run on a box without a GPU.
+"""
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtrtools_b200.so")
+
+TRT_OK = 0
+TRT_ENODEV, TRT_ECUDA, TRT_EINVAL, TRT_ESTATE, TRT_ENOMEM, TRT_ERECORD, TRT_ENCCL = -1, -2, -3, -4, -5, -6, -7
+
+VCF_TYPES = {"gangstr": 0, "advntr": 1, "hipstr": 2, "eh": 3, "popstr": 4, "longtr": 5}
+FMT_DP, FMT_DSTUTTER, FMT_DFLANKINDEL, FMT_Q, FMT_AUX_I32, FMT_AUX_F32, FMT_QEXP = range(7)
+CF_MIN, CF_MAX, CF_RATIO_GT, CF_QEXP_HET, CF_QEXP_HOM, CF_QEXP_TOT = range(6)
+LF_CALLRATE, LF_HWE, LF_HETLOW, LF_HETHIGH, LF_HRUN = range(5)
+AF_OK, AF_NO_CALLED, AF_ONE_ALLELE, AF_NON_MAJOR, AF_NCOVARS = range(5)
+HF_HAS_FULL, HF_MOTIF_N, HF_MOTIF_NONACGT, HF_LEN_DUPS, HF_SEQ_DUPS, HF_BAD_PERIOD = 1, 2, 4, 8, 16, 32
+
+# every symbol include/trtools_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "trt_device_count", "trt_init", "trt_destroy", "trt_last_error", "trt_device_info", "trt_synchronize",
+    "trt_host_alloc", "trt_host_free", "trt_launch_count", "trt_last_kernel_ms", "trt_last_scan_ms",
+    "trt_stopwatch_start", "trt_stopwatch_stop",
+    "trt_block_begin", "trt_block_set_gt", "trt_block_set_gt_device", "trt_block_set_format_i32",
+    "trt_block_set_format_f32", "trt_block_set_format_device", "trt_block_set_alleles",
+    "trt_harmonize", "trt_get_harmonized", "trt_pack_length_genotypes", "trt_get_packed_gt",
+    "trt_locus_stats", "trt_genotype_counts", "trt_call_filters", "trt_locus_filters", "trt_assoc_set_design", "trt_assoc_ols",
+    "trt_synth_fill", "trt_block_get_gt", "trt_block_get_format",
+    "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
+    "trt_dist_allreduce_sum_f64", "trt_dist_barrier",
+]
+
+
+class TrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("trtools_b200 [{}]: {}".format(code, msg))
+        self.code = code
+        self.msg = msg
+
+
+class DevInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+                ("sm_count", C.c_int32), ("total_mem_bytes", C.c_int64), ("free_mem_bytes", C.c_int64),
+                ("l2_bytes", C.c_int32), ("abi_version", C.c_int32)]
+
+
+class HarmonizeOut(C.Structure):
+    _fields_ = [("allele_len", C.c_void_p), ("trim_off", C.c_void_p), ("trim_len", C.c_void_p),
+                ("len_class", C.c_void_p), ("seq_class", C.c_void_p), ("len_order", C.c_void_p),
+                ("seq_order", C.c_void_p), ("hrun", C.c_void_p), ("flags", C.c_void_p),
+                ("motif", C.c_void_p), ("motif_off", C.c_void_p)]
+
+
+class LocusStatsOut(C.Structure):
+    _fields_ = [("ac", C.c_void_p), ("n_called", C.c_void_p), ("n_called_nonstrict", C.c_void_p),
+                ("n_hom", C.c_void_p), ("n_padded", C.c_void_p), ("thresh", C.c_void_p), ("het", C.c_void_p),
+                ("entropy", C.c_void_p), ("mean", C.c_void_p), ("mode", C.c_void_p), ("var", C.c_void_p),
+                ("hwep", C.c_void_p), ("nalleles", C.c_void_p)]
+
+
+class CallFilterSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("field_id", C.c_int32), ("threshold", C.c_double)]
+
+
+class CallFilterOut(C.Structure):
+    _fields_ = [("call_mask", C.c_void_p), ("trigger_values", C.c_void_p), ("gt_masked", C.c_void_p),
+                ("filter_counts", C.c_void_p), ("numcalls", C.c_void_p), ("totaldp", C.c_void_p),
+                ("negative_dp_locus", C.c_void_p)]
+
+
+class LocusFilterSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("threshold", C.c_double)]
+
+
+class LocusFilterOut(C.Structure):
+    _fields_ = [("flags", C.c_void_p), ("n_called", C.c_void_p), ("het", C.c_void_p), ("hwep", C.c_void_p),
+                ("ac", C.c_void_p), ("hrun", C.c_void_p)]
+
+
+class AssocOut(C.Structure):
+    _fields_ = [("filter_code", C.c_void_p), ("n_tested", C.c_void_p), ("p", C.c_void_p), ("coef", C.c_void_p),
+                ("se", C.c_void_p), ("r2", C.c_void_p), ("std_g", C.c_void_p), ("ac_len", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare signatures (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libtrtools_b200.so is not built ({}). Run `python -m trtools_b200.build` "
+            "(needs nvcc); there is no CPU fallback.".format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, u32, u64, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_double, C.c_size_t
+    sig = {
+        "trt_device_count": (i32, []),
+        "trt_init": (i32, [i32, C.POINTER(vp)]),
+        "trt_destroy": (None, [vp]),
+        "trt_last_error": (C.c_char_p, [vp]),
+        "trt_device_info": (i32, [vp, C.POINTER(DevInfo)]),
+        "trt_synchronize": (i32, [vp]),
+        "trt_host_alloc": (vp, [vp, sz]),
+        "trt_host_free": (i32, [vp, vp]),
+        "trt_launch_count": (i64, [vp]),
+        "trt_last_kernel_ms": (f64, [vp]),
+        "trt_last_scan_ms": (f64, [vp]),
+        "trt_stopwatch_start": (i32, [vp]),
+        "trt_stopwatch_stop": (i32, [vp, C.POINTER(f64)]),
+        "trt_block_begin": (i32, [vp, i64, i64, i32, i32]),
+        "trt_block_set_gt": (i32, [vp, vp]),
+        "trt_block_set_gt_device": (i32, [vp, vp, sz]),
+        "trt_block_set_format_i32": (i32, [vp, i32, vp]),
+        "trt_block_set_format_f32": (i32, [vp, i32, vp, i32]),
+        "trt_block_set_format_device": (i32, [vp, i32, vp, i32]),
+        "trt_block_set_alleles": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "trt_harmonize": (i32, [vp]),
+        "trt_get_harmonized": (i32, [vp, C.POINTER(HarmonizeOut)]),
+        "trt_pack_length_genotypes": (i32, [vp]),
+        "trt_get_packed_gt": (i32, [vp, vp]),
+        "trt_locus_stats": (i32, [vp, i32, vp, i32, f64, C.POINTER(LocusStatsOut)]),
+        "trt_genotype_counts": (i32, [vp, i64, vp, vp, i64]),
+        "trt_call_filters": (i32, [vp, C.POINTER(CallFilterSpec), i32, i32, C.POINTER(CallFilterOut)]),
+        "trt_locus_filters": (i32, [vp, C.POINTER(LocusFilterSpec), i32, i32, C.POINTER(LocusFilterOut)]),
+        "trt_assoc_set_design": (i32, [vp, vp, vp, vp, i64, i32]),
+        "trt_assoc_ols": (i32, [vp, f64, C.POINTER(AssocOut)]),
+        "trt_synth_fill": (i32, [vp, u64, i64, i64, i64, vp, u32, u32, i32]),
+        "trt_block_get_gt": (i32, [vp, i64, i64, vp]),
+        "trt_block_get_format": (i32, [vp, i32, i64, i64, vp]),
+        "trt_dist_unique_id": (i32, [vp]),
+        "trt_dist_init": (i32, [vp, i32, i32, vp]),
+        "trt_dist_allgather_f64": (i32, [vp, vp, i64, vp]),
+        "trt_dist_allreduce_sum_i64": (i32, [vp, vp, i64]),
+        "trt_dist_allreduce_sum_f64": (i32, [vp, vp, i64]),
+        "trt_dist_barrier": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    return int(load().trt_device_count())
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    """C-contiguous array of the exact dtype (no copy when already so)."""
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One GPU context (``trt_ctx``).  Not thread-safe; one per device per process."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.trt_init(int(device), C.byref(h))
+        if rc != TRT_OK:
+            msg = self.lib.trt_last_error(None)
+            raise TrtError(rc, msg.decode() if msg else "trt_init failed")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.trt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != TRT_OK:
+            msg = self.lib.trt_last_error(self.h)
+            raise TrtError(rc, msg.decode() if msg else "error")
+
+    # -- info -----------------------------------------------------------------------------------
+    def device_info(self) -> dict:
+        d = DevInfo()
+        self.check(self.lib.trt_device_info(self.h, C.byref(d)))
+        return dict(name=d.name.decode(), cc=(d.cc_major, d.cc_minor), sm_count=d.sm_count,
+                    total_mem_bytes=d.total_mem_bytes, free_mem_bytes=d.free_mem_bytes, l2_bytes=d.l2_bytes,
+                    abi_version=d.abi_version)
+
+    def launch_count(self) -> int:
+        return int(self.lib.trt_launch_count(self.h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.trt_last_kernel_ms(self.h))
+
+    def last_scan_ms(self) -> float:
+        return float(self.lib.trt_last_scan_ms(self.h))
+
+    def stopwatch_start(self):
+        self.check(self.lib.trt_stopwatch_start(self.h))
+
+    def stopwatch_stop(self) -> float:
+        ms = C.c_double()
+        self.check(self.lib.trt_stopwatch_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def synchronize(self):
+        self.check(self.lib.trt_synchronize(self.h))
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over cudaHostAlloc'd memory (freed when the context closes is NOT automatic:
+        keep the returned array's ``_trt_base`` alive and call ``free_pinned``)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = self.lib.trt_host_alloc(self.h, n)
+        if not p:
+            self.check(TRT_ENOMEM)
+        buf = (C.c_char * max(n, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        arr.flags.writeable = True
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def free_pinned(self, arr: np.ndarray):
+        p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if p:
+            self.check(self.lib.trt_host_free(self.h, p))
+
+    # -- block ----------------------------------------------------------------------------------
+    def block_begin(self, n_loci, n_samples, ploidy, vcftype):
+        vt = VCF_TYPES[vcftype] if isinstance(vcftype, str) else int(vcftype)
+        self.check(self.lib.trt_block_begin(self.h, int(n_loci), int(n_samples), int(ploidy), vt))
+        self.L, self.S, self.P = int(n_loci), int(n_samples), int(ploidy)
+
+    def block_set_gt(self, gt: np.ndarray):
+        gt = _c(gt, np.int16)
+        assert gt.shape == (self.L, self.S, self.P + 1), (gt.shape, (self.L, self.S, self.P + 1))
+        self.check(self.lib.trt_block_set_gt(self.h, _ptr(gt)))
+
+    def block_set_format(self, field_id: int, arr: np.ndarray):
+        if arr.dtype.kind == 'i':
+            a = _c(arr, np.int32).reshape(self.L, self.S)
+            self.check(self.lib.trt_block_set_format_i32(self.h, field_id, _ptr(a)))
+        else:
+            a = _c(arr, np.float32).reshape(self.L, self.S, -1)
+            self.check(self.lib.trt_block_set_format_f32(self.h, field_id, _ptr(a), a.shape[2]))
+
+    def block_set_alleles(self, seqs: bytes, allele_off, locus_off, pos, start, end, period, given_len=None,
+                          motifs: Optional[bytes] = None):
+        allele_off = _c(allele_off, np.int64)
+        locus_off = _c(locus_off, np.int32)
+        pos, start, end, period = (_c(x, np.int32) for x in (pos, start, end, period))
+        gl = None if given_len is None else _c(given_len, np.float64)
+        sbuf = C.create_string_buffer(seqs, len(seqs)) if len(seqs) else None
+        mbuf = C.create_string_buffer(motifs, len(motifs)) if motifs else None
+        self.nA = int(locus_off[-1]) if len(locus_off) else 0
+        self.locus_off = locus_off
+        self.check(self.lib.trt_block_set_alleles(
+            self.h, C.cast(sbuf, C.c_void_p) if sbuf is not None else None, _ptr(allele_off), _ptr(locus_off),
+            _ptr(pos), _ptr(start), _ptr(end), _ptr(period), _ptr(gl),
+            C.cast(mbuf, C.c_void_p) if mbuf is not None else None))
+        self._period = period
+
+    def harmonize(self) -> dict:
+        self.check(self.lib.trt_harmonize(self.h))
+        nA, L = self.nA, self.L
+        out = dict(allele_len=np.empty(nA, np.float64), trim_off=np.empty(nA, np.int32),
+                   trim_len=np.empty(nA, np.int32), len_class=np.empty(nA, np.int32),
+                   seq_class=np.empty(nA, np.int32), len_order=np.empty(nA, np.int32),
+                   seq_order=np.empty(nA, np.int32), hrun=np.empty(L, np.int32), flags=np.empty(L, np.int32),
+                   motif_off=np.empty(L + 1, np.int64))
+        mbytes = int(np.sum(np.maximum(self._period, 0)))
+        motif = np.empty(max(mbytes, 1), np.uint8)
+        ho = HarmonizeOut(**{k: _ptr(v) for k, v in out.items()}, motif=_ptr(motif))
+        self.check(self.lib.trt_get_harmonized(self.h, C.byref(ho)))
+        out["motif"] = motif[:mbytes].tobytes()
+        return out
+
+    def pack_length_genotypes(self) -> np.ndarray:
+        self.check(self.lib.trt_pack_length_genotypes(self.h))
+        out = np.empty((self.L, self.S, self.P), np.int16)
+        self.check(self.lib.trt_get_packed_gt(self.h, _ptr(out)))
+        return out
+
+    def locus_stats(self, use_length: bool, group_masks: Optional[np.ndarray] = None,
+                    nalleles_thresh: float = 0.01, want=None) -> dict:
+        G = 1 if group_masks is None else int(group_masks.shape[0])
+        gm = None if group_masks is None else _c(group_masks, np.uint8).reshape(G, self.S)
+        L, nA = self.L, self.nA
+        out = dict(ac=np.empty((G, nA), np.int32), n_called=np.empty((G, L), np.int64),
+                   n_called_nonstrict=np.empty((G, L), np.int64), n_hom=np.empty((G, L), np.int64),
+                   n_padded=np.empty((G, L), np.int64), thresh=np.empty((G, L)), het=np.empty((G, L)),
+                   entropy=np.empty((G, L)), mean=np.empty((G, L)), mode=np.empty((G, L)), var=np.empty((G, L)),
+                   hwep=np.empty((G, L)), nalleles=np.empty((G, L), np.int32))
+        if want is not None:
+            out = {k: v for k, v in out.items() if k in want}
+        so = LocusStatsOut(**{k: _ptr(v) for k, v in out.items()})
+        self.check(self.lib.trt_locus_stats(self.h, 1 if use_length else 0, _ptr(gm), G, float(nalleles_thresh),
+                                            C.byref(so)))
+        return out
+
+    def genotype_counts(self, locus: int, n_alleles: int, mask: Optional[np.ndarray] = None) -> np.ndarray:
+        """dense (A+2)^P table of sorted-index genotype counts of one locus (digit = allele + 2)."""
+        n = (n_alleles + 2) ** self.P
+        table = np.zeros(n, np.int64)
+        m = None if mask is None else _c(mask, np.uint8)
+        self.check(self.lib.trt_genotype_counts(self.h, int(locus), _ptr(m), _ptr(table), n))
+        return table.reshape((n_alleles + 2,) * self.P)
+
+    def synth_fill(self, seed, locus_offset, cum_freq, miss_thresh, half_thresh, with_format=True):
+        cf = _c(cum_freq, np.uint32)
+        self.check(self.lib.trt_synth_fill(self.h, int(seed), int(locus_offset), self.L, self.S, _ptr(cf),
+                                           int(miss_thresh), int(half_thresh), 1 if with_format else 0))
+
+    def block_get_gt(self, locus0, n) -> np.ndarray:
+        out = np.empty((n, self.S, self.P + 1), np.int16)
+        self.check(self.lib.trt_block_get_gt(self.h, int(locus0), int(n), _ptr(out)))
+        return out
+
+    def block_get_format(self, field_id, locus0, n, dtype, ncol=1) -> np.ndarray:
+        out = np.empty((n, self.S, ncol) if ncol > 1 else (n, self.S), dtype)
+        self.check(self.lib.trt_block_get_format(self.h, int(field_id), int(locus0), int(n), _ptr(out)))
+        return out
+
+
+_default_ctx = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    """Process-wide context for ``device`` (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("TRTOOLS_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,270 @@
+"""
+Blocked ingest: turn a run of cyvcf2 records into the stacked arrays the CUDA kernels consume.
+
+The reference pulls ``genotype.array()`` / ``format(key)`` per record
+(trtools/utils/tr_harmonizer.py:561-588, 829-862) and does the allele-string work of
+``HarmonizeRecord`` (:264-550) in Python per record.  Here a block of L records is staged once
+(GT int16 [L][S][P+1], numeric FORMAT [L][S], one concatenated allele table), copied to HBM and
+harmonized by one kernel launch; the per-record Python objects become thin views of the block.
+
+Only the caller-specific INFO validation (mandatory fields, ALT syntax) stays in Python, raising
+the same exception types and messages as the reference.
+"""
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+_beagle_error = "If this file was imputed by Beagle, did you remember to copy the info fields over?"
+
+# numeric FORMAT fields with a fixed slot in the C-ABI
+FIXED_FMT = {"DP": _lib.FMT_DP, "DSTUTTER": _lib.FMT_DSTUTTER, "DFLANKINDEL": _lib.FMT_DFLANKINDEL,
+             "Q": _lib.FMT_Q, "QEXP": _lib.FMT_QEXP}
+
+
+class RecordMeta:
+    """Caller-specific scalars of one record, validated like the reference's _Harmonize*Record."""
+    __slots__ = ("chrom", "vcf_pos", "record_id", "ref", "alts", "start", "end", "period", "given_len",
+                 "motif_in", "quality_field", "harmonized_pos", "vcftype", "fabricated_ref", "fabricated_alts")
+
+
+def record_meta(vcftype: str, rec) -> RecordMeta:
+    """INFO validation + scalars (tr_harmonizer.py:303-550).  Raises TypeError exactly where the
+    reference does."""
+    m = RecordMeta()
+    info = rec.INFO
+    m.vcftype = vcftype
+    m.chrom = rec.CHROM
+    m.vcf_pos = int(rec.POS)
+    m.ref = rec.REF
+    m.alts = list(rec.ALT) if rec.ALT else []
+    m.given_len = None
+    m.motif_in = None
+    m.harmonized_pos = None
+    m.fabricated_ref = False
+    m.fabricated_alts = False
+    where = "{}:{}".format(rec.CHROM, rec.POS)
+    if vcftype in ("hipstr", "longtr"):
+        if info.get('START') is None or info.get('END') is None or info.get('PERIOD') is None:
+            raise TypeError("Record at {} is missing one of the mandatory HipSTR/LongTR info fields "
+                            "START, END, PERIOD. ".format(where) + _beagle_error)
+        m.start = int(info['START'])
+        m.end = int(info['END'])
+        m.period = int(info['PERIOD'])
+        m.record_id = rec.ID
+        m.quality_field = 'Q' if info.get('IMP') is None else None
+        m.harmonized_pos = m.start
+    elif vcftype == "gangstr":
+        if info.get('RU') is None:
+            raise TypeError("Record at {} is missing mandatory GangSTR info field RU. ".format(where) + _beagle_error)
+        if info.get('VID') is not None:
+            raise TypeError("Trying to read an AdVNTR record as a GangSTR record {}".format(where))
+        if info.get('VARID') is not None:
+            raise TypeError("Trying to read an EH record as a GangSTR record {}".format(where))
+        m.motif_in = info["RU"].upper()
+        m.record_id = None
+        m.quality_field = 'Q' if info.get('IMP') is None else None
+    elif vcftype == "advntr":
+        if info.get('RU') is None or info.get('VID') is None:
+            raise TypeError("Record at {} is missing one of the mandatory ADVNTR info fields RU, VID. ".format(where)
+                            + _beagle_error)
+        m.motif_in = info["RU"].upper()
+        m.record_id = info["VID"]
+        m.quality_field = 'ML' if info.get('IMP') is None else None
+    elif vcftype == "popstr":
+        if info.get('Motif') is None:
+            raise TypeError("Record at {} is missing mandatory PopSTR info field MOTIF".format(where))
+        m.motif_in = info["Motif"].upper()
+        m.record_id = rec.ID
+        m.quality_field = None
+        lens = [np.nan]
+        for alt in m.alts:
+            alt = str(alt)
+            if alt[0] != "<" or alt[-1] != ">":
+                raise TypeError("This record does not look like a PopSTR record. Alt alleles were not formatted"
+                                " as expected")
+            lens.append(float(alt[1:-1]))
+        m.given_len = lens
+        m.fabricated_alts = True
+    elif vcftype == "eh":
+        if info.get('VARID') is None or info.get('RU') is None:
+            raise TypeError("Record at {} is missing one of the mandatory ExpansionHunter info fields VARID, RU. "
+                            .format(where) + _beagle_error)
+        m.record_id = info["VARID"]
+        m.motif_in = info["RU"].upper()
+        lens = [int(info["RL"]) / len(m.motif_in)]
+        for alt in m.alts:
+            alt = str(alt)
+            if alt[:4] != "<STR" or alt[-1] != ">":
+                raise TypeError("This record does not look like an EH  record. Alt alleles were not formatted"
+                                " as expected")
+            lens.append(float(alt[4:-1]))
+        m.given_len = lens
+        m.quality_field = None
+        m.fabricated_ref = True
+        m.fabricated_alts = True
+    else:
+        raise ValueError("{} is not an excepted TR vcf type".format(vcftype))
+    if vcftype not in ("hipstr", "longtr"):
+        m.start = m.vcf_pos
+        m.end = m.vcf_pos + len(m.ref) - 1
+        m.period = len(m.motif_in)
+    return m
+
+
+class Block:
+    """L harmonized loci resident on the GPU + the host-side tables describing them."""
+
+    def __init__(self, ctx: "_lib.Context", vcftype: str, metas: List[RecordMeta], gt: Optional[np.ndarray],
+                 fmt: Optional[Dict[str, np.ndarray]] = None):
+        self.ctx = ctx
+        self.vcftype = vcftype
+        self.metas = metas
+        L = len(metas)
+        self.L = L
+        self.has_samples = gt is not None
+        if gt is None:
+            gt = np.zeros((L, 0, 3), dtype=np.int16)
+        self.gt = np.ascontiguousarray(gt, dtype=np.int16)
+        self.S = self.gt.shape[1]
+        self.P = self.gt.shape[2] - 1
+        # ---- allele table ----------------------------------------------------------------------
+        seq_parts: List[bytes] = []
+        allele_off = [0]
+        locus_off = [0]
+        given: List[float] = []
+        any_given = False
+        motifs: List[bytes] = []
+        any_motif = False
+        for m in metas:
+            alleles = [m.ref] + m.alts
+            for j, a in enumerate(alleles):
+                if m.given_len is not None and not np.isnan(m.given_len[j]):
+                    b = b""
+                    given.append(m.given_len[j])
+                    any_given = True
+                else:
+                    b = str(a).encode("ascii", "replace")
+                    given.append(np.nan)
+                seq_parts.append(b)
+                allele_off.append(allele_off[-1] + len(b))
+            locus_off.append(locus_off[-1] + len(alleles))
+            if m.motif_in is not None:
+                motifs.append(m.motif_in.encode("ascii", "replace"))
+                any_motif = True
+            else:
+                motifs.append(b"N" * max(m.period, 0))
+        self.seqs = b"".join(seq_parts)
+        self.allele_off = np.array(allele_off, dtype=np.int64)
+        self.locus_off = np.array(locus_off, dtype=np.int32)
+        self.pos = np.array([m.vcf_pos for m in metas], dtype=np.int32)
+        self.start = np.array([m.start for m in metas], dtype=np.int32)
+        self.end = np.array([m.end for m in metas], dtype=np.int32)
+        self.period = np.array([m.period for m in metas], dtype=np.int32)
+        self.given_len = np.array(given, dtype=np.float64) if any_given else None
+        self.motifs_in = b"".join(motifs) if any_motif else None
+        # ---- upload + harmonize --------------------------------------------------------------
+        ctx.block_begin(L, self.S, self.P, vcftype)
+        ctx.block_set_gt(self.gt)
+        ctx.block_set_alleles(self.seqs, self.allele_off, self.locus_off, self.pos, self.start, self.end,
+                              self.period, self.given_len, self.motifs_in)
+        self.fmt = fmt or {}
+        for key, arr in self.fmt.items():
+            if key in FIXED_FMT and arr is not None:
+                ctx.block_set_format(FIXED_FMT[key], arr)
+        self.h = ctx.harmonize()
+        bad = np.nonzero(self.h["flags"] & _lib.HF_BAD_PERIOD)[0]
+        if len(bad):
+            raise ValueError("Record {}:{} has a non-positive period".format(metas[bad[0]].chrom, metas[bad[0]].vcf_pos))
+        self._stats = {}
+        ctx._current_block = self
+
+    # ---- cached block-level statistics (one GPU pass per (use_length)) --------------------------
+    def stats(self, use_length: bool, nalleles_thresh: float = 0.01, group_masks: Optional[np.ndarray] = None):
+        if group_masks is not None:
+            return self.ctx_stats(use_length, nalleles_thresh, group_masks)
+        key = (bool(use_length), float(nalleles_thresh))
+        if key not in self._stats:
+            self._stats[key] = self.ctx_stats(use_length, nalleles_thresh, None)
+        return self._stats[key]
+
+    def ctx_stats(self, use_length, nalleles_thresh, group_masks):
+        self._activate()
+        return self.ctx.locus_stats(use_length, group_masks, nalleles_thresh)
+
+    def _activate(self):
+        """Make this block the context's current block again (another block may have replaced it)."""
+        if getattr(self.ctx, "_current_block", None) is not self:
+            self.ctx.block_begin(self.L, self.S, self.P, self.vcftype)
+            self.ctx.block_set_gt(self.gt)
+            self.ctx.block_set_alleles(self.seqs, self.allele_off, self.locus_off, self.pos, self.start, self.end,
+                                       self.period, self.given_len, self.motifs_in)
+            for key, arr in self.fmt.items():
+                if key in FIXED_FMT and arr is not None:
+                    self.ctx.block_set_format(FIXED_FMT[key], arr)
+            self.ctx.harmonize()
+        self.ctx._current_block = self
+
+    # ---- per-locus views ---------------------------------------------------------------------------
+    def allele_slice(self, l: int) -> slice:
+        return slice(int(self.locus_off[l]), int(self.locus_off[l + 1]))
+
+    def trimmed_alleles(self, l: int) -> List[str]:
+        """Upper-cased trimmed allele strings of locus l (fabricated for length-only alleles)."""
+        sl = self.allele_slice(l)
+        out = []
+        m = self.metas[l]
+        motif = self.motif(l)
+        for j, a in enumerate(range(sl.start, sl.stop)):
+            tl = int(self.h["trim_len"][a])
+            if m.given_len is not None and not np.isnan(m.given_len[j]):
+                reps = tl // max(len(motif), 1) + 1
+                out.append((motif * reps)[:tl])
+            else:
+                o = int(self.allele_off[a]) + int(self.h["trim_off"][a])
+                out.append(self.seqs[o:o + tl].decode("ascii").upper())
+        return out
+
+    def motif(self, l: int) -> str:
+        o0, o1 = int(self.h["motif_off"][l]), int(self.h["motif_off"][l + 1])
+        return self.h["motif"][o0:o1].decode("ascii")
+
+
+def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[str] = ()) -> Block:
+    """Stage a run of cyvcf2-like records (same ploidy) as one GPU block."""
+    metas = [record_meta(vcftype, r) for r in records]
+    gts = []
+    has_samples = True
+    for r in records:
+        g = r.genotype
+        if g is None:
+            has_samples = False
+            break
+        gts.append(g.array())
+    gt = None
+    if has_samples and gts:
+        P = max(g.shape[1] for g in gts)
+        S = gts[0].shape[0]
+        gt = np.full((len(gts), S, P), -2, dtype=np.int16)
+        for i, g in enumerate(gts):
+            p = g.shape[1] - 1
+            gt[i, :, :p] = g[:, :p]
+            gt[i, :, P - 1] = g[:, p]
+    fmt = {}
+    for key in fmt_keys:
+        cols = []
+        ok = True
+        for r in records:
+            try:
+                v = r.format(key)
+            except KeyError:
+                ok = False
+                break
+            if v is None:
+                ok = False
+                break
+            cols.append(v)
+        if ok and cols:
+            fmt[key] = np.stack(cols, axis=0)
+    return Block(ctx, vcftype, metas, gt, fmt)

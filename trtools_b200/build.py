@@ -1,0 +1,74 @@
+"""
+Build libtrtools_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m trtools_b200.build [--force]
+
+The library travels to the GPU box with the repo snapshot (git-ignored, not gpurun-ignored).
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libtrtools_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _find_nccl():
+    """Prefer the NCCL that ships with torch (2.28.9) so the .so and torch.distributed agree."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            root = list(spec.submodule_search_locations)[0]
+            inc, lib = os.path.join(root, "include"), os.path.join(root, "lib")
+            if os.path.exists(os.path.join(inc, "nccl.h")) and glob.glob(os.path.join(lib, "libnccl.so*")):
+                return inc, lib, os.path.basename(sorted(glob.glob(os.path.join(lib, "libnccl.so*")))[0])
+    except Exception:
+        pass
+    return None, None, None
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(os.path.dirname(HERE), "include", "trtools_b200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    inc, libdir, soname = _find_nccl()
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    if inc:
+        cmd += ["-I", inc, "-L", libdir, "-l:" + soname, "-Xlinker", "-rpath=" + libdir]
+    else:
+        cmd += ["-lnccl"]
+    cmd += ["-o", LIB] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libtrtools_b200.so")
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,783 @@
+// K2 — per-locus statistics straight from the native cyvcf2 GT rows (6 B/call for diploids).
+//
+//   scan_diploid_tma_kernel : persistent CTAs, one locus at a time per CTA.  A producer warp
+//       streams the locus' GT row through a 4-stage shared-memory ring with 1-D bulk TMA copies
+//       (cp.async.bulk + mbarrier transaction bytes); 16 consumer warps read 48 B (= 8 calls)
+//       per thread with three conflict-free LDS.128 and count alleles in THREAD-PRIVATE 16-bit
+//       shared-memory counters (no atomics on the sample axis), plus called / padded /
+//       homozygous counters in registers.  One CTA-wide reduction per locus.
+//   scan_generic_kernel     : warp per locus; any ploidy, any allele count, tiny sample counts.
+//   locus_epilogue_kernel   : thread per (group, locus): allele-frequency statistics and the
+//       exact two-sided binomial HWE test in FP64 from the O(alleles) count tables.
+//
+// Reference semantics reproduced (file:line in the reference tree):
+//   TRRecord.GetAlleleCounts    trtools/utils/tr_harmonizer.py:1420-1499  (-1/-2 dropped; partial calls count)
+//   TRRecord.GetGenotypeCounts  :1326-1418 (sorted haplotypes; genotypes with a no-call dropped, pads kept)
+//   TRRecord.GetCalledSamples   :864-897, GetMaxAllele :1542-1575
+//   utils.GetHeterozygosity/GetEntropy/GetMean/GetMode/GetVariance  trtools/utils/utils.py:142-296
+//   utils.GetHardyWeinbergBinomialTest :298-338 -> scipy.stats.binomtest (two-sided, exact)
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "trt_internal.cuh"
+
+namespace {
+
+constexpr int kConsumerThreads = 512;
+constexpr int kConsumerWarps = kConsumerThreads / 32;
+constexpr int kThreads = kConsumerThreads + 32;          // + producer warp
+constexpr int kCallsPerThread = 8;                        // 8 calls x 6 B = 48 B = 3 x LDS.128
+constexpr int kChunkBytes = kConsumerThreads * 48;        // 24576
+constexpr int kChunkCalls = kConsumerThreads * kCallsPerThread;
+constexpr int kStages = 4;
+constexpr int kMaxFastAlleles = 96;                       // thread-private u16 counters: 1 KB per allele
+constexpr int kMinFastSamples = 2048;
+
+struct ScanParams {
+    const int16_t* gt;
+    size_t pitch;
+    int64_t L, S;
+    int P;
+    const int32_t* locus_off;
+    const int32_t* len_class;
+    const int32_t* seq_class;
+    const int32_t* len_rank;
+    const int32_t* seq_rank;
+    const int32_t* hflags;
+    const uint8_t* mask;   // [S] bytes or null
+    int32_t* ac;           // [nA]
+    long long* lc;         // [L][TRT_LC_N]
+    int only_ineligible;   // generic kernel: process only loci the fast kernel skipped
+    int fast_enabled;
+};
+
+__device__ __forceinline__ bool fast_eligible(int A) { return A <= kMaxFastAlleles; }
+
+// ------------------------------------------------------------------------------------------------
+// generic: one warp per locus
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scan_generic_kernel(ScanParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t l = warp; l < p.L; l += nwarps) {
+        const int a0 = p.locus_off[l];
+        const int A = p.locus_off[l + 1] - a0;
+        if (p.only_ineligible && p.fast_enabled && fast_eligible(A)) continue;
+        const int16_t* row = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch);
+        const int P = p.P;
+        long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
+        for (int64_t s = lane; s < p.S; s += 32) {
+            if (p.mask && !p.mask[s]) continue;
+            const int16_t* g = row + s * (P + 1);
+            bool any_m1 = false, any_called = false, any_pad = false;
+            // two smallest keys under each relation (pads sort first: key -2)
+            int i1 = INT_MAX, i2 = INT_MAX, l1 = INT_MAX, l2 = INT_MAX, q1 = INT_MAX, q2 = INT_MAX;
+            for (int h = 0; h < P; h++) {
+                int a = g[h];
+                int ki, kl, kq;
+                if (a == -1) {
+                    any_m1 = true;
+                    continue;
+                } else if (a == -2) {
+                    any_pad = true;
+                    ki = kl = kq = -2;
+                } else if (a >= 0 && a < A) {
+                    any_called = true;
+                    atomicAdd(&p.ac[a0 + a], 1);
+                    ki = a;
+                    kl = p.len_rank[a0 + a];
+                    kq = p.seq_rank[a0 + a];
+                } else {
+                    n_bad++;
+                    any_m1 = true;
+                    continue;
+                }
+                if (ki < i1) { i2 = i1; i1 = ki; } else if (ki < i2) i2 = ki;
+                if (kl < l1) { l2 = l1; l1 = kl; } else if (kl < l2) l2 = kl;
+                if (kq < q1) { q2 = q1; q1 = kq; } else if (kq < q2) q2 = kq;
+            }
+            if (any_called) n_non++;
+            if (!any_m1) {
+                n_full++;
+                if (any_pad) n_pad++;
+                if (P >= 2) {
+                    h_idx += (i1 == i2);
+                    h_len += (l1 == l2);
+                    h_seq += (q1 == q2);
+                }
+            }
+        }
+        n_full = warp_sum_ll(n_full); n_non = warp_sum_ll(n_non); n_pad = warp_sum_ll(n_pad);
+        h_idx = warp_sum_ll(h_idx); h_len = warp_sum_ll(h_len); h_seq = warp_sum_ll(h_seq);
+        n_bad = warp_sum_ll(n_bad);
+        if (lane == 0) {
+            long long* o = p.lc + l * TRT_LC_N;
+            o[TRT_LC_NFULL] = n_full; o[TRT_LC_NNONSTRICT] = n_non; o[TRT_LC_NPAD] = n_pad;
+            o[TRT_LC_HOM_IDX] = h_idx; o[TRT_LC_HOM_LEN] = h_len; o[TRT_LC_HOM_SEQ] = h_seq;
+            o[6] = n_bad; o[7] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast diploid path
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) FastSmemHeader {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    long long warp_part[kConsumerWarps][8];
+    uint32_t cls[kMaxFastAlleles];   // (len_class << 16) | seq_class
+};
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+
+template <bool MASKED>
+__global__ void __launch_bounds__(kThreads, 1) scan_diploid_tma_kernel(ScanParams p, int max_alleles_smem) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* ring = smem;                                             // kStages * kChunkBytes
+    FastSmemHeader* hdr = (FastSmemHeader*)(smem + kStages * kChunkBytes);
+    uint16_t* cnt = (uint16_t*)(smem + kStages * kChunkBytes + sizeof(FastSmemHeader));  // [A][512]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const size_t row_bytes = (size_t)p.S * 6;
+    const size_t copy_bytes = (row_bytes + 15) & ~size_t(15);               // <= pitch
+    const int nchunks = (int)((copy_bytes + kChunkBytes - 1) / kChunkBytes);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&hdr->full[s], 1);
+            mbar_init(&hdr->empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    // zero the private counters
+    for (int i = tid; i < max_alleles_smem * kConsumerThreads / 2; i += kThreads) ((uint32_t*)cnt)[i] = 0u;
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===== producer warp: one elected lane feeds the ring, running ahead across loci =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
+                const int A = p.locus_off[l + 1] - p.locus_off[l];
+                if (!fast_eligible(A)) continue;
+                const char* src = (const char*)p.gt + (size_t)l * p.pitch;
+                for (int c = 0; c < nchunks; c++, it++) {
+                    const int stage = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1u;
+                    mbar_wait(&hdr->empty[stage], phase ^ 1u);
+                    const size_t off = (size_t)c * kChunkBytes;
+                    const uint32_t bytes = (uint32_t)min((size_t)kChunkBytes, copy_bytes - off);
+                    mbar_arrive_expect_tx(&hdr->full[stage], bytes);
+                    tma_load_1d(ring + (size_t)stage * kChunkBytes, src + off, bytes, &hdr->full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    uint16_t* my = cnt + tid;   // counter of allele a at my[a * 512]
+    uint32_t it = 0;
+    for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
+        const int a0 = p.locus_off[l];
+        const int A = p.locus_off[l + 1] - a0;
+        if (!fast_eligible(A)) continue;
+        const int hf = p.hflags[l];
+        const bool dups = (hf & (TRT_HF_LEN_DUPS | TRT_HF_SEQ_DUPS)) != 0;
+        if (dups) {
+            for (int a = tid; a < A; a += kConsumerThreads)
+                hdr->cls[a] = ((uint32_t)p.len_class[a0 + a] << 16) | (uint32_t)p.seq_class[a0 + a];
+            consumer_bar();
+        }
+        int n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
+
+        for (int c = 0; c < nchunks; c++, it++) {
+            const int stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1u;
+            mbar_wait(&hdr->full[stage], phase);
+            const uint4* src = (const uint4*)(ring + (size_t)stage * kChunkBytes + (size_t)tid * 48);
+            const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+            // all smem reads of this stage are done once the registers are loaded
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            const int64_t s_base = (int64_t)c * kChunkCalls + (int64_t)tid * kCallsPerThread;
+            uint32_t mbits = 0xffu;
+            if (MASKED) {
+                mbits = 0;
+#pragma unroll
+                for (int j = 0; j < kCallsPerThread; j++)
+                    if (s_base + j < p.S && p.mask[s_base + j]) mbits |= 1u << j;
+            }
+#pragma unroll
+            for (int j = 0; j < kCallsPerThread; j++) {
+                // halves 3j and 3j+1 of the 24-half window
+                const int k0 = 3 * j, k1 = 3 * j + 1;
+                const int a = (int)(short)((k0 & 1) ? (w[k0 >> 1] >> 16) : (w[k0 >> 1] & 0xffffu));
+                const int b = (int)(short)((k1 & 1) ? (w[k1 >> 1] >> 16) : (w[k1 >> 1] & 0xffffu));
+                bool live = (s_base + j < p.S);
+                if (MASKED) live = live && ((mbits >> j) & 1u);
+                if (!live) continue;
+                const bool va = (unsigned)a < (unsigned)A, vb = (unsigned)b < (unsigned)A;
+                if (va) my[a * kConsumerThreads] += 1;
+                if (vb) my[b * kConsumerThreads] += 1;
+                const bool bad = (a < -2) | (b < -2) | (a >= A) | (b >= A);
+                const bool m1 = (a == -1) | (b == -1) | bad;
+                n_bad += bad;
+                n_non += (va | vb);
+                if (!m1) {
+                    n_full++;
+                    n_pad += ((a == -2) | (b == -2));
+                    h_idx += (a == b);
+                    if (dups) {
+                        const uint32_t ca = va ? hdr->cls[a] : 0xfffffffeu, cb = vb ? hdr->cls[b] : 0xfffffffdu;
+                        h_len += ((ca >> 16) == (cb >> 16)) | (a == b);
+                        h_seq += ((ca & 0xffffu) == (cb & 0xffffu)) | (a == b);
+                    }
+                }
+            }
+        }
+        if (!dups) {
+            h_len = h_idx;
+            h_seq = h_idx;
+        }
+        // ---- per-locus reduction ---------------------------------------------------------------
+        n_full = warp_sum(n_full); n_non = warp_sum(n_non); n_pad = warp_sum(n_pad);
+        h_idx = warp_sum(h_idx); h_len = warp_sum(h_len); h_seq = warp_sum(h_seq); n_bad = warp_sum(n_bad);
+        if (lane == 0) {
+            long long* wp = hdr->warp_part[warp];
+            wp[0] = n_full; wp[1] = n_non; wp[2] = n_pad; wp[3] = h_idx; wp[4] = h_len; wp[5] = h_seq; wp[6] = n_bad;
+        }
+        consumer_bar();   // all private counters and warp partials of this locus are final
+        for (int a = warp; a < A; a += kConsumerWarps) {
+            uint32_t* rowp = (uint32_t*)(cnt + (size_t)a * kConsumerThreads);   // 256 words
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < kConsumerThreads / 64; k++) {
+                const uint32_t x = rowp[lane + 32 * k];
+                rowp[lane + 32 * k] = 0u;
+                sum += (int)(x & 0xffffu) + (int)(x >> 16);
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) p.ac[a0 + a] = sum;
+        }
+        if (tid < 7) {
+            long long t = 0;
+            for (int w2 = 0; w2 < kConsumerWarps; w2++) t += hdr->warp_part[w2][tid];
+            p.lc[l * TRT_LC_N + tid] = t;
+        }
+        if (tid == 7) p.lc[l * TRT_LC_N + 7] = 0;
+        consumer_bar();   // counters are zero again, partials consumed
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue: exact binomial machinery (scipy.stats.binomtest two-sided)
+// ------------------------------------------------------------------------------------------------
+__device__ double stirlerr(double n) {
+    // log(n!) - log(sqrt(2 pi n) (n/e)^n) for integer n (Loader's saddle-point algorithm)
+    const double sfe[16] = {0.0, 0.0810614667953272582196702, 0.0413406959554092940938221,
+                            0.02767792568499833914878929, 0.02079067210376509311152277,
+                            0.01664469118982119216319487, 0.01387612882307074799874573,
+                            0.01189670994589177009505572, 0.010411265261972096497478567,
+                            0.009255462182712732917728637, 0.008330563433362871256469318,
+                            0.007573675487951840794972024, 0.006942840107209529865664152,
+                            0.006408994188004207068439631, 0.005951370112758847735624416,
+                            0.005554733551962801371038690};
+    if (n < 16.0) return sfe[(int)n];
+    const double S0 = 1.0 / 12.0, S1 = 1.0 / 360.0, S2 = 1.0 / 1260.0, S3 = 1.0 / 1680.0, S4 = 1.0 / 1188.0;
+    const double nn = n * n;
+    if (n > 500.0) return (S0 - S1 / nn) / n;
+    if (n > 80.0) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35.0) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+__device__ double bd0(double x, double np) {
+    // deviance part x log(x/np) + np - x, evaluated stably
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * v;
+        if (fabs(s) < DBL_MIN) return s;
+        double ej = 2.0 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            const double s1 = s + ej / (double)((j << 1) + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+__device__ double binom_pmf(double x, double n, double pr) {
+    const double q = 1.0 - pr;
+    if (x < 0.0 || x > n) return 0.0;
+    if (pr == 0.0) return x == 0.0 ? 1.0 : 0.0;
+    if (q == 0.0) return x == n ? 1.0 : 0.0;
+    if (x == 0.0) {
+        if (n == 0.0) return 1.0;
+        const double lc = (pr < 0.1) ? -bd0(n, n * q) - n * pr : n * log(q);
+        return exp(lc);
+    }
+    if (x == n) {
+        const double lc = (q < 0.1) ? -bd0(n, n * pr) - n * q : n * log(pr);
+        return exp(lc);
+    }
+    const double lc = stirlerr(n) - stirlerr(x) - stirlerr(n - x) - bd0(x, n * pr) - bd0(n - x, n * q);
+    const double lf = 1.837877066409345483560659472811 + log(x) + log1p(-x / n);
+    return exp(lc - 0.5 * lf);
+}
+
+// P(X <= k): terms summed outward from k (decreasing away from the mode)
+__device__ double binom_cdf(double k, double n, double pr) {
+    if (k < 0.0) return 0.0;
+    if (k >= n) return 1.0;
+    const double q = 1.0 - pr;
+    if (pr == 0.0) return 1.0;
+    if (q == 0.0) return 0.0;
+    double t = binom_pmf(k, n, pr), sum = t;
+    const double r = q / pr;
+    for (double i = k; i >= 1.0; i -= 1.0) {
+        const double ratio = i / (n - i + 1.0) * r;
+        t *= ratio;
+        sum += t;
+        if (ratio < 1.0 && t < sum * 1e-18) break;
+    }
+    return sum;
+}
+
+// P(X >= k)
+__device__ double binom_upper(double k, double n, double pr) {
+    if (k <= 0.0) return 1.0;
+    if (k > n) return 0.0;
+    const double q = 1.0 - pr;
+    if (pr == 0.0) return 0.0;
+    if (q == 0.0) return 1.0;
+    double t = binom_pmf(k, n, pr), sum = t;
+    const double r = pr / q;
+    for (double i = k; i < n; i += 1.0) {
+        const double ratio = (n - i) / (i + 1.0) * r;
+        t *= ratio;
+        sum += t;
+        if (ratio < 1.0 && t < sum * 1e-18) break;
+    }
+    return sum;
+}
+
+__device__ double binomtest_two_sided(double k, double n, double pr) {
+    if (!(n >= 1.0) || !(pr >= 0.0 && pr <= 1.0) || k < 0.0 || k > n) return nan("");
+    const double d = binom_pmf(k, n, pr);
+    const double dr = d * (1.0 + 1e-7);
+    double pval;
+    if (k < pr * n) {
+        double lo = ceil(pr * n), hi = n;
+        while (lo < hi) {
+            const double mid = lo + floor((hi - lo) / 2.0);
+            const double v = -binom_pmf(mid, n, pr);
+            if (v < -dr) lo = mid + 1.0;
+            else if (v > -dr) hi = mid - 1.0;
+            else { lo = mid; hi = mid; }
+        }
+        const double plo = binom_pmf(lo, n, pr);
+        const double ix = ((lo <= n) && (-plo <= -dr)) ? lo : lo - 1.0;
+        const double y = n - ix + ((dr == binom_pmf(ix, n, pr)) ? 1.0 : 0.0);
+        // cdf(k) + sf(n - y),  sf(x) = P(X > x) = P(X >= x + 1)
+        pval = binom_cdf(k, n, pr) + binom_upper(n - y + 1.0, n, pr);
+    } else {
+        double lo = 0.0, hi = floor(pr * n);
+        while (lo < hi) {
+            const double mid = lo + floor((hi - lo) / 2.0);
+            const double v = binom_pmf(mid, n, pr);
+            if (v < dr) lo = mid + 1.0;
+            else if (v > dr) hi = mid - 1.0;
+            else { lo = mid; hi = mid; }
+        }
+        const double plo = binom_pmf(lo, n, pr);
+        const double ix = ((lo >= 0.0) && (plo <= dr)) ? lo : lo - 1.0;
+        // cdf(y - 1) + sf(k - 1) with y = ix + 1
+        pval = binom_cdf(ix, n, pr) + binom_upper(k, n, pr);
+    }
+    return fmin(1.0, pval);
+}
+
+struct EpiParams {
+    int64_t L;
+    int G;
+    int64_t nA;
+    const int32_t* locus_off;
+    const double* allele_len;
+    const int32_t* len_class;
+    const int32_t* seq_class;
+    const int32_t* len_order;
+    const int32_t* seq_order;
+    const int32_t* ac;       // [G][nA]
+    const long long* lc;     // [G][L][8]
+    int use_length;
+    double nalleles_thresh;
+    int P;
+    // outputs [G][L]
+    double *thresh, *het, *entropy, *mean, *mode, *var, *hwep;
+    int32_t* nalleles;
+    long long* n_hom;
+};
+
+__global__ void __launch_bounds__(128) locus_epilogue_kernel(EpiParams p) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.L * p.G) return;
+    const int64_t g = idx / p.L, l = idx % p.L;
+    const int a0 = p.locus_off[l];
+    const int A = p.locus_off[l + 1] - a0;
+    const int32_t* ac = p.ac + g * p.nA + a0;
+    const long long* lc = p.lc + (g * p.L + l) * TRT_LC_N;
+    long long total = 0;
+    for (int a = 0; a < A; a++) total += ac[a];
+    const double tot = (double)total;
+    const double NaN = nan("");
+
+    // ---- length-keyed statistics: thresh, mean, mode, var (always by length) -------------------
+    double mean = NaN, mode = NaN, var = NaN, thresh = NaN;
+    // statistics under the selected relation
+    double het = NaN, ent = NaN, sumsq = NaN;
+    int nall = 0;
+    if (total > 0) {
+        const int32_t* order = p.len_order + a0;
+        const int32_t* cls = p.len_class + a0;
+        // pass 1: mean, mode, thresh, (het/entropy when use_length)
+        double m = 0.0, best_f = -1.0, best_len = NaN, fsum = 0.0, ssq = 0.0;
+        int i = 0;
+        while (i < A) {
+            const int c = cls[order[i]];
+            long long cnt = 0;
+            int j = i;
+            while (j < A && cls[order[j]] == c) { cnt += ac[order[j]]; j++; }
+            if (cnt > 0) {
+                const double f = (double)cnt / tot;
+                const double len = p.allele_len[a0 + c];
+                m += len * f;
+                if (f > best_f) { best_f = f; best_len = len; }   // ascending length: ties keep the smallest
+                thresh = len;                                       // last present class = max allele
+                fsum += f;
+                ssq += f * f;
+                if (p.use_length && f >= p.nalleles_thresh) nall++;
+            }
+            i = j;
+        }
+        mean = m;
+        mode = best_len;
+        // pass 2: variance
+        double v = 0.0;
+        i = 0;
+        while (i < A) {
+            const int c = cls[order[i]];
+            long long cnt = 0;
+            int j = i;
+            while (j < A && cls[order[j]] == c) { cnt += ac[order[j]]; j++; }
+            if (cnt > 0) {
+                const double f = (double)cnt / tot;
+                const double dl = p.allele_len[a0 + c] - m;
+                v += f * dl * dl;
+            }
+            i = j;
+        }
+        var = v;
+        const int32_t* rorder = p.use_length ? order : p.seq_order + a0;
+        const int32_t* rcls = p.use_length ? cls : p.seq_class + a0;
+        if (!p.use_length) {
+            fsum = 0.0;
+            ssq = 0.0;
+            i = 0;
+            while (i < A) {
+                const int c = rcls[rorder[i]];
+                long long cnt = 0;
+                int j = i;
+                while (j < A && rcls[rorder[j]] == c) { cnt += ac[rorder[j]]; j++; }
+                if (cnt > 0) {
+                    const double f = (double)cnt / tot;
+                    fsum += f;
+                    ssq += f * f;
+                    if (f >= p.nalleles_thresh) nall++;
+                }
+                i = j;
+            }
+        }
+        sumsq = ssq;
+        het = 1.0 - ssq;
+        // entropy: scipy.stats.entropy normalises pk by its sum, sums -p ln p, divides by ln 2
+        double e = 0.0;
+        i = 0;
+        while (i < A) {
+            const int c = rcls[rorder[i]];
+            long long cnt = 0;
+            int j = i;
+            while (j < A && rcls[rorder[j]] == c) { cnt += ac[rorder[j]]; j++; }
+            if (cnt > 0) {
+                const double pk = ((double)cnt / tot) / fsum;
+                e += -pk * log(pk);
+            }
+            i = j;
+        }
+        ent = e / 0.693147180559945309417232121458;
+        if (fabs(1.0 - fsum) > 0.001) {   // ValidateAlleleFreqs utils.py:140 (cannot trigger for count-derived freqs)
+            het = ent = mean = mode = var = NaN;
+        }
+    }
+    // ---- HWE ---------------------------------------------------------------------------------
+    const long long n_full = lc[TRT_LC_NFULL];
+    const long long n_hom = p.use_length ? lc[TRT_LC_HOM_LEN] : lc[TRT_LC_HOM_SEQ];
+    double hwep = NaN;
+    if (total > 0 && lc[TRT_LC_NPAD] == 0 && p.P >= 2 && !isnan(het))
+        hwep = binomtest_two_sided((double)n_hom, (double)n_full, sumsq);
+    const int64_t o = g * p.L + l;
+    if (p.thresh) p.thresh[o] = thresh;
+    if (p.het) p.het[o] = het;
+    if (p.entropy) p.entropy[o] = ent;
+    if (p.mean) p.mean[o] = mean;
+    if (p.mode) p.mode[o] = mode;
+    if (p.var) p.var[o] = var;
+    if (p.hwep) p.hwep[o] = hwep;
+    if (p.nalleles) p.nalleles[o] = nall;
+    if (p.n_hom) p.n_hom[o] = n_hom;
+}
+
+// dense class ranks (needed for the sorted-genotype semantics when ploidy > 2)
+__global__ void class_rank_kernel(const int32_t* __restrict__ locus_off, const int32_t* __restrict__ order,
+                                  const int32_t* __restrict__ cls, int64_t L, int32_t* __restrict__ rank_out) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int a0 = locus_off[l], A = locus_off[l + 1] - a0;
+    int rank = -1, prev = -1;
+    for (int i = 0; i < A; i++) {
+        const int a = order[a0 + i];
+        const int c = cls[a0 + a];
+        if (c != prev) { rank++; prev = c; }
+        rank_out[a0 + a] = rank;
+    }
+}
+
+// dense table of sorted-index genotypes of ONE locus: key digit = allele + 2 (-2 -> 0, -1 -> 1)
+__global__ void genotype_table_kernel(const int16_t* __restrict__ row, int64_t S, int P, int A,
+                                      const uint8_t* __restrict__ mask, unsigned long long* __restrict__ table,
+                                      unsigned long long* __restrict__ n_bad) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[s]) continue;
+        int k[8];
+        bool bad = false;
+        for (int h = 0; h < P; h++) {
+            int a = row[s * (P + 1) + h];
+            if (a < -2 || a >= A) bad = true;
+            k[h] = a + 2;
+        }
+        if (bad) {
+            atomicAdd(n_bad, 1ull);
+            continue;
+        }
+        for (int i = 1; i < P; i++) {   // insertion sort, P <= 8
+            int v = k[i], j = i - 1;
+            while (j >= 0 && k[j] > v) { k[j + 1] = k[j]; j--; }
+            k[j + 1] = v;
+        }
+        long long idx = 0;
+        for (int h = 0; h < P; h++) idx = idx * (A + 2) + k[h];
+        atomicAdd(&table[idx], 1ull);
+    }
+}
+
+}  // namespace
+
+// run the scan (fast + generic) for one group mask; results into ctx->ac / ctx->lc at group g
+int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
+    const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
+    ScanParams sp;
+    sp.gt = ctx->d_gt_active;
+    sp.pitch = ctx->gt_active_pitch;
+    sp.L = L;
+    sp.S = S;
+    sp.P = ctx->P;
+    sp.locus_off = (const int32_t*)ctx->locus_off.p;
+    sp.len_class = (const int32_t*)ctx->len_class.p;
+    sp.seq_class = (const int32_t*)ctx->seq_class.p;
+    sp.len_rank = (const int32_t*)ctx->stat_i32.p;
+    sp.seq_rank = (const int32_t*)ctx->stat_i32.p + nA;
+    sp.hflags = (const int32_t*)ctx->hflags.p;
+    sp.mask = d_mask;
+    sp.ac = (int32_t*)ctx->ac.p + (size_t)g * nA;
+    sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
+    const bool fast = (ctx->P == 2 && S >= kMinFastSamples);
+    sp.fast_enabled = fast ? 1 : 0;
+    sp.only_ineligible = fast ? 1 : 0;
+    if (fast) {
+        const int amax = std::min(ctx->maxA, kMaxFastAlleles);
+        const size_t smem = (size_t)kStages * kChunkBytes + sizeof(FastSmemHeader) + (size_t)amax * kConsumerThreads * 2;
+        const int grid = (int)std::min<int64_t>(L, ctx->sm_count);
+        if (d_mask) {
+            TRT_CUDA(cudaFuncSetAttribute(scan_diploid_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            scan_diploid_tma_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(sp, amax);
+        } else {
+            TRT_CUDA(cudaFuncSetAttribute(scan_diploid_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            scan_diploid_tma_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(sp, amax);
+        }
+        TRT_KERNEL_CHECK();
+    }
+    if (!fast || ctx->maxA > kMaxFastAlleles) {
+        const int warps_per_block = 8;
+        const int64_t blocks = std::min<int64_t>((L + warps_per_block - 1) / warps_per_block, (int64_t)ctx->sm_count * 8);
+        scan_generic_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, ctx->stream>>>(sp);
+        TRT_KERNEL_CHECK();
+    }
+    return TRT_OK;
+}
+
+// (re)compute dense class ranks into ctx->stat_i32 = [len_rank[nA] | seq_rank[nA]]
+int trt_prepare_ranks(trt_ctx* ctx) {
+    const int64_t L = ctx->L, nA = ctx->nA;
+    TRT_TRY(trt_ensure(ctx, ctx->stat_i32, (size_t)nA * 8 + 16));
+    if (L > 0) {
+        class_rank_kernel<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(
+            (const int32_t*)ctx->locus_off.p, (const int32_t*)ctx->len_order.p, (const int32_t*)ctx->len_class.p, L,
+            (int32_t*)ctx->stat_i32.p);
+        TRT_KERNEL_CHECK();
+        class_rank_kernel<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(
+            (const int32_t*)ctx->locus_off.p, (const int32_t*)ctx->seq_order.p, (const int32_t*)ctx->seq_class.p, L,
+            (int32_t*)ctx->stat_i32.p + nA);
+        TRT_KERNEL_CHECK();
+    }
+    return TRT_OK;
+}
+
+extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* group_masks, int n_groups,
+                               double nalleles_thresh, trt_locus_stats_out* out) {
+    if (!ctx || !ctx->block_open || !ctx->have_gt || !ctx->harmonized)
+        return trt_set_error(ctx, TRT_ESTATE, "trt_locus_stats: needs a block with GT and trt_harmonize");
+    if (!out || n_groups < 1 || (n_groups > 1 && !group_masks))
+        return trt_set_error(ctx, TRT_EINVAL, "trt_locus_stats: bad arguments");
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
+    const int G = n_groups;
+    TRT_TRY(trt_ensure(ctx, ctx->ac, (size_t)G * nA * 4 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->lc, (size_t)G * L * TRT_LC_N * 8 + 16));
+    const size_t n_out = (size_t)G * L;
+    TRT_TRY(trt_ensure(ctx, ctx->stat_f64, n_out * 8 * 9 + 16));
+    if (group_masks) {
+        TRT_TRY(trt_ensure(ctx, ctx->group_masks, (size_t)G * S + 16));
+        TRT_CUDA(cudaMemcpyAsync(ctx->group_masks.p, group_masks, (size_t)G * S, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    trt_timer_begin(ctx);
+    TRT_TRY(trt_prepare_ranks(ctx));
+    TRT_CUDA(cudaMemsetAsync(ctx->ac.p, 0, (size_t)G * nA * 4 + 16, ctx->stream));
+    TRT_CUDA(cudaMemsetAsync(ctx->lc.p, 0, (size_t)G * L * TRT_LC_N * 8 + 16, ctx->stream));
+    if (L > 0) {
+        TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
+        for (int g = 0; g < G; g++) {
+            const uint8_t* m = group_masks ? (const uint8_t*)ctx->group_masks.p + (size_t)g * S : nullptr;
+            TRT_TRY(trt_run_scan(ctx, m, g, G));
+        }
+        TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
+        double* f = (double*)ctx->stat_f64.p;
+        EpiParams ep;
+        ep.L = L; ep.G = G; ep.nA = nA;
+        ep.locus_off = (const int32_t*)ctx->locus_off.p;
+        ep.allele_len = (const double*)ctx->allele_len.p;
+        ep.len_class = (const int32_t*)ctx->len_class.p;
+        ep.seq_class = (const int32_t*)ctx->seq_class.p;
+        ep.len_order = (const int32_t*)ctx->len_order.p;
+        ep.seq_order = (const int32_t*)ctx->seq_order.p;
+        ep.ac = (const int32_t*)ctx->ac.p;
+        ep.lc = (const long long*)ctx->lc.p;
+        ep.use_length = use_length;
+        ep.nalleles_thresh = nalleles_thresh;
+        ep.P = ctx->P;
+        ep.thresh = f; ep.het = f + n_out; ep.entropy = f + 2 * n_out; ep.mean = f + 3 * n_out;
+        ep.mode = f + 4 * n_out; ep.var = f + 5 * n_out; ep.hwep = f + 6 * n_out;
+        ep.nalleles = (int32_t*)(f + 7 * n_out);
+        ep.n_hom = (long long*)(f + 8 * n_out);
+        locus_epilogue_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(ep);
+        TRT_KERNEL_CHECK();
+    }
+    trt_timer_end(ctx);
+    ctx->last_scan_ms = 0.0;
+    if (L > 0) {
+        float ms = 0.f;
+        TRT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1));
+        ctx->last_scan_ms = ms;
+    }
+    // ---- results to the caller's host buffers --------------------------------------------------
+    const double* f = (const double*)ctx->stat_f64.p;
+#define D2H(dst, src, bytes) \
+    if ((dst) && (bytes)) TRT_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+    D2H(out->ac, ctx->ac.p, (size_t)G * nA * 4);
+    D2H(out->thresh, f, n_out * 8);
+    D2H(out->het, f + n_out, n_out * 8);
+    D2H(out->entropy, f + 2 * n_out, n_out * 8);
+    D2H(out->mean, f + 3 * n_out, n_out * 8);
+    D2H(out->mode, f + 4 * n_out, n_out * 8);
+    D2H(out->var, f + 5 * n_out, n_out * 8);
+    D2H(out->hwep, f + 6 * n_out, n_out * 8);
+    D2H(out->nalleles, f + 7 * n_out, n_out * 4);
+    D2H(out->n_hom, f + 8 * n_out, n_out * 8);
+#undef D2H
+    std::vector<long long> lc;
+    if (n_out && (out->n_called || out->n_called_nonstrict || out->n_padded)) {
+        lc.resize(n_out * TRT_LC_N);
+        TRT_CUDA(cudaMemcpyAsync(lc.data(), ctx->lc.p, n_out * TRT_LC_N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (n_out) {
+        lc.resize(n_out * TRT_LC_N);
+        TRT_CUDA(cudaMemcpyAsync(lc.data(), ctx->lc.p, n_out * TRT_LC_N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    long long bad = 0;
+    for (size_t i = 0; i < n_out; i++) {
+        if (out->n_called) out->n_called[i] = lc[i * TRT_LC_N + TRT_LC_NFULL];
+        if (out->n_called_nonstrict) out->n_called_nonstrict[i] = lc[i * TRT_LC_N + TRT_LC_NNONSTRICT];
+        if (out->n_padded) out->n_padded[i] = lc[i * TRT_LC_N + TRT_LC_NPAD];
+        bad += lc[i * TRT_LC_N + 6];
+    }
+    if (bad)
+        return trt_set_error(ctx, TRT_ERECORD,
+                             "%lld genotype entries index an allele the record does not have (or are < -2)", bad);
+    return TRT_OK;
+}
+
+// TRRecord.GetGenotypeCounts tr_harmonizer.py:1326-1418 for one locus (API edge): counts of the
+// index genotypes with haplotypes sorted, as a dense base-(A+2) table (digit = allele + 2).
+extern "C" int trt_genotype_counts(trt_ctx* ctx, int64_t locus, const uint8_t* mask_host, int64_t* table_host,
+                                   int64_t table_len) {
+    if (!ctx || !ctx->block_open || !ctx->have_gt || !ctx->have_alleles)
+        return trt_set_error(ctx, TRT_ESTATE, "trt_genotype_counts: needs a block with GT and alleles");
+    if (locus < 0 || locus >= ctx->L) return trt_set_error(ctx, TRT_EINVAL, "trt_genotype_counts: locus out of range");
+    const int A = ctx->h_locus_off[locus + 1] - ctx->h_locus_off[locus];
+    double need = 1.0;
+    for (int h = 0; h < ctx->P; h++) need *= (double)(A + 2);
+    if (need > (double)(1 << 26) || (int64_t)need != table_len)
+        return trt_set_error(ctx, TRT_EINVAL, "trt_genotype_counts: table_len must be (A+2)^P = %.0f (max 2^26)", need);
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    TRT_TRY(trt_ensure(ctx, ctx->misc, (size_t)(table_len + 1) * 8 + 16));
+    TRT_CUDA(cudaMemsetAsync(ctx->misc.p, 0, (size_t)(table_len + 1) * 8, ctx->stream));
+    const uint8_t* d_mask = nullptr;
+    if (mask_host) {
+        TRT_TRY(trt_ensure(ctx, ctx->group_masks, (size_t)ctx->S + 16));
+        TRT_CUDA(cudaMemcpyAsync(ctx->group_masks.p, mask_host, (size_t)ctx->S, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = (const uint8_t*)ctx->group_masks.p;
+    }
+    if (ctx->S > 0) {
+        const int16_t* row = (const int16_t*)((const char*)ctx->d_gt_active + (size_t)locus * ctx->gt_active_pitch);
+        const int blocks = (int)std::min<int64_t>((ctx->S + 255) / 256, (int64_t)ctx->sm_count * 4);
+        genotype_table_kernel<<<blocks, 256, 0, ctx->stream>>>(row, ctx->S, ctx->P, A, d_mask,
+                                                               (unsigned long long*)ctx->misc.p,
+                                                               (unsigned long long*)ctx->misc.p + table_len);
+        TRT_KERNEL_CHECK();
+    }
+    std::vector<int64_t> tmp((size_t)table_len + 1);
+    TRT_CUDA(cudaMemcpyAsync(tmp.data(), ctx->misc.p, (size_t)(table_len + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(table_host, tmp.data(), (size_t)table_len * 8);
+    if (tmp[table_len])
+        return trt_set_error(ctx, TRT_ERECORD, "%lld genotypes index an allele the record does not have", (long long)tmp[table_len]);
+    return TRT_OK;
+}

@@ -262,3 +262,25 @@ def write_vcf(path: str, loci: SynthLoci, calls: SynthCalls, sample_names: Optio
                 cols.append("{}:{:.8g}:{}:{}:{}".format(g, calls.q[i, s], calls.dp[i, s],
                                                         calls.dstutter[i, s], calls.dflankindel[i, s]))
             f.write("\t".join(cols) + "\n")
+
+
+def allele_tables(loci: SynthLoci, lo: int = 0, hi: Optional[int] = None):
+    """Arrays for ``trt_block_set_alleles`` covering loci [lo, hi): (seqs, allele_off, locus_off,
+    pos, start, end, period)."""
+    hi = loci.n_loci if hi is None else hi
+    parts = []
+    lens = []
+    counts = []
+    for i in range(lo, hi):
+        alleles = [loci.ref[i]] + loci.alts[i]
+        counts.append(len(alleles))
+        for a in alleles:
+            parts.append(a)
+            lens.append(len(a))
+    seqs = "".join(parts).encode("ascii")
+    allele_off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=allele_off[1:])
+    locus_off = np.zeros(hi - lo + 1, dtype=np.int32)
+    np.cumsum(counts, out=locus_off[1:])
+    return (seqs, allele_off, locus_off, loci.pos[lo:hi].copy(), loci.start[lo:hi].copy(),
+            loci.end[lo:hi].copy(), loci.period[lo:hi].copy())
