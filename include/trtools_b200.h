@@ -52,10 +52,10 @@ extern "C" {
 #define TRT_FMT_DSTUTTER     1   /* int32 [L][S]                                                  */
 #define TRT_FMT_DFLANKINDEL  2   /* int32 [L][S]                                                  */
 #define TRT_FMT_Q            3   /* float32 [L][S]                                                */
-#define TRT_FMT_AUX_I32      4   /* any other Integer field used by a min/max call filter         */
-#define TRT_FMT_AUX_F32      5   /* any other Float field used by a min/max call filter           */
-#define TRT_FMT_QEXP         6   /* float32 [L][S][3]  (GangSTR)                                  */
-#define TRT_FMT_NFIELDS      7
+#define TRT_FMT_QEXP         4   /* float32 [L][S][3]  (GangSTR)                                  */
+#define TRT_FMT_AUX0         5   /* AUX0..AUX7: any other Integer/Float [L][S] field a call filter */
+#define TRT_FMT_NAUX         8   /*   reads (SR, FR, ML, LC, ADFL ..., or host-evaluated filters)  */
+#define TRT_FMT_NFIELDS      13
 
 typedef struct trt_ctx trt_ctx;
 
@@ -106,7 +106,7 @@ int trt_block_set_gt_device(trt_ctx* ctx, const int16_t* gt_dev, size_t row_pitc
 
 int trt_block_set_format_i32(trt_ctx* ctx, int field_id, const int32_t* v_host /*[L][S]*/);
 int trt_block_set_format_f32(trt_ctx* ctx, int field_id, const float* v_host /*[L][S][ncol]*/, int ncol);
-int trt_block_set_format_device(trt_ctx* ctx, int field_id, const void* v_dev, int ncol);
+int trt_block_set_format_device(trt_ctx* ctx, int field_id, const void* v_dev, int ncol, int is_float);
 
 /* Allele table of the block.  seqs: concatenated REF/ALT strings exactly as in the VCF (any
  * case); allele_off[nA+1] byte offsets; locus_off[L+1] allele index ranges (first allele of a
@@ -205,6 +205,9 @@ int trt_genotype_counts(trt_ctx* ctx, int64_t locus, const uint8_t* mask, int64_
 #define TRT_CF_QEXP_HET  3   /* QEXP[1] < thr on called samples                                   */
 #define TRT_CF_QEXP_HOM  4   /* QEXP[2] < thr                                                     */
 #define TRT_CF_QEXP_TOT  5   /* QEXP[1]+QEXP[2] < thr                                             */
+#define TRT_CF_HOST_VALUE 6  /* float32 field holds the operator's own output (NaN = keep): the
+                                string-parsing filters of filters.py:486-567,676-757,835-867 are
+                                evaluated by the caller and merged here in filter order           */
 typedef struct {
     int32_t kind;        /* TRT_CF_*                                                              */
     int32_t field_id;    /* TRT_FMT_* the operator reads (numerator for RATIO_GT)                 */

@@ -18,8 +18,9 @@ TRT_OK = 0
 TRT_ENODEV, TRT_ECUDA, TRT_EINVAL, TRT_ESTATE, TRT_ENOMEM, TRT_ERECORD, TRT_ENCCL = -1, -2, -3, -4, -5, -6, -7
 
 VCF_TYPES = {"gangstr": 0, "advntr": 1, "hipstr": 2, "eh": 3, "popstr": 4, "longtr": 5}
-FMT_DP, FMT_DSTUTTER, FMT_DFLANKINDEL, FMT_Q, FMT_AUX_I32, FMT_AUX_F32, FMT_QEXP = range(7)
-CF_MIN, CF_MAX, CF_RATIO_GT, CF_QEXP_HET, CF_QEXP_HOM, CF_QEXP_TOT = range(6)
+FMT_DP, FMT_DSTUTTER, FMT_DFLANKINDEL, FMT_Q, FMT_QEXP, FMT_AUX0 = range(6)
+FMT_NAUX = 8
+CF_MIN, CF_MAX, CF_RATIO_GT, CF_QEXP_HET, CF_QEXP_HOM, CF_QEXP_TOT, CF_HOST_VALUE = range(7)
 LF_CALLRATE, LF_HWE, LF_HETLOW, LF_HETHIGH, LF_HRUN = range(5)
 AF_OK, AF_NO_CALLED, AF_ONE_ALLELE, AF_NON_MAJOR, AF_NCOVARS = range(5)
 HF_HAS_FULL, HF_MOTIF_N, HF_MOTIF_NONACGT, HF_LEN_DUPS, HF_SEQ_DUPS, HF_BAD_PERIOD = 1, 2, 4, 8, 16, 32
@@ -123,7 +124,7 @@ def load():
         "trt_block_set_gt_device": (i32, [vp, vp, sz]),
         "trt_block_set_format_i32": (i32, [vp, i32, vp]),
         "trt_block_set_format_f32": (i32, [vp, i32, vp, i32]),
-        "trt_block_set_format_device": (i32, [vp, i32, vp, i32]),
+        "trt_block_set_format_device": (i32, [vp, i32, vp, i32, i32]),
         "trt_block_set_alleles": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "trt_harmonize": (i32, [vp]),
         "trt_get_harmonized": (i32, [vp, C.POINTER(HarmonizeOut)]),
@@ -325,6 +326,45 @@ class Context:
         m = None if mask is None else _c(mask, np.uint8)
         self.check(self.lib.trt_genotype_counts(self.h, int(locus), _ptr(m), _ptr(table), n))
         return table.reshape((n_alleles + 2,) * self.P)
+
+    def call_filters(self, specs, dp_field, filter_counts, numcalls, totaldp, want_mask=True, want_trigger=False,
+                     want_gt=True) -> dict:
+        """ApplyCallFilters on the current block.  ``specs``: list of (kind, field_id, threshold) in filter
+        order.  The per-sample accumulators (int64 [n_specs, S], int64 [S], float64 [S]) are updated in place."""
+        n = len(specs)
+        arr = (CallFilterSpec * max(n, 1))()
+        for i, (kind, fld, thr) in enumerate(specs):
+            arr[i].kind, arr[i].field_id, arr[i].threshold = int(kind), int(fld), float(thr)
+        L, S, P = self.L, self.S, self.P
+        assert filter_counts.dtype == np.int64 and filter_counts.flags.c_contiguous and filter_counts.shape == (n, S)
+        assert numcalls.dtype == np.int64 and totaldp.dtype == np.float64
+        res = {}
+        if want_mask:
+            res["call_mask"] = np.empty((L, S), np.uint32)
+        if want_trigger and n:
+            res["trigger_values"] = np.empty((n, L, S), np.float64)
+        if want_gt:
+            res["gt_masked"] = np.empty((L, S, P + 1), np.int16)
+        neg = np.full(1, -1, np.int32)
+        out = CallFilterOut(call_mask=_ptr(res.get("call_mask")), trigger_values=_ptr(res.get("trigger_values")),
+                            gt_masked=_ptr(res.get("gt_masked")), filter_counts=_ptr(filter_counts) if n else None,
+                            numcalls=_ptr(numcalls), totaldp=_ptr(totaldp), negative_dp_locus=_ptr(neg))
+        self.check(self.lib.trt_call_filters(self.h, arr, n, int(dp_field), C.byref(out)))
+        res["negative_dp_locus"] = int(neg[0])
+        return res
+
+    def locus_filters(self, specs, use_length: bool) -> dict:
+        """ApplyLocusFilters + INFO recompute on the current block.  ``specs``: list of (kind, threshold)."""
+        n = len(specs)
+        arr = (LocusFilterSpec * max(n, 1))()
+        for i, (kind, thr) in enumerate(specs):
+            arr[i].kind, arr[i].threshold = int(kind), float(0.0 if thr is None else thr)
+        L, nA = self.L, self.nA
+        res = dict(flags=np.empty(L, np.uint32), n_called=np.empty(L, np.int64), het=np.empty(L), hwep=np.empty(L),
+                   ac=np.empty(nA, np.int32), hrun=np.empty(L, np.int32))
+        out = LocusFilterOut(**{k: _ptr(v) for k, v in res.items()})
+        self.check(self.lib.trt_locus_filters(self.h, arr, n, 1 if use_length else 0, C.byref(out)))
+        return res
 
     def synth_fill(self, seed, locus_offset, cum_freq, miss_thresh, half_thresh, with_format=True):
         cf = _c(cum_freq, np.uint32)

@@ -21,6 +21,7 @@ _beagle_error = "If this file was imputed by Beagle, did you remember to copy th
 # numeric FORMAT fields with a fixed slot in the C-ABI
 FIXED_FMT = {"DP": _lib.FMT_DP, "DSTUTTER": _lib.FMT_DSTUTTER, "DFLANKINDEL": _lib.FMT_DFLANKINDEL,
              "Q": _lib.FMT_Q, "QEXP": _lib.FMT_QEXP}
+# any other numeric FORMAT field a call filter reads gets one of the AUX slots, in order of appearance
 
 
 class RecordMeta:
@@ -170,9 +171,8 @@ class Block:
         ctx.block_set_alleles(self.seqs, self.allele_off, self.locus_off, self.pos, self.start, self.end,
                               self.period, self.given_len, self.motifs_in)
         self.fmt = fmt or {}
-        for key, arr in self.fmt.items():
-            if key in FIXED_FMT and arr is not None:
-                ctx.block_set_format(FIXED_FMT[key], arr)
+        self.fmt_slot: Dict[str, int] = {}
+        self._upload_fmt()
         self.h = ctx.harmonize()
         bad = np.nonzero(self.h["flags"] & _lib.HF_BAD_PERIOD)[0]
         if len(bad):
@@ -193,6 +193,36 @@ class Block:
         self._activate()
         return self.ctx.locus_stats(use_length, group_masks, nalleles_thresh)
 
+    def _upload_fmt(self):
+        """numeric FORMAT arrays -> device slots (fixed slots for the HipSTR/GangSTR fields, AUX otherwise)"""
+        self.fmt_slot = {}
+        aux = 0
+        for key, arr in self.fmt.items():
+            if arr is None or arr.dtype.kind not in "if":
+                continue
+            if key in FIXED_FMT:
+                slot = FIXED_FMT[key]
+            else:
+                if aux >= _lib.FMT_NAUX:
+                    raise ValueError("too many auxiliary FORMAT fields in one block")
+                slot = _lib.FMT_AUX0 + aux
+                aux += 1
+            self.ctx.block_set_format(slot, arr)
+            self.fmt_slot[key] = slot
+
+    def add_host_filter_values(self, name: str, values: np.ndarray) -> int:
+        """Upload a host-evaluated call filter's output (float [L][S], NaN = keep) as an AUX field."""
+        self._activate()
+        used = [s for s in self.fmt_slot.values() if s >= _lib.FMT_AUX0]
+        slot = (max(used) + 1) if used else _lib.FMT_AUX0
+        if slot >= _lib.FMT_AUX0 + _lib.FMT_NAUX:
+            raise ValueError("too many auxiliary FORMAT fields in one block")
+        arr = np.ascontiguousarray(values, dtype=np.float32)
+        self.fmt[name] = arr
+        self.ctx.block_set_format(slot, arr)
+        self.fmt_slot[name] = slot
+        return slot
+
     def _activate(self):
         """Make this block the context's current block again (another block may have replaced it)."""
         if getattr(self.ctx, "_current_block", None) is not self:
@@ -200,9 +230,7 @@ class Block:
             self.ctx.block_set_gt(self.gt)
             self.ctx.block_set_alleles(self.seqs, self.allele_off, self.locus_off, self.pos, self.start, self.end,
                                        self.period, self.given_len, self.motifs_in)
-            for key, arr in self.fmt.items():
-                if key in FIXED_FMT and arr is not None:
-                    self.ctx.block_set_format(FIXED_FMT[key], arr)
+            self._upload_fmt()
             self.ctx.harmonize()
         self.ctx._current_block = self
 

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libtrtools_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-shared", "-fmad=false",
 ]
 
 
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     inc, libdir, soname = _find_nccl()
-    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    cmd = [nvcc] + list(NVCC_FLAGS)
     if verbose:
         cmd += ["-Xptxas", "-v"]
     if inc:

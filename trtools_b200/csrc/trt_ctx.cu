@@ -250,7 +250,7 @@ int trt_block_set_gt_device(trt_ctx* ctx, const int16_t* gt_dev, size_t row_pitc
     return TRT_OK;
 }
 
-static int set_format_host(trt_ctx* ctx, int field_id, const void* v_host, int ncol, size_t elem) {
+static int set_format_host(trt_ctx* ctx, int field_id, const void* v_host, int ncol, size_t elem, int is_float) {
     if (!ctx || !ctx->block_open) return trt_set_error(ctx, TRT_ESTATE, "trt_block_set_format: no open block");
     if (field_id < 0 || field_id >= TRT_FMT_NFIELDS || ncol < 1)
         return trt_set_error(ctx, TRT_EINVAL, "trt_block_set_format: bad field id %d / ncol %d", field_id, ncol);
@@ -259,21 +259,23 @@ static int set_format_host(trt_ctx* ctx, int field_id, const void* v_host, int n
     if (bytes) TRT_CUDA(cudaMemcpyAsync(ctx->fmt_buf[field_id].p, v_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->d_fmt[field_id] = ctx->fmt_buf[field_id].p;
     ctx->fmt_ncol[field_id] = ncol;
+    ctx->fmt_is_float[field_id] = is_float;
     return TRT_OK;
 }
 
 int trt_block_set_format_i32(trt_ctx* ctx, int field_id, const int32_t* v_host) {
-    return set_format_host(ctx, field_id, v_host, 1, sizeof(int32_t));
+    return set_format_host(ctx, field_id, v_host, 1, sizeof(int32_t), 0);
 }
 int trt_block_set_format_f32(trt_ctx* ctx, int field_id, const float* v_host, int ncol) {
-    return set_format_host(ctx, field_id, v_host, ncol, sizeof(float));
+    return set_format_host(ctx, field_id, v_host, ncol, sizeof(float), 1);
 }
-int trt_block_set_format_device(trt_ctx* ctx, int field_id, const void* v_dev, int ncol) {
+int trt_block_set_format_device(trt_ctx* ctx, int field_id, const void* v_dev, int ncol, int is_float) {
     if (!ctx || !ctx->block_open) return trt_set_error(ctx, TRT_ESTATE, "trt_block_set_format_device: no open block");
     if (field_id < 0 || field_id >= TRT_FMT_NFIELDS || ncol < 1 || ((uintptr_t)v_dev & 15))
         return trt_set_error(ctx, TRT_EINVAL, "trt_block_set_format_device: bad field id / ncol / alignment");
     ctx->d_fmt[field_id] = v_dev;
     ctx->fmt_ncol[field_id] = ncol;
+    ctx->fmt_is_float[field_id] = is_float;
     return TRT_OK;
 }
 

@@ -1,11 +1,504 @@
-// K3 — dumpSTR call-level and locus-level filters (placeholder until the kernels land).
+// K3 — dumpSTR: call-level filter operators + ApplyCallFilters bookkeeping, and locus-level filters.
+//
+// call_filter_kernel: the grid tiles [loci chunk] x [sample slab]; a thread owns 8 CONSECUTIVE samples
+// (48 B of GT = 3 x 16 B vector loads, 32 B per int32/float32 FORMAT field = 2 x 16 B) and walks down
+// the loci of its chunk, so the per-sample accumulators of dumpSTR's sample log (numcalls, totaldp,
+// one counter per filter) live in registers / thread-private shared memory and are flushed with one
+// atomic per (sample, counter) per chunk instead of one per call.  It writes the masked genotypes
+// (filtered call -> all haplotypes -1, phase 0) that every later statistic reads, and a per-call
+// bitmask of the filters that fired.
+//
+// Reference semantics reproduced (file:line in the reference tree):
+//   filters.CallFilterMinValue/MaxValue           trtools/dumpSTR/filters.py:327-409
+//   filters.HipSTRCallFlankIndels / CallStutter   :415-484   (int32/int32 -> float64 ratio)
+//   filters.GangSTRCallExpansionProb{Hom,Het,Total} :573-674 (float32 compare, called samples only)
+//   dumpSTR.ApplyCallFilters                      trtools/dumpSTR/dumpSTR.py:613-774
+//   filters.Filter_MinLocusCallrate/HWEP/Het/MaxLocusHet/LocusHrun  filters.py:35-217
+//   dumpSTR.ApplyLocusFilters :917-973 and the INFO recompute :1307-1336
+#include <math.h>
+
+#include <algorithm>
+
 #include "trt_internal.cuh"
+#include "trt_scan.cuh"
+
+
+namespace {
+
+constexpr int kSlab = 8;              // samples per thread
+constexpr int kCfThreads = 256;
+constexpr int kSlabSamples = kSlab * kCfThreads;   // 2048 samples per CTA
+constexpr int kMaxSpecs = TRT_MAX_CALL_FILTERS;
+
+struct CfSpec {
+    int kind;
+    int field;      // TRT_FMT_*
+    int is_float;   // field holds float32
+    double thr;
+    float thr_f32;  // threshold rounded to float32 (numpy weak-scalar comparison for float32 arrays)
+};
+
+struct CfParams {
+    const int16_t* gt;
+    size_t pitch;
+    int16_t* gt_out;       // same pitch
+    int64_t L, S;
+    const void* fmt[TRT_FMT_NFIELDS];
+    int fmt_ncol[TRT_FMT_NFIELDS];
+    int n_specs;
+    CfSpec specs[kMaxSpecs];
+    int dp_field;          // field used for totaldp (-1: none)
+    uint32_t* call_mask;   // [L][S] or null
+    double* trig;          // [n_specs][L][S] or null
+    long long* filter_counts;  // [n_specs][S]
+    long long* numcalls;       // [S]
+    long long* dpsum;          // [S]
+    unsigned int* dp_poison;   // [S] non-zero: a PASS call had a missing DP
+    int* neg_dp_locus;         // min locus index with a PASS call of negative DP
+    int loci_per_chunk;
+};
+
+__device__ __forceinline__ void load8_i32(const int32_t* base, int64_t s0, int64_t S, int32_t (&v)[8], bool aligned) {
+    if (aligned && s0 + 8 <= S) {
+        const int4 a = *reinterpret_cast<const int4*>(base + s0);
+        const int4 b = *reinterpret_cast<const int4*>(base + s0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (s0 + j < S) ? base[s0 + j] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kCfThreads, 2) call_filter_kernel(CfParams p) {
+    extern __shared__ unsigned int fcnt[];   // [n_specs][2048] thread-private columns (no conflicts)
+    const int tid = threadIdx.x;
+    const int64_t s0 = (int64_t)blockIdx.x * kSlabSamples + (int64_t)tid * kSlab;
+    const int64_t l_begin = (int64_t)blockIdx.y * p.loci_per_chunk;
+    const int64_t l_end = min(p.L, l_begin + p.loci_per_chunk);
+    for (int f = 0; f < p.n_specs; f++)
+#pragma unroll
+        for (int j = 0; j < kSlab; j++) fcnt[f * kSlabSamples + tid * kSlab + j] = 0;
+    int ncalls[kSlab];
+    long long dps[kSlab];
+    unsigned int poison = 0;
+#pragma unroll
+    for (int j = 0; j < kSlab; j++) { ncalls[j] = 0; dps[j] = 0; }
+    const bool live_thread = s0 < p.S;
+    // rows of int32/float32 FORMAT arrays are S*4 bytes: 16-byte aligned vector loads need S % 4 == 0
+    const bool fmt_aligned = (p.S % 4) == 0;
+    const bool gt_vec = (s0 + kSlab <= p.S);
+
+    if (live_thread) {
+        for (int64_t l = l_begin; l < l_end; l++) {
+            // ---- GT: 8 calls = 24 int16 ------------------------------------------------------------
+            const int16_t* row = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch);
+            int16_t h[24];
+            if (gt_vec) {
+                const uint4* src = reinterpret_cast<const uint4*>(row + s0 * 3);
+                uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+                const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+                for (int k = 0; k < 24; k++) h[k] = (int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 24; k++) h[k] = (s0 + k / 3 < p.S) ? row[s0 * 3 + k] : (int16_t)-1;
+            }
+            // ---- FORMAT fields used by the filters ---------------------------------------------------
+            int32_t dpv[8];
+            bool have_dp = false;
+            if (p.dp_field >= 0) {
+                load8_i32((const int32_t*)p.fmt[p.dp_field] + l * p.S, s0, p.S, dpv, fmt_aligned);
+                have_dp = true;
+            }
+            uint32_t fired[8];
+            bool nocall[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                fired[j] = 0;
+                nocall[j] = (h[3 * j] == -1) | (h[3 * j + 1] == -1);
+            }
+            for (int f = 0; f < p.n_specs; f++) {
+                const CfSpec sp = p.specs[f];
+                int32_t raw[8], den[8];
+                if (sp.kind <= TRT_CF_RATIO_GT || sp.kind == TRT_CF_HOST_VALUE)
+                    load8_i32((const int32_t*)p.fmt[sp.field] + l * p.S, s0, p.S, raw, fmt_aligned);
+                if (sp.kind == TRT_CF_RATIO_GT)
+                    load8_i32((const int32_t*)p.fmt[TRT_FMT_DP] + l * p.S, s0, p.S, den, fmt_aligned);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool in = s0 + j < p.S;
+                    bool hit;
+                    double val;
+                    if (sp.kind == TRT_CF_MIN || sp.kind == TRT_CF_MAX) {
+                        if (sp.is_float) {
+                            const float x = __int_as_float(raw[j]);
+                            hit = (sp.kind == TRT_CF_MIN) ? (x < sp.thr_f32) : (x > sp.thr_f32);
+                            val = (double)x;
+                        } else {
+                            val = (double)raw[j];
+                            hit = (sp.kind == TRT_CF_MIN) ? (val < sp.thr) : (val > sp.thr);
+                        }
+                    } else if (sp.kind == TRT_CF_RATIO_GT) {
+                        val = (double)raw[j] / (double)den[j];   // numpy int32/int32 -> float64
+                        hit = val > sp.thr;
+                    } else if (sp.kind == TRT_CF_HOST_VALUE) {
+                        const float x = __int_as_float(raw[j]);
+                        hit = !isnan(x);
+                        val = (double)x;
+                    } else {   // GangSTR QEXP, float32 [L][S][3], called samples only
+                        float x = 0.f;
+                        if (in) {
+                            const float* q = (const float*)p.fmt[TRT_FMT_QEXP] + (l * p.S + s0 + j) * 3;
+                            x = sp.kind == TRT_CF_QEXP_HET ? q[1] : (sp.kind == TRT_CF_QEXP_HOM ? q[2] : __fadd_rn(q[1], q[2]));
+                        }
+                        hit = !nocall[j] && (x < sp.thr_f32);
+                        val = (double)x;
+                    }
+                    if (in && hit) {
+                        fired[j] |= 1u << f;
+                        if (!nocall[j]) fcnt[f * kSlabSamples + tid * kSlab + j] += 1;
+                    }
+                    if (p.trig && in) p.trig[((size_t)f * p.L + l) * p.S + s0 + j] = hit ? val : nan("");
+                }
+            }
+            // ---- bookkeeping + masked genotypes ---------------------------------------------------------
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (s0 + j >= p.S) continue;
+                const bool pass = (fired[j] == 0) && !nocall[j];
+                if (pass) {
+                    ncalls[j]++;
+                    if (have_dp) {
+                        const int d = dpv[j];
+                        if (d == INT_MIN) poison |= 1u << j;
+                        else if (d < 0) atomicMin(p.neg_dp_locus, (int)l);
+                        else dps[j] += d;
+                    }
+                }
+                if (fired[j] != 0 && !nocall[j]) {   // filtered call: every haplotype -> '.', unphased
+                    h[3 * j] = -1;
+                    h[3 * j + 1] = -1;
+                    h[3 * j + 2] = 0;
+                }
+                if (p.call_mask) p.call_mask[(size_t)l * p.S + s0 + j] = fired[j] | (nocall[j] ? 0x80000000u : 0u);
+            }
+            int16_t* orow = (int16_t*)((char*)p.gt_out + (size_t)l * p.pitch);
+            if (gt_vec) {
+                uint32_t w[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) w[k] = (uint32_t)(uint16_t)h[2 * k] | ((uint32_t)(uint16_t)h[2 * k + 1] << 16);
+                uint4* dst = reinterpret_cast<uint4*>(orow + s0 * 3);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 24; k++)
+                    if (s0 + k / 3 < p.S) orow[s0 * 3 + k] = h[k];
+            }
+        }
+        // ---- flush the per-sample accumulators of this (chunk, slab) -----------------------------------
+#pragma unroll
+        for (int j = 0; j < kSlab; j++) {
+            if (s0 + j >= p.S) continue;
+            if (ncalls[j]) atomicAdd((unsigned long long*)&p.numcalls[s0 + j], (unsigned long long)ncalls[j]);
+            if (dps[j]) atomicAdd((unsigned long long*)&p.dpsum[s0 + j], (unsigned long long)dps[j]);
+            if ((poison >> j) & 1u) atomicOr(&p.dp_poison[s0 + j], 1u);
+            for (int f = 0; f < p.n_specs; f++) {
+                const unsigned int c = fcnt[f * kSlabSamples + tid * kSlab + j];
+                if (c) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + s0 + j], (unsigned long long)c);
+            }
+        }
+    }
+}
+
+// generic ploidy variant (P != 2): one thread per call, plain atomics; correctness path only
+__global__ void call_filter_generic_kernel(CfParams p, int P) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.L * p.S;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = idx / p.S, s = idx % p.S;
+        const int16_t* g = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch) + s * (P + 1);
+        int16_t* go = (int16_t*)((char*)p.gt_out + (size_t)l * p.pitch) + s * (P + 1);
+        bool nocall = false;
+        for (int h = 0; h < P; h++) nocall |= (g[h] == -1);
+        uint32_t fired = 0;
+        for (int f = 0; f < p.n_specs; f++) {
+            const CfSpec sp = p.specs[f];
+            bool hit;
+            double val;
+            if (sp.kind == TRT_CF_MIN || sp.kind == TRT_CF_MAX) {
+                if (sp.is_float) {
+                    const float x = ((const float*)p.fmt[sp.field])[l * p.S + s];
+                    hit = sp.kind == TRT_CF_MIN ? x < sp.thr_f32 : x > sp.thr_f32;
+                    val = x;
+                } else {
+                    const double x = ((const int32_t*)p.fmt[sp.field])[l * p.S + s];
+                    hit = sp.kind == TRT_CF_MIN ? x < sp.thr : x > sp.thr;
+                    val = x;
+                }
+            } else if (sp.kind == TRT_CF_RATIO_GT) {
+                const double r = (double)((const int32_t*)p.fmt[sp.field])[l * p.S + s] /
+                                 (double)((const int32_t*)p.fmt[TRT_FMT_DP])[l * p.S + s];
+                hit = r > sp.thr;
+                val = r;
+            } else if (sp.kind == TRT_CF_HOST_VALUE) {
+                const float x = ((const float*)p.fmt[sp.field])[l * p.S + s];
+                hit = !isnan(x);
+                val = x;
+            } else {
+                const float* q = (const float*)p.fmt[TRT_FMT_QEXP] + (l * p.S + s) * 3;
+                const float x = sp.kind == TRT_CF_QEXP_HET ? q[1] : (sp.kind == TRT_CF_QEXP_HOM ? q[2] : __fadd_rn(q[1], q[2]));
+                hit = !nocall && x < sp.thr_f32;
+                val = x;
+            }
+            if (hit) {
+                fired |= 1u << f;
+                if (!nocall) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + s], 1ull);
+            }
+            if (p.trig) p.trig[((size_t)f * p.L + l) * p.S + s] = hit ? val : nan("");
+        }
+        const bool pass = fired == 0 && !nocall;
+        if (pass) {
+            atomicAdd((unsigned long long*)&p.numcalls[s], 1ull);
+            if (p.dp_field >= 0) {
+                const int d = ((const int32_t*)p.fmt[p.dp_field])[l * p.S + s];
+                if (d == INT_MIN) atomicOr(&p.dp_poison[s], 1u);
+                else if (d < 0) atomicMin(p.neg_dp_locus, (int)l);
+                else if (d > 0) atomicAdd((unsigned long long*)&p.dpsum[s], (unsigned long long)d);
+            }
+        }
+        const bool filtered = fired != 0 && !nocall;
+        for (int h = 0; h < P; h++) go[h] = filtered ? (int16_t)-1 : g[h];
+        go[P] = filtered ? (int16_t)0 : g[P];
+        if (p.call_mask) p.call_mask[idx] = fired | (nocall ? 0x80000000u : 0u);
+    }
+}
+
+struct LfSpec {
+    int kind;
+    double thr;
+};
+
+__global__ void locus_flags_kernel(int64_t L, int64_t S, int n_specs, const LfSpec* __restrict__ specs,
+                                   const long long* __restrict__ lc, const double* __restrict__ het,
+                                   const double* __restrict__ hwep, const int32_t* __restrict__ hrun,
+                                   const int32_t* __restrict__ period, int has_period_info, uint32_t* __restrict__ flags,
+                                   double* __restrict__ het_out, double* __restrict__ hwep_out,
+                                   long long* __restrict__ n_called_out) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const long long n_called = lc[l * TRT_LC_N + TRT_LC_NFULL];
+    uint32_t fl = 0;
+    for (int i = 0; i < n_specs; i++) {
+        const LfSpec sp = specs[i];
+        bool hit = false;
+        switch (sp.kind) {
+            case TRT_LF_CALLRATE: hit = ((double)n_called / (double)S) < sp.thr; break;   // filters.py:57-59
+            case TRT_LF_HWE: hit = hwep[l] < sp.thr; break;                               // NaN never filters
+            case TRT_LF_HETLOW: hit = het[l] < sp.thr; break;
+            case TRT_LF_HETHIGH: hit = het[l] > sp.thr; break;
+            case TRT_LF_HRUN:                                                              // filters.py:205-214
+                hit = has_period_info && (period[l] == 5 || period[l] == 6) && hrun[l] >= period[l];
+                break;
+        }
+        if (hit) fl |= 1u << i;
+    }
+    if (n_called == 0) fl |= 0x80000000u;   // NO_CALLS_REMAINING dumpSTR.py:957-965
+    flags[l] = fl;
+    het_out[l] = n_called > 0 ? het[l] : -1.0;      // INFO HET/HWEP dumpSTR.py:1314-1336
+    hwep_out[l] = n_called > 0 ? hwep[l] : -1.0;
+    n_called_out[l] = n_called;
+}
+
+}  // namespace
 
 extern "C" {
-int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec*, int, int, trt_call_filter_out*) {
-    return trt_set_error(ctx, TRT_ESTATE, "trt_call_filters: not built in this library revision");
+
+int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_specs, int dp_field_id,
+                     trt_call_filter_out* out) {
+    if (!ctx || !ctx->block_open || !ctx->have_gt)
+        return trt_set_error(ctx, TRT_ESTATE, "trt_call_filters: needs a block with GT");
+    if (!out || n_specs < 0 || n_specs > kMaxSpecs || (n_specs > 0 && !specs))
+        return trt_set_error(ctx, TRT_EINVAL, "trt_call_filters: bad arguments (at most %d filters)", kMaxSpecs);
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    const int64_t L = ctx->L, S = ctx->S;
+    CfParams p;
+    memset(&p, 0, sizeof(p));
+    p.gt = ctx->d_gt;
+    p.pitch = ctx->gt_pitch;
+    p.L = L;
+    p.S = S;
+    for (int i = 0; i < TRT_FMT_NFIELDS; i++) {
+        p.fmt[i] = ctx->d_fmt[i];
+        p.fmt_ncol[i] = ctx->fmt_ncol[i];
+    }
+    p.n_specs = n_specs;
+    for (int f = 0; f < n_specs; f++) {
+        const trt_call_filter_spec& s = specs[f];
+        if (s.kind < TRT_CF_MIN || s.kind > TRT_CF_HOST_VALUE)
+            return trt_set_error(ctx, TRT_EINVAL, "trt_call_filters: unknown filter kind %d", s.kind);
+        int field = s.field_id;
+        if (s.kind >= TRT_CF_QEXP_HET && s.kind <= TRT_CF_QEXP_TOT) field = TRT_FMT_QEXP;
+        if (field < 0 || field >= TRT_FMT_NFIELDS || !ctx->d_fmt[field])
+            return trt_set_error(ctx, TRT_ESTATE, "trt_call_filters: FORMAT field %d needed by filter %d is not in the block", field, f);
+        if (s.kind == TRT_CF_RATIO_GT && !ctx->d_fmt[TRT_FMT_DP])
+            return trt_set_error(ctx, TRT_ESTATE, "trt_call_filters: ratio filter %d needs FORMAT DP", f);
+        if (s.kind >= TRT_CF_QEXP_HET && s.kind <= TRT_CF_QEXP_TOT && ctx->fmt_ncol[TRT_FMT_QEXP] != 3)
+            return trt_set_error(ctx, TRT_EINVAL, "trt_call_filters: QEXP must have 3 columns");
+        p.specs[f].kind = s.kind;
+        p.specs[f].field = field;
+        p.specs[f].is_float = ctx->fmt_is_float[field];
+        if (s.kind == TRT_CF_HOST_VALUE && !ctx->fmt_is_float[field])
+            return trt_set_error(ctx, TRT_EINVAL, "trt_call_filters: HOST_VALUE filter %d needs a float32 field", f);
+        if (s.kind == TRT_CF_RATIO_GT && (ctx->fmt_is_float[field] || ctx->fmt_is_float[TRT_FMT_DP]))
+            return trt_set_error(ctx, TRT_EINVAL, "trt_call_filters: ratio filter %d needs int32 fields", f);
+        p.specs[f].thr = s.threshold;
+        p.specs[f].thr_f32 = (float)s.threshold;
+    }
+    p.dp_field = (dp_field_id >= 0 && dp_field_id < TRT_FMT_NFIELDS && ctx->d_fmt[dp_field_id]) ? dp_field_id : -1;
+    // outputs / scratch
+    TRT_TRY(trt_ensure(ctx, ctx->gt_masked_buf, ctx->gt_pitch * (size_t)L + 16));
+    p.gt_out = (int16_t*)ctx->gt_masked_buf.p;
+    const size_t n_ctr = (size_t)(n_specs + 2) * S;
+    TRT_TRY(trt_ensure(ctx, ctx->samp_counts, n_ctr * 8 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->samp_dp, (size_t)S * 4 + 32));
+    TRT_CUDA(cudaMemsetAsync(ctx->samp_counts.p, 0, n_ctr * 8 + 16, ctx->stream));
+    TRT_CUDA(cudaMemsetAsync(ctx->samp_dp.p, 0, (size_t)S * 4 + 16, ctx->stream));
+    p.filter_counts = (long long*)ctx->samp_counts.p;
+    p.numcalls = p.filter_counts + (size_t)n_specs * S;
+    p.dpsum = p.numcalls + S;
+    p.dp_poison = (unsigned int*)ctx->samp_dp.p;
+    p.neg_dp_locus = (int*)((char*)ctx->samp_dp.p + (((size_t)S * 4 + 15) & ~size_t(15)));
+    const int big = 0x7fffffff;
+    TRT_CUDA(cudaMemcpyAsync(p.neg_dp_locus, &big, 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (out->call_mask) {
+        TRT_TRY(trt_ensure(ctx, ctx->call_mask, (size_t)L * S * 4 + 16));
+        p.call_mask = (uint32_t*)ctx->call_mask.p;
+    }
+    if (out->trigger_values && n_specs) {
+        TRT_TRY(trt_ensure(ctx, ctx->trig, (size_t)n_specs * L * S * 8 + 16));
+        p.trig = (double*)ctx->trig.p;
+    }
+    trt_timer_begin(ctx);
+    TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
+    if (L > 0 && S > 0) {
+        if (ctx->P == 2) {
+            const int64_t slabs = (S + kSlabSamples - 1) / kSlabSamples;
+            // enough CTAs to fill the machine several times over, chunks of at least 64 loci
+            int64_t chunks = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 16 + slabs - 1) / slabs);
+            int64_t per = std::max<int64_t>(64, (L + chunks - 1) / chunks);
+            chunks = (L + per - 1) / per;
+            p.loci_per_chunk = (int)per;
+            dim3 grid((unsigned)slabs, (unsigned)chunks);
+            call_filter_kernel<<<grid, kCfThreads, (size_t)std::max(n_specs, 1) * kSlabSamples * 4, ctx->stream>>>(p);
+        } else {
+            const int blocks = (int)std::min<int64_t>((L * S + 255) / 256, (int64_t)ctx->sm_count * 16);
+            call_filter_generic_kernel<<<blocks, 256, 0, ctx->stream>>>(p, ctx->P);
+        }
+        TRT_KERNEL_CHECK();
+    }
+    TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
+    trt_timer_end(ctx);
+    {
+        float ms = 0.f;
+        TRT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1));
+        ctx->last_scan_ms = ms;
+    }
+    // ---- results ------------------------------------------------------------------------------------
+    std::vector<long long> ctr(n_ctr);
+    std::vector<unsigned int> poison((size_t)S);
+    int neg = big;
+    if (n_ctr) TRT_CUDA(cudaMemcpyAsync(ctr.data(), ctx->samp_counts.p, n_ctr * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (S) TRT_CUDA(cudaMemcpyAsync(poison.data(), ctx->samp_dp.p, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TRT_CUDA(cudaMemcpyAsync(&neg, p.neg_dp_locus, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->call_mask && L * S)
+        TRT_CUDA(cudaMemcpyAsync(out->call_mask, ctx->call_mask.p, (size_t)L * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->trigger_values && n_specs && L * S)
+        TRT_CUDA(cudaMemcpyAsync(out->trigger_values, ctx->trig.p, (size_t)n_specs * L * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->gt_masked && L * S) {
+        const size_t row = (size_t)S * (ctx->P + 1) * 2;
+        TRT_CUDA(cudaMemcpy2DAsync(out->gt_masked, row, ctx->gt_masked_buf.p, ctx->gt_pitch, row, (size_t)L,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < n_specs; f++)
+        if (out->filter_counts)
+            for (int64_t s = 0; s < S; s++) out->filter_counts[(size_t)f * S + s] += ctr[(size_t)f * S + s];
+    for (int64_t s = 0; s < S; s++) {
+        if (out->numcalls) out->numcalls[s] += ctr[(size_t)n_specs * S + s];
+        if (out->totaldp) {
+            if (p.dp_field < 0) out->totaldp[s] = nan("");                       // dumpSTR.py:714-715
+            else if (poison[s]) out->totaldp[s] = nan("");                       // dumpSTR.py:710-713
+            else out->totaldp[s] += (double)ctr[(size_t)(n_specs + 1) * S + s];
+        }
+    }
+    if (out->negative_dp_locus) *out->negative_dp_locus = (neg == big) ? -1 : neg;
+    // later statistics read the masked genotypes (the rebuilt TRRecord of dumpSTR.py:748-774)
+    ctx->d_gt_active = (const int16_t*)ctx->gt_masked_buf.p;
+    ctx->gt_active_pitch = ctx->gt_pitch;
+    ctx->have_packed = false;
+    return TRT_OK;
 }
-int trt_locus_filters(trt_ctx* ctx, const trt_locus_filter_spec*, int, int, trt_locus_filter_out*) {
-    return trt_set_error(ctx, TRT_ESTATE, "trt_locus_filters: not built in this library revision");
+
+int trt_locus_filters(trt_ctx* ctx, const trt_locus_filter_spec* specs, int n_specs, int use_length,
+                      trt_locus_filter_out* out) {
+    if (!ctx || !ctx->block_open || !ctx->have_gt || !ctx->harmonized)
+        return trt_set_error(ctx, TRT_ESTATE, "trt_locus_filters: needs a block with GT and trt_harmonize");
+    if (!out || n_specs < 0 || n_specs > 31 || (n_specs > 0 && !specs))
+        return trt_set_error(ctx, TRT_EINVAL, "trt_locus_filters: bad arguments");
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
+    TRT_TRY(trt_ensure(ctx, ctx->ac, (size_t)nA * 4 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->lc, (size_t)L * TRT_LC_N * 8 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->stat_f64, (size_t)L * 8 * 9 + 16));
+    // scratch for the flag kernel: [flags u32 L][het f64 L][hwep f64 L][n_called i64 L][specs]
+    const size_t off_het = (((size_t)L * 4 + 15) & ~size_t(15));
+    const size_t off_hwep = off_het + (size_t)L * 8, off_nc = off_hwep + (size_t)L * 8, off_specs = off_nc + (size_t)L * 8;
+    TRT_TRY(trt_ensure(ctx, ctx->misc, off_specs + 32 * sizeof(LfSpec) + 16));
+    std::vector<LfSpec> hs((size_t)std::max(n_specs, 1));
+    for (int i = 0; i < n_specs; i++) {
+        if (specs[i].kind < TRT_LF_CALLRATE || specs[i].kind > TRT_LF_HRUN)
+            return trt_set_error(ctx, TRT_EINVAL, "trt_locus_filters: unknown filter kind %d", specs[i].kind);
+        hs[i].kind = specs[i].kind;
+        hs[i].thr = specs[i].threshold;
+    }
+    char* base = (char*)ctx->misc.p;
+    if (n_specs)
+        TRT_CUDA(cudaMemcpyAsync(base + off_specs, hs.data(), n_specs * sizeof(LfSpec), cudaMemcpyHostToDevice, ctx->stream));
+    trt_timer_begin(ctx);
+    TRT_TRY(trt_prepare_ranks(ctx));
+    TRT_CUDA(cudaMemsetAsync(ctx->ac.p, 0, (size_t)nA * 4 + 16, ctx->stream));
+    TRT_CUDA(cudaMemsetAsync(ctx->lc.p, 0, (size_t)L * TRT_LC_N * 8 + 16, ctx->stream));
+    if (L > 0) {
+        TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
+        TRT_TRY(trt_run_scan(ctx, nullptr, 0, 1));
+        TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
+        TRT_TRY(trt_run_epilogue(ctx, use_length, 0.01, 1));
+        const double* f = (const double*)ctx->stat_f64.p;
+        const int has_period = (ctx->vcftype == TRT_VCF_HIPSTR || ctx->vcftype == TRT_VCF_LONGTR) ? 1 : 0;
+        locus_flags_kernel<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(
+            L, S, n_specs, (const LfSpec*)(base + off_specs), (const long long*)ctx->lc.p, f + L /*het*/, f + 6 * L /*hwep*/,
+            (const int32_t*)ctx->hrun.p, (const int32_t*)ctx->period.p, has_period, (uint32_t*)base, (double*)(base + off_het),
+            (double*)(base + off_hwep), (long long*)(base + off_nc));
+        TRT_KERNEL_CHECK();
+    }
+    trt_timer_end(ctx);
+    if (L > 0) {
+        float ms = 0.f;
+        TRT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1));
+        ctx->last_scan_ms = ms;
+    }
+#define D2H(dst, src, bytes) \
+    if ((dst) && (bytes)) TRT_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+    D2H(out->flags, base, (size_t)L * 4);
+    D2H(out->het, base + off_het, (size_t)L * 8);
+    D2H(out->hwep, base + off_hwep, (size_t)L * 8);
+    D2H(out->n_called, base + off_nc, (size_t)L * 8);
+    D2H(out->ac, ctx->ac.p, (size_t)nA * 4);
+    D2H(out->hrun, ctx->hrun.p, (size_t)L * 4);
+#undef D2H
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TRT_OK;
 }
-}
+
+}  // extern "C"

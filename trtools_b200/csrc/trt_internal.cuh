@@ -38,6 +38,7 @@ struct trt_ctx {
     bool    have_gt = false;
     const void* d_fmt[TRT_FMT_NFIELDS] = {nullptr};
     int     fmt_ncol[TRT_FMT_NFIELDS] = {0};
+    int     fmt_is_float[TRT_FMT_NFIELDS] = {0};
     DevBuf  fmt_buf[TRT_FMT_NFIELDS];
 
     // allele table

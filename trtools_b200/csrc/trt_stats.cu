@@ -1,14 +1,7 @@
-// K2 — per-locus statistics straight from the native cyvcf2 GT rows (6 B/call for diploids).
+// K2b — per-locus statistics from the O(alleles) count tables the GT scan (trt_scan.cu) produces.
 //
-//   scan_diploid_tma_kernel : persistent CTAs, one locus at a time per CTA.  A producer warp
-//       streams the locus' GT row through a 4-stage shared-memory ring with 1-D bulk TMA copies
-//       (cp.async.bulk + mbarrier transaction bytes); 16 consumer warps read 48 B (= 8 calls)
-//       per thread with three conflict-free LDS.128 and count alleles in THREAD-PRIVATE 16-bit
-//       shared-memory counters (no atomics on the sample axis), plus called / padded /
-//       homozygous counters in registers.  One CTA-wide reduction per locus.
-//   scan_generic_kernel     : warp per locus; any ploidy, any allele count, tiny sample counts.
 //   locus_epilogue_kernel   : thread per (group, locus): allele-frequency statistics and the
-//       exact two-sided binomial HWE test in FP64 from the O(alleles) count tables.
+//       exact two-sided binomial HWE test in FP64.
 //
 // Reference semantics reproduced (file:line in the reference tree):
 //   TRRecord.GetAlleleCounts    trtools/utils/tr_harmonizer.py:1420-1499  (-1/-2 dropped; partial calls count)
@@ -22,259 +15,9 @@
 #include <algorithm>
 
 #include "trt_internal.cuh"
+#include "trt_scan.cuh"
 
 namespace {
-
-constexpr int kConsumerThreads = 512;
-constexpr int kConsumerWarps = kConsumerThreads / 32;
-constexpr int kThreads = kConsumerThreads + 32;          // + producer warp
-constexpr int kCallsPerThread = 8;                        // 8 calls x 6 B = 48 B = 3 x LDS.128
-constexpr int kChunkBytes = kConsumerThreads * 48;        // 24576
-constexpr int kChunkCalls = kConsumerThreads * kCallsPerThread;
-constexpr int kStages = 4;
-constexpr int kMaxFastAlleles = 96;                       // thread-private u16 counters: 1 KB per allele
-constexpr int kMinFastSamples = 2048;
-
-struct ScanParams {
-    const int16_t* gt;
-    size_t pitch;
-    int64_t L, S;
-    int P;
-    const int32_t* locus_off;
-    const int32_t* len_class;
-    const int32_t* seq_class;
-    const int32_t* len_rank;
-    const int32_t* seq_rank;
-    const int32_t* hflags;
-    const uint8_t* mask;   // [S] bytes or null
-    int32_t* ac;           // [nA]
-    long long* lc;         // [L][TRT_LC_N]
-    int only_ineligible;   // generic kernel: process only loci the fast kernel skipped
-    int fast_enabled;
-};
-
-__device__ __forceinline__ bool fast_eligible(int A) { return A <= kMaxFastAlleles; }
-
-// ------------------------------------------------------------------------------------------------
-// generic: one warp per locus
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) scan_generic_kernel(ScanParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t l = warp; l < p.L; l += nwarps) {
-        const int a0 = p.locus_off[l];
-        const int A = p.locus_off[l + 1] - a0;
-        if (p.only_ineligible && p.fast_enabled && fast_eligible(A)) continue;
-        const int16_t* row = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch);
-        const int P = p.P;
-        long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
-        for (int64_t s = lane; s < p.S; s += 32) {
-            if (p.mask && !p.mask[s]) continue;
-            const int16_t* g = row + s * (P + 1);
-            bool any_m1 = false, any_called = false, any_pad = false;
-            // two smallest keys under each relation (pads sort first: key -2)
-            int i1 = INT_MAX, i2 = INT_MAX, l1 = INT_MAX, l2 = INT_MAX, q1 = INT_MAX, q2 = INT_MAX;
-            for (int h = 0; h < P; h++) {
-                int a = g[h];
-                int ki, kl, kq;
-                if (a == -1) {
-                    any_m1 = true;
-                    continue;
-                } else if (a == -2) {
-                    any_pad = true;
-                    ki = kl = kq = -2;
-                } else if (a >= 0 && a < A) {
-                    any_called = true;
-                    atomicAdd(&p.ac[a0 + a], 1);
-                    ki = a;
-                    kl = p.len_rank[a0 + a];
-                    kq = p.seq_rank[a0 + a];
-                } else {
-                    n_bad++;
-                    any_m1 = true;
-                    continue;
-                }
-                if (ki < i1) { i2 = i1; i1 = ki; } else if (ki < i2) i2 = ki;
-                if (kl < l1) { l2 = l1; l1 = kl; } else if (kl < l2) l2 = kl;
-                if (kq < q1) { q2 = q1; q1 = kq; } else if (kq < q2) q2 = kq;
-            }
-            if (any_called) n_non++;
-            if (!any_m1) {
-                n_full++;
-                if (any_pad) n_pad++;
-                if (P >= 2) {
-                    h_idx += (i1 == i2);
-                    h_len += (l1 == l2);
-                    h_seq += (q1 == q2);
-                }
-            }
-        }
-        n_full = warp_sum_ll(n_full); n_non = warp_sum_ll(n_non); n_pad = warp_sum_ll(n_pad);
-        h_idx = warp_sum_ll(h_idx); h_len = warp_sum_ll(h_len); h_seq = warp_sum_ll(h_seq);
-        n_bad = warp_sum_ll(n_bad);
-        if (lane == 0) {
-            long long* o = p.lc + l * TRT_LC_N;
-            o[TRT_LC_NFULL] = n_full; o[TRT_LC_NNONSTRICT] = n_non; o[TRT_LC_NPAD] = n_pad;
-            o[TRT_LC_HOM_IDX] = h_idx; o[TRT_LC_HOM_LEN] = h_len; o[TRT_LC_HOM_SEQ] = h_seq;
-            o[6] = n_bad; o[7] = 0;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// fast diploid path
-// ------------------------------------------------------------------------------------------------
-struct __align__(16) FastSmemHeader {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
-    long long warp_part[kConsumerWarps][8];
-    uint32_t cls[kMaxFastAlleles];   // (len_class << 16) | seq_class
-};
-
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
-
-template <bool MASKED>
-__global__ void __launch_bounds__(kThreads, 1) scan_diploid_tma_kernel(ScanParams p, int max_alleles_smem) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* ring = smem;                                             // kStages * kChunkBytes
-    FastSmemHeader* hdr = (FastSmemHeader*)(smem + kStages * kChunkBytes);
-    uint16_t* cnt = (uint16_t*)(smem + kStages * kChunkBytes + sizeof(FastSmemHeader));  // [A][512]
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const size_t row_bytes = (size_t)p.S * 6;
-    const size_t copy_bytes = (row_bytes + 15) & ~size_t(15);               // <= pitch
-    const int nchunks = (int)((copy_bytes + kChunkBytes - 1) / kChunkBytes);
-
-    if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
-            mbar_init(&hdr->full[s], 1);
-            mbar_init(&hdr->empty[s], kConsumerWarps);
-        }
-        mbar_fence_init();
-    }
-    // zero the private counters
-    for (int i = tid; i < max_alleles_smem * kConsumerThreads / 2; i += kThreads) ((uint32_t*)cnt)[i] = 0u;
-    __syncthreads();
-
-    if (warp == kConsumerWarps) {
-        // ===== producer warp: one elected lane feeds the ring, running ahead across loci =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
-                const int A = p.locus_off[l + 1] - p.locus_off[l];
-                if (!fast_eligible(A)) continue;
-                const char* src = (const char*)p.gt + (size_t)l * p.pitch;
-                for (int c = 0; c < nchunks; c++, it++) {
-                    const int stage = it % kStages;
-                    const uint32_t phase = (it / kStages) & 1u;
-                    mbar_wait(&hdr->empty[stage], phase ^ 1u);
-                    const size_t off = (size_t)c * kChunkBytes;
-                    const uint32_t bytes = (uint32_t)min((size_t)kChunkBytes, copy_bytes - off);
-                    mbar_arrive_expect_tx(&hdr->full[stage], bytes);
-                    tma_load_1d(ring + (size_t)stage * kChunkBytes, src + off, bytes, &hdr->full[stage]);
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== consumers =====
-    uint16_t* my = cnt + tid;   // counter of allele a at my[a * 512]
-    uint32_t it = 0;
-    for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
-        const int a0 = p.locus_off[l];
-        const int A = p.locus_off[l + 1] - a0;
-        if (!fast_eligible(A)) continue;
-        const int hf = p.hflags[l];
-        const bool dups = (hf & (TRT_HF_LEN_DUPS | TRT_HF_SEQ_DUPS)) != 0;
-        if (dups) {
-            for (int a = tid; a < A; a += kConsumerThreads)
-                hdr->cls[a] = ((uint32_t)p.len_class[a0 + a] << 16) | (uint32_t)p.seq_class[a0 + a];
-            consumer_bar();
-        }
-        int n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
-
-        for (int c = 0; c < nchunks; c++, it++) {
-            const int stage = it % kStages;
-            const uint32_t phase = (it / kStages) & 1u;
-            mbar_wait(&hdr->full[stage], phase);
-            const uint4* src = (const uint4*)(ring + (size_t)stage * kChunkBytes + (size_t)tid * 48);
-            const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
-            // all smem reads of this stage are done once the registers are loaded
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hdr->empty[stage]);
-            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            const int64_t s_base = (int64_t)c * kChunkCalls + (int64_t)tid * kCallsPerThread;
-            uint32_t mbits = 0xffu;
-            if (MASKED) {
-                mbits = 0;
-#pragma unroll
-                for (int j = 0; j < kCallsPerThread; j++)
-                    if (s_base + j < p.S && p.mask[s_base + j]) mbits |= 1u << j;
-            }
-#pragma unroll
-            for (int j = 0; j < kCallsPerThread; j++) {
-                // halves 3j and 3j+1 of the 24-half window
-                const int k0 = 3 * j, k1 = 3 * j + 1;
-                const int a = (int)(short)((k0 & 1) ? (w[k0 >> 1] >> 16) : (w[k0 >> 1] & 0xffffu));
-                const int b = (int)(short)((k1 & 1) ? (w[k1 >> 1] >> 16) : (w[k1 >> 1] & 0xffffu));
-                bool live = (s_base + j < p.S);
-                if (MASKED) live = live && ((mbits >> j) & 1u);
-                if (!live) continue;
-                const bool va = (unsigned)a < (unsigned)A, vb = (unsigned)b < (unsigned)A;
-                if (va) my[a * kConsumerThreads] += 1;
-                if (vb) my[b * kConsumerThreads] += 1;
-                const bool bad = (a < -2) | (b < -2) | (a >= A) | (b >= A);
-                const bool m1 = (a == -1) | (b == -1) | bad;
-                n_bad += bad;
-                n_non += (va | vb);
-                if (!m1) {
-                    n_full++;
-                    n_pad += ((a == -2) | (b == -2));
-                    h_idx += (a == b);
-                    if (dups) {
-                        const uint32_t ca = va ? hdr->cls[a] : 0xfffffffeu, cb = vb ? hdr->cls[b] : 0xfffffffdu;
-                        h_len += ((ca >> 16) == (cb >> 16)) | (a == b);
-                        h_seq += ((ca & 0xffffu) == (cb & 0xffffu)) | (a == b);
-                    }
-                }
-            }
-        }
-        if (!dups) {
-            h_len = h_idx;
-            h_seq = h_idx;
-        }
-        // ---- per-locus reduction ---------------------------------------------------------------
-        n_full = warp_sum(n_full); n_non = warp_sum(n_non); n_pad = warp_sum(n_pad);
-        h_idx = warp_sum(h_idx); h_len = warp_sum(h_len); h_seq = warp_sum(h_seq); n_bad = warp_sum(n_bad);
-        if (lane == 0) {
-            long long* wp = hdr->warp_part[warp];
-            wp[0] = n_full; wp[1] = n_non; wp[2] = n_pad; wp[3] = h_idx; wp[4] = h_len; wp[5] = h_seq; wp[6] = n_bad;
-        }
-        consumer_bar();   // all private counters and warp partials of this locus are final
-        for (int a = warp; a < A; a += kConsumerWarps) {
-            uint32_t* rowp = (uint32_t*)(cnt + (size_t)a * kConsumerThreads);   // 256 words
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < kConsumerThreads / 64; k++) {
-                const uint32_t x = rowp[lane + 32 * k];
-                rowp[lane + 32 * k] = 0u;
-                sum += (int)(x & 0xffffu) + (int)(x >> 16);
-            }
-            sum = warp_sum(sum);
-            if (lane == 0) p.ac[a0 + a] = sum;
-        }
-        if (tid < 7) {
-            long long t = 0;
-            for (int w2 = 0; w2 < kConsumerWarps; w2++) t += hdr->warp_part[w2][tid];
-            p.lc[l * TRT_LC_N + tid] = t;
-        }
-        if (tid == 7) p.lc[l * TRT_LC_N + 7] = 0;
-        consumer_bar();   // counters are zero again, partials consumed
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // epilogue: exact binomial machinery (scipy.stats.binomtest two-sided)
@@ -591,49 +334,6 @@ __global__ void genotype_table_kernel(const int16_t* __restrict__ row, int64_t S
 
 }  // namespace
 
-// run the scan (fast + generic) for one group mask; results into ctx->ac / ctx->lc at group g
-int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
-    const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
-    ScanParams sp;
-    sp.gt = ctx->d_gt_active;
-    sp.pitch = ctx->gt_active_pitch;
-    sp.L = L;
-    sp.S = S;
-    sp.P = ctx->P;
-    sp.locus_off = (const int32_t*)ctx->locus_off.p;
-    sp.len_class = (const int32_t*)ctx->len_class.p;
-    sp.seq_class = (const int32_t*)ctx->seq_class.p;
-    sp.len_rank = (const int32_t*)ctx->stat_i32.p;
-    sp.seq_rank = (const int32_t*)ctx->stat_i32.p + nA;
-    sp.hflags = (const int32_t*)ctx->hflags.p;
-    sp.mask = d_mask;
-    sp.ac = (int32_t*)ctx->ac.p + (size_t)g * nA;
-    sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
-    const bool fast = (ctx->P == 2 && S >= kMinFastSamples);
-    sp.fast_enabled = fast ? 1 : 0;
-    sp.only_ineligible = fast ? 1 : 0;
-    if (fast) {
-        const int amax = std::min(ctx->maxA, kMaxFastAlleles);
-        const size_t smem = (size_t)kStages * kChunkBytes + sizeof(FastSmemHeader) + (size_t)amax * kConsumerThreads * 2;
-        const int grid = (int)std::min<int64_t>(L, ctx->sm_count);
-        if (d_mask) {
-            TRT_CUDA(cudaFuncSetAttribute(scan_diploid_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            scan_diploid_tma_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(sp, amax);
-        } else {
-            TRT_CUDA(cudaFuncSetAttribute(scan_diploid_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            scan_diploid_tma_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(sp, amax);
-        }
-        TRT_KERNEL_CHECK();
-    }
-    if (!fast || ctx->maxA > kMaxFastAlleles) {
-        const int warps_per_block = 8;
-        const int64_t blocks = std::min<int64_t>((L + warps_per_block - 1) / warps_per_block, (int64_t)ctx->sm_count * 8);
-        scan_generic_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, ctx->stream>>>(sp);
-        TRT_KERNEL_CHECK();
-    }
-    return TRT_OK;
-}
-
 // (re)compute dense class ranks into ctx->stat_i32 = [len_rank[nA] | seq_rank[nA]]
 int trt_prepare_ranks(trt_ctx* ctx) {
     const int64_t L = ctx->L, nA = ctx->nA;
@@ -648,6 +348,34 @@ int trt_prepare_ranks(trt_ctx* ctx) {
             (int32_t*)ctx->stat_i32.p + nA);
         TRT_KERNEL_CHECK();
     }
+    return TRT_OK;
+}
+
+// epilogue over ctx->ac / ctx->lc -> ctx->stat_f64 = [thresh|het|entropy|mean|mode|var|hwep|nalleles(i32)|n_hom(i64)] x G*L
+int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G) {
+    const int64_t L = ctx->L, nA = ctx->nA;
+    const size_t n_out = (size_t)G * L;
+    if (n_out == 0) return TRT_OK;
+    double* f = (double*)ctx->stat_f64.p;
+    EpiParams ep;
+    ep.L = L; ep.G = G; ep.nA = nA;
+    ep.locus_off = (const int32_t*)ctx->locus_off.p;
+    ep.allele_len = (const double*)ctx->allele_len.p;
+    ep.len_class = (const int32_t*)ctx->len_class.p;
+    ep.seq_class = (const int32_t*)ctx->seq_class.p;
+    ep.len_order = (const int32_t*)ctx->len_order.p;
+    ep.seq_order = (const int32_t*)ctx->seq_order.p;
+    ep.ac = (const int32_t*)ctx->ac.p;
+    ep.lc = (const long long*)ctx->lc.p;
+    ep.use_length = use_length;
+    ep.nalleles_thresh = nalleles_thresh;
+    ep.P = ctx->P;
+    ep.thresh = f; ep.het = f + n_out; ep.entropy = f + 2 * n_out; ep.mean = f + 3 * n_out;
+    ep.mode = f + 4 * n_out; ep.var = f + 5 * n_out; ep.hwep = f + 6 * n_out;
+    ep.nalleles = (int32_t*)(f + 7 * n_out);
+    ep.n_hom = (long long*)(f + 8 * n_out);
+    locus_epilogue_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(ep);
+    TRT_KERNEL_CHECK();
     return TRT_OK;
 }
 
@@ -679,26 +407,7 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
             TRT_TRY(trt_run_scan(ctx, m, g, G));
         }
         TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
-        double* f = (double*)ctx->stat_f64.p;
-        EpiParams ep;
-        ep.L = L; ep.G = G; ep.nA = nA;
-        ep.locus_off = (const int32_t*)ctx->locus_off.p;
-        ep.allele_len = (const double*)ctx->allele_len.p;
-        ep.len_class = (const int32_t*)ctx->len_class.p;
-        ep.seq_class = (const int32_t*)ctx->seq_class.p;
-        ep.len_order = (const int32_t*)ctx->len_order.p;
-        ep.seq_order = (const int32_t*)ctx->seq_order.p;
-        ep.ac = (const int32_t*)ctx->ac.p;
-        ep.lc = (const long long*)ctx->lc.p;
-        ep.use_length = use_length;
-        ep.nalleles_thresh = nalleles_thresh;
-        ep.P = ctx->P;
-        ep.thresh = f; ep.het = f + n_out; ep.entropy = f + 2 * n_out; ep.mean = f + 3 * n_out;
-        ep.mode = f + 4 * n_out; ep.var = f + 5 * n_out; ep.hwep = f + 6 * n_out;
-        ep.nalleles = (int32_t*)(f + 7 * n_out);
-        ep.n_hom = (long long*)(f + 8 * n_out);
-        locus_epilogue_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(ep);
-        TRT_KERNEL_CHECK();
+        TRT_TRY(trt_run_epilogue(ctx, use_length, nalleles_thresh, G));
     }
     trt_timer_end(ctx);
     ctx->last_scan_ms = 0.0;

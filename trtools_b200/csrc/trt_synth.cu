@@ -143,6 +143,7 @@ extern "C" int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset,
         for (int i = 0; i < 4; i++) {
             ctx->d_fmt[ids[i]] = ctx->fmt_buf[ids[i]].p;
             ctx->fmt_ncol[ids[i]] = 1;
+            ctx->fmt_is_float[ids[i]] = (ids[i] == TRT_FMT_Q) ? 1 : 0;
         }
     }
     return TRT_OK;
