@@ -353,3 +353,38 @@ def test_trrecord_api_known_answers(ctx):
         trh.TRRecord(rec, "CAG", ["CAG"], "CAG", "", None, alt_allele_lengths=[1])
     with pytest.raises(ValueError):
         trh.TRRecord(rec, "CAGCAGCAG", ["CAG"], "CAG", "", None)      # wrong number of alts
+
+
+@pytest.mark.parametrize("L,S,seed", [(3000, 4100, 5), (1500, 9000, 6)])
+def test_many_loci_per_cta(ctx, L, S, seed):
+    """Persistent CTAs process many loci back to back (L >> 148): device-generated block, sampled loci
+    checked against the oracle (catches cross-locus hazards in the thread-private tables)."""
+    from oracle import stats as ostats, trh as otrh
+    from oracle.records import synth_to_loci
+    from trtools_b200 import synth
+    sl = synth.make_loci(L, seed=seed)
+    ctx.block_begin(L, S, 2, "hipstr")
+    ctx.synth_fill(seed, 0, sl.cum_freq, sl.miss_thresh, sl.half_thresh, with_format=False)
+    ctx.block_set_alleles(*synth.allele_tables(sl))
+    ctx._current_block = None
+    ctx.harmonize()
+    rng = np.random.default_rng(seed)
+    for uselength in (True, False):
+        st = ctx.locus_stats(uselength, None, 0.01)
+        picks = sorted(set(rng.integers(0, L, 10).tolist() + [0, L - 1, 147, 148, 149, 296]))
+        for j in picks:
+            calls = synth.fill_calls(sl, S, slice(j, j + 1))
+            sub = synth.SynthLoci(seed=sl.seed, n_loci=1, chrom=sl.chrom[j:j + 1], pos=sl.pos[j:j + 1],
+                                  start=sl.start[j:j + 1], end=sl.end[j:j + 1], period=sl.period[j:j + 1],
+                                  ref=sl.ref[j:j + 1], alts=sl.alts[j:j + 1], n_alleles=sl.n_alleles[j:j + 1],
+                                  cum_freq=sl.cum_freq[j:j + 1], locus_offset=j)
+            locus = synth_to_loci(sub, calls, with_fmt=False)[0]
+            h = otrh.harmonize(locus)
+            want = ostats.locus_stats(h, locus.gt, ostats.STAT_ORDER, [None], uselength=uselength)
+            ac = otrh.allele_counts(h, locus.gt, index=True)
+            a0, a1 = int(ctx.locus_off[j]), int(ctx.locus_off[j + 1])
+            got = st["ac"][0, a0:a1]
+            assert {int(k): int(v) for k, v in ac.items()} == {i: int(v) for i, v in enumerate(got) if v > 0}, j
+            assert int(st["n_called"][0, j]) == want["numcalled"][0], j
+            for stat in ("thresh", "hwep", "het", "entropy", "mean", "mode", "var"):
+                assert_close(st[stat][0, j], want[stat][0], "locus {} {}".format(j, stat), abs_tol=1e-300)

@@ -48,6 +48,7 @@ struct CfParams {
     int n_specs;
     CfSpec specs[kMaxSpecs];
     int dp_field;          // field used for totaldp (-1: none)
+    int dp_is_float;       // e.g. ExpansionHunter LC: float32 coverage (generic kernel only)
     uint32_t* call_mask;   // [L][S] or null
     double* trig;          // [n_specs][L][S] or null
     long long* filter_counts;  // [n_specs][S]
@@ -260,7 +261,12 @@ __global__ void call_filter_generic_kernel(CfParams p, int P) {
         const bool pass = fired == 0 && !nocall;
         if (pass) {
             atomicAdd((unsigned long long*)&p.numcalls[s], 1ull);
-            if (p.dp_field >= 0) {
+            if (p.dp_field >= 0 && p.dp_is_float) {
+                // float32 depth (dumpSTR.py:688-713 on a float array: NaN never compares, no INT_MIN sentinel)
+                const float d = ((const float*)p.fmt[p.dp_field])[l * p.S + s];
+                if (d < 0.f) atomicMin(p.neg_dp_locus, (int)l);
+                else if (d > 0.f) atomicAdd((double*)&p.dpsum[s], (double)d);
+            } else if (p.dp_field >= 0) {
                 const int d = ((const int32_t*)p.fmt[p.dp_field])[l * p.S + s];
                 if (d == INT_MIN) atomicOr(&p.dp_poison[s], 1u);
                 else if (d < 0) atomicMin(p.neg_dp_locus, (int)l);
@@ -356,6 +362,7 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
         p.specs[f].thr_f32 = (float)s.threshold;
     }
     p.dp_field = (dp_field_id >= 0 && dp_field_id < TRT_FMT_NFIELDS && ctx->d_fmt[dp_field_id]) ? dp_field_id : -1;
+    p.dp_is_float = (p.dp_field >= 0) ? ctx->fmt_is_float[p.dp_field] : 0;
     // outputs / scratch
     TRT_TRY(trt_ensure(ctx, ctx->gt_masked_buf, ctx->gt_pitch * (size_t)L + 16));
     p.gt_out = (int16_t*)ctx->gt_masked_buf.p;
@@ -382,7 +389,7 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
     trt_timer_begin(ctx);
     TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
     if (L > 0 && S > 0) {
-        if (ctx->P == 2) {
+        if (ctx->P == 2 && !p.dp_is_float) {
             const int64_t slabs = (S + kSlabSamples - 1) / kSlabSamples;
             // enough CTAs to fill the machine several times over, chunks of at least 64 loci
             int64_t chunks = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 16 + slabs - 1) / slabs);
@@ -429,7 +436,11 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
         if (out->totaldp) {
             if (p.dp_field < 0) out->totaldp[s] = nan("");                       // dumpSTR.py:714-715
             else if (poison[s]) out->totaldp[s] = nan("");                       // dumpSTR.py:710-713
-            else out->totaldp[s] += (double)ctr[(size_t)(n_specs + 1) * S + s];
+            else if (p.dp_is_float) {
+                double d;
+                memcpy(&d, &ctr[(size_t)(n_specs + 1) * S + s], 8);
+                out->totaldp[s] += d;
+            } else out->totaldp[s] += (double)ctr[(size_t)(n_specs + 1) * S + s];
         }
     }
     if (out->negative_dp_locus) *out->negative_dp_locus = (neg == big) ? -1 : neg;

@@ -17,6 +17,8 @@
 //       per-call flag logic at all (~13 instructions per call; the roofline allows ~33).
 //   scan_wide_kernel   (diploid, A <= 96): same TMA ring, thread-private per-haplotype 16-bit counters.
 //   scan_generic_kernel: warp per locus; any ploidy, any allele count, tiny sample counts.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "trt_internal.cuh"
@@ -92,83 +94,105 @@ __global__ void __launch_bounds__(256) scan_generic_kernel(ScanParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// pair-table tier
+// pair-table tiers
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPT = 256;                       // consumer threads
+constexpr int kPT = 512;                       // consumer threads (16 warps: 4 per scheduler hide the RMW latency)
 constexpr int kPWarps = kPT / 32;
+constexpr int kPPairs = kPWarps / 2;
 constexpr int kPThreads = kPT + 32;            // + producer warp
-constexpr int kPChunkBytes = 24576;            // 4096 calls; thread t owns bytes [48t,48t+48) and [12288+48t, ...)
-constexpr int kPChunkCalls = 4096;
-constexpr int kPStages = 3;
-constexpr int kPMaxDigits = kPairsMaxAllelesU16 + 3;   // 17
+constexpr int kPChunkBytes = kPT * 48;         // 24576 B = 4096 calls; thread t owns bytes [48t, 48t+48) = 8 calls
+constexpr int kPChunkCalls = kPT * 8;
+constexpr int kPMaxStages = 6;
+constexpr int kPMinStages = 3;
+constexpr int kPMaxDigits = kPairsMaxAlleles + 3;
+constexpr int kPMaxBins = kPMaxDigits * (kPMaxDigits + 1) / 2;   // unordered digit pairs of the largest tier
+constexpr int kPRowBytes = kPT * 2;            // one table row: 512 thread-private 16-bit cells
 
+// Table cell of (bin b, thread t): 16-bit, at halfword  b*512 + 64*(t/64) + 2*(t%32) + ((t/32)&1).
+// The two warps of a warp PAIR share 32-bit words (low / high half), so within one warp the 32 lanes
+// always touch 32 different banks whatever bins they address: conflict-free without 32-bit cells.
 struct __align__(16) PairHeader {
-    uint64_t full[kPStages];
-    uint64_t empty[kPStages];
-    unsigned int T[2][kPMaxDigits * kPMaxDigits];   // CTA-reduced pair table, double buffered by locus parity
-    int cls_len[2][kPMaxDigits];                    // class of each digit (pad digit: -2; bad/nocall: -1)
-    int cls_seq[2][kPMaxDigits];
+    uint64_t full[kPMaxStages];
+    uint64_t empty[kPMaxStages];
+    unsigned int partial[2][kPPairs][kPMaxBins];   // per-warp-pair sums, double buffered by locus parity
+    unsigned int T[kPMaxBins];                     // warp 0's CTA-wide pair table
 };
-
-__device__ __forceinline__ void pbar() { asm volatile("bar.sync 1, %0;" ::"n"(kPT) : "memory"); }
 
 // digit of a haplotype: pad(-2) -> 0, no-call(-1) -> 1, allele a -> a+2, anything else -> D-1 ("bad")
 __device__ __forceinline__ unsigned digit(int a, unsigned Dm1) { return min((unsigned)(a + 2), Dm1); }
+// bin of an UNORDERED digit pair (genotypes are unphased for every statistic): tri(hi, lo), lo <= hi
+__device__ __forceinline__ unsigned tri(unsigned hi, unsigned lo) { return ((hi * (hi + 1u)) >> 1) + lo; }
 
-template <typename CT>
-__device__ __forceinline__ void bump2(CT* my, unsigned i0, unsigned i1) {
-    // two thread-private increments with both loads in flight; equal bins are handled by writing x+2 twice
-    CT* p0 = my + (size_t)i0 * kPT;
-    CT* p1 = my + (size_t)i1 * kPT;
+// two thread-private increments with both loads in flight; equal bins both store x + 2
+__device__ __forceinline__ void bump2(uint16_t* my, unsigned i0, unsigned i1) {
+    uint16_t* p0 = my + (size_t)i0 * kPT;
+    uint16_t* p1 = my + (size_t)i1 * kPT;
     const unsigned x0 = *p0, x1 = *p1;
     const unsigned e = (i0 == i1) ? 2u : 1u;
-    *p0 = (CT)(x0 + e);
-    *p1 = (CT)(x1 + e);
+    *p0 = (uint16_t)(x0 + e);
+    *p1 = (uint16_t)(x1 + e);
 }
 
-template <typename CT, bool MASKED>
-__global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_digits) {
+// next locus of this CTA that belongs to `tier` (or L)
+__device__ __forceinline__ int64_t next_locus(const ScanParams& p, int64_t l, int tier, int& A, int& a0) {
+    for (; l < p.L; l += gridDim.x) {
+        a0 = p.locus_off[l];
+        A = p.locus_off[l + 1] - a0;
+        if (scan_tier(A) == tier) return l;
+    }
+    return p.L;
+}
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Per locus the bins are ORDERED digit pairs d0*D + d1 (one IMAD per call, D^2 rows) while D^2 <= kSquareRows,
+// otherwise UNORDERED pairs (D(D+1)/2 rows, ~4 more instructions per call).
+template <bool MASKED>
+__global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
-    PairHeader* hdr = (PairHeader*)(smem + kPStages * kPChunkBytes);
-    CT* table = (CT*)(smem + kPStages * kPChunkBytes + sizeof(PairHeader));   // [D*D][256]
+    PairHeader* hdr = (PairHeader*)(smem + (size_t)stages * kPChunkBytes);
+    uint16_t* table = (uint16_t*)(smem + (size_t)stages * kPChunkBytes + sizeof(PairHeader));   // [max_rows + 1][512]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const size_t row_bytes = (size_t)p.S * 6;
     const size_t copy_bytes = (row_bytes + 15) & ~size_t(15);
     const int nchunks = (int)((copy_bytes + kPChunkBytes - 1) / kPChunkBytes);
-    const int nfull = (int)(p.S / kPChunkCalls);   // chunks whose 4096 calls are all real samples
+    const int nfull = (int)(p.S / kPChunkCalls);   // chunks whose calls are all real samples
+    const unsigned trash = (unsigned)max_rows;     // extra row: calls beyond S in the last chunk land here
+    // the non-blocking hand-off to warp 0 relies on the ring keeping the warps within one locus of each other
+    const bool loose = nchunks > stages;
 
     if (tid == 0) {
-        for (int s = 0; s < kPStages; s++) {
+        for (int s = 0; s < stages; s++) {
             mbar_init(&hdr->full[s], 1);
             mbar_init(&hdr->empty[s], kPWarps);
         }
         mbar_fence_init();
     }
     {
-        const int words = max_digits * max_digits * kPT * (int)sizeof(CT) / 4;
+        const int words = (max_rows + 1) * kPRowBytes / 4;
         for (int i = tid; i < words; i += kPThreads) ((uint32_t*)table)[i] = 0u;
     }
     __syncthreads();
 
     if (warp == kPWarps) {
-        // ===== producer warp =====
+        // ===== producer warp: one elected lane feeds the ring, running ahead across loci =====
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
-                const int A = p.locus_off[l + 1] - p.locus_off[l];
-                if (scan_tier(A) != tier) continue;
+            int stage = 0;
+            uint32_t phase = 0;
+            int A, a0;
+            for (int64_t l = next_locus(p, blockIdx.x, tier, A, a0); l < p.L; l = next_locus(p, l + gridDim.x, tier, A, a0)) {
                 const char* src = (const char*)p.gt + (size_t)l * p.pitch;
-                for (int c = 0; c < nchunks; c++, it++) {
-                    const int stage = it % kPStages;
-                    const uint32_t phase = (it / kPStages) & 1u;
+                for (int c = 0; c < nchunks; c++) {
                     mbar_wait(&hdr->empty[stage], phase ^ 1u);
                     const size_t off = (size_t)c * kPChunkBytes;
                     const uint32_t bytes = (uint32_t)min((size_t)kPChunkBytes, copy_bytes - off);
                     mbar_arrive_expect_tx(&hdr->full[stage], bytes);
                     tma_load_1d(ring + (size_t)stage * kPChunkBytes, src + off, bytes, &hdr->full[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -176,106 +200,145 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     }
 
     // ===== consumers =====
-    CT* my = table + tid;
-    uint32_t it = 0;
+    const int pair = warp >> 1, half = warp & 1;
+    uint16_t* my = table + 64 * pair + 2 * lane + half;
+    int stage = 0;
+    uint32_t phase = 0;
     int parity = 0;
-    for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
-        const int a0 = p.locus_off[l];
-        const int A = p.locus_off[l + 1] - a0;
-        if (scan_tier(A) != tier) continue;
+    long long dbg_wait = 0, dbg_proc = 0, dbg_end = 0, dbg_chunks = 0;
+    int A, a0, A_next = 0, a0_next = 0;
+    int64_t l = next_locus(p, blockIdx.x, tier, A, a0);
+    while (l < p.L) {
+        // metadata of the following locus is fetched now so its latency hides under this locus' stream
+        const int64_t l_next = next_locus(p, l + gridDim.x, tier, A_next, a0_next);
         const unsigned D = (unsigned)A + 3u, Dm1 = D - 1u;
-        if (tid < (int)D) {
-            int cl = -1, cq = -1;
-            if (tid == 0) cl = cq = -2;
-            else if (tid >= 2 && tid < A + 2) {
-                cl = p.len_class[a0 + tid - 2];
-                cq = p.seq_class[a0 + tid - 2];
-            }
-            hdr->cls_len[parity][tid] = cl;
-            hdr->cls_seq[parity][tid] = cq;
-        }
+        const bool sq = pairs_square(A);
 
-        for (int c = 0; c < nchunks; c++, it++) {
-            const int stage = it % kPStages;
-            const uint32_t phase = (it / kPStages) & 1u;
+        for (int c = 0; c < nchunks; c++) {
+            const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&hdr->full[stage], phase);
-            const unsigned char* base = ring + (size_t)stage * kPChunkBytes;
-            const uint4* s0p = (const uint4*)(base + (size_t)tid * 48);
-            const uint4* s1p = (const uint4*)(base + 12288 + (size_t)tid * 48);
-            const uint4 v0 = s0p[0], v1 = s0p[1], v2 = s0p[2], v3 = s1p[0], v4 = s1p[1], v5 = s1p[2];
+            if (p.dbg && tid == 32 && blockIdx.x == 0) dbg_wait += clock64() - t0;
+            if (p.stream_only) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                continue;
+            }
+            const uint4* sp = (const uint4*)(ring + (size_t)stage * kPChunkBytes + (size_t)tid * 48);
+            const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->empty[stage]);
-            const uint32_t w[24] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w,
-                                    v3.x, v3.y, v3.z, v3.w, v4.x, v4.y, v4.z, v4.w, v5.x, v5.y, v5.z, v5.w};
-            unsigned idx[16];
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            unsigned idx[8], dg0[8], dg1[8];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int piece = j >> 3, jj = j & 7;
-                const int k0 = piece * 24 + 3 * jj, k1 = k0 + 1;      // half-word indices
+            for (int j = 0; j < 8; j++) {
+                const int k0 = 3 * j, k1 = k0 + 1;      // half-word indices of the call's two alleles
                 const int a = (k0 & 1) ? ((int)w[k0 >> 1] >> 16) : (int)(short)(w[k0 >> 1] & 0xffffu);
                 const int b = (k1 & 1) ? ((int)w[k1 >> 1] >> 16) : (int)(short)(w[k1 >> 1] & 0xffffu);
-                idx[j] = digit(a, Dm1) * D + digit(b, Dm1);
+                dg0[j] = digit(a, Dm1);
+                dg1[j] = digit(b, Dm1);
             }
-            if (!MASKED && c < nfull) {
+            if (sq) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) bump2<CT>(my, idx[j], idx[j + 1]);
+                for (int j = 0; j < 8; j++) idx[j] = dg0[j] * D + dg1[j];
             } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) idx[j] = tri(max(dg0[j], dg1[j]), min(dg0[j], dg1[j]));
+            }
+            if (MASKED || c >= nfull) {
                 const int64_t sb0 = (int64_t)c * kPChunkCalls + (int64_t)tid * 8;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int64_t s = sb0 + (j >> 3) * 2048 + (j & 7);
+                for (int j = 0; j < 8; j++) {
+                    const int64_t s = sb0 + j;
                     bool live = s < p.S;
                     if (MASKED) live = live && p.mask[live ? s : 0] != 0;
-                    if (live) my[(size_t)idx[j] * kPT] += 1;
+                    idx[j] = live ? idx[j] : trash;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) bump2(my, idx[j], idx[j + 1]);
+            if (p.dbg && tid == 32 && blockIdx.x == 0) { dbg_proc += clock64() - t0; dbg_chunks++; }
         }
+        const long long t_end0 = p.dbg ? clock64() : 0;
 
-        // ---- reduce the thread-private tables of this locus to the CTA table ----------------------
-        pbar();
-        const int nb = (int)(D * D);
-        unsigned int* T = hdr->T[parity];
-        for (int b = warp; b < nb; b += kPWarps) {
-            uint32_t* rowp = (uint32_t*)(table + (size_t)b * kPT);
-            unsigned sum = 0;
-            if (sizeof(CT) == 4) {
-#pragma unroll
-                for (int k = 0; k < kPT / 32; k++) {
-                    sum += rowp[lane + 32 * k];
-                    rowp[lane + 32 * k] = 0u;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < kPT / 64; k++) {
-                    const uint32_t x = rowp[lane + 32 * k];
-                    rowp[lane + 32 * k] = 0u;
+        // ---- each warp PAIR folds its own 64 threads' table columns (pair-local barrier only) ----------
+        const int nrows = sq ? (int)(D * D) : (int)(D * (D + 1u) / 2u);
+        named_sync(3 + pair, 64);
+        unsigned int* part = hdr->partial[parity][pair];
+        for (int b0 = half * 32; b0 < nrows; b0 += 64) {
+            const int b = b0 + lane;
+            if (b < nrows) {
+                uint32_t* rowp = (uint32_t*)table + (size_t)b * (kPT / 2) + pair * 32;
+                unsigned sum = 0;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const int kk = (k + lane) & 31;       // rotate: the 32 lanes hit 32 different banks
+                    const uint32_t x = rowp[kk];
+                    rowp[kk] = 0u;
                     sum += (x & 0xffffu) + (x >> 16);
                 }
+                part[b] = sum;
             }
-            sum = (unsigned)warp_sum((int)sum);
-            if (lane == 0) T[b] = sum;
         }
-        pbar();
-        // ---- derive the per-locus outputs from the pair table (the other warps run ahead) ----------
-        if (warp == 0) {
-            const int* cl = hdr->cls_len[parity];
-            const int* cq = hdr->cls_seq[parity];
-            long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
+        // the words just folded/zeroed hold BOTH warps' cells: neither may start the next locus earlier
+        named_sync(3 + pair, 64);
+        // hand the partials to warp 0; the other warps only signal and move on to the next locus
+        if (warp != 0) {
+            if (loose) {
+                named_arrive(1 + parity, kPT);
+            } else {
+                named_sync(1, kPT);
+                named_sync(2, kPT);
+            }
+        } else {
+            named_sync(loose ? 1 + parity : 1, kPT);
+            // ---- warp 0: CTA-wide table of UNORDERED pairs, then every per-locus output -----------------
+            const int nb = (int)(D * (D + 1u) / 2u);
+            unsigned int* T = hdr->T;
             for (int b = lane; b < nb; b += 32) {
-                const unsigned d0 = (unsigned)b / D, d1 = (unsigned)b % D;
-                const long long n = T[b];
-                if (n == 0) continue;
-                const bool bad = (d0 == Dm1) | (d1 == Dm1);
-                const bool m1 = (d0 == 1u) | (d1 == 1u) | bad;
-                const bool v0 = (d0 >= 2u) & (d0 < Dm1), v1 = (d1 >= 2u) & (d1 < Dm1);
+                unsigned hi = (unsigned)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+                while (tri(hi + 1u, 0u) <= (unsigned)b) hi++;
+                while (tri(hi, 0u) > (unsigned)b) hi--;
+                const unsigned lo = (unsigned)b - tri(hi, 0u);
+                unsigned t = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < kPPairs; w2++) {
+                    const unsigned int* pp = hdr->partial[parity][w2];
+                    if (sq) t += pp[hi * D + lo] + ((lo != hi) ? pp[lo * D + hi] : 0u);
+                    else t += pp[b];
+                }
+                T[b] = t;
+            }
+            // class of digit `lane` (pad digit: -2; no-call / bad: -1), exchanged by shuffles below
+            int cl = -1, cq = -1;
+            if (lane == 0) cl = cq = -2;
+            else if (lane >= 2 && lane < A + 2) {
+                cl = p.len_class[a0 + lane - 2];
+                cq = p.seq_class[a0 + lane - 2];
+            }
+            __syncwarp();
+            long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
+            for (int b0 = 0; b0 < nb; b0 += 32) {
+                const int b = min(b0 + lane, nb - 1);
+                unsigned hi = (unsigned)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+                while (tri(hi + 1u, 0u) <= (unsigned)b) hi++;
+                while (tri(hi, 0u) > (unsigned)b) hi--;
+                const unsigned lo = (unsigned)b - tri(hi, 0u);
+                const int cl_lo = __shfl_sync(0xffffffffu, cl, lo), cl_hi = __shfl_sync(0xffffffffu, cl, hi);
+                const int cq_lo = __shfl_sync(0xffffffffu, cq, lo), cq_hi = __shfl_sync(0xffffffffu, cq, hi);
+                const long long n = (b0 + lane < nb) ? (long long)T[b] : 0;
+                const bool bad = (hi == Dm1);                        // lo <= hi
+                const bool m1 = (lo == 1u) | (hi == 1u) | bad;
+                const bool vlo = (lo >= 2u) & (lo < Dm1), vhi = (hi >= 2u) & (hi < Dm1);
                 if (bad) n_bad += n;
-                if (v0 | v1) n_non += n;
+                if (vlo | vhi) n_non += n;
                 if (!m1) {
                     n_full += n;
-                    if ((d0 == 0u) | (d1 == 0u)) n_pad += n;
-                    if (d0 == d1) h_idx += n;
-                    if (cl[d0] == cl[d1]) h_len += n;
-                    if (cq[d0] == cq[d1]) h_seq += n;
+                    if (lo == 0u) n_pad += n;
+                    if (lo == hi) h_idx += n;
+                    if (cl_lo == cl_hi) h_len += n;
+                    if (cq_lo == cq_hi) h_seq += n;
                 }
             }
             n_full = warp_sum_ll(n_full); n_non = warp_sum_ll(n_non); n_pad = warp_sum_ll(n_pad);
@@ -289,12 +352,22 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             }
             for (int a = lane; a < A; a += 32) {
                 const unsigned d = (unsigned)a + 2u;
-                unsigned cnt = 0;
-                for (unsigned e = 0; e < D; e++) cnt += T[d * D + e] + T[e * D + d];
+                unsigned cnt = 2u * T[tri(d, d)];
+                for (unsigned e = 0; e < d; e++) cnt += T[tri(d, e)];
+                for (unsigned e = d + 1u; e < D; e++) cnt += T[tri(e, d)];
                 p.ac[a0 + a] = (int)cnt;
             }
+            __syncwarp();
+            if (!loose) named_sync(2, kPT);
         }
+        if (p.dbg && tid == 32 && blockIdx.x == 0) dbg_end += clock64() - t_end0;
         parity ^= 1;
+        l = l_next;
+        A = A_next;
+        a0 = a0_next;
+    }
+    if (p.dbg && tid == 32 && blockIdx.x == 0) {
+        p.dbg[0] = dbg_wait; p.dbg[1] = dbg_proc; p.dbg[2] = dbg_end; p.dbg[3] = dbg_chunks;
     }
 }
 
@@ -464,37 +537,40 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
     const bool fast = (ctx->P == 2 && S >= kMinFastSamples);
     sp.fast_enabled = fast ? 1 : 0;
+    sp.dbg = nullptr;
+    if (getenv("TRT_SCAN_DEBUG")) {
+        TRT_TRY(trt_ensure(ctx, ctx->work_counter, 64));
+        TRT_CUDA(cudaMemsetAsync(ctx->work_counter.p, 0, 64, ctx->stream));
+        sp.dbg = (unsigned long long*)ctx->work_counter.p;
+    }
+    sp.stream_only = getenv("TRT_SCAN_STREAM_ONLY") ? 1 : 0;   // HBM-read ceiling of this access pattern (calibration)
     // which tiers occur in this block
-    int n_tier[4] = {0, 0, 0, 0};
-    int max_in_tier[4] = {0, 0, 0, 0};
+    int n_tier[TIER_COUNT] = {0};
+    int max_in_tier[TIER_COUNT] = {0};
+    int rows_in_tier[TIER_COUNT] = {0};
     for (int64_t l = 0; l < L; l++) {
         const int A = ctx->h_locus_off[l + 1] - ctx->h_locus_off[l];
         const int t = fast ? scan_tier(A) : TIER_GENERIC;
         n_tier[t]++;
         max_in_tier[t] = std::max(max_in_tier[t], A);
+        rows_in_tier[t] = std::max(rows_in_tier[t], pairs_rows(A));
     }
     const int grid_persist = (int)std::min<int64_t>(L, ctx->sm_count);
-    if (n_tier[TIER_PAIRS32]) {
-        const int D = max_in_tier[TIER_PAIRS32] + 3;
-        const size_t smem = (size_t)kPStages * kPChunkBytes + sizeof(PairHeader) + (size_t)D * D * kPT * 4;
+    const size_t smem_limit = (size_t)ctx->max_smem_optin;
+    for (int t = TIER_PAIRS_A; t <= TIER_PAIRS_B; t++) {
+        if (!n_tier[t]) continue;
+        const int rows = rows_in_tier[t];
+        const size_t table = (size_t)(rows + 1) * kPRowBytes;
+        int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
+        stages = std::max(kPMinStages, std::min(kPMaxStages, stages));
+        const size_t smem = (size_t)stages * kPChunkBytes + sizeof(PairHeader) + table;
+        if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
         if (d_mask) {
-            TRT_TRY(set_smem(ctx, scan_pairs_kernel<uint32_t, true>, smem));
-            scan_pairs_kernel<uint32_t, true><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, TIER_PAIRS32, D);
+            TRT_TRY(set_smem(ctx, scan_pairs_kernel<true>, smem));
+            scan_pairs_kernel<true><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
         } else {
-            TRT_TRY(set_smem(ctx, scan_pairs_kernel<uint32_t, false>, smem));
-            scan_pairs_kernel<uint32_t, false><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, TIER_PAIRS32, D);
-        }
-        TRT_KERNEL_CHECK();
-    }
-    if (n_tier[TIER_PAIRS16]) {
-        const int D = max_in_tier[TIER_PAIRS16] + 3;
-        const size_t smem = (size_t)kPStages * kPChunkBytes + sizeof(PairHeader) + (size_t)D * D * kPT * 2;
-        if (d_mask) {
-            TRT_TRY(set_smem(ctx, scan_pairs_kernel<uint16_t, true>, smem));
-            scan_pairs_kernel<uint16_t, true><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, TIER_PAIRS16, D);
-        } else {
-            TRT_TRY(set_smem(ctx, scan_pairs_kernel<uint16_t, false>, smem));
-            scan_pairs_kernel<uint16_t, false><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, TIER_PAIRS16, D);
+            TRT_TRY(set_smem(ctx, scan_pairs_kernel<false>, smem));
+            scan_pairs_kernel<false><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
         }
         TRT_KERNEL_CHECK();
     }
@@ -509,6 +585,13 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
             scan_wide_kernel<false><<<grid_persist, kWThreads, smem, ctx->stream>>>(sp, amax);
         }
         TRT_KERNEL_CHECK();
+    }
+    if (sp.dbg) {
+        unsigned long long h[4];
+        TRT_CUDA(cudaMemcpyAsync(h, sp.dbg, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[scan dbg] wait=%llu proc(incl wait)=%llu end=%llu chunks=%llu  per-chunk wait=%.0f proc=%.0f\n", h[0], h[1], h[2], h[3],
+                h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0);
     }
     if (n_tier[TIER_GENERIC]) {
         const int warps_per_block = 8;

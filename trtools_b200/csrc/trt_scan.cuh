@@ -17,16 +17,25 @@ struct ScanParams {
     int32_t* ac;           // [nA]
     long long* lc;         // [L][TRT_LC_N]
     int fast_enabled;      // the TMA tiers are in use (diploid, enough samples)
+    unsigned long long* dbg;   // optional [4]: cycles waiting / processing / end-of-locus, chunks (warp 1 of CTA 0)
+    int stream_only;       // calibration: consumers only drain the TMA ring (results are meaningless)
 };
 
-enum { TIER_PAIRS32 = 0, TIER_PAIRS16 = 1, TIER_WIDE = 2, TIER_GENERIC = 3 };
-constexpr int kPairsMaxAllelesU32 = 9;    // (9+3)^2 bins x 256 threads x 4 B = 144 KB
-constexpr int kPairsMaxAllelesU16 = 14;   // (14+3)^2 bins x 256 threads x 2 B = 144.5 KB
-constexpr int kWideMaxAlleles = 96;       // 96 alleles x 512 threads x 2 B = 96 KB
+enum { TIER_PAIRS_A = 0, TIER_PAIRS_B = 1, TIER_WIDE = 2, TIER_GENERIC = 3, TIER_COUNT = 4 };
+constexpr int kSquareRows = 100;            // ordered digit pairs while (A+3)^2 <= 100 rows (A <= 7)
+constexpr int kPairsMainMaxAlleles = 9;     // tier A: A <= 9 (unordered pairs need 78 rows) -> table <= 101 KB
+constexpr int kPairsMaxAlleles = 13;        // tier B: unordered pairs, 136 rows x 1 KB (3 ring stages still fit)
+constexpr int kWideMaxAlleles = 96;         // 96 alleles x 512 threads x 2 B = 96 KB
 constexpr int kMinFastSamples = 2048;
 
 __host__ __device__ __forceinline__ int scan_tier(int A) {
-    return A <= kPairsMaxAllelesU32 ? TIER_PAIRS32 : (A <= kPairsMaxAllelesU16 ? TIER_PAIRS16 : (A <= kWideMaxAlleles ? TIER_WIDE : TIER_GENERIC));
+    return A <= kPairsMainMaxAlleles ? TIER_PAIRS_A
+           : (A <= kPairsMaxAlleles ? TIER_PAIRS_B : (A <= kWideMaxAlleles ? TIER_WIDE : TIER_GENERIC));
+}
+__host__ __device__ __forceinline__ bool pairs_square(int A) { return (A + 3) * (A + 3) <= kSquareRows; }
+__host__ __device__ __forceinline__ int pairs_rows(int A) {
+    const int D = A + 3;
+    return pairs_square(A) ? D * D : D * (D + 1) / 2;
 }
 
 int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G);
