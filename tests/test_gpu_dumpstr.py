@@ -88,7 +88,7 @@ def test_dumpstr_cli_matches_reference(golden_dir, data_dir, tmp_path, name, vcf
         ac = [] if (ac == 0 and len(r["AC"]) == 0) else ([ac] if isinstance(ac, int) else list(ac))
         assert ac == r["AC"] or (r["AC"] == [] and ac == [0]), (i, ac, r["AC"])
         assert rec.INFO["REFAC"] == r["REFAC"], i
-        assert_close(rec.INFO["HET"], r["HET"], "HET %d" % i, rel=2e-6)      # INFO floats are written with %g
+        assert_close(rec.INFO["HET"], r["HET"], "HET %d" % i, rel=1e-5)      # INFO floats are written with %g, read as float32
         assert_close(rec.INFO["HWEP"], r["HWEP"], "HWEP %d" % i, rel=2e-5, abs_tol=1e-300)
         if i < len(ref["calls"]):
             assert [str(x) for x in rec.format("FILTER")] == ref["calls"][i]["filter_text"], i

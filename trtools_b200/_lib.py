@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtrtools_b200.so")
+LIB_PATH = os.environ.get("TRTOOLS_B200_LIB", os.path.join(HERE, "libtrtools_b200.so"))
 
 TRT_OK = 0
 TRT_ENODEV, TRT_ECUDA, TRT_EINVAL, TRT_ESTATE, TRT_ENOMEM, TRT_ERECORD, TRT_ENCCL = -1, -2, -3, -4, -5, -6, -7

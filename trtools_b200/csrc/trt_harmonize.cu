@@ -187,13 +187,21 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
 
     // ---- 3. homopolymer run of the full REF (utils.py:340-360) ---------------------------------
     {
-        const char* r = P.seqs + ref_off;
+        // full REF when flanks exist (filters.py:205-208), else the (possibly fabricated) ref allele
+        AlleleStr r;
+        if (flanked) {
+            r.base = P.seqs + ref_off;
+            r.len = ref_n;
+            r.mlen = 0;
+        } else {
+            r = make_str(0);
+        }
         int best = 0;
-        for (int i = lane; i < ref_n; i += 32) {
-            if (i == 0 || up(r[i]) != up(r[i - 1])) {
+        for (int i = lane; i < r.len; i += 32) {
+            if (i == 0 || r.at(i) != r.at(i - 1)) {
                 int j = i + 1;
-                const char c = up(r[i]);
-                while (j < ref_n && up(r[j]) == c) j++;
+                const char c = r.at(i);
+                while (j < r.len && r.at(j) == c) j++;
                 best = max(best, j - i);
             }
         }

@@ -316,6 +316,9 @@ class Variant:
         else:
             parts = [r.split(',') for r in raw]
             ncol = max((len(p) for p in parts), default=1)
+            number = hrec.get('Number', '1') if hrec else '1'
+            if str(number).isdigit():      # htslib sizes fixed-Number fields from the header
+                ncol = max(ncol, int(number))
             if typ == 'Integer':
                 out = np.full((len(raw), ncol), INT32_VECTOR_END, dtype=np.int32)
                 for i, p in enumerate(parts):
