@@ -1,0 +1,159 @@
+"""
+GPU parity tests for the associaTR path (trt_assoc_set_design / trt_assoc_ols and the drop-in
+``associaTR.main``) against the unmodified reference's outputs (plink2-pinned fixtures and synthetic
+blocks) and against the oracle at full precision (1e-6 relative on p, beta, se, R^2; integers exact).
+"""
+import argparse
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+_cache = {}
+
+
+def fixture(golden_dir, name):
+    from oracle.records import load_loci
+    if name not in _cache:
+        _cache[name] = load_loci(os.path.join(golden_dir, name + ".npz"))
+    return _cache[name]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from trtools_b200 import _lib
+    return _lib.default_context()
+
+
+def _assoc_args(out, vcf, traits, **kw):
+    ns = argparse.Namespace(outfile=out, tr_vcf=vcf, phenotype_name="test_pheno", traits=traits, vcftype=None,
+                            same_samples=True, sample_list=None, region=None, non_major_cutoff=0, beagle_dosages=False,
+                            plotting_phenotype=None, paired_genotype_plot=False, plot_phenotype_residuals=False,
+                            plotting_ci_alphas=[], imputed_ukb_strs_paper_period_check=False, block_size=100)
+    for k, v in kw.items():
+        assert hasattr(ns, k), k
+        setattr(ns, k, v)
+    return ns
+
+
+def _compare_tsv(got: str, want: str):
+    g, w = got.splitlines(), want.splitlines()
+    assert len(g) == len(w)
+    assert g[0] == w[0]
+    for i, (a, b) in enumerate(zip(g[1:], w[1:])):
+        ca, cb = a.split("\t"), b.split("\t")
+        assert ca[:5] == cb[:5], (i, ca[:5], cb[:5])
+        assert ca[9:] == cb[9:], (i, ca[9:], cb[9:])
+        if cb[5] == "nan":
+            assert ca[5:9] == cb[5:9], i
+            continue
+        # p is printed with 3 significant digits: allow the last digit to differ by one unit
+        assert abs(float(ca[5]) - float(cb[5])) <= 1.01e-2 * float(cb[5]), (i, ca[5], cb[5])
+        for c in (6, 7, 8):
+            assert_close(float(ca[c]), float(cb[c]), "row %d col %d" % (i, c), rel=1e-6)
+
+
+@pytest.mark.parametrize("key,traits,kw", [
+    ("single", ["traits_0.npy"], {}),
+    ("combined", ["traits_0.npy", "traits_1.npy"], {}),
+    ("cutoff_5", ["traits_0.npy"], {"non_major_cutoff": 5}),
+    ("cutoff_20", ["traits_0.npy", "traits_1.npy"], {"non_major_cutoff": 20}),
+    ("single_40", ["traits_0.npy"], {"sample_list": "samples_6_to_45.txt"}),
+    ("multi", ["traits_0.npy"], {"vcf": "many_samples_multiallelic.vcf.gz"}),
+    ("multi_cutoff", ["traits_0.npy", "traits_1.npy"], {"vcf": "many_samples_multiallelic.vcf.gz", "non_major_cutoff": 6}),
+])
+def test_associatr_cli_matches_reference(golden_dir, data_dir, tmp_path, key, traits, kw):
+    """associaTR.main on the reference's plink2-pinned fixtures == the unmodified reference's TSV."""
+    import contextlib
+    import io
+    from trtools_b200 import associaTR
+    want = json.load(open(os.path.join(golden_dir, "associatr.json")))[key]
+    kw = dict(kw)
+    vcf = os.path.join(data_dir, kw.pop("vcf", "many_samples_biallelic.vcf.gz"))
+    if "sample_list" in kw:
+        kw["sample_list"] = os.path.join(data_dir, kw["sample_list"])
+    out = str(tmp_path / "assoc.tsv")
+    with contextlib.redirect_stdout(io.StringIO()):
+        associaTR.main(_assoc_args(out, vcf, [os.path.join(data_dir, t) for t in traits], **kw))
+    _compare_tsv(open(out).read(), want)
+
+
+@pytest.mark.parametrize("name", ["synth_small", "synth_wide"])
+@pytest.mark.parametrize("key,cutoff,use_mask", [("assoc", 20, False), ("assoc_subset", 5, True)])
+def test_assoc_kernels_vs_reference_and_oracle_on_synthetic(golden_dir, ctx, name, key, cutoff, use_mask):
+    """C-ABI level on the synthetic golden blocks: filter codes / n_tested exact vs the reference's rows; p, beta,
+    se, R^2 within 1e-6 of the oracle's full-precision OLS (pinv) on the same arrays."""
+    from oracle import assoc as oassoc, trh as otrh
+    from oracle.records import LocusAsVariant
+    from trtools_b200 import _lib, block
+    loci, extra, _ = fixture(golden_dir, name)
+    traits = np.array(extra["traits"], dtype=float)
+    S = loci[0].gt.shape[0]
+    mask = np.array(extra["sample_mask"], dtype=bool) if use_mask else None
+    design = oassoc.prepare_design([traits], S, mask)
+    blk = block.build_block(ctx, "hipstr", [LocusAsVariant(l) for l in loci])
+    ctx.assoc_set_design(design.covars, design.outcome, np.nonzero(design.sample_filter)[0].astype(np.int32))
+    res = ctx.assoc_ols(cutoff)
+    lines = extra[key].splitlines()[1:]
+    reasons = {_lib.AF_NO_CALLED: 'No called samples', _lib.AF_ONE_ALLELE: 'Only one called allele',
+               _lib.AF_NCOVARS: 'n covars >= n samples', _lib.AF_NON_MAJOR: 'non-major allele count<{}'.format(cutoff)}
+    n_ok = 0
+    for i, l in enumerate(loci):
+        ref_cols = lines[i].split("\t")
+        assert int(ref_cols[3]) == int(res["n_tested"][i]), i
+        code = int(res["filter_code"][i])
+        assert (ref_cols[4] == 'False') == (code == _lib.AF_OK), (i, ref_cols[4], code)
+        if code != _lib.AF_OK:
+            assert reasons[code] == ref_cols[4], (i, reasons[code], ref_cols[4])
+            continue
+        h = otrh.harmonize(l)
+        loaded = oassoc.load_locus(l, h, design.sample_filter.copy(), cutoff)
+        row = oassoc.regress_locus(loaded, design)
+        what = "{} {} locus {}".format(name, key, i)
+        assert_close(res["p"][i], row.p, what + " p", abs_tol=1e-300)
+        assert_close(res["coef"][i] * design.pheno_std, row.coef, what + " coef")
+        assert_close(res["se"][i] * design.pheno_std, row.se, what + " se")
+        assert_close(res["r2"][i], row.r2, what + " r2", rel=1e-6, abs_tol=1e-12)
+        n_ok += 1
+    assert n_ok > 0
+
+
+def test_assoc_extreme_pvalues_and_missingness(ctx):
+    """Strong effects (p down to ~1e-300) and heavy per-locus missingness: the t-test tail and the exact
+    down-dates stay within 1e-6 of scipy/numpy."""
+    from oracle import assoc as oassoc, trh as otrh
+    from oracle.records import Locus, LocusAsVariant
+    from trtools_b200 import _lib, block
+    rng = np.random.default_rng(3)
+    S = 6000
+    loci = []
+    base = rng.integers(0, 3, size=(S, 2))
+    for j, miss in enumerate([0.0, 0.02, 0.4, 0.9]):
+        gt = np.concatenate([base, np.ones((S, 1), int)], axis=1).astype(np.int16)
+        m = rng.random(S) < miss
+        gt[m, 0] = -1
+        gt[m, 1] = -2
+        loci.append(Locus("hipstr", "1", 100 + 50 * j, "ACACACAC", ["ACACAC", "ACACACACACAC"],
+                          {"START": 100 + 50 * j, "END": 107 + 50 * j, "PERIOD": 2}, gt))
+    g = np.array([4.0, 3.0, 6.0])[base].sum(axis=1)
+    pcs = rng.standard_normal((S, 10))
+    for effect in (0.0, 0.05, 1.0, 5.0):
+        trait = effect * g + pcs[:, 0] * 0.3 + rng.standard_normal(S)
+        traits = np.hstack([trait[:, None], pcs])
+        design = oassoc.prepare_design([traits], S, None)
+        blk = block.build_block(ctx, "hipstr", [LocusAsVariant(l) for l in loci])
+        ctx.assoc_set_design(design.covars, design.outcome, np.arange(S, dtype=np.int32))
+        res = ctx.assoc_ols(0)
+        for i, l in enumerate(loci):
+            h = otrh.harmonize(l)
+            row = oassoc.regress_locus(oassoc.load_locus(l, h, design.sample_filter.copy(), 0), design)
+            what = "effect {} locus {}".format(effect, i)
+            assert int(res["filter_code"][i]) == _lib.AF_OK
+            assert_close(res["p"][i], row.p, what + " p", abs_tol=1e-305)
+            assert_close(res["coef"][i] * design.pheno_std, row.coef, what + " coef", rel=1e-6, abs_tol=1e-12)
+            assert_close(res["se"][i] * design.pheno_std, row.se, what + " se")
+            assert_close(res["r2"][i], row.r2, what + " r2", rel=1e-6, abs_tol=1e-12)

@@ -366,6 +366,23 @@ class Context:
         self.check(self.lib.trt_locus_filters(self.h, arr, n, 1 if use_length else 0, C.byref(out)))
         return res
 
+    def assoc_set_design(self, covars: np.ndarray, outcome: np.ndarray, sample_index: np.ndarray):
+        """Standardised design (associaTR.py:190-194): covars float64 [n, K] with column 0 reserved for the
+        genotype and column 1 = 1; outcome float64 [n]; sample_index int32 [n] = VCF sample of each row."""
+        cv = _c(covars, np.float64)
+        oc = _c(outcome, np.float64)
+        si = _c(sample_index, np.int32)
+        assert cv.ndim == 2 and cv.shape[0] == oc.shape[0] == si.shape[0]
+        self.check(self.lib.trt_assoc_set_design(self.h, _ptr(cv), _ptr(oc), _ptr(si), cv.shape[0], cv.shape[1]))
+
+    def assoc_ols(self, non_major_cutoff: float) -> dict:
+        L, nA = self.L, self.nA
+        res = dict(filter_code=np.empty(L, np.int32), n_tested=np.empty(L, np.int64), p=np.empty(L), coef=np.empty(L),
+                   se=np.empty(L), r2=np.empty(L), std_g=np.empty(L), ac_len=np.empty(nA, np.int32))
+        out = AssocOut(**{k: _ptr(v) for k, v in res.items()})
+        self.check(self.lib.trt_assoc_ols(self.h, float(non_major_cutoff), C.byref(out)))
+        return res
+
     def synth_fill(self, seed, locus_offset, cum_freq, miss_thresh, half_thresh, with_format=True):
         cf = _c(cum_freq, np.uint32)
         self.check(self.lib.trt_synth_fill(self.h, int(seed), int(locus_offset), self.L, self.S, _ptr(cf),

@@ -61,7 +61,8 @@ struct trt_ctx {
     bool    have_packed = false;
 
     // stats scratch (device)
-    DevBuf  ac, lc, group_masks, stat_f64, stat_i32, work_counter;
+    DevBuf  ac, ac_part, lc, group_masks, stat_f64, stat_i32, work_counter;
+    bool    want_ac_part = false;
     // dumpSTR scratch
     DevBuf  cf_specs, call_mask, trig, samp_counts, samp_dp, misc;
     // associaTR

@@ -71,6 +71,12 @@ __global__ void __launch_bounds__(256) scan_generic_kernel(ScanParams p) {
                 if (kq < q1) { q2 = q1; q1 = kq; } else if (kq < q2) q2 = kq;
             }
             if (any_called) n_non++;
+            if (any_m1 && any_called && p.ac_part) {
+                for (int h = 0; h < P; h++) {
+                    const int a = g[h];
+                    if (a >= 0 && a < A) atomicAdd(&p.ac_part[a0 + a], 1);
+                }
+            }
             if (!any_m1) {
                 n_full++;
                 if (any_pad) n_pad++;
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 for (unsigned e = 0; e < d; e++) cnt += T[tri(d, e)];
                 for (unsigned e = d + 1u; e < D; e++) cnt += T[tri(e, d)];
                 p.ac[a0 + a] = (int)cnt;
+                if (p.ac_part) p.ac_part[a0 + a] = (int)(T[tri(d, 1u)] + T[tri(Dm1, d)]);   // partner '.' or invalid
             }
             __syncwarp();
             if (!loose) named_sync(2, kPT);
@@ -469,6 +476,10 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
                 const bool m1 = (a == -1) | (b == -1) | bad;
                 n_bad += bad;
                 n_non += (va | vb);
+                if (m1 && p.ac_part) {
+                    if (va) atomicAdd(&p.ac_part[a0 + a], 1);
+                    if (vb) atomicAdd(&p.ac_part[a0 + b], 1);
+                }
                 if (!m1) {
                     n_full++;
                     n_pad += ((a == -2) | (b == -2));
@@ -534,6 +545,7 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     sp.hflags = (const int32_t*)ctx->hflags.p;
     sp.mask = d_mask;
     sp.ac = (int32_t*)ctx->ac.p + (size_t)g * nA;
+    sp.ac_part = ctx->want_ac_part ? (int32_t*)ctx->ac_part.p + (size_t)g * nA : nullptr;
     sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
     const bool fast = (ctx->P == 2 && S >= kMinFastSamples);
     sp.fast_enabled = fast ? 1 : 0;

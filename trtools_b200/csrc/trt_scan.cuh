@@ -15,6 +15,7 @@ struct ScanParams {
     const int32_t* hflags;
     const uint8_t* mask;   // [S] bytes or null
     int32_t* ac;           // [nA]
+    int32_t* ac_part;      // optional [nA], zero-initialised: alleles carried by PARTIALLY called samples (a/.)
     long long* lc;         // [L][TRT_LC_N]
     int fast_enabled;      // the TMA tiers are in use (diploid, enough samples)
     unsigned long long* dbg;   // optional [4]: cycles waiting / processing / end-of-locus, chunks (warp 1 of CTA 0)
