@@ -129,6 +129,52 @@ def cpu_statstr(n_loci, S, cores, seed=SEED):
     return done / wall, done, wall
 
 
+def _cpu_other_worker(args):
+    """oracle ports of the dumpSTR and associaTR per-locus paths on a few loci (seconds per locus on one core)."""
+    lo, hi, S, seed = args
+    from oracle import dumpstr as od, assoc as oassoc, trh as otrh
+    from oracle.records import synth_to_loci
+    from trtools_b200 import synth
+    sl = synth.make_loci(hi, seed=seed)
+    calls = synth.fill_calls(sl, S, slice(lo, hi))
+    sub = synth.SynthLoci(seed=sl.seed, n_loci=hi - lo, chrom=sl.chrom[lo:hi], pos=sl.pos[lo:hi], start=sl.start[lo:hi],
+                          end=sl.end[lo:hi], period=sl.period[lo:hi], ref=sl.ref[lo:hi], alts=sl.alts[lo:hi],
+                          n_alleles=sl.n_alleles[lo:hi], cum_freq=sl.cum_freq[lo:hi], locus_offset=lo)
+    loci = synth_to_loci(sub, calls, with_fmt=True)
+    cf = [od.hipstr_flank_indels(0.15), od.min_value("HipSTRCallMinDepth", "DP", 20)]
+    lf = [od.LocusFilter("hwe", 1e-4, False)]
+    sinfo, linfo = od.new_sample_info(S, cf), od.new_loc_info(lf)
+    t0 = time.perf_counter()
+    for l in loci:
+        h = otrh.harmonize(l)
+        r = od.apply_call_filters(l, cf, sinfo)
+        od.apply_locus_filters(l, h, r.gt, lf, linfo)
+        od.recompute_info(h, r.gt, False)
+    t_dump = time.perf_counter() - t0
+    rng = np.random.default_rng(seed)
+    traits = np.hstack([rng.standard_normal((S, 1)), rng.standard_normal((S, 10))])
+    design = oassoc.prepare_design([traits], S, None)
+    t0 = time.perf_counter()
+    for l in loci:
+        h = otrh.harmonize(l)
+        oassoc.regress_locus(oassoc.load_locus(l, h, design.sample_filter.copy(), 20), design).to_text()
+    t_assoc = time.perf_counter() - t0
+    return t_dump, t_assoc, len(loci)
+
+
+def cpu_other_tools(n_loci, S, cores, seed=SEED):
+    import multiprocessing as mp
+    per = max(1, n_loci // cores)
+    jobs = [(i * per, (i + 1) * per, S, seed) for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_other_worker, jobs)
+    done = sum(r[2] for r in res)
+    return {"dumpSTR": {"value": done / max(r[0] for r in res), "unit": "loci/s", "cores": cores, "kind": "port",
+                        "sample": "{} loci x {} samples".format(done, S)},
+            "associaTR": {"value": done / max(r[1] for r in res), "unit": "loci/s", "cores": cores, "kind": "port",
+                          "sample": "{} loci x {} samples".format(done, S)}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,13 +213,8 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from trtools_b200 import _lib, synth
+    from trtools_b200 import _lib, synth, dist as tdist
+    dist = tdist.init("nccl") if world > 1 else None
 
     ctx = _lib.Context(local_rank)
     info = ctx.device_info()
@@ -198,12 +239,8 @@ def run_gpu(args):
         """NCCL gather of the fixed-width per-locus result rows (north_star: the only collective)."""
         if dist is None:
             return
-        import torch
         rows = np.stack([st[k][0] for k in ("thresh", "het", "entropy", "mean", "mode", "var", "hwep")], axis=1)
-        t = torch.from_numpy(rows).cuda(non_blocking=True)
-        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, out, dst=0)
-        torch.cuda.synchronize()
+        tdist.gather_table(dist, rows)
 
     for _ in range(max(args.warmup, 0)):
         gather_rows(step())
@@ -227,11 +264,7 @@ def run_gpu(args):
     # then the max over ranks
     ms = max(ms, 0.0)
     step_ms = max(ms, wall_ms) / args.steps
-    if dist is not None:
-        import torch
-        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
+    step_ms = tdist.max_over_ranks(dist, step_ms)
     value = world * L / (step_ms / 1000.0)
 
     # ---- roofline of the dominant kernel (GT scan): 6 algorithmic bytes per call ----------------
@@ -282,13 +315,64 @@ def run_gpu(args):
         e2e_step()
     ctx.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = tdist.max_over_ranks(dist, e2e_ms)
     e2e_value = world * L / (e2e_ms / 1000.0)
     ctx.free_pinned(host_gt)
+
+    # ---- the other two tools of the metric on the same resident block (device-timed, results copied to host) ----
+    tools = {}
+    if not args.statstr_only:
+        from trtools_b200 import _lib as L_
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=5)   # DP + DFLANKINDEL
+        ctx.block_set_alleles(*tables)
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        rng = np.random.default_rng(SEED + rank)
+        traits = np.hstack([rng.standard_normal((S, 1)), rng.standard_normal((S, 10))])
+        covars = np.hstack([np.full((S, 1), -1.0), traits])
+        covars = (covars - covars.mean(axis=0)) / np.maximum(covars.std(axis=0), 1e-300)
+        outcome = covars[:, 1].copy()
+        covars[:, 1] = 1.0
+        ctx.assoc_set_design(covars, outcome, np.arange(S, dtype=np.int32))
+
+        def timed(fn, steps, warm):
+            for _ in range(warm):
+                fn()
+            scan = []
+            barrier()
+            ctx.stopwatch_start()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+                scan.append(ctx.last_scan_ms())
+            dev = ctx.stopwatch_stop()
+            wall = (time.perf_counter() - t0) * 1000.0
+            ms_ = max(dev, wall) / steps
+            return tdist.max_over_ranks(dist, ms_), float(np.mean(scan))
+
+        ms_a, k_a = timed(lambda: ctx.assoc_ols(20.0), max(2, min(args.steps, 5)), 2)
+        tools["associaTR"] = {"value": world * L / (ms_a / 1000.0), "unit": "loci/s", "ms_per_step": ms_a,
+                              "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; scan + FP64 moments "
+                                          "+ down-dates + solve, results to host",
+                              "kernel_ms": k_a, "algorithmic_bytes_per_call": 18,
+                              "roofline_frac": (18.0 * L * S / (k_a / 1000.0) / 1e9) / peak if k_a > 0 else None}
+        cf_specs = [(L_.CF_RATIO_GT, L_.FMT_DFLANKINDEL, 0.15), (L_.CF_MIN, L_.FMT_DP, 20)]
+        counts = np.zeros((2, S), np.int64)
+        numcalls = np.zeros(S, np.int64)
+        totaldp = np.zeros(S)
+
+        def dump_step():
+            ctx.call_filters(cf_specs, L_.FMT_DP, counts, numcalls, totaldp, want_mask=False, want_trigger=False, want_gt=False)
+            k1 = ctx.last_scan_ms()
+            ctx.locus_filters([(L_.LF_HWE, 1e-4)], False)
+            dump_step.kernel = k1 + ctx.last_scan_ms()
+
+        ms_d, _ = timed(dump_step, max(2, min(args.steps, 5)), 2)
+        tools["dumpSTR"] = {"value": world * L / (ms_d / 1000.0), "unit": "loci/s", "ms_per_step": ms_d,
+                            "workload": "call filters min-call-DP 20 + max-call-flank-indel 0.15 (masked GT written), locus filter "
+                                        "HWE 1e-4 on the masked genotypes, sample/locus accumulators to host",
+                            "kernel_ms": dump_step.kernel, "algorithmic_bytes_per_call": 26,
+                            "roofline_frac": (26.0 * L * S / (dump_step.kernel / 1000.0) / 1e9) / peak}
 
     if rank == 0:
         cores = os.cpu_count() or 1
@@ -299,6 +383,8 @@ def run_gpu(args):
             cpu = {"value": v, "unit": "loci/s", "cores": cores, "kind": "port",
                    "sample": "{} loci x {} samples, statSTR 6 stats (sequence grouping), {} processes, {:.1f} s".format(
                        done, S, cores, wall)}
+            if not args.statstr_only:
+                cpu["tools"] = cpu_other_tools(cores, S, cores)
         out = {
             "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -312,7 +398,7 @@ def run_gpu(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "tools": tools,
             "timing": {"device_ms_total": ms, "wall_ms_total": wall_ms},
         }
         print(json.dumps(out), flush=True)
@@ -331,6 +417,7 @@ def main():
     ap.add_argument("--samples", type=int, default=50000)
     ap.add_argument("--e2e-block", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--statstr-only", action="store_true", help="skip the dumpSTR / associaTR measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

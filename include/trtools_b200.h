@@ -284,7 +284,7 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out);
  * Device twin of trtools_b200/synth.py::fill_calls — bit-identical arrays.                        */
 int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset, int64_t n_loci, int64_t n_samples,
                    const uint32_t* cum_freq_host /*[n_loci][16]*/, uint32_t miss_thresh, uint32_t half_thresh,
-                   int with_format /* also DP/DSTUTTER/DFLANKINDEL/Q */);
+                   int with_format /* bitmask: 1 DP, 2 DSTUTTER, 4 DFLANKINDEL, 8 Q (1 alone = all four) */);
 /* after trt_synth_fill the block's GT (and FORMAT) arrays are the generated ones; these copy
  * a locus range back for parity checks                                                          */
 int trt_block_get_gt(trt_ctx* ctx, int64_t locus0, int64_t n, int16_t* out_host /*[n][S][P+1]*/);

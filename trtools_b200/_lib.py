@@ -386,7 +386,7 @@ class Context:
     def synth_fill(self, seed, locus_offset, cum_freq, miss_thresh, half_thresh, with_format=True):
         cf = _c(cum_freq, np.uint32)
         self.check(self.lib.trt_synth_fill(self.h, int(seed), int(locus_offset), self.L, self.S, _ptr(cf),
-                                           int(miss_thresh), int(half_thresh), 1 if with_format else 0))
+                                           int(miss_thresh), int(half_thresh), int(with_format) if not isinstance(with_format, bool) else (15 if with_format else 0)))
 
     def block_get_gt(self, locus0, n) -> np.ndarray:
         out = np.empty((n, self.S, self.P + 1), np.int16)

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(uint64_t seed, int64_t 
             row[s * 3 + 0] = (int16_t)a0;
             row[s * 3 + 1] = (int16_t)a1;
             row[s * 3 + 2] = (int16_t)ph;
-            if (dp) {
+            if (dp || dst || dfl || q) {
                 const uint64_t h_dp = call_hash(keys[F_DP], s), h_dp2 = call_hash(keys[F_DP2], s);
                 long long d = (long long)__popcll(h_dp) + (long long)(h_dp2 % 33ull) - 16;
                 if (d < 0) d = 0;
@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(uint64_t seed, int64_t 
                     dv = fl = st = INT_MIN;
                     qv = __int_as_float(0x7fc00000);
                 }
-                dp[l * S + s] = dv;
-                dfl[l * S + s] = fl;
-                dst[l * S + s] = st;
-                q[l * S + s] = qv;
+                if (dp) dp[l * S + s] = dv;
+                if (dfl) dfl[l * S + s] = fl;
+                if (dst) dst[l * S + s] = st;
+                if (q) q[l * S + s] = qv;
             }
         }
     }
@@ -111,16 +111,16 @@ extern "C" int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset,
     if (L) TRT_CUDA(cudaMemcpyAsync(ctx->misc.p, cum_freq_host, (size_t)L * 16 * 4, cudaMemcpyHostToDevice, ctx->stream));
     int32_t *dp = nullptr, *dst = nullptr, *dfl = nullptr;
     float* q = nullptr;
-    if (with_format) {
+    const int ids[4] = {TRT_FMT_DP, TRT_FMT_DSTUTTER, TRT_FMT_DFLANKINDEL, TRT_FMT_Q};
+    if (with_format == 1) with_format = 15;   // "all four fields"
+    {
         const size_t b = (size_t)L * S * 4 + 16;
-        TRT_TRY(trt_ensure(ctx, ctx->fmt_buf[TRT_FMT_DP], b));
-        TRT_TRY(trt_ensure(ctx, ctx->fmt_buf[TRT_FMT_DSTUTTER], b));
-        TRT_TRY(trt_ensure(ctx, ctx->fmt_buf[TRT_FMT_DFLANKINDEL], b));
-        TRT_TRY(trt_ensure(ctx, ctx->fmt_buf[TRT_FMT_Q], b));
-        dp = (int32_t*)ctx->fmt_buf[TRT_FMT_DP].p;
-        dst = (int32_t*)ctx->fmt_buf[TRT_FMT_DSTUTTER].p;
-        dfl = (int32_t*)ctx->fmt_buf[TRT_FMT_DFLANKINDEL].p;
-        q = (float*)ctx->fmt_buf[TRT_FMT_Q].p;
+        for (int i = 0; i < 4; i++)
+            if (with_format & (1 << i)) TRT_TRY(trt_ensure(ctx, ctx->fmt_buf[ids[i]], b));
+        if (with_format & 1) dp = (int32_t*)ctx->fmt_buf[TRT_FMT_DP].p;
+        if (with_format & 2) dst = (int32_t*)ctx->fmt_buf[TRT_FMT_DSTUTTER].p;
+        if (with_format & 4) dfl = (int32_t*)ctx->fmt_buf[TRT_FMT_DFLANKINDEL].p;
+        if (with_format & 8) q = (float*)ctx->fmt_buf[TRT_FMT_Q].p;
     }
     if (L > 0 && S > 0) {
         if (pitch != row) TRT_CUDA(cudaMemsetAsync(ctx->gt_buf.p, 0xFE, pitch * (size_t)L, ctx->stream));
@@ -138,9 +138,9 @@ extern "C" int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset,
     ctx->gt_active_pitch = pitch;
     ctx->have_gt = true;
     ctx->have_packed = false;
-    if (with_format) {
-        const int ids[4] = {TRT_FMT_DP, TRT_FMT_DSTUTTER, TRT_FMT_DFLANKINDEL, TRT_FMT_Q};
+    {
         for (int i = 0; i < 4; i++) {
+            if (!(with_format & (1 << i))) continue;
             ctx->d_fmt[ids[i]] = ctx->fmt_buf[ids[i]].p;
             ctx->fmt_ncol[ids[i]] = 1;
             ctx->fmt_is_float[ids[i]] = (ids[i] == TRT_FMT_Q) ? 1 : 0;

@@ -1,0 +1,87 @@
+"""
+Multi-GPU plumbing: loci shard by contiguous ranges (one process per GPU, ``torch.distributed``); there is no
+data-path collective.  NCCL (or gloo on CPU boxes, for the tests) is used only to gather the fixed-width per-locus
+result tables on rank 0 and to sum dumpSTR's per-sample accumulators.
+"""
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def locus_shard(n_loci: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous locus range [lo, hi) of ``rank``: concatenating the ranks' outputs restores VCF order."""
+    base, rem = divmod(n_loci, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init(backend: Optional[str] = None):
+    """Initialise torch.distributed from the torchrun environment; returns the module (or None when world == 1)."""
+    rank, world, local_rank = env_rank_world()
+    if world == 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return dist
+
+
+def _device(dist):
+    import torch
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def gather_table(dist, local: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
+    """Gather per-locus rows float64 [n_local, C] of every rank on ``dst`` in rank order (row counts may differ)."""
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if dist is None:
+        return local
+    import torch
+    dev = _device(dist)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    cols = local.shape[1] if local.ndim == 2 else 1
+    pad = max(sizes) if sizes else 0
+    buf = torch.zeros((pad, cols), dtype=torch.float64, device=dev)
+    if local.shape[0]:
+        buf[:local.shape[0]] = torch.from_numpy(local.reshape(local.shape[0], cols)).to(dev)
+    out = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, out, dst=dst)
+    if rank != dst:
+        return None
+    return np.concatenate([o[:k].cpu().numpy() for o, k in zip(out, sizes)], axis=0)
+
+
+def allreduce_sum(dist, arr: np.ndarray) -> np.ndarray:
+    """Sum an int64 / float64 array over ranks (dumpSTR per-sample accumulators; NaN poison propagates)."""
+    if dist is None:
+        return arr
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(_device(dist))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def max_over_ranks(dist, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=_device(dist))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
