@@ -276,10 +276,11 @@ def run_gpu(args):
     tp = os.path.join(REPO, "profiles", "scan_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            # measured DRAM bytes per call of the scan (one ncu --set full capture), scaled to this launch's calls
+            traffic = float(json.load(open(tp))["dram_bytes_per_call"]) * L * S
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "scan_diploid_tma_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "scan_pairs_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": scan, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_share_of_step": scan / step_ms if step_ms > 0 else None}
