@@ -95,9 +95,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's statSTR path on a bounded locus sample
 # ---------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    lo, hi, S, seed = args
-    from oracle import stats as ostats, trh as otrh
+def _synth_sub(lo, hi, S, seed, with_fmt):
     from oracle.records import synth_to_loci
     from trtools_b200 import synth
     sl = synth.make_loci(hi, seed=seed)
@@ -105,9 +103,41 @@ def _cpu_worker(args):
     sub = synth.SynthLoci(seed=sl.seed, n_loci=hi - lo, chrom=sl.chrom[lo:hi], pos=sl.pos[lo:hi], start=sl.start[lo:hi],
                           end=sl.end[lo:hi], period=sl.period[lo:hi], ref=sl.ref[lo:hi], alts=sl.alts[lo:hi],
                           n_alleles=sl.n_alleles[lo:hi], cum_freq=sl.cum_freq[lo:hi], locus_offset=lo)
-    loci = synth_to_loci(sub, calls, with_fmt=False)
-    t0 = time.perf_counter()
+    return synth_to_loci(sub, calls, with_fmt=with_fmt)
+
+
+def reference_kind():
+    """"reference" when the unmodified TRTools code is importable (baseline/_ref, see baseline/install_ref.py, or
+    /root/reference in the build container), else "port" (the oracle restatement)."""
+    from oracle import ref_import
+    return "reference" if ref_import.reference_code_available() else "port"
+
+
+def _cpu_worker(args):
+    lo, hi, S, seed, kind = args
+    loci = _synth_sub(lo, hi, S, seed, False)
     rows = []
+    if kind == "reference":
+        # the reference's own per-record loop body (trtools/statSTR/statSTR.py:576-630) on cyvcf2-layout records
+        from oracle import ref_import
+        from oracle.records import LocusAsVariant
+        ref_import.enable()
+        import trtools.utils.tr_harmonizer as rtrh
+        import trtools.statSTR.statSTR as rstat
+        recs = [LocusAsVariant(l) for l in loci]
+        t0 = time.perf_counter()
+        for rec in recs:
+            tr = rtrh.HarmonizeRecord(rtrh.VcfTypes.hipstr, rec)
+            items = [rec.CHROM, rec.POS, rec.POS + len(tr.ref_allele)]
+            items += rstat.GetAFreq(tr, [None], uselength=False)
+            for fn in (rstat.GetHet, rstat.GetHWEP):
+                items += fn(tr, [None], uselength=False)
+            items += rstat.GetMean(tr, [None]) + rstat.GetVariance(tr, [None])
+            items += rstat.GetEntropy(tr, [None], uselength=False)
+            rows.append("\t".join(str(x) for x in items))
+        return time.perf_counter() - t0, len(rows)
+    from oracle import stats as ostats, trh as otrh
+    t0 = time.perf_counter()
     for l in loci:
         h = otrh.harmonize(l)                                           # HarmonizeRecord
         vals = ostats.locus_stats(h, l.gt, STATS6, [None], uselength=False)   # statSTR stat wrappers
@@ -115,12 +145,13 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, len(rows)
 
 
-def cpu_statstr(n_loci, S, cores, seed=SEED):
-    """loci/s of the oracle port with one process per core on disjoint loci (wall clock of the
+def cpu_statstr(n_loci, S, cores, seed=SEED, kind=None):
+    """loci/s of the reference's statSTR path with one process per core on disjoint loci (wall clock of the
     timed sections, data generation excluded)."""
     import multiprocessing as mp
+    kind = kind or reference_kind()
     per = max(1, n_loci // cores)
-    jobs = [(i * per, (i + 1) * per, S, seed) for i in range(cores)]
+    jobs = [(i * per, (i + 1) * per, S, seed, kind) for i in range(cores)]
     ctxmp = mp.get_context("fork")
     with ctxmp.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
@@ -133,14 +164,7 @@ def _cpu_other_worker(args):
     """oracle ports of the dumpSTR and associaTR per-locus paths on a few loci (seconds per locus on one core)."""
     lo, hi, S, seed = args
     from oracle import dumpstr as od, assoc as oassoc, trh as otrh
-    from oracle.records import synth_to_loci
-    from trtools_b200 import synth
-    sl = synth.make_loci(hi, seed=seed)
-    calls = synth.fill_calls(sl, S, slice(lo, hi))
-    sub = synth.SynthLoci(seed=sl.seed, n_loci=hi - lo, chrom=sl.chrom[lo:hi], pos=sl.pos[lo:hi], start=sl.start[lo:hi],
-                          end=sl.end[lo:hi], period=sl.period[lo:hi], ref=sl.ref[lo:hi], alts=sl.alts[lo:hi],
-                          n_alleles=sl.n_alleles[lo:hi], cum_freq=sl.cum_freq[lo:hi], locus_offset=lo)
-    loci = synth_to_loci(sub, calls, with_fmt=True)
+    loci = _synth_sub(lo, hi, S, seed, True)
     cf = [od.hipstr_flank_indels(0.15), od.min_value("HipSTRCallMinDepth", "DP", 20)]
     lf = [od.LocusFilter("hwe", 1e-4, False)]
     sinfo, linfo = od.new_sample_info(S, cf), od.new_loc_info(lf)
@@ -180,26 +204,29 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    kind = reference_kind()
     L, S = args.loci, args.samples
-    n_sub = max(cores, min(4 * cores, 64))
+    n_sub = cores * (1 if kind == "reference" else 4)      # ~1.5 s (reference) / ~0.9 s (port) per locus per core at S = 50k
     vals = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_statstr(cores, S, cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_statstr(cores, S, cores, kind=kind)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, done, wall = cpu_statstr(n_sub, S, cores)
+        v, done, wall = cpu_statstr(n_sub, S, cores, kind=kind)
         vals.append(v)
     total = time.perf_counter() - t0
     value = float(np.mean(vals))
+    what = ("the UNMODIFIED reference (trtools.utils.tr_harmonizer.HarmonizeRecord + trtools.statSTR.statSTR stat functions, "
+            "baseline/_ref) on cyvcf2-layout records") if kind == "reference" else "oracle port of the reference's Python/numpy path"
     sample = "{} loci x {} samples per step (of the {}-locus workload), {} processes".format(n_sub, S, L, cores)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "statSTR --afreq --het --hwep --mean --var --entropy, synthetic HipSTR {}x{}".format(L, S),
-                   "loci": L, "samples": S, "note": "oracle port of the reference's Python/numpy path; loci/s extrapolates "
-                   "linearly (loci are independent)"},
-        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": "port", "sample": sample},
+                   "loci": L, "samples": S, "note": what + "; VCF parsing excluded; loci/s extrapolates linearly "
+                   "(loci are independent)"},
+        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,7 +255,7 @@ def run_gpu(args):
 
     def step():
         ctx.check(ctx.lib.trt_harmonize(ctx.h))
-        return ctx.locus_stats(False, None, 0.01)
+        return ctx.locus_stats(False, None, 0.01, pinned=True)      # results land in page-locked host arrays
 
     def barrier():
         if dist is not None:
@@ -303,7 +330,7 @@ def run_gpu(args):
             ctx.block_set_gt(host_gt[:n])
             ctx.block_set_alleles(*blk_tables[b])
             ctx.check(ctx.lib.trt_harmonize(ctx.h))
-            st = ctx.locus_stats(False, None, 0.01)
+            st = ctx.locus_stats(False, None, 0.01, pinned=True)
             h2d += host_gt[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
             d2h += sum(v.nbytes for v in st.values())
         return st
@@ -351,7 +378,7 @@ def run_gpu(args):
             ms_ = max(dev, wall) / steps
             return tdist.max_over_ranks(dist, ms_), float(np.mean(scan))
 
-        ms_a, k_a = timed(lambda: ctx.assoc_ols(20.0), max(2, min(args.steps, 5)), 2)
+        ms_a, k_a = timed(lambda: ctx.assoc_ols(20.0, pinned=True), max(2, min(args.steps, 5)), 2)
         tools["associaTR"] = {"value": world * L / (ms_a / 1000.0), "unit": "loci/s", "ms_per_step": ms_a,
                               "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; scan + FP64 moments "
                                           "+ down-dates + solve, results to host",
@@ -365,7 +392,7 @@ def run_gpu(args):
         def dump_step():
             ctx.call_filters(cf_specs, L_.FMT_DP, counts, numcalls, totaldp, want_mask=False, want_trigger=False, want_gt=False)
             k1 = ctx.last_scan_ms()
-            ctx.locus_filters([(L_.LF_HWE, 1e-4)], False)
+            ctx.locus_filters([(L_.LF_HWE, 1e-4)], False, pinned=True)
             dump_step.kernel = k1 + ctx.last_scan_ms()
 
         ms_d, _ = timed(dump_step, max(2, min(args.steps, 5)), 2)
@@ -379,9 +406,10 @@ def run_gpu(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            n_sub = max(cores, min(4 * cores, 64))
-            v, done, wall = cpu_statstr(n_sub, S, cores)
-            cpu = {"value": v, "unit": "loci/s", "cores": cores, "kind": "port",
+            kind = reference_kind()
+            n_sub = cores * (1 if kind == "reference" else 4)
+            v, done, wall = cpu_statstr(n_sub, S, cores, kind=kind)
+            cpu = {"value": v, "unit": "loci/s", "cores": cores, "kind": kind,
                    "sample": "{} loci x {} samples, statSTR 6 stats (sequence grouping), {} processes, {:.1f} s".format(
                        done, S, cores, wall)}
             if not args.statstr_only:

@@ -157,3 +157,57 @@ def test_assoc_extreme_pvalues_and_missingness(ctx):
             assert_close(res["coef"][i] * design.pheno_std, row.coef, what + " coef", rel=1e-6, abs_tol=1e-12)
             assert_close(res["se"][i] * design.pheno_std, row.se, what + " se")
             assert_close(res["r2"][i], row.r2, what + " r2", rel=1e-6, abs_tol=1e-12)
+
+
+@pytest.mark.parametrize("n_cov,S,use_subset", [(10, 3001, False), (3, 2048, True), (0, 1000, False)])
+def test_assoc_tile_fast_path_matches_generic_kernels_and_oracle(ctx, monkeypatch, n_cov, S, use_subset):
+    """The thread-per-locus TMA tile path (trt_assoc_tile.cu) against the generic kernels on the same block
+    (several 256-locus tiles, one of them forced generic by a locus with > 14 alleles, S not a multiple of the
+    40-sample chunk, optional sample subset) and against the oracle's pinv OLS on a sample of loci."""
+    from oracle import assoc as oassoc, trh as otrh
+    from oracle.records import synth_to_loci
+    from trtools_b200 import _lib, synth
+    L = 700
+    sl = synth.make_loci(L, seed=77, max_alleles=16)
+    # locus 300 gets 16 alleles (> 14): its whole 256-locus tile must take the generic kernels
+    sl.alts[300] = [sl.ref[300] + "ACGT"[k % 4] * (k + 1) for k in range(15)]
+    sl.n_alleles[300] = 16
+    sl.cum_freq[300] = (np.arange(1, 17, dtype=np.float64) / 16 * 2 ** 32 - 1).astype(np.uint32)
+    calls = synth.fill_calls(sl, S)
+    rng = np.random.default_rng(5)
+    traits = rng.standard_normal((S, 1 + n_cov))
+    mask = (rng.random(S) < 0.7) if use_subset else None
+    design = oassoc.prepare_design([traits], S, mask)
+    idx = np.nonzero(design.sample_filter)[0].astype(np.int32)
+
+    def run():
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt(calls.gt)
+        ctx.block_set_alleles(*synth.allele_tables(sl))
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        ctx.assoc_set_design(design.covars, design.outcome, idx)
+        return ctx.assoc_ols(5)
+
+    fast = run()
+    monkeypatch.setenv("TRT_ASSOC_GENERIC", "1")
+    gen = run()
+    monkeypatch.delenv("TRT_ASSOC_GENERIC")
+    assert np.array_equal(fast["filter_code"], gen["filter_code"])
+    assert np.array_equal(fast["n_tested"], gen["n_tested"])
+    assert np.array_equal(fast["ac_len"], gen["ac_len"])
+    for k in ("p", "coef", "se", "r2", "std_g"):
+        for i in range(L):
+            assert_close(fast[k][i], gen[k][i], "{} locus {}".format(k, i), rel=1e-7, abs_tol=1e-300 if k == "p" else 1e-13)
+    loci = synth_to_loci(sl, calls, with_fmt=False)
+    n_ok = 0
+    for i in list(range(0, L, 23)) + [300]:
+        if int(fast["filter_code"][i]) != _lib.AF_OK:
+            continue
+        h = otrh.harmonize(loci[i])
+        row = oassoc.regress_locus(oassoc.load_locus(loci[i], h, design.sample_filter.copy(), 5), design)
+        assert_close(fast["p"][i], row.p, "p locus %d" % i, abs_tol=1e-300)
+        assert_close(fast["coef"][i] * design.pheno_std, row.coef, "coef locus %d" % i, rel=1e-6, abs_tol=1e-12)
+        assert_close(fast["se"][i] * design.pheno_std, row.se, "se locus %d" % i)
+        assert_close(fast["r2"][i], row.r2, "r2 locus %d" % i, rel=1e-6, abs_tol=1e-12)
+        n_ok += 1
+    assert n_ok > 5

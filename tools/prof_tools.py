@@ -19,7 +19,7 @@ if "stat" in tools:
         t0 = time.perf_counter()
         ctx.check(ctx.lib.trt_harmonize(ctx.h))
         t1 = time.perf_counter()
-        ctx.locus_stats(False, None, 0.01)
+        ctx.locus_stats(False, None, 0.01, pinned=True)
         t2 = time.perf_counter()
         print("statSTR harmonize wall %.3f ms, locus_stats wall %.3f ms (kernels %.3f, scan %.3f)" % (
             (t1 - t0) * 1e3, (t2 - t1) * 1e3, ctx.last_kernel_ms(), ctx.last_scan_ms()), flush=True)
@@ -33,7 +33,7 @@ if "assoc" in tools:
     ctx.assoc_set_design(covars, outcome, np.arange(S, dtype=np.int32))
     for i in range(reps):
         t0 = time.perf_counter()
-        ctx.assoc_ols(20.0)
+        ctx.assoc_ols(20.0, pinned=True)
         print("associaTR wall %.3f ms (kernels %.3f, sample-axis kernels %.3f)" % (
             (time.perf_counter() - t0) * 1e3, ctx.last_kernel_ms(), ctx.last_scan_ms()), flush=True)
 if "dump" in tools:
@@ -43,7 +43,7 @@ if "dump" in tools:
         t0 = time.perf_counter()
         ctx.call_filters(cf, _lib.FMT_DP, counts, numcalls, totaldp, want_mask=False, want_trigger=False, want_gt=False)
         t1 = time.perf_counter(); k1 = ctx.last_scan_ms()
-        ctx.locus_filters([(_lib.LF_HWE, 1e-4)], False)
+        ctx.locus_filters([(_lib.LF_HWE, 1e-4)], False, pinned=True)
         t2 = time.perf_counter()
         print("dumpSTR call_filters wall %.3f ms (kernel %.3f); locus_filters wall %.3f ms (scan %.3f)" % (
             (t1 - t0) * 1e3, k1, (t2 - t1) * 1e3, ctx.last_scan_ms()), flush=True)

@@ -241,6 +241,21 @@ class Context:
         self._pinned[arr.ctypes.data] = p
         return arr
 
+    def _result(self, pinned: bool, name: str, shape, dtype) -> np.ndarray:
+        """Result buffer of one output.  ``pinned=True`` hands out page-locked arrays cached per (name, shape):
+        the device->host copies then run at PCIe speed instead of through the driver's pageable staging, and the
+        arrays are REUSED by the next call with the same shapes (copy what must outlive it)."""
+        if not pinned:
+            return np.empty(shape, dtype)
+        shape = tuple(int(x) for x in (shape if isinstance(shape, tuple) else (shape,)))
+        key = (name, shape, np.dtype(dtype).str)
+        arena = self.__dict__.setdefault("_arena", {})
+        if key not in arena:
+            for k in [k for k in arena if k[0] == name]:
+                self.free_pinned(arena.pop(k))
+            arena[key] = self.pinned_empty(shape, dtype)
+        return arena[key]
+
     def free_pinned(self, arr: np.ndarray):
         p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
         if p:
@@ -302,18 +317,18 @@ class Context:
         self.check(self.lib.trt_get_packed_gt(self.h, _ptr(out)))
         return out
 
+    _STAT_OUT = (("ac", np.int32), ("n_called", np.int64), ("n_called_nonstrict", np.int64), ("n_hom", np.int64),
+                 ("n_padded", np.int64), ("thresh", np.float64), ("het", np.float64), ("entropy", np.float64),
+                 ("mean", np.float64), ("mode", np.float64), ("var", np.float64), ("hwep", np.float64),
+                 ("nalleles", np.int32))
+
     def locus_stats(self, use_length: bool, group_masks: Optional[np.ndarray] = None,
-                    nalleles_thresh: float = 0.01, want=None) -> dict:
+                    nalleles_thresh: float = 0.01, want=None, pinned: bool = False) -> dict:
         G = 1 if group_masks is None else int(group_masks.shape[0])
         gm = None if group_masks is None else _c(group_masks, np.uint8).reshape(G, self.S)
         L, nA = self.L, self.nA
-        out = dict(ac=np.empty((G, nA), np.int32), n_called=np.empty((G, L), np.int64),
-                   n_called_nonstrict=np.empty((G, L), np.int64), n_hom=np.empty((G, L), np.int64),
-                   n_padded=np.empty((G, L), np.int64), thresh=np.empty((G, L)), het=np.empty((G, L)),
-                   entropy=np.empty((G, L)), mean=np.empty((G, L)), mode=np.empty((G, L)), var=np.empty((G, L)),
-                   hwep=np.empty((G, L)), nalleles=np.empty((G, L), np.int32))
-        if want is not None:
-            out = {k: v for k, v in out.items() if k in want}
+        out = {k: self._result(pinned, "stat_" + k, (G, nA if k == "ac" else L), dt)
+               for k, dt in self._STAT_OUT if want is None or k in want}
         so = LocusStatsOut(**{k: _ptr(v) for k, v in out.items()})
         self.check(self.lib.trt_locus_stats(self.h, 1 if use_length else 0, _ptr(gm), G, float(nalleles_thresh),
                                             C.byref(so)))
@@ -353,15 +368,16 @@ class Context:
         res["negative_dp_locus"] = int(neg[0])
         return res
 
-    def locus_filters(self, specs, use_length: bool) -> dict:
+    def locus_filters(self, specs, use_length: bool, pinned: bool = False) -> dict:
         """ApplyLocusFilters + INFO recompute on the current block.  ``specs``: list of (kind, threshold)."""
         n = len(specs)
         arr = (LocusFilterSpec * max(n, 1))()
         for i, (kind, thr) in enumerate(specs):
             arr[i].kind, arr[i].threshold = int(kind), float(0.0 if thr is None else thr)
         L, nA = self.L, self.nA
-        res = dict(flags=np.empty(L, np.uint32), n_called=np.empty(L, np.int64), het=np.empty(L), hwep=np.empty(L),
-                   ac=np.empty(nA, np.int32), hrun=np.empty(L, np.int32))
+        r = lambda k, n_, dt: self._result(pinned, "lf_" + k, (n_,), dt)
+        res = dict(flags=r("flags", L, np.uint32), n_called=r("n_called", L, np.int64), het=r("het", L, np.float64),
+                   hwep=r("hwep", L, np.float64), ac=r("ac", nA, np.int32), hrun=r("hrun", L, np.int32))
         out = LocusFilterOut(**{k: _ptr(v) for k, v in res.items()})
         self.check(self.lib.trt_locus_filters(self.h, arr, n, 1 if use_length else 0, C.byref(out)))
         return res
@@ -375,10 +391,12 @@ class Context:
         assert cv.ndim == 2 and cv.shape[0] == oc.shape[0] == si.shape[0]
         self.check(self.lib.trt_assoc_set_design(self.h, _ptr(cv), _ptr(oc), _ptr(si), cv.shape[0], cv.shape[1]))
 
-    def assoc_ols(self, non_major_cutoff: float) -> dict:
+    def assoc_ols(self, non_major_cutoff: float, pinned: bool = False) -> dict:
         L, nA = self.L, self.nA
-        res = dict(filter_code=np.empty(L, np.int32), n_tested=np.empty(L, np.int64), p=np.empty(L), coef=np.empty(L),
-                   se=np.empty(L), r2=np.empty(L), std_g=np.empty(L), ac_len=np.empty(nA, np.int32))
+        r = lambda k, n_, dt: self._result(pinned, "assoc_" + k, (n_,), dt)
+        res = dict(filter_code=r("filter_code", L, np.int32), n_tested=r("n_tested", L, np.int64), p=r("p", L, np.float64),
+                   coef=r("coef", L, np.float64), se=r("se", L, np.float64), r2=r("r2", L, np.float64),
+                   std_g=r("std_g", L, np.float64), ac_len=r("ac_len", nA, np.int32))
         out = AssocOut(**{k: _ptr(v) for k, v in res.items()})
         self.check(self.lib.trt_assoc_ols(self.h, float(non_major_cutoff), C.byref(out)))
         return res

@@ -31,6 +31,7 @@
 
 #include "trt_internal.cuh"
 #include "trt_scan.cuh"
+#include "trt_assoc_tile.cuh"
 
 namespace {
 
@@ -44,21 +45,28 @@ static_assert(kLociPerWarp == 2, "the moments kernel keeps two loci per thread i
 // z-vector of a design row: z[0..K-2] = covars columns 1..K-1 (intercept first), z[K-1] = outcome
 __host__ __device__ inline int tri_entries(int K) { return K * (K + 1) / 2; }
 
-__global__ void design_totals_kernel(const double* __restrict__ covars, const double* __restrict__ outcome, int64_t n, int K,
-                                     double* __restrict__ tot) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= tri_entries(K)) return;
+// one CTA per triangle entry; strided partial sums + a fixed-order tree (bit-reproducible)
+__global__ void __launch_bounds__(256) design_totals_kernel(const double* __restrict__ covars, const double* __restrict__ outcome,
+                                                            int64_t n, int K, double* __restrict__ tot) {
+    __shared__ double part[256];
+    const int e = blockIdx.x;
     // entry e -> (a, b), a <= b, row-major upper triangle
     int a = 0, rem = e;
     while (rem >= K - a) { rem -= K - a; a++; }
     const int b = a + rem;
     double s = 0.0;
-    for (int64_t i = 0; i < n; i++) {
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
         const double za = (a == K - 1) ? outcome[i] : covars[i * K + a + 1];
         const double zb = (b == K - 1) ? outcome[i] : covars[i * K + b + 1];
         s += za * zb;
     }
-    tot[e] = s;
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tot[e] = part[0];
 }
 
 struct AssocParams {
@@ -74,6 +82,7 @@ struct AssocParams {
     int K;
     double* mom;                    // [L][K+3]: n, sum g', sum g'^2, g'.y, g'.c_1..c_{K-1}
     double* dd;                     // [L][K(K+1)/2] outer products of the uncalled design rows
+    const uint8_t* tile_fast;       // [ceil(L/256)] non-zero: the 256-locus tile is handled by trt_assoc_tile.cu
 };
 
 // summed length genotype of one call; returns false if the sample is not (strictly) called
@@ -98,6 +107,7 @@ __global__ void __launch_bounds__(kMomThreads) assoc_moments_kernel(AssocParams 
     const int K = p.K, nacc = K + 3;
     const int64_t ntiles = (p.L + kTileLoci - 1) / kTileLoci;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (p.tile_fast && p.tile_fast[(tile * kTileLoci) / kAssocTileLoci]) continue;   // uniform per CTA
         const int64_t q[2] = {tile * kTileLoci + warp * 2, tile * kTileLoci + warp * 2 + 1};
         const int16_t* grow[2];
         const double* len[2];
@@ -184,6 +194,7 @@ __global__ void __launch_bounds__(256) assoc_downdate_kernel(AssocParams p) {
         eb[r] = a + rem;
     }
     for (int64_t l = warp; l < p.L; l += nwarps) {
+        if (p.tile_fast && p.tile_fast[l / kAssocTileLoci]) continue;
         const int a0 = p.locus_off[l];
         const int A = p.locus_off[l + 1] - a0;
         const int16_t* row = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch);
@@ -482,7 +493,7 @@ int trt_assoc_set_design(trt_ctx* ctx, const double* covars, const double* outco
         TRT_CUDA(cudaMemcpyAsync(ctx->sample_index.p, sample_index, (size_t)n_design * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     const int ne = tri_entries(K);
-    design_totals_kernel<<<(ne + 63) / 64, 64, 0, ctx->stream>>>((const double*)ctx->covars.p, (const double*)ctx->outcome.p,
+    design_totals_kernel<<<ne, 256, 0, ctx->stream>>>((const double*)ctx->covars.p, (const double*)ctx->outcome.p,
                                                                  n_design, K, (double*)ctx->assoc_tot.p);
     TRT_KERNEL_CHECK();
     TRT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -546,6 +557,28 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
         ap.K = K;
         ap.mom = (double*)ctx->assoc_acc.p;
         ap.dd = ap.mom + (size_t)L * nacc;
+        // ---- split the block into 256-locus tiles: fast path (thread per locus, TMA ring) vs generic kernels ----
+        const int64_t ntiles256 = (L + kAssocTileLoci - 1) / kAssocTileLoci;
+        std::vector<uint8_t> tile_fast((size_t)ntiles256, 0);
+        std::vector<int32_t> fast_tiles;
+        const bool fast_ok = ctx->P == 2 && K <= kAssocFastMaxK && S >= kAssocFastMinSamples && !getenv("TRT_ASSOC_GENERIC") &&
+                             (ctx->gt_active_pitch % 16) == 0 && ((uintptr_t)ctx->d_gt_active % 16) == 0;
+        if (fast_ok) {
+            for (int64_t t = 0; t < ntiles256; t++) {
+                int maxA = 0;
+                const int64_t l1 = std::min<int64_t>(L, (t + 1) * kAssocTileLoci);
+                for (int64_t l = t * kAssocTileLoci; l < l1; l++) maxA = std::max(maxA, ctx->h_locus_off[l + 1] - ctx->h_locus_off[l]);
+                if (maxA <= kAssocFastMaxAlleles) {
+                    tile_fast[t] = 1;
+                    fast_tiles.push_back((int32_t)t);
+                }
+            }
+        }
+        TRT_TRY(trt_ensure(ctx, ctx->assoc_tile_fast, (size_t)ntiles256 + 16));
+        TRT_CUDA(cudaMemcpyAsync(ctx->assoc_tile_fast.p, tile_fast.data(), (size_t)ntiles256, cudaMemcpyHostToDevice, ctx->stream));
+        ap.tile_fast = (const uint8_t*)ctx->assoc_tile_fast.p;
+        TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, fast_tiles, ap.tile_fast, ap.mom, ap.dd));
+        const bool need_generic = (int64_t)fast_tiles.size() < ntiles256;
         const int64_t ntiles = (L + kTileLoci - 1) / kTileLoci;
         const size_t smem = (size_t)K * 256 * 8;
         const unsigned mgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
@@ -559,7 +592,8 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
         assoc_downdate_kernel<KP><<<(unsigned)wblocks, 256, 0, ctx->stream>>>(ap);                                      \
         TRT_KERNEL_CHECK();                                                                                             \
     } while (0)
-        if (K <= 8) LAUNCH_MOMENTS(8);
+        if (!need_generic) {
+        } else if (K <= 8) LAUNCH_MOMENTS(8);
         else if (K <= 16) LAUNCH_MOMENTS(16);
         else LAUNCH_MOMENTS(32);
 #undef LAUNCH_MOMENTS

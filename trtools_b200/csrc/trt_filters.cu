@@ -461,7 +461,7 @@ int trt_locus_filters(trt_ctx* ctx, const trt_locus_filter_spec* specs, int n_sp
     const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
     TRT_TRY(trt_ensure(ctx, ctx->ac, (size_t)nA * 4 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->lc, (size_t)L * TRT_LC_N * 8 + 16));
-    TRT_TRY(trt_ensure(ctx, ctx->stat_f64, (size_t)L * 8 * 9 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->stat_f64, (size_t)L * 8 * 12 + 16));
     // scratch for the flag kernel: [flags u32 L][het f64 L][hwep f64 L][n_called i64 L][specs]
     const size_t off_het = (((size_t)L * 4 + 15) & ~size_t(15));
     const size_t off_hwep = off_het + (size_t)L * 8, off_nc = off_hwep + (size_t)L * 8, off_specs = off_nc + (size_t)L * 8;

@@ -67,6 +67,7 @@ struct trt_ctx {
     DevBuf  cf_specs, call_mask, trig, samp_counts, samp_dp, misc;
     // associaTR
     DevBuf  covars, outcome, sample_index, design_row_of_sample, assoc_acc, assoc_out, assoc_tot;
+    DevBuf  assoc_zt, assoc_fast_tiles, assoc_tile_fast, assoc_masks, assoc_mom_part;   // fast path (trt_assoc_tile.cu)
     int64_t n_design = 0;
     int     K = 0;
     bool    have_design = false;

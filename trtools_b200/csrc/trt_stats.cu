@@ -169,6 +169,8 @@ struct EpiParams {
     double *thresh, *het, *entropy, *mean, *mode, *var, *hwep;
     int32_t* nalleles;
     long long* n_hom;
+    long long *n_called, *n_nonstrict, *n_padded;
+    unsigned long long* n_bad;   // device-wide count of genotype entries outside [-2, A)
 };
 
 __global__ void __launch_bounds__(128) locus_epilogue_kernel(EpiParams p) {
@@ -287,6 +289,10 @@ __global__ void __launch_bounds__(128) locus_epilogue_kernel(EpiParams p) {
     if (p.hwep) p.hwep[o] = hwep;
     if (p.nalleles) p.nalleles[o] = nall;
     if (p.n_hom) p.n_hom[o] = n_hom;
+    p.n_called[o] = n_full;
+    p.n_nonstrict[o] = lc[TRT_LC_NNONSTRICT];
+    p.n_padded[o] = lc[TRT_LC_NPAD];
+    if (lc[6]) atomicAdd(p.n_bad, (unsigned long long)lc[6]);
 }
 
 // dense class ranks (needed for the sorted-genotype semantics when ploidy > 2)
@@ -351,7 +357,8 @@ int trt_prepare_ranks(trt_ctx* ctx) {
     return TRT_OK;
 }
 
-// epilogue over ctx->ac / ctx->lc -> ctx->stat_f64 = [thresh|het|entropy|mean|mode|var|hwep|nalleles(i32)|n_hom(i64)] x G*L
+// epilogue over ctx->ac / ctx->lc -> ctx->stat_f64 = [thresh|het|entropy|mean|mode|var|hwep|nalleles(i32)|n_hom(i64)|
+// n_called|n_called_nonstrict|n_padded (i64)] x G*L, then one u64 bad-entry counter
 int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G) {
     const int64_t L = ctx->L, nA = ctx->nA;
     const size_t n_out = (size_t)G * L;
@@ -374,6 +381,11 @@ int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G
     ep.mode = f + 4 * n_out; ep.var = f + 5 * n_out; ep.hwep = f + 6 * n_out;
     ep.nalleles = (int32_t*)(f + 7 * n_out);
     ep.n_hom = (long long*)(f + 8 * n_out);
+    ep.n_called = (long long*)(f + 9 * n_out);
+    ep.n_nonstrict = (long long*)(f + 10 * n_out);
+    ep.n_padded = (long long*)(f + 11 * n_out);
+    ep.n_bad = (unsigned long long*)(f + 12 * n_out);
+    TRT_CUDA(cudaMemsetAsync(ep.n_bad, 0, 8, ctx->stream));
     locus_epilogue_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(ep);
     TRT_KERNEL_CHECK();
     return TRT_OK;
@@ -391,7 +403,7 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
     TRT_TRY(trt_ensure(ctx, ctx->ac, (size_t)G * nA * 4 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->lc, (size_t)G * L * TRT_LC_N * 8 + 16));
     const size_t n_out = (size_t)G * L;
-    TRT_TRY(trt_ensure(ctx, ctx->stat_f64, n_out * 8 * 9 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->stat_f64, n_out * 8 * 12 + 16));
     if (group_masks) {
         TRT_TRY(trt_ensure(ctx, ctx->group_masks, (size_t)G * S + 16));
         TRT_CUDA(cudaMemcpyAsync(ctx->group_masks.p, group_masks, (size_t)G * S, cudaMemcpyHostToDevice, ctx->stream));
@@ -430,26 +442,16 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
     D2H(out->hwep, f + 6 * n_out, n_out * 8);
     D2H(out->nalleles, f + 7 * n_out, n_out * 4);
     D2H(out->n_hom, f + 8 * n_out, n_out * 8);
+    D2H(out->n_called, f + 9 * n_out, n_out * 8);
+    D2H(out->n_called_nonstrict, f + 10 * n_out, n_out * 8);
+    D2H(out->n_padded, f + 11 * n_out, n_out * 8);
+    unsigned long long bad = 0;
+    if (n_out) TRT_CUDA(cudaMemcpyAsync(&bad, f + 12 * n_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
 #undef D2H
-    std::vector<long long> lc;
-    if (n_out && (out->n_called || out->n_called_nonstrict || out->n_padded)) {
-        lc.resize(n_out * TRT_LC_N);
-        TRT_CUDA(cudaMemcpyAsync(lc.data(), ctx->lc.p, n_out * TRT_LC_N * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    } else if (n_out) {
-        lc.resize(n_out * TRT_LC_N);
-        TRT_CUDA(cudaMemcpyAsync(lc.data(), ctx->lc.p, n_out * TRT_LC_N * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
     TRT_CUDA(cudaStreamSynchronize(ctx->stream));
-    long long bad = 0;
-    for (size_t i = 0; i < n_out; i++) {
-        if (out->n_called) out->n_called[i] = lc[i * TRT_LC_N + TRT_LC_NFULL];
-        if (out->n_called_nonstrict) out->n_called_nonstrict[i] = lc[i * TRT_LC_N + TRT_LC_NNONSTRICT];
-        if (out->n_padded) out->n_padded[i] = lc[i * TRT_LC_N + TRT_LC_NPAD];
-        bad += lc[i * TRT_LC_N + 6];
-    }
     if (bad)
         return trt_set_error(ctx, TRT_ERECORD,
-                             "%lld genotype entries index an allele the record does not have (or are < -2)", bad);
+                             "%lld genotype entries index an allele the record does not have (or are < -2)", (long long)bad);
     return TRT_OK;
 }
 
