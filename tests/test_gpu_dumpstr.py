@@ -168,7 +168,7 @@ def test_call_and_locus_filter_kernels_vs_reference_on_synthetic(golden_dir, ctx
         assert_close(lres["hwep"][i], r["HWEP"], "HWEP %d" % i, abs_tol=1e-300)
 
 
-@pytest.mark.parametrize("L,S", [(300, 3001), (40, 20480), (700, 4096)])
+@pytest.mark.parametrize("L,S", [(300, 3001), (40, 20480), (700, 4096), (130, 6152), (33, 2900)])
 def test_call_filters_vs_oracle_large(ctx, L, S):
     """Device-generated FORMAT arrays (trt_synth_fill) through the call-filter kernel vs the oracle on sampled
     loci, and the per-sample accumulators vs a numpy restatement over the whole block."""

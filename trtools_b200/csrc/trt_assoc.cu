@@ -82,7 +82,8 @@ struct AssocParams {
     int K;
     double* mom;                    // [L][K+3]: n, sum g', sum g'^2, g'.y, g'.c_1..c_{K-1}
     double* dd;                     // [L][K(K+1)/2] outer products of the uncalled design rows
-    const uint8_t* tile_fast;       // [ceil(L/256)] non-zero: the 256-locus tile is handled by trt_assoc_tile.cu
+    const int32_t* list;            // loci handled by the generic kernels (null: all L loci)
+    int64_t n_list;
 };
 
 // summed length genotype of one call; returns false if the sample is not (strictly) called
@@ -105,10 +106,12 @@ __global__ void __launch_bounds__(kMomThreads) assoc_moments_kernel(AssocParams 
     __shared__ int rows[256];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.K, nacc = K + 3;
-    const int64_t ntiles = (p.L + kTileLoci - 1) / kTileLoci;
+    const int64_t n_loci = p.list ? p.n_list : p.L;
+    const int64_t ntiles = (n_loci + kTileLoci - 1) / kTileLoci;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if (p.tile_fast && p.tile_fast[(tile * kTileLoci) / kAssocTileLoci]) continue;   // uniform per CTA
-        const int64_t q[2] = {tile * kTileLoci + warp * 2, tile * kTileLoci + warp * 2 + 1};
+        // q = locus ids of this warp's two slots (p.L = none)
+        int64_t q[2] = {tile * kTileLoci + warp * 2, tile * kTileLoci + warp * 2 + 1};
+        for (int j = 0; j < 2; j++) q[j] = (q[j] < n_loci) ? (p.list ? (int64_t)p.list[q[j]] : q[j]) : p.L;
         const int16_t* grow[2];
         const double* len[2];
         int A[2];
@@ -193,8 +196,9 @@ __global__ void __launch_bounds__(256) assoc_downdate_kernel(AssocParams p) {
         ea[r] = a;
         eb[r] = a + rem;
     }
-    for (int64_t l = warp; l < p.L; l += nwarps) {
-        if (p.tile_fast && p.tile_fast[l / kAssocTileLoci]) continue;
+    const int64_t n_loci = p.list ? p.n_list : p.L;
+    for (int64_t li = warp; li < n_loci; li += nwarps) {
+        const int64_t l = p.list ? (int64_t)p.list[li] : li;
         const int a0 = p.locus_off[l];
         const int A = p.locus_off[l + 1] - a0;
         const int16_t* row = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch);
@@ -557,32 +561,33 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
         ap.K = K;
         ap.mom = (double*)ctx->assoc_acc.p;
         ap.dd = ap.mom + (size_t)L * nacc;
-        // ---- split the block into 256-locus tiles: fast path (thread per locus, TMA ring) vs generic kernels ----
-        const int64_t ntiles256 = (L + kAssocTileLoci - 1) / kAssocTileLoci;
-        std::vector<uint8_t> tile_fast((size_t)ntiles256, 0);
-        std::vector<int32_t> fast_tiles;
+        // ---- fast path (thread per locus, TMA ring) for loci with <= kAssocFastMaxAlleles alleles; the rest
+        //      (or everything, for ploidy != 2 / K > 16 / tiny sample counts) through the generic kernels ----
         const bool fast_ok = ctx->P == 2 && K <= kAssocFastMaxK && S >= kAssocFastMinSamples && !getenv("TRT_ASSOC_GENERIC") &&
                              (ctx->gt_active_pitch % 16) == 0 && ((uintptr_t)ctx->d_gt_active % 16) == 0;
+        std::vector<int32_t> generic_list;
+        ap.list = nullptr;
+        ap.n_list = 0;
+        bool need_generic = true;
         if (fast_ok) {
-            for (int64_t t = 0; t < ntiles256; t++) {
-                int maxA = 0;
-                const int64_t l1 = std::min<int64_t>(L, (t + 1) * kAssocTileLoci);
-                for (int64_t l = t * kAssocTileLoci; l < l1; l++) maxA = std::max(maxA, ctx->h_locus_off[l + 1] - ctx->h_locus_off[l]);
-                if (maxA <= kAssocFastMaxAlleles) {
-                    tile_fast[t] = 1;
-                    fast_tiles.push_back((int32_t)t);
-                }
+            for (int64_t l = 0; l < L; l++)
+                if (ctx->h_locus_off[l + 1] - ctx->h_locus_off[l] > kAssocFastMaxAlleles) generic_list.push_back((int32_t)l);
+            need_generic = !generic_list.empty();
+            if (need_generic) {
+                TRT_TRY(trt_ensure(ctx, ctx->assoc_fast_tiles, generic_list.size() * 4 + 16));
+                TRT_CUDA(cudaMemcpyAsync(ctx->assoc_fast_tiles.p, generic_list.data(), generic_list.size() * 4, cudaMemcpyHostToDevice,
+                                         ctx->stream));
+                TRT_CUDA(cudaStreamSynchronize(ctx->stream));   // generic_list is a local
+                ap.list = (const int32_t*)ctx->assoc_fast_tiles.p;
+                ap.n_list = (int64_t)generic_list.size();
             }
+            TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, ap.mom, ap.dd));
         }
-        TRT_TRY(trt_ensure(ctx, ctx->assoc_tile_fast, (size_t)ntiles256 + 16));
-        TRT_CUDA(cudaMemcpyAsync(ctx->assoc_tile_fast.p, tile_fast.data(), (size_t)ntiles256, cudaMemcpyHostToDevice, ctx->stream));
-        ap.tile_fast = (const uint8_t*)ctx->assoc_tile_fast.p;
-        TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, fast_tiles, ap.tile_fast, ap.mom, ap.dd));
-        const bool need_generic = (int64_t)fast_tiles.size() < ntiles256;
-        const int64_t ntiles = (L + kTileLoci - 1) / kTileLoci;
+        const int64_t n_gen = ap.list ? ap.n_list : L;
+        const int64_t ntiles = (n_gen + kTileLoci - 1) / kTileLoci;
         const size_t smem = (size_t)K * 256 * 8;
-        const unsigned mgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
-        const int64_t wblocks = std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)ctx->sm_count * 8));
+        const unsigned mgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
+        const int64_t wblocks = std::max<int64_t>(1, std::min<int64_t>((n_gen + 7) / 8, (int64_t)ctx->sm_count * 8));
 #define LAUNCH_MOMENTS(KP)                                                                                              \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \

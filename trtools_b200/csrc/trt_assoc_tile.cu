@@ -3,18 +3,20 @@
 // The per-locus regression needs, over the called design samples of the locus (associaTR.py:246-291 in the
 // reference tree), n, sum g, sum g^2, g.y and g.c_k for every covariate column: a skinny FP64 contraction
 // G[loci x samples] . Z[samples x K].  Mapping that keeps every operand cheap:
-//   * a CTA owns a tile of 256 consecutive loci x a segment of the sample axis; thread t <-> locus t of the tile;
-//   * a producer warp streams the tile through a shared-memory ring: ONE 2-D TMA tensor copy per stage brings
-//     256 rows x 40 samples of native cyvcf2 GT (240 B per row: an odd multiple of 16 B, so the 32 lanes of a
-//     warp read their own rows with conflict-free LDS.128), one 1-D bulk copy brings the 40 z-rows
+//   * a CTA owns a tile of 256 x NL consecutive loci x a segment of the sample axis; thread t <-> loci t, t + 256, ..
+//     of the tile (NL = 2: the z-row fetched from shared memory is reused by both loci, which is what bounds the
+//     kernel — measured 19 shared-memory wavefronts per call with NL = 1, 14 of them the z-row);
+//   * a producer warp streams the tile through a shared-memory ring: 2-D TMA tensor copies (256 rows each) bring
+//     24 samples of native cyvcf2 GT per locus (144 B per row: an odd multiple of 16 B, so the 32 lanes of a
+//     warp read their own rows with conflict-free LDS.128), one 1-D bulk copy brings the 24 z-rows
 //     (y, c_1..c_{K-1}, in-design flag) of the same samples;
 //   * every lane of a warp is at the SAME sample at the same time, so the z-row is a broadcast LDS.128 stream
-//     (1 wavefront per 2 doubles) and the K+2 DFMAs per call have all operands in registers;
-//   * allele length lookups go to a thread-private column of a [16][256] FP64 table (2-wavefront LDS.64,
+//     and the K+2 DFMAs per call have all operands in registers;
+//   * allele length lookups go to a thread-private column of a [16][256 NL] FP64 table (2-wavefront LDS.64,
 //     never a bank conflict whatever alleles the lanes carry);
 //   * the accumulators live in registers for the whole segment, so there is no cross-thread reduction at all.
 // Uncalled design samples (the rows whose outer products must be removed from C'C, C'y, y'y for this locus)
-// are emitted as one 40-bit mask per (locus, chunk); assoc_downdate_mask_kernel turns the masks into the exact
+// are emitted as one 24-bit mask per (locus, chunk); assoc_downdate_mask_kernel turns the masks into the exact
 // down-dates without reading GT again.
 //
 // Algorithmic traffic: 6 B/call of GT once (+ 0.2 B/call of masks written and read back).
@@ -27,12 +29,16 @@
 
 namespace {
 
-constexpr int kTLoci = kAssocTileLoci;          // 256 loci per tile = consumer threads
-constexpr int kTWarps = kTLoci / 32;            // 8 consumer warps
-constexpr int kTThreads = kTLoci + 32;          // + producer warp
-constexpr int kTChunk = kAssocChunk;            // 40 samples per stage
-constexpr int kTRowBytes = kTChunk * 6;         // 240 B = 15 x 16 B
-constexpr int kTGtBytes = kTLoci * kTRowBytes;  // 61440 B per stage
+constexpr int kNL = kAssocLociPerThread;        // loci per consumer thread
+constexpr int kTCons = 256;                     // consumer threads
+constexpr int kTLoci = kAssocTileLoci;          // 256 x NL loci per tile
+constexpr int kTWarps = kTCons / 32;            // 8 consumer warps
+constexpr int kTThreads = kTCons + 32;          // + producer warp
+constexpr int kTChunk = kAssocChunk;            // samples per stage
+constexpr int kTRowBytes = kTChunk * 6;         // 144 B = 9 x 16 B (NL = 2) / 240 B = 15 x 16 B (NL = 1)
+constexpr int kTGtBytes = kTLoci * kTRowBytes;  // bytes of GT per stage
+static_assert((kTRowBytes / 16) % 2 == 1 && kTRowBytes % 48 == 0, "rows: odd multiple of 16 B, whole 8-call groups");
+static_assert(kTLoci == kTCons * kNL, "tile = consumer threads x loci per thread");
 constexpr int kTMaxD = kAssocFastMaxAlleles + 2;   // digits: pad, no-call, alleles
 constexpr int kTMaxStages = 4;
 
@@ -40,13 +46,12 @@ struct TileParams {
     int64_t L, S;
     const int32_t* locus_off;
     const double* allele_len;
-    const int32_t* fast_tiles;      // [n_fast] tile ids (tile t covers loci [256 t, 256 t + 256))
-    int n_fast;
-    int nchunks;                    // ceil(S / 40)
+    int n_tiles;                    // ceil(L / tile loci)
+    int nchunks;                    // ceil(S / chunk)
     int nseg, chunks_per_seg;       // sample-axis segments (work unit = tile x segment)
     const double* zt;               // [nchunks * 40][ZW] z-rows in VCF sample order (zeros outside the design)
     double* mom_part;               // [nseg][L][K + 3]
-    unsigned long long* masks;      // [n_fast][nchunks][256]
+    uint32_t* masks;                // [n_tiles][nchunks][tile loci]: bit i = sample i of the chunk is an uncalled design sample
     int stages;
 };
 
@@ -66,9 +71,9 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
     constexpr int kZBytes = kTChunk * ZW * 8;
     extern __shared__ __align__(128) unsigned char smem[];
     const int stages = p.stages;
-    unsigned char* gt_ring = smem;                                            // [stages][61440]
+    unsigned char* gt_ring = smem;                                            // [stages][kTGtBytes]
     unsigned char* z_ring = smem + (size_t)stages * kTGtBytes;                // [stages][kZBytes]
-    double* table = (double*)(z_ring + (size_t)stages * kZBytes);             // [kTMaxD][256]
+    double* table = (double*)(z_ring + (size_t)stages * kZBytes);             // [kTMaxD][kTLoci]
     uint64_t* full = (uint64_t*)(table + kTMaxD * kTLoci);
     uint64_t* empty = full + kTMaxStages;
 
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
         mbar_fence_init();
     }
     __syncthreads();
-    const int n_units = p.n_fast * p.nseg;
+    const int n_units = p.n_tiles * p.nseg;
 
     if (warp == kTWarps) {
         // ===== producer: one elected lane feeds the ring across work units =====
@@ -89,13 +94,16 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int tile = p.fast_tiles[u / p.nseg];
+                const int tile = u / p.nseg;
                 const int seg = u % p.nseg;
                 const int c0 = seg * p.chunks_per_seg, c1 = min(p.nchunks, c0 + p.chunks_per_seg);
                 for (int c = c0; c < c1; c++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)(kTGtBytes + kZBytes));
-                    tma_load_2d(gt_ring + (size_t)stage * kTGtBytes, &tmap, c * (kTChunk * 3), tile * kTLoci, &full[stage]);
+#pragma unroll
+                    for (int h = 0; h < kNL; h++)
+                        tma_load_2d(gt_ring + (size_t)stage * kTGtBytes + (size_t)h * kTCons * kTRowBytes, &tmap, c * (kTChunk * 3),
+                                    tile * kTLoci + h * kTCons, &full[stage]);
                     tma_load_1d(z_ring + (size_t)stage * kZBytes, p.zt + (size_t)c * kTChunk * ZW, kZBytes, &full[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
@@ -104,57 +112,66 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
         return;
     }
 
-    // ===== consumers: thread <-> locus =====
+    // ===== consumers: thread <-> loci tid, tid + 256, .. of the tile =====
     int stage = 0;
     uint32_t phase = 0;
     double* mytab = table + tid;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int slot = u / p.nseg;
-        const int tile = p.fast_tiles[slot];
+        const int tile = u / p.nseg;
         const int seg = u % p.nseg;
         const int c0 = seg * p.chunks_per_seg, c1 = min(p.nchunks, c0 + p.chunks_per_seg);
-        const int64_t l = (int64_t)tile * kTLoci + tid;
-        const bool valid = l < p.L;
-        unsigned D = 2;
-        {
+        bool valid[kNL];
+        unsigned D[kNL];
+#pragma unroll
+        for (int h = 0; h < kNL; h++) {
             // thread-private length table by digit d = allele + 2: pad -> -2 - ref, no-call -> 0, allele -> len - ref
             // (the per-haplotype shift by the reference length is the conditioning shift of the generic kernel)
+            const int64_t l = (int64_t)tile * kTLoci + h * kTCons + tid;
             double ref = 0.0;
             int a0 = 0, A = 0;
-            if (valid) {
+            if (l < p.L) {
                 a0 = p.locus_off[l];
                 A = p.locus_off[l + 1] - a0;
-                ref = p.allele_len[a0];
             }
-            D = (unsigned)A + 2u;
-            mytab[0] = -2.0 - ref;
-            mytab[kTLoci] = 0.0;
-            for (int a = 0; a < A; a++) mytab[(a + 2) * kTLoci] = p.allele_len[a0 + a] - ref;
+            valid[h] = (l < p.L) && A <= kAssocFastMaxAlleles;      // wider loci go through the generic kernels
+            if (!valid[h]) A = 0;
+            if (A > 0) ref = p.allele_len[a0];
+            D[h] = (unsigned)A + 2u;
+            double* t = mytab + h * kTCons;
+            t[0] = -2.0 - ref;
+            t[kTLoci] = 0.0;
+            for (int a = 0; a < A; a++) t[(a + 2) * kTLoci] = p.allele_len[a0 + a] - ref;
         }
-        double accz[K];
+        double accz[kNL][K], sg[kNL], sgg[kNL];
+        int n[kNL];
 #pragma unroll
-        for (int k = 0; k < K; k++) accz[k] = 0.0;
-        double sg = 0.0, sgg = 0.0;
-        int n = 0;
-        unsigned long long* mrow = p.masks + ((size_t)slot * p.nchunks) * kTLoci + tid;
+        for (int h = 0; h < kNL; h++) {
+#pragma unroll
+            for (int k = 0; k < K; k++) accz[h][k] = 0.0;
+            sg[h] = sgg[h] = 0.0;
+            n[h] = 0;
+        }
+        uint32_t* mrow = p.masks + ((size_t)tile * p.nchunks) * kTLoci + tid;
         for (int c = c0; c < c1; c++) {
             mbar_wait(&full[stage], phase);
-            const uint4* row = (const uint4*)(gt_ring + (size_t)stage * kTGtBytes + (size_t)tid * kTRowBytes);
+            const unsigned char* gts = gt_ring + (size_t)stage * kTGtBytes + (size_t)tid * kTRowBytes;
             const double2* zc = (const double2*)(z_ring + (size_t)stage * kZBytes);
-            unsigned long long mask = 0ull;
+            uint32_t mask[kNL];
+#pragma unroll
+            for (int h = 0; h < kNL; h++) mask[h] = 0u;
 #pragma unroll
             for (int grp = 0; grp < kTChunk / 8; grp++) {
-                const uint4 v0 = row[3 * grp], v1 = row[3 * grp + 1], v2 = row[3 * grp + 2];
-                const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+                uint32_t w[kNL][12];
+#pragma unroll
+                for (int h = 0; h < kNL; h++) {
+                    const uint4* row = (const uint4*)(gts + (size_t)h * kTCons * kTRowBytes);
+                    const uint4 v0 = row[3 * grp], v1 = row[3 * grp + 1], v2 = row[3 * grp + 2];
+                    w[h][0] = v0.x; w[h][1] = v0.y; w[h][2] = v0.z; w[h][3] = v0.w;
+                    w[h][4] = v1.x; w[h][5] = v1.y; w[h][6] = v1.z; w[h][7] = v1.w;
+                    w[h][8] = v2.x; w[h][9] = v2.y; w[h][10] = v2.z; w[h][11] = v2.w;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const int k0 = 3 * j, k1 = k0 + 1;
-                    const int a = (k0 & 1) ? ((int)w[k0 >> 1] >> 16) : (int)(short)(w[k0 >> 1] & 0xffffu);
-                    const int b = (k1 & 1) ? ((int)w[k1 >> 1] >> 16) : (int)(short)(w[k1 >> 1] & 0xffffu);
-                    const unsigned da = (unsigned)(a + 2), db = (unsigned)(b + 2);
-                    const bool va = (da < D) & (da != 1u), vb = (db < D) & (db != 1u);
-                    const double la = mytab[(va ? da : 1u) * kTLoci];
-                    const double lb = mytab[(vb ? db : 1u) * kTLoci];
                     const int sidx = grp * 8 + j;
                     const double2* zr = zc + sidx * NZ2;
                     double z[ZW];
@@ -165,30 +182,45 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                         z[2 * q + 1] = t.y;
                     }
                     const bool ind = z[K] != 0.0;
-                    const bool called = va & vb;
-                    const bool ok = called & ind & valid;
-                    const double g = ok ? la + lb : 0.0;
-                    n += ok ? 1 : 0;
-                    mask |= (unsigned long long)((ind & !called) ? 1u : 0u) << sidx;
-                    sg += g;
-                    sgg = fma(g, g, sgg);
+                    const int k0 = 3 * j, k1 = k0 + 1;
 #pragma unroll
-                    for (int k = 0; k < K; k++) accz[k] = fma(g, z[k], accz[k]);   // explicit: the library builds with -fmad=false
+                    for (int h = 0; h < kNL; h++) {
+                        const int a = (k0 & 1) ? ((int)w[h][k0 >> 1] >> 16) : (int)(short)(w[h][k0 >> 1] & 0xffffu);
+                        const int b = (k1 & 1) ? ((int)w[h][k1 >> 1] >> 16) : (int)(short)(w[h][k1 >> 1] & 0xffffu);
+                        const unsigned da = (unsigned)(a + 2), db = (unsigned)(b + 2);
+                        const bool va = (da < D[h]) & (da != 1u), vb = (db < D[h]) & (db != 1u);
+                        const double* t = mytab + h * kTCons;
+                        const double la = t[(va ? da : 1u) * kTLoci];
+                        const double lb = t[(vb ? db : 1u) * kTLoci];
+                        const bool called = va & vb;
+                        const bool ok = called & ind & valid[h];
+                        const double g = ok ? la + lb : 0.0;
+                        n[h] += ok ? 1 : 0;
+                        mask[h] |= ((ind & !called) ? 1u : 0u) << sidx;
+                        sg[h] += g;
+                        sgg[h] = fma(g, g, sgg[h]);      // explicit fma: the library builds with -fmad=false
+#pragma unroll
+                        for (int k = 0; k < K; k++) accz[h][k] = fma(g, z[k], accz[h][k]);
+                    }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
-            mrow[(size_t)c * kTLoci] = valid ? mask : 0ull;
-        }
-        if (valid) {
-            // mom layout of the solve kernel: n, sum g', sum g'^2, g'.y, g'.c_1 .. g'.c_{K-1}
-            double* o = p.mom_part + ((size_t)seg * p.L + l) * (K + 3);
-            o[0] = (double)n;
-            o[1] = sg;
-            o[2] = sgg;
 #pragma unroll
-            for (int k = 0; k < K; k++) o[3 + k] = accz[k];
+            for (int h = 0; h < kNL; h++) mrow[(size_t)c * kTLoci + h * kTCons] = valid[h] ? mask[h] : 0u;
+        }
+#pragma unroll
+        for (int h = 0; h < kNL; h++) {
+            if (!valid[h]) continue;
+            // mom layout of the solve kernel: n, sum g', sum g'^2, g'.y, g'.c_1 .. g'.c_{K-1}
+            const int64_t l = (int64_t)tile * kTLoci + h * kTCons + tid;
+            double* o = p.mom_part + ((size_t)seg * p.L + l) * (K + 3);
+            o[0] = (double)n[h];
+            o[1] = sg[h];
+            o[2] = sgg[h];
+#pragma unroll
+            for (int k = 0; k < K; k++) o[3 + k] = accz[h][k];
         }
     }
 }
@@ -212,10 +244,11 @@ __global__ void assoc_ztable_kernel(const double* __restrict__ covars, const dou
 }
 
 __global__ void assoc_reduce_mom_kernel(const double* __restrict__ part, int nseg, int64_t n, double* __restrict__ mom,
-                                        const uint8_t* __restrict__ tile_fast, int nacc) {
+                                        const int32_t* __restrict__ locus_off, int nacc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (!tile_fast[(i / nacc) / kTLoci]) return;
+    const int64_t l = i / nacc;
+    if (locus_off[l + 1] - locus_off[l] > kAssocFastMaxAlleles) return;   // generic-path locus
     double s = 0.0;
     for (int g = 0; g < nseg; g++) s += part[(size_t)g * n + i];   // fixed order: bit-reproducible
     mom[i] = s;
@@ -227,7 +260,7 @@ template <int KP>
 __global__ void __launch_bounds__(256) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
     constexpr int kR = (KP * (KP + 1) / 2 + 31) / 32;
     constexpr int kBatch = 8;
-    __shared__ uint16_t lst_all[8][32 * kTChunk];
+    __shared__ uint16_t lst_all[8][32 * kTChunk];   // uncalled samples of a 32-chunk window, relative to its first sample
     __shared__ double zs_all[8][kBatch][KP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint16_t* lst = lst_all[wib];
@@ -247,19 +280,18 @@ __global__ void __launch_bounds__(256) assoc_downdate_mask_kernel(TileParams p, 
         eb[r] = a + rem;
     }
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t nloci = (int64_t)p.n_fast * kTLoci;
-    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; i < nloci; i += nwarps) {
-        const int slot = (int)(i / kTLoci), tl = (int)(i % kTLoci);
-        const int64_t l = (int64_t)p.fast_tiles[slot] * kTLoci + tl;
-        if (l >= p.L) continue;
-        const unsigned long long* mrow = p.masks + ((size_t)slot * p.nchunks) * kTLoci + tl;
+    for (int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; l < p.L; l += nwarps) {
+        if (p.locus_off[l + 1] - p.locus_off[l] > kAssocFastMaxAlleles) continue;   // generic-path locus
+        const int64_t tile = l / kTLoci;
+        const int tl = (int)(l % kTLoci);
+        const uint32_t* mrow = p.masks + ((size_t)tile * p.nchunks) * kTLoci + tl;
         double acc[kR];
 #pragma unroll
         for (int r = 0; r < kR; r++) acc[r] = 0.0;
         for (int cb = 0; cb < p.nchunks; cb += 32) {
             const int c = cb + lane;
-            unsigned long long m = (c < p.nchunks) ? mrow[(size_t)c * kTLoci] : 0ull;
-            const int cnt = __popcll(m);
+            uint32_t m = (c < p.nchunks) ? mrow[(size_t)c * kTLoci] : 0u;
+            const int cnt = __popc(m);
             int off = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -270,7 +302,7 @@ __global__ void __launch_bounds__(256) assoc_downdate_mask_kernel(TileParams p, 
             if (total == 0) continue;
             off -= cnt;
             while (m) {
-                const int b = __ffsll((long long)m) - 1;
+                const int b = __ffs((int)m) - 1;
                 m &= m - 1;
                 lst[off++] = (uint16_t)(lane * kTChunk + b);
             }
@@ -343,22 +375,22 @@ int launch_tile(trt_ctx* ctx, const CUtensorMap& tmap, TileParams& tp, int grid)
 
 int trt_assoc_fast_zw(int K) { return (K + 2) & ~1; }
 
-// Moments (into mom [L][K+3]) and down-dates (into dd [L][K(K+1)/2]) of every locus in a fast tile.
-int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, const std::vector<int32_t>& fast_tiles,
-                   const uint8_t* d_tile_fast, double* mom, double* dd) {
+// Moments (into mom [L][K+3]) and down-dates (into dd [L][K(K+1)/2]) of every locus with at most
+// kAssocFastMaxAlleles alleles; the others are left to the generic kernels.
+int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, double* dd) {
     const int64_t L = ctx->L, S = ctx->S;
     const int K = ctx->K, nacc = K + 3, ZW = trt_assoc_fast_zw(K);
-    const int n_fast = (int)fast_tiles.size();
-    if (n_fast == 0) return TRT_OK;
+    if (L == 0) return TRT_OK;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return trt_set_error(ctx, TRT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const int n_tiles = (int)((L + kTLoci - 1) / kTLoci);
     const int nchunks = (int)((S + kTChunk - 1) / kTChunk);
     const int64_t S_pad = (int64_t)nchunks * kTChunk;
     // work units = tile x sample segment, sized so the persistent grid's last wave is >= 95% full
     const int sms = ctx->sm_count;
     int nseg = 1;
     for (; nseg < 16; nseg++) {
-        const int64_t units = (int64_t)n_fast * nseg;
+        const int64_t units = (int64_t)n_tiles * nseg;
         const int64_t waves = (units + sms - 1) / sms;
         if ((double)units / (double)(waves * sms) >= 0.95 || nchunks / (nseg + 1) < 32) break;
     }
@@ -367,10 +399,8 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, const std::vect
     nseg = (nchunks + cps - 1) / cps;
 
     TRT_TRY(trt_ensure(ctx, ctx->assoc_zt, (size_t)S_pad * ZW * 8 + 64));
-    TRT_TRY(trt_ensure(ctx, ctx->assoc_fast_tiles, (size_t)n_fast * 4 + 16));
-    TRT_TRY(trt_ensure(ctx, ctx->assoc_masks, (size_t)n_fast * nchunks * kTLoci * 8 + 64));
+    TRT_TRY(trt_ensure(ctx, ctx->assoc_masks, (size_t)n_tiles * nchunks * kTLoci * 4 + 64));
     TRT_TRY(trt_ensure(ctx, ctx->assoc_mom_part, (size_t)nseg * L * nacc * 8 + 64));
-    TRT_CUDA(cudaMemcpyAsync(ctx->assoc_fast_tiles.p, fast_tiles.data(), (size_t)n_fast * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         const int64_t n = S_pad * ZW;
         assoc_ztable_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
@@ -381,7 +411,7 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, const std::vect
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)S * 3, (cuuint64_t)L};
         const cuuint64_t gstr[1] = {(cuuint64_t)ctx->gt_active_pitch};
-        const cuuint32_t box[2] = {(cuuint32_t)kTChunk * 3, (cuuint32_t)kTLoci};
+        const cuuint32_t box[2] = {(cuuint32_t)kTChunk * 3, (cuuint32_t)kTCons};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)ctx->d_gt_active, gdim, gstr, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -394,16 +424,15 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, const std::vect
     tp.L = L; tp.S = S;
     tp.locus_off = (const int32_t*)ctx->locus_off.p;
     tp.allele_len = (const double*)ctx->allele_len.p;
-    tp.fast_tiles = (const int32_t*)ctx->assoc_fast_tiles.p;
-    tp.n_fast = n_fast;
+    tp.n_tiles = n_tiles;
     tp.nchunks = nchunks;
     tp.nseg = nseg;
     tp.chunks_per_seg = cps;
     tp.zt = (const double*)ctx->assoc_zt.p;
     tp.mom_part = (double*)ctx->assoc_mom_part.p;
-    tp.masks = (unsigned long long*)ctx->assoc_masks.p;
+    tp.masks = (uint32_t*)ctx->assoc_masks.p;
     tp.stages = 0;
-    const int grid = (int)std::min<int64_t>((int64_t)n_fast * nseg, sms);
+    const int grid = (int)std::min<int64_t>((int64_t)n_tiles * nseg, sms);
     switch (K) {
 #define CASE(KK) case KK: TRT_TRY(launch_tile<KK>(ctx, tmap, tp, grid)); break;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
@@ -413,12 +442,11 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, const std::vect
     {
         const int64_t n = L * nacc;
         assoc_reduce_mom_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-            (const double*)ctx->assoc_mom_part.p, nseg, n, mom, d_tile_fast, nacc);
+            (const double*)ctx->assoc_mom_part.p, nseg, n, mom, tp.locus_off, nacc);
         TRT_KERNEL_CHECK();
     }
     {
-        const int64_t warps = (int64_t)n_fast * kTLoci;
-        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)sms * 8));
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)sms * 8));
         if (K <= 8) assoc_downdate_mask_kernel<8><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
         else assoc_downdate_mask_kernel<16><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
         TRT_KERNEL_CHECK();

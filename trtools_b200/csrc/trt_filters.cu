@@ -213,6 +213,235 @@ __global__ void __launch_bounds__(kCfThreads, 2) call_filter_kernel(CfParams p) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// TMA-pipelined variant (diploid, int32/float32 [L][S] fields, at most kTmaMaxFields distinct fields).
+// Work item = (2048-sample slab, chunk of loci); persistent CTAs walk their items locus by locus.  A producer
+// warp brings the slab of one locus — GT (12 KB) and every FORMAT field the filters read (8 KB each) — into a
+// shared-memory ring with 1-D bulk TMA copies; 256 consumer threads own 8 consecutive samples each (per-sample
+// counters in registers / thread-private shared-memory columns), patch filtered calls IN PLACE in the ring stage,
+// and one elected thread writes the stage's GT back to the masked-genotype tensor with a bulk TMA store
+// (contiguous 12 KB instead of 48-byte-strided 16-byte stores).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTmaMaxFields = 4;
+constexpr int kTmaMaxStages = 8;
+constexpr int kTmaGtBytes = kSlabSamples * 6;       // 12288
+constexpr int kTmaFieldBytes = kSlabSamples * 4;    // 8192
+
+struct CfTmaParams {
+    CfParams base;
+    int n_fields;                       // distinct fields staged per locus
+    int field_of_slot[kTmaMaxFields];   // TRT_FMT_* of each staged slot
+    int slot_of_spec[kMaxSpecs];        // slot the filter reads (numerator for RATIO_GT)
+    int dp_slot;                        // slot of TRT_FMT_DP for ratio filters (-1: none)
+    int acc_slot;                       // slot of the depth field summed into totaldp (-1: none)
+    int stages;
+    int loci_per_item;
+    int64_t n_slabs, n_items;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfTmaParams q) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const CfParams& p = q.base;
+    const int stages = q.stages;
+    const size_t stage_bytes = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes;
+    unsigned char* ring = smem;
+    unsigned int* fcnt = (unsigned int*)(smem + (size_t)stages * stage_bytes);   // [n_specs][8][256] thread-private columns
+    uint64_t* full = (uint64_t*)(fcnt + (size_t)max(p.n_specs, 1) * kSlabSamples);
+    uint64_t* empty = full + kTmaMaxStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kCfThreads / 32) {
+        // ===== producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t item = blockIdx.x; item < q.n_items; item += gridDim.x) {
+                const int64_t slab = item % q.n_slabs, chunk = item / q.n_slabs;
+                const int64_t s0 = slab * kSlabSamples;
+                const int64_t ns = min((int64_t)kSlabSamples, p.S - s0);
+                const uint32_t gt_bytes = (uint32_t)((ns * 6 + 15) & ~int64_t(15));
+                const uint32_t f_bytes = (uint32_t)(ns * 4);                 // S % 4 == 0 on this path
+                const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
+                for (int64_t l = l0; l < l1; l++) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    unsigned char* dst = ring + (size_t)stage * stage_bytes;
+                    mbar_arrive_expect_tx(&full[stage], gt_bytes + (uint32_t)q.n_fields * f_bytes);
+                    tma_load_1d(dst, (const char*)p.gt + (size_t)l * p.pitch + (size_t)s0 * 6, gt_bytes, &full[stage]);
+                    for (int k = 0; k < q.n_fields; k++)
+                        tma_load_1d(dst + kTmaGtBytes + (size_t)k * kTmaFieldBytes,
+                                    (const char*)p.fmt[q.field_of_slot[k]] + ((size_t)l * p.S + s0) * 4, f_bytes, &full[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int pending_stage = -1;      // thread 0: stage whose GT is still being read by the previous bulk store
+    for (int64_t item = blockIdx.x; item < q.n_items; item += gridDim.x) {
+        const int64_t slab = item % q.n_slabs, chunk = item / q.n_slabs;
+        const int64_t s0 = slab * kSlabSamples;
+        const int64_t ns = min((int64_t)kSlabSamples, p.S - s0);
+        const uint32_t gt_bytes = (uint32_t)((ns * 6 + 15) & ~int64_t(15));
+        const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
+        const int64_t sb = s0 + (int64_t)tid * kSlab;          // first sample of this thread
+        for (int f = 0; f < p.n_specs; f++)
+#pragma unroll
+            for (int j = 0; j < kSlab; j++) fcnt[(f * kSlab + j) * kCfThreads + tid] = 0;
+        int ncalls[kSlab];
+        long long dps[kSlab];
+        unsigned int poison = 0;
+#pragma unroll
+        for (int j = 0; j < kSlab; j++) { ncalls[j] = 0; dps[j] = 0; }
+
+        for (int64_t l = l0; l < l1; l++) {
+            mbar_wait(&full[stage], phase);
+            unsigned char* st = ring + (size_t)stage * stage_bytes;
+            uint4* gsrc = reinterpret_cast<uint4*>(st + (size_t)tid * 48);
+            const uint4 v0 = gsrc[0], v1 = gsrc[1], v2 = gsrc[2];
+            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            int16_t h[24];
+#pragma unroll
+            for (int k = 0; k < 24; k++) h[k] = (int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
+            uint32_t fired[8];
+            bool nocall[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                fired[j] = 0;
+                nocall[j] = (h[3 * j] == -1) | (h[3 * j + 1] == -1);
+            }
+            int32_t den[8];
+            if (q.dp_slot >= 0) {
+                const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.dp_slot * kTmaFieldBytes + (size_t)tid * 32);
+                const int4 a = d[0], b = d[1];
+                den[0] = a.x; den[1] = a.y; den[2] = a.z; den[3] = a.w; den[4] = b.x; den[5] = b.y; den[6] = b.z; den[7] = b.w;
+            }
+            for (int f = 0; f < p.n_specs; f++) {
+                const CfSpec sp = p.specs[f];
+                const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.slot_of_spec[f] * kTmaFieldBytes + (size_t)tid * 32);
+                const int4 a = d[0], b = d[1];
+                const int32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    bool hit;
+                    if (sp.kind == TRT_CF_MIN || sp.kind == TRT_CF_MAX) {
+                        if (sp.is_float) {
+                            const float x = __int_as_float(raw[j]);
+                            hit = (sp.kind == TRT_CF_MIN) ? (x < sp.thr_f32) : (x > sp.thr_f32);
+                        } else {
+                            const double val = (double)raw[j];
+                            hit = (sp.kind == TRT_CF_MIN) ? (val < sp.thr) : (val > sp.thr);
+                        }
+                    } else if (sp.kind == TRT_CF_RATIO_GT) {
+                        hit = ((double)raw[j] / (double)den[j]) > sp.thr;     // numpy int32/int32 -> float64
+                    } else {                                                   // TRT_CF_HOST_VALUE
+                        hit = !isnan(__int_as_float(raw[j]));
+                    }
+                    if (hit && sb + j < p.S) {
+                        fired[j] |= 1u << f;
+                        if (!nocall[j]) fcnt[(f * kSlab + j) * kCfThreads + tid] += 1;
+                    }
+                }
+            }
+            bool changed = false;
+            int32_t dpv[8];
+            if (q.acc_slot >= 0) {
+                const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 32);
+                const int4 a = d[0], b = d[1];
+                dpv[0] = a.x; dpv[1] = a.y; dpv[2] = a.z; dpv[3] = a.w; dpv[4] = b.x; dpv[5] = b.y; dpv[6] = b.z; dpv[7] = b.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (sb + j >= p.S) continue;
+                const bool pass = (fired[j] == 0) && !nocall[j];
+                if (pass) {
+                    ncalls[j]++;
+                    if (q.acc_slot >= 0) {
+                        const int d = dpv[j];
+                        if (d == INT_MIN) poison |= 1u << j;
+                        else if (d < 0) atomicMin(p.neg_dp_locus, (int)l);
+                        else dps[j] += d;
+                    }
+                }
+                if (fired[j] != 0 && !nocall[j]) {   // filtered call: every haplotype -> '.', unphased
+                    h[3 * j] = -1;
+                    h[3 * j + 1] = -1;
+                    h[3 * j + 2] = 0;
+                    changed = true;
+                }
+            }
+            if (p.call_mask && sb < p.S) {
+                uint32_t* cm = p.call_mask + (size_t)l * p.S + sb;
+                if (sb + 8 <= p.S) {
+                    uint32_t m[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) m[j] = fired[j] | (nocall[j] ? 0x80000000u : 0u);
+                    reinterpret_cast<uint4*>(cm)[0] = make_uint4(m[0], m[1], m[2], m[3]);
+                    reinterpret_cast<uint4*>(cm)[1] = make_uint4(m[4], m[5], m[6], m[7]);
+                } else {
+                    for (int j = 0; j < 8 && sb + j < p.S; j++) cm[j] = fired[j] | (nocall[j] ? 0x80000000u : 0u);
+                }
+            }
+            if (changed) {
+                uint32_t o[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) o[k] = (uint32_t)(uint16_t)h[2 * k] | ((uint32_t)(uint16_t)h[2 * k + 1] << 16);
+                gsrc[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                gsrc[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                gsrc[2] = make_uint4(o[8], o[9], o[10], o[11]);
+            }
+            fence_proxy_async_smem();                 // generic-proxy writes -> visible to the bulk store
+            asm volatile("bar.sync 1, %0;" ::"n"(kCfThreads) : "memory");
+            if (tid == 0) {
+                tma_store_1d((char*)p.gt_out + (size_t)l * p.pitch + (size_t)s0 * 6, st, gt_bytes);
+                tma_store_commit();
+                if (pending_stage >= 0) {
+                    tma_store_wait_read<1>();        // the PREVIOUS store has finished reading its stage
+                    mbar_arrive(&empty[pending_stage]);
+                }
+                pending_stage = stage;
+            }
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        // ---- flush the per-sample accumulators of this item -----------------------------------------
+#pragma unroll
+        for (int j = 0; j < kSlab; j++) {
+            if (sb + j >= p.S) continue;
+            if (ncalls[j]) atomicAdd((unsigned long long*)&p.numcalls[sb + j], (unsigned long long)ncalls[j]);
+            if (dps[j]) atomicAdd((unsigned long long*)&p.dpsum[sb + j], (unsigned long long)dps[j]);
+            if ((poison >> j) & 1u) atomicOr(&p.dp_poison[sb + j], 1u);
+            for (int f = 0; f < p.n_specs; f++) {
+                const unsigned int c = fcnt[(f * kSlab + j) * kCfThreads + tid];
+                if (c) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + sb + j], (unsigned long long)c);
+            }
+        }
+    }
+    if (tid == 0 && pending_stage >= 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&empty[pending_stage]);
+    }
+}
+
 // generic ploidy variant (P != 2): one thread per call, plain atomics; correctness path only
 __global__ void call_filter_generic_kernel(CfParams p, int P) {
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.L * p.S;
@@ -389,7 +618,56 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
     trt_timer_begin(ctx);
     TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
     if (L > 0 && S > 0) {
-        if (ctx->P == 2 && !p.dp_is_float) {
+        // TMA-pipelined path: diploid, plain [L][S] 4-byte fields, vector-aligned rows, no per-call float64 output
+        bool tma_ok = ctx->P == 2 && !p.dp_is_float && !p.trig && (S % 4) == 0 && S >= kSlabSamples && (ctx->gt_pitch % 16) == 0 &&
+                      ((uintptr_t)ctx->d_gt % 16) == 0 && !getenv("TRT_CF_LEGACY");
+        CfTmaParams q;
+        memset(&q, 0, sizeof(q));
+        q.dp_slot = q.acc_slot = -1;
+        if (tma_ok) {
+            auto slot_of = [&](int field) -> int {
+                for (int k = 0; k < q.n_fields; k++)
+                    if (q.field_of_slot[k] == field) return k;
+                if (q.n_fields == kTmaMaxFields || ctx->fmt_ncol[field] != 1 || ((uintptr_t)ctx->d_fmt[field] % 16) != 0) return -1;
+                q.field_of_slot[q.n_fields] = field;
+                return q.n_fields++;
+            };
+            for (int f = 0; f < n_specs && tma_ok; f++) {
+                if (p.specs[f].kind >= TRT_CF_QEXP_HET && p.specs[f].kind <= TRT_CF_QEXP_TOT) { tma_ok = false; break; }
+                q.slot_of_spec[f] = slot_of(p.specs[f].field);
+                if (q.slot_of_spec[f] < 0) tma_ok = false;
+                if (p.specs[f].kind == TRT_CF_RATIO_GT) {
+                    q.dp_slot = slot_of(TRT_FMT_DP);
+                    if (q.dp_slot < 0) tma_ok = false;
+                }
+            }
+            if (tma_ok && p.dp_field >= 0) {
+                q.acc_slot = slot_of(p.dp_field);
+                if (q.acc_slot < 0) tma_ok = false;
+            }
+        }
+        if (tma_ok) {
+            q.base = p;
+            const size_t stage_bytes = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes;
+            const size_t fixed = (size_t)std::max(n_specs, 1) * kSlabSamples * 4 + 2 * kTmaMaxStages * 8 + 128;
+            int stages = (int)(((size_t)ctx->max_smem_optin - fixed) / stage_bytes);
+            stages = std::min(stages, kTmaMaxStages);
+            if (stages < 3) tma_ok = false;
+            else {
+                q.stages = stages;
+                q.n_slabs = (S + kSlabSamples - 1) / kSlabSamples;
+                // items small enough to balance 148 persistent CTAs, large enough to amortise the counter flush
+                int64_t per = std::max<int64_t>(32, std::min<int64_t>(256, (L * q.n_slabs) / ((int64_t)ctx->sm_count * 24) + 1));
+                q.loci_per_item = (int)per;
+                q.n_items = q.n_slabs * ((L + per - 1) / per);
+                const size_t smem = (size_t)stages * stage_bytes + fixed;
+                TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const int grid = (int)std::min<int64_t>(q.n_items, ctx->sm_count);
+                call_filter_tma_kernel<<<grid, kCfThreads + 32, smem, ctx->stream>>>(q);
+            }
+        }
+        if (tma_ok) {
+        } else if (ctx->P == 2 && !p.dp_is_float) {
             const int64_t slabs = (S + kSlabSamples - 1) / kSlabSamples;
             // enough CTAs to fill the machine several times over, chunks of at least 64 loci
             int64_t chunks = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 16 + slabs - 1) / slabs);
