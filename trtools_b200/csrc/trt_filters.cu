@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "trt_internal.cuh"
 #include "trt_scan.cuh"
@@ -36,7 +37,10 @@ struct CfSpec {
     int is_float;   // field holds float32
     double thr;
     float thr_f32;  // threshold rounded to float32 (numpy weak-scalar comparison for float32 arrays)
+    int variant;    // CFV_*: the comparison the TMA kernel runs for this filter (kind x dtype, resolved on the host)
+    long long thr_i64;   // int32 fields: value < thr <=> value < ceil(thr); value > thr <=> value > floor(thr)
 };
+enum { CFV_NEVER = 0, CFV_MIN_I32, CFV_MAX_I32, CFV_MIN_F32, CFV_MAX_F32, CFV_RATIO_FAST, CFV_RATIO_EXACT, CFV_HOST };
 
 struct CfParams {
     const int16_t* gt;
@@ -248,6 +252,7 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+template <bool WANT_MASK>
 __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfTmaParams q) {
     extern __shared__ __align__(128) unsigned char smem[];
     const CfParams& p = q.base;
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
         const uint32_t gt_bytes = (uint32_t)((ns * 6 + 15) & ~int64_t(15));
         const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
         const int64_t sb = s0 + (int64_t)tid * kSlab;          // first sample of this thread
+        const uint32_t valid_mask = (sb + 8 <= p.S) ? 0xffu : (sb >= p.S ? 0u : ((1u << (int)(p.S - sb)) - 1u));
         for (int f = 0; f < p.n_specs; f++)
 #pragma unroll
             for (int j = 0; j < kSlab; j++) fcnt[(f * kSlab + j) * kCfThreads + tid] = 0;
@@ -319,96 +325,144 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
             unsigned char* st = ring + (size_t)stage * stage_bytes;
             uint4* gsrc = reinterpret_cast<uint4*>(st + (size_t)tid * 48);
             const uint4 v0 = gsrc[0], v1 = gsrc[1], v2 = gsrc[2];
-            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            int16_t h[24];
-#pragma unroll
-            for (int k = 0; k < 24; k++) h[k] = (int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
-            uint32_t fired[8];
-            bool nocall[8];
+            uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            // bit j of the 8-bit masks = call j of this thread
+            uint32_t nocall = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                fired[j] = 0;
-                nocall[j] = (h[3 * j] == -1) | (h[3 * j + 1] == -1);
+                const int k0 = 3 * j, k1 = k0 + 1;
+                const uint32_t a = (k0 & 1) ? (w[k0 >> 1] >> 16) : (w[k0 >> 1] & 0xffffu);
+                const uint32_t b = (k1 & 1) ? (w[k1 >> 1] >> 16) : (w[k1 >> 1] & 0xffffu);
+                nocall |= ((a == 0xffffu) | (b == 0xffffu)) ? (1u << j) : 0u;
             }
-            int32_t den[8];
+            uint32_t fired_any = 0;
+            uint32_t fired[8];
+            if (WANT_MASK) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) fired[j] = 0;
+            }
+            double den[8];
+            int32_t deni[8];
             if (q.dp_slot >= 0) {
                 const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.dp_slot * kTmaFieldBytes + (size_t)tid * 32);
                 const int4 a = d[0], b = d[1];
-                den[0] = a.x; den[1] = a.y; den[2] = a.z; den[3] = a.w; den[4] = b.x; den[5] = b.y; den[6] = b.z; den[7] = b.w;
+                deni[0] = a.x; deni[1] = a.y; deni[2] = a.z; deni[3] = a.w; deni[4] = b.x; deni[5] = b.y; deni[6] = b.z; deni[7] = b.w;
+#pragma unroll
+                for (int j = 0; j < 8; j++) den[j] = (double)deni[j];
             }
             for (int f = 0; f < p.n_specs; f++) {
-                const CfSpec sp = p.specs[f];
+                const int variant = p.specs[f].variant;
                 const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.slot_of_spec[f] * kTmaFieldBytes + (size_t)tid * 32);
                 const int4 a = d[0], b = d[1];
                 const int32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint32_t hit = 0;
+                switch (variant) {      // uniform across the grid
+                    case CFV_MIN_I32: {
+                        const long long t = p.specs[f].thr_i64;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    bool hit;
-                    if (sp.kind == TRT_CF_MIN || sp.kind == TRT_CF_MAX) {
-                        if (sp.is_float) {
-                            const float x = __int_as_float(raw[j]);
-                            hit = (sp.kind == TRT_CF_MIN) ? (x < sp.thr_f32) : (x > sp.thr_f32);
-                        } else {
-                            const double val = (double)raw[j];
-                            hit = (sp.kind == TRT_CF_MIN) ? (val < sp.thr) : (val > sp.thr);
+                        for (int j = 0; j < 8; j++) hit |= ((long long)raw[j] < t) ? (1u << j) : 0u;
+                    } break;
+                    case CFV_MAX_I32: {
+                        const long long t = p.specs[f].thr_i64;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hit |= ((long long)raw[j] > t) ? (1u << j) : 0u;
+                    } break;
+                    case CFV_MIN_F32: {
+                        const float t = p.specs[f].thr_f32;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hit |= (__int_as_float(raw[j]) < t) ? (1u << j) : 0u;
+                    } break;
+                    case CFV_MAX_F32: {
+                        const float t = p.specs[f].thr_f32;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hit |= (__int_as_float(raw[j]) > t) ? (1u << j) : 0u;
+                    } break;
+                    case CFV_RATIO_FAST: {
+                        // RN(raw/den) > thr decided without dividing when raw is clear of thr*den by 2^-50 relative
+                        // (thr > 0 finite, den > 0, raw >= 0); the exact float64 division otherwise (numpy int32/int32)
+                        const double t = p.specs[f].thr;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const double r = (double)raw[j];
+                            const double prod = t * den[j];
+                            const double hi = fma(prod, 0x1p-50, prod), lo = fma(prod, -0x1p-50, prod);
+                            bool h1;
+                            if (deni[j] > 0 && raw[j] >= 0 && (r > hi || r < lo)) h1 = r > hi;
+                            else h1 = (r / den[j]) > t;
+                            hit |= h1 ? (1u << j) : 0u;
                         }
-                    } else if (sp.kind == TRT_CF_RATIO_GT) {
-                        hit = ((double)raw[j] / (double)den[j]) > sp.thr;     // numpy int32/int32 -> float64
-                    } else {                                                   // TRT_CF_HOST_VALUE
-                        hit = !isnan(__int_as_float(raw[j]));
-                    }
-                    if (hit && sb + j < p.S) {
-                        fired[j] |= 1u << f;
-                        if (!nocall[j]) fcnt[(f * kSlab + j) * kCfThreads + tid] += 1;
-                    }
+                    } break;
+                    case CFV_RATIO_EXACT: {
+                        const double t = p.specs[f].thr;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hit |= (((double)raw[j] / den[j]) > t) ? (1u << j) : 0u;
+                    } break;
+                    case CFV_HOST: {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hit |= !isnan(__int_as_float(raw[j])) ? (1u << j) : 0u;
+                    } break;
+                    default: break;
+                }
+                hit &= valid_mask;
+                fired_any |= hit;
+                uint32_t cnt = hit & ~nocall;
+                if (cnt) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if ((cnt >> j) & 1u) fcnt[(f * kSlab + j) * kCfThreads + tid] += 1;
+                }
+                if (WANT_MASK) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) fired[j] |= ((hit >> j) & 1u) << f;
                 }
             }
-            bool changed = false;
-            int32_t dpv[8];
+            const uint32_t pass = ~fired_any & ~nocall & valid_mask;
+#pragma unroll
+            for (int j = 0; j < 8; j++) ncalls[j] += (pass >> j) & 1u;
             if (q.acc_slot >= 0) {
                 const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 32);
                 const int4 a = d[0], b = d[1];
-                dpv[0] = a.x; dpv[1] = a.y; dpv[2] = a.z; dpv[3] = a.w; dpv[4] = b.x; dpv[5] = b.y; dpv[6] = b.z; dpv[7] = b.w;
-            }
+                const int32_t dpv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (sb + j >= p.S) continue;
-                const bool pass = (fired[j] == 0) && !nocall[j];
-                if (pass) {
-                    ncalls[j]++;
-                    if (q.acc_slot >= 0) {
-                        const int d = dpv[j];
-                        if (d == INT_MIN) poison |= 1u << j;
-                        else if (d < 0) atomicMin(p.neg_dp_locus, (int)l);
-                        else dps[j] += d;
+                for (int j = 0; j < 8; j++) {
+                    const bool ps = (pass >> j) & 1u;
+                    const int dd = dpv[j];
+                    if (ps && dd < 0) {                       // rare: missing depth poisons, negative depth is an error
+                        if (dd == INT_MIN) poison |= 1u << j;
+                        else atomicMin(p.neg_dp_locus, (int)l);
+                    } else {
+                        dps[j] += ps ? (long long)dd : 0ll;
                     }
                 }
-                if (fired[j] != 0 && !nocall[j]) {   // filtered call: every haplotype -> '.', unphased
-                    h[3 * j] = -1;
-                    h[3 * j + 1] = -1;
-                    h[3 * j + 2] = 0;
-                    changed = true;
-                }
             }
-            if (p.call_mask && sb < p.S) {
+            if (WANT_MASK && sb < p.S) {
                 uint32_t* cm = p.call_mask + (size_t)l * p.S + sb;
-                if (sb + 8 <= p.S) {
-                    uint32_t m[8];
+                uint32_t m[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) m[j] = fired[j] | (nocall[j] ? 0x80000000u : 0u);
+                for (int j = 0; j < 8; j++) m[j] = fired[j] | (((nocall >> j) & 1u) ? 0x80000000u : 0u);
+                if (sb + 8 <= p.S) {
                     reinterpret_cast<uint4*>(cm)[0] = make_uint4(m[0], m[1], m[2], m[3]);
                     reinterpret_cast<uint4*>(cm)[1] = make_uint4(m[4], m[5], m[6], m[7]);
                 } else {
-                    for (int j = 0; j < 8 && sb + j < p.S; j++) cm[j] = fired[j] | (nocall[j] ? 0x80000000u : 0u);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (sb + j < p.S) cm[j] = m[j];
                 }
             }
-            if (changed) {
-                uint32_t o[12];
+            const uint32_t filt = fired_any & ~nocall;       // filtered calls: every haplotype -> '.', unphased
+            if (filt) {
 #pragma unroll
-                for (int k = 0; k < 12; k++) o[k] = (uint32_t)(uint16_t)h[2 * k] | ((uint32_t)(uint16_t)h[2 * k + 1] << 16);
-                gsrc[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                gsrc[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                gsrc[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                for (int j = 0; j < 8; j++) {
+                    if (!((filt >> j) & 1u)) continue;
+#pragma unroll
+                    for (int k = 3 * j; k < 3 * j + 3; k++) {
+                        const uint32_t val = (k == 3 * j + 2) ? 0u : 0xffffu;
+                        w[k >> 1] = (k & 1) ? ((w[k >> 1] & 0x0000ffffu) | (val << 16)) : ((w[k >> 1] & 0xffff0000u) | val);
+                    }
+                }
+                gsrc[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                gsrc[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                gsrc[2] = make_uint4(w[8], w[9], w[10], w[11]);
             }
             fence_proxy_async_smem();                 // generic-proxy writes -> visible to the bulk store
             asm volatile("bar.sync 1, %0;" ::"n"(kCfThreads) : "memory");
@@ -589,6 +643,23 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
             return trt_set_error(ctx, TRT_EINVAL, "trt_call_filters: ratio filter %d needs int32 fields", f);
         p.specs[f].thr = s.threshold;
         p.specs[f].thr_f32 = (float)s.threshold;
+        {   // comparison variant of the TMA kernel
+            CfSpec& c = p.specs[f];
+            const double t = s.threshold;
+            c.thr_i64 = 0;
+            c.variant = CFV_NEVER;
+            if (s.kind == TRT_CF_HOST_VALUE) c.variant = CFV_HOST;
+            else if (s.kind == TRT_CF_RATIO_GT) c.variant = (t > 0.0 && std::isfinite(t)) ? CFV_RATIO_FAST : CFV_RATIO_EXACT;
+            else if (s.kind == TRT_CF_MIN || s.kind == TRT_CF_MAX) {
+                if (c.is_float) c.variant = (s.kind == TRT_CF_MIN) ? CFV_MIN_F32 : CFV_MAX_F32;   // NaN threshold: never true
+                else if (!std::isnan(t)) {
+                    const double lim = 4.0e18;
+                    const double e = (s.kind == TRT_CF_MIN) ? ceil(t) : floor(t);
+                    c.thr_i64 = (long long)std::max(-lim, std::min(lim, e));
+                    c.variant = (s.kind == TRT_CF_MIN) ? CFV_MIN_I32 : CFV_MAX_I32;
+                }
+            }
+        }
     }
     p.dp_field = (dp_field_id >= 0 && dp_field_id < TRT_FMT_NFIELDS && ctx->d_fmt[dp_field_id]) ? dp_field_id : -1;
     p.dp_is_float = (p.dp_field >= 0) ? ctx->fmt_is_float[p.dp_field] : 0;
@@ -661,9 +732,14 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
                 q.loci_per_item = (int)per;
                 q.n_items = q.n_slabs * ((L + per - 1) / per);
                 const size_t smem = (size_t)stages * stage_bytes + fixed;
-                TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const int grid = (int)std::min<int64_t>(q.n_items, ctx->sm_count);
-                call_filter_tma_kernel<<<grid, kCfThreads + 32, smem, ctx->stream>>>(q);
+                if (p.call_mask) {
+                    TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    call_filter_tma_kernel<true><<<grid, kCfThreads + 32, smem, ctx->stream>>>(q);
+                } else {
+                    TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    call_filter_tma_kernel<false><<<grid, kCfThreads + 32, smem, ctx->stream>>>(q);
+                }
             }
         }
         if (tma_ok) {

@@ -62,6 +62,9 @@ struct trt_ctx {
 
     // stats scratch (device)
     DevBuf  ac, ac_part, lc, group_masks, stat_f64, stat_i32, work_counter;
+    DevBuf  scan_lists;              // per-tier locus lists of the current block (trt_scan.cu)
+    bool    scan_lists_valid = false;
+    int     scan_tier_off[8] = {0};   // list offsets per tier (+ end)
     bool    want_ac_part = false;
     // dumpSTR scratch
     DevBuf  cf_specs, call_mask, trig, samp_counts, samp_dp, misc;

@@ -139,14 +139,13 @@ __device__ __forceinline__ void bump2(uint16_t* my, unsigned i0, unsigned i1) {
     *p1 = (uint16_t)(x1 + e);
 }
 
-// next locus of this CTA that belongs to `tier` (or L)
-__device__ __forceinline__ int64_t next_locus(const ScanParams& p, int64_t l, int tier, int& A, int& a0) {
-    for (; l < p.L; l += gridDim.x) {
-        a0 = p.locus_off[l];
-        A = p.locus_off[l + 1] - a0;
-        if (scan_tier(A) == tier) return l;
-    }
-    return p.L;
+// metadata of the i-th locus of this launch's tier list (or L past the end)
+__device__ __forceinline__ int64_t list_locus(const ScanParams& p, int i, int& A, int& a0) {
+    if (i >= p.n_list) return p.L;
+    const int64_t l = p.list[i];
+    a0 = p.locus_off[l];
+    A = p.locus_off[l + 1] - a0;
+    return l;
 }
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -189,8 +188,8 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int A, a0;
-            for (int64_t l = next_locus(p, blockIdx.x, tier, A, a0); l < p.L; l = next_locus(p, l + gridDim.x, tier, A, a0)) {
+            for (int i = blockIdx.x; i < p.n_list; i += gridDim.x) {
+                const int64_t l = p.list[i];
                 const char* src = (const char*)p.gt + (size_t)l * p.pitch;
                 for (int c = 0; c < nchunks; c++) {
                     mbar_wait(&hdr->empty[stage], phase ^ 1u);
@@ -213,10 +212,12 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     int parity = 0;
     long long dbg_wait = 0, dbg_proc = 0, dbg_end = 0, dbg_chunks = 0;
     int A, a0, A_next = 0, a0_next = 0;
-    int64_t l = next_locus(p, blockIdx.x, tier, A, a0);
+    int li = blockIdx.x;
+    int64_t l = list_locus(p, li, A, a0);
     while (l < p.L) {
         // metadata of the following locus is fetched now so its latency hides under this locus' stream
-        const int64_t l_next = next_locus(p, l + gridDim.x, tier, A_next, a0_next);
+        li += gridDim.x;
+        const int64_t l_next = list_locus(p, li, A_next, a0_next);
         const unsigned D = (unsigned)A + 3u, Dm1 = D - 1u;
         const bool sq = pairs_square(A);
 
@@ -275,14 +276,17 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
         for (int b0 = half * 32; b0 < nrows; b0 += 64) {
             const int b = b0 + lane;
             if (b < nrows) {
-                uint32_t* rowp = (uint32_t*)table + (size_t)b * (kPT / 2) + pair * 32;
+                // this pair's 64 cells of row b = 128 B = 8 x 16 B; lanes own different rows (same bank offset), so each
+                // rotates its 16-byte slot: the 8 lanes of a quarter-warp hit 8 different bank groups (conflict-free)
+                uint4* rowp = (uint4*)((uint32_t*)table + (size_t)b * (kPT / 2) + pair * 32);
                 unsigned sum = 0;
-#pragma unroll 8
-                for (int k = 0; k < 32; k++) {
-                    const int kk = (k + lane) & 31;       // rotate: the 32 lanes hit 32 different banks
-                    const uint32_t x = rowp[kk];
-                    rowp[kk] = 0u;
-                    sum += (x & 0xffffu) + (x >> 16);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int kk = (k + lane) & 7;
+                    const uint4 x = rowp[kk];
+                    rowp[kk] = make_uint4(0u, 0u, 0u, 0u);
+                    sum += (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) +
+                           (x.w & 0xffffu) + (x.w >> 16);
                 }
                 part[b] = sum;
             }
@@ -423,9 +427,8 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
     if (warp == kWWarps) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
-                const int A = p.locus_off[l + 1] - p.locus_off[l];
-                if (scan_tier(A) != TIER_WIDE) continue;
+            for (int i = blockIdx.x; i < p.n_list; i += gridDim.x) {
+                const int64_t l = p.list[i];
                 const char* src = (const char*)p.gt + (size_t)l * p.pitch;
                 for (int c = 0; c < nchunks; c++, it++) {
                     const int stage = it % kWStages;
@@ -443,10 +446,10 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
 
     uint16_t* my = cnt + tid;
     uint32_t it = 0;
-    for (int64_t l = blockIdx.x; l < p.L; l += gridDim.x) {
+    for (int i = blockIdx.x; i < p.n_list; i += gridDim.x) {
+        const int64_t l = p.list[i];
         const int a0 = p.locus_off[l];
         const int A = p.locus_off[l + 1] - a0;
-        if (scan_tier(A) != TIER_WIDE) continue;
         for (int a = tid; a < A; a += kWT)
             hdr->cls[a] = ((uint32_t)p.len_class[a0 + a] << 16) | (uint32_t)p.seq_class[a0 + a];
         wbar();
@@ -555,8 +558,10 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
         TRT_CUDA(cudaMemsetAsync(ctx->work_counter.p, 0, 64, ctx->stream));
         sp.dbg = (unsigned long long*)ctx->work_counter.p;
     }
+    sp.list = nullptr;
+    sp.n_list = 0;
     sp.stream_only = getenv("TRT_SCAN_STREAM_ONLY") ? 1 : 0;   // HBM-read ceiling of this access pattern (calibration)
-    // which tiers occur in this block
+    // which tiers occur in this block, and the locus list of each (cached per block: the allele table fixes them)
     int n_tier[TIER_COUNT] = {0};
     int max_in_tier[TIER_COUNT] = {0};
     int rows_in_tier[TIER_COUNT] = {0};
@@ -567,10 +572,29 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
         max_in_tier[t] = std::max(max_in_tier[t], A);
         rows_in_tier[t] = std::max(rows_in_tier[t], pairs_rows(A));
     }
-    const int grid_persist = (int)std::min<int64_t>(L, ctx->sm_count);
+    if (!ctx->scan_lists_valid) {
+        std::vector<int32_t> lists((size_t)L);
+        int off[TIER_COUNT + 1];
+        off[0] = 0;
+        for (int t = 0; t < TIER_COUNT; t++) off[t + 1] = off[t] + n_tier[t];
+        int fill[TIER_COUNT];
+        for (int t = 0; t < TIER_COUNT; t++) fill[t] = off[t];
+        for (int64_t l = 0; l < L; l++) {
+            const int A = ctx->h_locus_off[l + 1] - ctx->h_locus_off[l];
+            lists[(size_t)fill[fast ? scan_tier(A) : TIER_GENERIC]++] = (int32_t)l;
+        }
+        TRT_TRY(trt_ensure(ctx, ctx->scan_lists, (size_t)L * 4 + 16));
+        if (L) TRT_CUDA(cudaMemcpyAsync(ctx->scan_lists.p, lists.data(), (size_t)L * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRT_CUDA(cudaStreamSynchronize(ctx->stream));   // `lists` is a local
+        for (int t = 0; t <= TIER_COUNT; t++) ctx->scan_tier_off[t] = off[t];
+        ctx->scan_lists_valid = true;
+    }
+    const int grid_persist = (int)std::min<int64_t>(std::max<int64_t>(L, 1), ctx->sm_count);
     const size_t smem_limit = (size_t)ctx->max_smem_optin;
     for (int t = TIER_PAIRS_A; t <= TIER_PAIRS_B; t++) {
         if (!n_tier[t]) continue;
+        sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[t];
+        sp.n_list = n_tier[t];
         const int rows = rows_in_tier[t];
         const size_t table = (size_t)(rows + 1) * kPRowBytes;
         int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
@@ -579,22 +603,24 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
         if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
         if (d_mask) {
             TRT_TRY(set_smem(ctx, scan_pairs_kernel<true>, smem));
-            scan_pairs_kernel<true><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
+            scan_pairs_kernel<true><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
         } else {
             TRT_TRY(set_smem(ctx, scan_pairs_kernel<false>, smem));
-            scan_pairs_kernel<false><<<grid_persist, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
+            scan_pairs_kernel<false><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
         }
         TRT_KERNEL_CHECK();
     }
     if (n_tier[TIER_WIDE]) {
+        sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[TIER_WIDE];
+        sp.n_list = n_tier[TIER_WIDE];
         const int amax = max_in_tier[TIER_WIDE];
         const size_t smem = (size_t)kWStages * kWChunkBytes + sizeof(WideHeader) + (size_t)amax * kWT * 2;
         if (d_mask) {
             TRT_TRY(set_smem(ctx, scan_wide_kernel<true>, smem));
-            scan_wide_kernel<true><<<grid_persist, kWThreads, smem, ctx->stream>>>(sp, amax);
+            scan_wide_kernel<true><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
         } else {
             TRT_TRY(set_smem(ctx, scan_wide_kernel<false>, smem));
-            scan_wide_kernel<false><<<grid_persist, kWThreads, smem, ctx->stream>>>(sp, amax);
+            scan_wide_kernel<false><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
         }
         TRT_KERNEL_CHECK();
     }

@@ -20,6 +20,8 @@ struct ScanParams {
     int fast_enabled;      // the TMA tiers are in use (diploid, enough samples)
     unsigned long long* dbg;   // optional [4]: cycles waiting / processing / end-of-locus, chunks (warp 1 of CTA 0)
     int stream_only;       // calibration: consumers only drain the TMA ring (results are meaningless)
+    const int32_t* list;   // loci of the tier this launch handles (built on the host per block)
+    int n_list;
 };
 
 enum { TIER_PAIRS_A = 0, TIER_PAIRS_B = 1, TIER_WIDE = 2, TIER_GENERIC = 3, TIER_COUNT = 4 };
