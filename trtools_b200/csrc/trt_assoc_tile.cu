@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
         unsigned D[kNL];
 #pragma unroll
         for (int h = 0; h < kNL; h++) {
-            // thread-private length table by digit d = allele + 2: pad -> -2 - ref, no-call -> 0, allele -> len - ref
-            // (the per-haplotype shift by the reference length is the conditioning shift of the generic kernel)
+            // thread-private length table by digit d = allele + 2: pad -> -2 - ref, no-call -> NaN, allele -> len - ref
+            // (the per-haplotype shift by the reference length is the conditioning shift of the generic kernel);
+            // g = tab[da] + tab[db] is NaN exactly when a haplotype is missing or out of range: "called" = (g == g)
             const int64_t l = (int64_t)tile * kTLoci + h * kTCons + tid;
             double ref = 0.0;
             int a0 = 0, A = 0;
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
             if (A > 0) ref = p.allele_len[a0];
             D[h] = (unsigned)A + 2u;
             double* t = mytab + h * kTCons;
-            t[0] = -2.0 - ref;
-            t[kTLoci] = 0.0;
+            t[0] = valid[h] ? -2.0 - ref : nan("");
+            t[kTLoci] = nan("");
             for (int a = 0; a < A; a++) t[(a + 2) * kTLoci] = p.allele_len[a0 + a] - ref;
         }
         double accz[kNL][K], sg[kNL], sgg[kNL];
@@ -188,15 +189,15 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                         const int a = (k0 & 1) ? ((int)w[h][k0 >> 1] >> 16) : (int)(short)(w[h][k0 >> 1] & 0xffffu);
                         const int b = (k1 & 1) ? ((int)w[h][k1 >> 1] >> 16) : (int)(short)(w[h][k1 >> 1] & 0xffffu);
                         const unsigned da = (unsigned)(a + 2), db = (unsigned)(b + 2);
-                        const bool va = (da < D[h]) & (da != 1u), vb = (db < D[h]) & (db != 1u);
                         const double* t = mytab + h * kTCons;
-                        const double la = t[(va ? da : 1u) * kTLoci];
-                        const double lb = t[(vb ? db : 1u) * kTLoci];
-                        const bool called = va & vb;
-                        const bool ok = called & ind & valid[h];
-                        const double g = ok ? la + lb : 0.0;
-                        n[h] += ok ? 1 : 0;
-                        mask[h] |= ((ind & !called) ? 1u : 0u) << sidx;
+                        const double la = t[((da < D[h]) ? da : 1u) * kTLoci];
+                        const double lb = t[((db < D[h]) ? db : 1u) * kTLoci];
+                        const double gs = la + lb;
+                        const bool called = (gs == gs);             // an invalid locus has D = 2 and a NaN pad entry: never called
+                        const bool ok = called & ind;
+                        const double g = ok ? gs : 0.0;
+                        if (ok) n[h]++;
+                        if (ind & !called) mask[h] |= 1u << sidx;
                         sg[h] += g;
                         sgg[h] = fma(g, g, sgg[h]);      // explicit fma: the library builds with -fmad=false
 #pragma unroll
@@ -254,40 +255,42 @@ __global__ void assoc_reduce_mom_kernel(const double* __restrict__ part, int nse
     mom[i] = s;
 }
 
-// exact down-dates from the uncalled-sample masks: warp per locus, lanes own entries of the K(K+1)/2 triangle of
-// sum z z' over the uncalled design rows, z = (c_1 .. c_{K-1}, y)
-template <int KP>
-__global__ void __launch_bounds__(256) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
-    constexpr int kR = (KP * (KP + 1) / 2 + 31) / 32;
-    constexpr int kBatch = 8;
+// exact down-dates from the uncalled-sample masks: warp per locus.  The K x K matrix sum z z' over the uncalled design
+// rows (z = (c_1 .. c_{K-1}, y)) is tiled into 4 x 4 register blocks of its upper triangle: a lane owns one block of
+// one sample group, so a z-row staged in shared memory costs 4 LDS.128 for 16 DFMAs, and G = 32 / blocks samples
+// are processed by the warp at once (K = 12: 6 blocks, 5 samples in flight).  Groups are summed by shuffles per locus.
+template <int NB>
+__global__ void __launch_bounds__(256, 2) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
+    constexpr int kBlocks = NB * (NB + 1) / 2;
+    constexpr int kG = 32 / kBlocks;             // samples processed concurrently by a warp
+    constexpr int kBatch = (kG >= 8) ? kG : (kG * 2 >= 8 ? kG * 2 : kG * 3);   // z-rows staged per round trip to L2
+    constexpr int kZS = 18;                      // staged row pitch in doubles (144 B: odd multiple of 16 B)
     __shared__ uint16_t lst_all[8][32 * kTChunk];   // uncalled samples of a 32-chunk window, relative to its first sample
-    __shared__ double zs_all[8][kBatch][KP];
+    __shared__ __align__(16) double zs_all[8][kBatch][kZS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint16_t* lst = lst_all[wib];
-    double(*zs)[KP] = zs_all[wib];
+    double(*zs)[kZS] = zs_all[wib];
     const int ne = K * (K + 1) / 2;
-    int ea[kR], eb[kR];
-#pragma unroll
-    for (int r = 0; r < kR; r++) {
-        const int e = lane + 32 * r;
-        int a = 0, rem = e;
-        if (e < ne) {
-            while (rem >= K - a) { rem -= K - a; a++; }
-        } else {
-            rem = 0;
-        }
-        ea[r] = a;
-        eb[r] = a + rem;
-    }
+    // this lane's block (bi <= bj) and sample group
+    const int grp = lane / kBlocks, blk = lane % kBlocks;
+    int bi = 0, rem = blk;
+    while (rem >= NB - bi) { rem -= NB - bi; bi++; }
+    const int bj = bi + rem;
+    const bool worker = grp < kG;
+    // zero the staging rows once: columns >= K stay zero for the whole kernel
+    for (int i = lane; i < kBatch * kZS; i += 32) (&zs[0][0])[i] = 0.0;
+    __syncwarp();
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; l < p.L; l += nwarps) {
         if (p.locus_off[l + 1] - p.locus_off[l] > kAssocFastMaxAlleles) continue;   // generic-path locus
         const int64_t tile = l / kTLoci;
         const int tl = (int)(l % kTLoci);
         const uint32_t* mrow = p.masks + ((size_t)tile * p.nchunks) * kTLoci + tl;
-        double acc[kR];
+        double acc[4][4];
 #pragma unroll
-        for (int r = 0; r < kR; r++) acc[r] = 0.0;
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
         for (int cb = 0; cb < p.nchunks; cb += 32) {
             const int c = cb + lane;
             uint32_t m = (c < p.nchunks) ? mrow[(size_t)c * kTLoci] : 0u;
@@ -309,33 +312,57 @@ __global__ void __launch_bounds__(256) assoc_downdate_mask_kernel(TileParams p, 
             __syncwarp();
             const int64_t s_base = (int64_t)cb * kTChunk;
             for (int e0 = 0; e0 < total; e0 += kBatch) {
-                // z = (c_1 .. c_{K-1}, y): zt row holds [y, c_1 .. c_{K-1}, ...]
-                const int zsrc = (lane < K - 1) ? lane + 1 : 0;
-                double zv[kBatch];
+                // stage up to kBatch z-rows: lanes (2 rows per load round) fetch z = (c_1 .. c_{K-1}, y) from
+                // zt rows [y, c_1 .. c_{K-1}, ..]
+                const int sub = lane >> 4, col = lane & 15;
+                const int zsrc = (col < K - 1) ? col + 1 : 0;
+                double zv[(kBatch + 1) / 2];
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    const int e = e0 + j;
-                    zv[j] = 0.0;
-                    if (e < total && lane < K) zv[j] = p.zt[(size_t)(s_base + lst[e]) * ZW + zsrc];
+                for (int r = 0; r < (kBatch + 1) / 2; r++) {
+                    const int slot = 2 * r + sub, e = e0 + slot;
+                    zv[r] = 0.0;
+                    if (slot < kBatch && e < total && col < K) zv[r] = p.zt[(size_t)(s_base + lst[e]) * ZW + zsrc];
                 }
 #pragma unroll
-                for (int j = 0; j < kBatch; j++)
-                    if (lane < KP) zs[j][lane] = zv[j];
+                for (int r = 0; r < (kBatch + 1) / 2; r++) {
+                    const int slot = 2 * r + sub;
+                    if (slot < kBatch) zs[slot][col] = zv[r];      // rows past `total` become zero rows
+                }
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
+                for (int r0 = 0; r0 < kBatch; r0 += kG) {
+                    const int slot = r0 + grp;
+                    if (worker && slot < kBatch) {
+                        const double2* za2 = (const double2*)&zs[slot][4 * bi];
+                        const double2* zb2 = (const double2*)&zs[slot][4 * bj];
+                        const double2 a01 = za2[0], a23 = za2[1], b01 = zb2[0], b23 = zb2[1];
+                        const double za[4] = {a01.x, a01.y, a23.x, a23.y}, zb[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-                    for (int r = 0; r < kR; r++)
-                        if (32 * r < ne) acc[r] = fma(zs[j][ea[r]], zs[j][eb[r]], acc[r]);
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[i][j] = fma(za[i], zb[j], acc[i][j]);
+                    }
                 }
                 __syncwarp();
             }
         }
+        // sum the sample groups into group 0, then write the block's entries of the upper triangle
 #pragma unroll
-        for (int r = 0; r < kR; r++) {
-            const int e = lane + 32 * r;
-            if (e < ne) dd[l * ne + e] = acc[r];
-        }
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double v = worker ? acc[i][j] : 0.0;
+                double tot = v;
+#pragma unroll
+                for (int g = 1; g < kG; g++) {
+                    const double o = __shfl_sync(0xffffffffu, v, (lane + g * kBlocks) & 31);
+                    tot += o;
+                }
+                if (grp == 0) {
+                    const int ra = 4 * bi + i, rb = 4 * bj + j;
+                    if (ra <= rb && rb < K) dd[l * ne + (ra * K - ra * (ra - 1) / 2 + (rb - ra))] = tot;
+                }
+            }
     }
 }
 
@@ -447,8 +474,10 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     }
     {
         const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)sms * 8));
-        if (K <= 8) assoc_downdate_mask_kernel<8><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-        else assoc_downdate_mask_kernel<16><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+        if (K <= 4) assoc_downdate_mask_kernel<1><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+        else if (K <= 8) assoc_downdate_mask_kernel<2><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+        else if (K <= 12) assoc_downdate_mask_kernel<3><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+        else assoc_downdate_mask_kernel<4><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
         TRT_KERNEL_CHECK();
     }
     return TRT_OK;
