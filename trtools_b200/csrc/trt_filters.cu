@@ -252,14 +252,16 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+constexpr int kTS = 4;                               // samples per consumer thread
+constexpr int kTmaCons = kSlabSamples / kTS;         // 512 consumer threads: 4 warps per scheduler hide the dependent chains
 template <bool WANT_MASK>
-__global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfTmaParams q) {
+__global__ void __launch_bounds__(kTmaCons + 32, 1) call_filter_tma_kernel(CfTmaParams q) {
     extern __shared__ __align__(128) unsigned char smem[];
     const CfParams& p = q.base;
     const int stages = q.stages;
     const size_t stage_bytes = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes;
     unsigned char* ring = smem;
-    unsigned int* fcnt = (unsigned int*)(smem + (size_t)stages * stage_bytes);   // [n_specs][8][256] thread-private columns
+    unsigned int* fcnt = (unsigned int*)(smem + (size_t)stages * stage_bytes);   // [n_specs][kTS][512] thread-private columns
     uint64_t* full = (uint64_t*)(fcnt + (size_t)max(p.n_specs, 1) * kSlabSamples);
     uint64_t* empty = full + kTmaMaxStages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
     }
     __syncthreads();
 
-    if (warp == kCfThreads / 32) {
+    if (warp == kTmaCons / 32) {
         // ===== producer =====
         if (lane == 0) {
             int stage = 0;
@@ -299,90 +301,90 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
         return;
     }
 
-    // ===== consumers =====
+    // ===== consumers: thread <-> kTS consecutive samples of the slab =====
     int stage = 0;
     uint32_t phase = 0;
     int pending_stage = -1;      // thread 0: stage whose GT is still being read by the previous bulk store
+    constexpr uint32_t kAll = (1u << kTS) - 1u;
     for (int64_t item = blockIdx.x; item < q.n_items; item += gridDim.x) {
         const int64_t slab = item % q.n_slabs, chunk = item / q.n_slabs;
         const int64_t s0 = slab * kSlabSamples;
         const int64_t ns = min((int64_t)kSlabSamples, p.S - s0);
         const uint32_t gt_bytes = (uint32_t)((ns * 6 + 15) & ~int64_t(15));
         const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
-        const int64_t sb = s0 + (int64_t)tid * kSlab;          // first sample of this thread
-        const uint32_t valid_mask = (sb + 8 <= p.S) ? 0xffu : (sb >= p.S ? 0u : ((1u << (int)(p.S - sb)) - 1u));
+        const int64_t sb = s0 + (int64_t)tid * kTS;          // first sample of this thread
+        const uint32_t valid_mask = (sb + kTS <= p.S) ? kAll : (sb >= p.S ? 0u : ((1u << (int)(p.S - sb)) - 1u));
         for (int f = 0; f < p.n_specs; f++)
 #pragma unroll
-            for (int j = 0; j < kSlab; j++) fcnt[(f * kSlab + j) * kCfThreads + tid] = 0;
-        int ncalls[kSlab];
-        long long dps[kSlab];
+            for (int j = 0; j < kTS; j++) fcnt[(f * kTS + j) * kTmaCons + tid] = 0;
+        int ncalls[kTS];
+        long long dps[kTS];
         unsigned int poison = 0;
 #pragma unroll
-        for (int j = 0; j < kSlab; j++) { ncalls[j] = 0; dps[j] = 0; }
+        for (int j = 0; j < kTS; j++) { ncalls[j] = 0; dps[j] = 0; }
 
         for (int64_t l = l0; l < l1; l++) {
             mbar_wait(&full[stage], phase);
             unsigned char* st = ring + (size_t)stage * stage_bytes;
-            uint4* gsrc = reinterpret_cast<uint4*>(st + (size_t)tid * 48);
-            const uint4 v0 = gsrc[0], v1 = gsrc[1], v2 = gsrc[2];
-            uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            // bit j of the 8-bit masks = call j of this thread
+            // 4 calls = 12 int16 = 24 B (8-byte aligned; 24-byte lane stride is conflict-free for 64-bit accesses)
+            uint2* gsrc = reinterpret_cast<uint2*>(st + (size_t)tid * (kTS * 6));
+            const uint2 v0 = gsrc[0], v1 = gsrc[1], v2 = gsrc[2];
+            uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+            // bit j of the masks = call j of this thread
             uint32_t nocall = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < kTS; j++) {
                 const int k0 = 3 * j, k1 = k0 + 1;
                 const uint32_t a = (k0 & 1) ? (w[k0 >> 1] >> 16) : (w[k0 >> 1] & 0xffffu);
                 const uint32_t b = (k1 & 1) ? (w[k1 >> 1] >> 16) : (w[k1 >> 1] & 0xffffu);
                 nocall |= ((a == 0xffffu) | (b == 0xffffu)) ? (1u << j) : 0u;
             }
             uint32_t fired_any = 0;
-            uint32_t fired[8];
+            uint32_t fired[kTS];
             if (WANT_MASK) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) fired[j] = 0;
+                for (int j = 0; j < kTS; j++) fired[j] = 0;
             }
-            double den[8];
-            int32_t deni[8];
+            double den[kTS];
+            int32_t deni[kTS];
             if (q.dp_slot >= 0) {
-                const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.dp_slot * kTmaFieldBytes + (size_t)tid * 32);
-                const int4 a = d[0], b = d[1];
-                deni[0] = a.x; deni[1] = a.y; deni[2] = a.z; deni[3] = a.w; deni[4] = b.x; deni[5] = b.y; deni[6] = b.z; deni[7] = b.w;
+                const int4 a = *reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.dp_slot * kTmaFieldBytes + (size_t)tid * 16);
+                deni[0] = a.x; deni[1] = a.y; deni[2] = a.z; deni[3] = a.w;
 #pragma unroll
-                for (int j = 0; j < 8; j++) den[j] = (double)deni[j];
+                for (int j = 0; j < kTS; j++) den[j] = (double)deni[j];
             }
             for (int f = 0; f < p.n_specs; f++) {
                 const int variant = p.specs[f].variant;
-                const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.slot_of_spec[f] * kTmaFieldBytes + (size_t)tid * 32);
-                const int4 a = d[0], b = d[1];
-                const int32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const int4 a = *reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.slot_of_spec[f] * kTmaFieldBytes + (size_t)tid * 16);
+                const int32_t raw[kTS] = {a.x, a.y, a.z, a.w};
                 uint32_t hit = 0;
                 switch (variant) {      // uniform across the grid
                     case CFV_MIN_I32: {
                         const long long t = p.specs[f].thr_i64;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hit |= ((long long)raw[j] < t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= ((long long)raw[j] < t) ? (1u << j) : 0u;
                     } break;
                     case CFV_MAX_I32: {
                         const long long t = p.specs[f].thr_i64;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hit |= ((long long)raw[j] > t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= ((long long)raw[j] > t) ? (1u << j) : 0u;
                     } break;
                     case CFV_MIN_F32: {
                         const float t = p.specs[f].thr_f32;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hit |= (__int_as_float(raw[j]) < t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= (__int_as_float(raw[j]) < t) ? (1u << j) : 0u;
                     } break;
                     case CFV_MAX_F32: {
                         const float t = p.specs[f].thr_f32;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hit |= (__int_as_float(raw[j]) > t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= (__int_as_float(raw[j]) > t) ? (1u << j) : 0u;
                     } break;
                     case CFV_RATIO_FAST: {
                         // RN(raw/den) > thr decided without dividing when raw is clear of thr*den by 2^-50 relative
                         // (thr > 0 finite, den > 0, raw >= 0); the exact float64 division otherwise (numpy int32/int32)
                         const double t = p.specs[f].thr;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
+                        for (int j = 0; j < kTS; j++) {
                             const double r = (double)raw[j];
                             const double prod = t * den[j];
                             const double hi = fma(prod, 0x1p-50, prod), lo = fma(prod, -0x1p-50, prod);
@@ -395,36 +397,35 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
                     case CFV_RATIO_EXACT: {
                         const double t = p.specs[f].thr;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hit |= (((double)raw[j] / den[j]) > t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= (((double)raw[j] / den[j]) > t) ? (1u << j) : 0u;
                     } break;
                     case CFV_HOST: {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hit |= !isnan(__int_as_float(raw[j])) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= !isnan(__int_as_float(raw[j])) ? (1u << j) : 0u;
                     } break;
                     default: break;
                 }
                 hit &= valid_mask;
                 fired_any |= hit;
-                uint32_t cnt = hit & ~nocall;
+                const uint32_t cnt = hit & ~nocall;
                 if (cnt) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        if ((cnt >> j) & 1u) fcnt[(f * kSlab + j) * kCfThreads + tid] += 1;
+                    for (int j = 0; j < kTS; j++)
+                        if ((cnt >> j) & 1u) fcnt[(f * kTS + j) * kTmaCons + tid] += 1;
                 }
                 if (WANT_MASK) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) fired[j] |= ((hit >> j) & 1u) << f;
+                    for (int j = 0; j < kTS; j++) fired[j] |= ((hit >> j) & 1u) << f;
                 }
             }
             const uint32_t pass = ~fired_any & ~nocall & valid_mask;
 #pragma unroll
-            for (int j = 0; j < 8; j++) ncalls[j] += (pass >> j) & 1u;
+            for (int j = 0; j < kTS; j++) ncalls[j] += (pass >> j) & 1u;
             if (q.acc_slot >= 0) {
-                const int4* d = reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 32);
-                const int4 a = d[0], b = d[1];
-                const int32_t dpv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const int4 a = *reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 16);
+                const int32_t dpv[kTS] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < kTS; j++) {
                     const bool ps = (pass >> j) & 1u;
                     const int dd = dpv[j];
                     if (ps && dd < 0) {                       // rare: missing depth poisons, negative depth is an error
@@ -437,22 +438,21 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
             }
             if (WANT_MASK && sb < p.S) {
                 uint32_t* cm = p.call_mask + (size_t)l * p.S + sb;
-                uint32_t m[8];
+                uint32_t m[kTS];
 #pragma unroll
-                for (int j = 0; j < 8; j++) m[j] = fired[j] | (((nocall >> j) & 1u) ? 0x80000000u : 0u);
-                if (sb + 8 <= p.S) {
+                for (int j = 0; j < kTS; j++) m[j] = fired[j] | (((nocall >> j) & 1u) ? 0x80000000u : 0u);
+                if (sb + kTS <= p.S) {
                     reinterpret_cast<uint4*>(cm)[0] = make_uint4(m[0], m[1], m[2], m[3]);
-                    reinterpret_cast<uint4*>(cm)[1] = make_uint4(m[4], m[5], m[6], m[7]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    for (int j = 0; j < kTS; j++)
                         if (sb + j < p.S) cm[j] = m[j];
                 }
             }
             const uint32_t filt = fired_any & ~nocall;       // filtered calls: every haplotype -> '.', unphased
             if (filt) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < kTS; j++) {
                     if (!((filt >> j) & 1u)) continue;
 #pragma unroll
                     for (int k = 3 * j; k < 3 * j + 3; k++) {
@@ -460,12 +460,12 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
                         w[k >> 1] = (k & 1) ? ((w[k >> 1] & 0x0000ffffu) | (val << 16)) : ((w[k >> 1] & 0xffff0000u) | val);
                     }
                 }
-                gsrc[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                gsrc[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                gsrc[2] = make_uint4(w[8], w[9], w[10], w[11]);
+                gsrc[0] = make_uint2(w[0], w[1]);
+                gsrc[1] = make_uint2(w[2], w[3]);
+                gsrc[2] = make_uint2(w[4], w[5]);
             }
             fence_proxy_async_smem();                 // generic-proxy writes -> visible to the bulk store
-            asm volatile("bar.sync 1, %0;" ::"n"(kCfThreads) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmaCons) : "memory");
             if (tid == 0) {
                 tma_store_1d((char*)p.gt_out + (size_t)l * p.pitch + (size_t)s0 * 6, st, gt_bytes);
                 tma_store_commit();
@@ -479,13 +479,13 @@ __global__ void __launch_bounds__(kCfThreads + 32, 1) call_filter_tma_kernel(CfT
         }
         // ---- flush the per-sample accumulators of this item -----------------------------------------
 #pragma unroll
-        for (int j = 0; j < kSlab; j++) {
+        for (int j = 0; j < kTS; j++) {
             if (sb + j >= p.S) continue;
             if (ncalls[j]) atomicAdd((unsigned long long*)&p.numcalls[sb + j], (unsigned long long)ncalls[j]);
             if (dps[j]) atomicAdd((unsigned long long*)&p.dpsum[sb + j], (unsigned long long)dps[j]);
             if ((poison >> j) & 1u) atomicOr(&p.dp_poison[sb + j], 1u);
             for (int f = 0; f < p.n_specs; f++) {
-                const unsigned int c = fcnt[(f * kSlab + j) * kCfThreads + tid];
+                const unsigned int c = fcnt[(f * kTS + j) * kTmaCons + tid];
                 if (c) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + sb + j], (unsigned long long)c);
             }
         }
@@ -735,10 +735,10 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
                 const int grid = (int)std::min<int64_t>(q.n_items, ctx->sm_count);
                 if (p.call_mask) {
                     TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    call_filter_tma_kernel<true><<<grid, kCfThreads + 32, smem, ctx->stream>>>(q);
+                    call_filter_tma_kernel<true><<<grid, kTmaCons + 32, smem, ctx->stream>>>(q);
                 } else {
                     TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    call_filter_tma_kernel<false><<<grid, kCfThreads + 32, smem, ctx->stream>>>(q);
+                    call_filter_tma_kernel<false><<<grid, kTmaCons + 32, smem, ctx->stream>>>(q);
                 }
             }
         }
