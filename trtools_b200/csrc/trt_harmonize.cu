@@ -88,9 +88,14 @@ __device__ int rot_cmp(const char* s, int p, int r1, int r2) {
     return 0;
 }
 
+// GS lanes cooperate on one locus (GS = 32: warp per locus; GS = 8: four loci per warp — most loci have only a
+// handful of alleles, so a full warp per locus leaves 80% of the lanes idle).  `lane` is the lane within the group
+// and every shuffle / vote / barrier below is restricted to the group's lanes.
+template <int GS>
 __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
-    const int lane = threadIdx.x & 31;
-    const int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x % GS;
+    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) / GS * GS));
+    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
     if (l >= P.L) return;
     const int a0 = P.locus_off[l];
     const int A = P.locus_off[l + 1] - a0;
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
     const char* motif_in = P.motif_in ? P.motif_in + P.motif_off[l] : nullptr;
 
     // ---- 1. trim window + repeat-unit length per allele -------------------------------------
-    for (int a = lane; a < A; a += 32) {
+    for (int a = lane; a < A; a += GS) {
         const int64_t off = P.allele_off[a0 + a];
         const int n = (int)(P.allele_off[a0 + a + 1] - off);
         const double g = P.given_len[a0 + a];
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
         P.trim_len[a0 + a] = len;
         P.allele_len[a0 + a] = rl;
     }
-    __syncwarp();
+    __syncwarp(gmask);
 
     auto make_str = [&](int a) -> AlleleStr {
         AlleleStr x;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
 
     // ---- 2. equivalence classes and sort ranks (rank by counting; A is small) ------------------
     bool len_dups = false, seq_dups = false;
-    for (int a = lane; a < A; a += 32) {
+    for (int a = lane; a < A; a += GS) {
         const double la = P.allele_len[a0 + a];
         const AlleleStr sa = make_str(a);
         int lclass = a, sclass = a, lrank = 0, srank = 0;
@@ -182,8 +187,8 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
         len_dups |= (lclass != a);
         seq_dups |= (sclass != a);
     }
-    if (__any_sync(0xffffffffu, len_dups)) flags |= TRT_HF_LEN_DUPS;
-    if (__any_sync(0xffffffffu, seq_dups)) flags |= TRT_HF_SEQ_DUPS;
+    if (__any_sync(gmask, len_dups)) flags |= TRT_HF_LEN_DUPS;
+    if (__any_sync(gmask, seq_dups)) flags |= TRT_HF_SEQ_DUPS;
 
     // ---- 3. homopolymer run of the full REF (utils.py:340-360) ---------------------------------
     {
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
             r = make_str(0);
         }
         int best = 0;
-        for (int i = lane; i < r.len; i += 32) {
+        for (int i = lane; i < r.len; i += GS) {
             if (i == 0 || r.at(i) != r.at(i - 1)) {
                 int j = i + 1;
                 const char c = r.at(i);
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        for (int o = GS / 2; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(gmask, best, o));
         if (lane == 0) P.hrun[l] = best;
     }
 
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
         char* mout = P.motif + P.motif_off[l];
         if (!flanked) {
             // RU / Motif supplied by the caller: pass through upper-cased
-            for (int j = lane; j < period; j += 32) mout[j] = motif_in ? up(motif_in[j]) : 'N';
+            for (int j = lane; j < period; j += GS) mout[j] = motif_in ? up(motif_in[j]) : 'N';
         } else {
             // InferRepeatSequence(ref_allele[start_offset:], PERIOD)  tr_harmonizer.py:397 — the
             // ALREADY trimmed REF is sliced by start_offset a second time (reference quirk).
@@ -224,14 +229,14 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
             const char* seq = P.seqs + ref_off + P.trim_off[a0] + s2;
             const int n = tn - s2;
             if (period > n) {
-                for (int j = lane; j < period; j += 32) mout[j] = 'N';
+                for (int j = lane; j < period; j += GS) mout[j] = 'N';
                 flags |= TRT_HF_MOTIF_N;
             } else {
                 const int K = n / period;
                 // running count c_i of k-mer i among k-mers 0..i; the winner is the k-mer that first
                 // reaches the final maximum count (see oracle/trh.py::infer_repeat_sequence)
                 int best_c = 0, best_i = 0x7fffffff;
-                for (int i = lane; i < K; i += 32) {
+                for (int i = lane; i < K; i += GS) {
                     int c = 0;
                     for (int j = 0; j <= i; j++) {
                         bool eq = true;
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
                     }
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-                    int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                for (int o = GS / 2; o > 0; o >>= 1) {
+                    int oc = __shfl_xor_sync(gmask, best_c, o);
+                    int oi = __shfl_xor_sync(gmask, best_i, o);
                     if (oc > best_c || (oc == best_c && oi < best_i)) {
                         best_c = oc;
                         best_i = oi;
@@ -258,22 +263,22 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
                 }
                 const char* kmer = seq + (size_t)best_i * period;
                 bool bad = false;
-                for (int j = lane; j < period; j += 32) bad |= (nuc_code(up(kmer[j])) < 0);
-                if (__any_sync(0xffffffffu, bad)) {
+                for (int j = lane; j < period; j += GS) bad |= (nuc_code(up(kmer[j])) < 0);
+                if (__any_sync(gmask, bad)) {
                     flags |= TRT_HF_MOTIF_NONACGT;  // GetCanonicalOneStrand would raise KeyError
-                    for (int j = lane; j < period; j += 32) mout[j] = up(kmer[j]);
+                    for (int j = lane; j < period; j += GS) mout[j] = up(kmer[j]);
                 } else {
                     int br = 0x7fffffff;  // best rotation seen by this lane
-                    for (int r = lane; r < period; r += 32)
+                    for (int r = lane; r < period; r += GS)
                         if (br == 0x7fffffff || rot_cmp(kmer, period, r, br) < 0) br = r;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        int orr = __shfl_xor_sync(0xffffffffu, br, o);
+                    for (int o = GS / 2; o > 0; o >>= 1) {
+                        int orr = __shfl_xor_sync(gmask, br, o);
                         if (orr != 0x7fffffff && (br == 0x7fffffff || rot_cmp(kmer, period, orr, br) < 0 ||
                                                   (rot_cmp(kmer, period, orr, br) == 0 && orr < br)))
                             br = orr;
                     }
-                    for (int j = lane; j < period; j += 32) mout[j] = up(kmer[(j + period - br) % period]);
+                    for (int j = lane; j < period; j += GS) mout[j] = up(kmer[(j + period - br) % period]);
                 }
             }
         }
@@ -370,9 +375,14 @@ int trt_harmonize(trt_ctx* ctx) {
     P.motif = (char*)ctx->motif.p;
     if (L > 0) {
         trt_timer_begin(ctx);
-        const int warps_per_block = 4;
-        dim3 grid((unsigned)((L + warps_per_block - 1) / warps_per_block));
-        harmonize_kernel<<<grid, warps_per_block * 32, 0, ctx->stream>>>(P);
+        // 8 lanes per locus unless the block has loci with many alleles (lanes stride over alleles / k-mers)
+        if (ctx->maxA <= 16 && !getenv("TRT_HARMONIZE_WARP")) {
+            const int64_t per = 128 / 8;
+            harmonize_kernel<8><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
+        } else {
+            const int64_t per = 128 / 32;
+            harmonize_kernel<32><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
+        }
         TRT_KERNEL_CHECK();
         trt_timer_end(ctx);
     }
