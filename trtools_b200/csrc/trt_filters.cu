@@ -222,9 +222,10 @@ __global__ void __launch_bounds__(kCfThreads, 2) call_filter_kernel(CfParams p) 
 // Work item = (2048-sample slab, chunk of loci); persistent CTAs walk their items locus by locus.  A producer
 // warp brings the slab of one locus — GT (12 KB) and every FORMAT field the filters read (8 KB each) — into a
 // shared-memory ring with 1-D bulk TMA copies; 256 consumer threads own 8 consecutive samples each (per-sample
-// counters in registers / thread-private shared-memory columns), patch filtered calls IN PLACE in the ring stage,
-// and one elected thread writes the stage's GT back to the masked-genotype tensor with a bulk TMA store
-// (contiguous 12 KB instead of 48-byte-strided 16-byte stores).
+// counters in registers / thread-private shared-memory columns), patch filtered calls IN PLACE in the ring stage and
+// signal a per-stage "done" mbarrier; a store warp then writes the stage's GT back to the masked-genotype tensor
+// with a bulk TMA store (contiguous 12 KB instead of 48-byte-strided 16-byte stores) and recycles the stage.  No
+// CTA-wide barrier sits in the loop: consumer warps run ahead of each other by up to the ring depth.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTmaMaxFields = 4;
 constexpr int kTmaMaxStages = 8;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 constexpr int kTS = 4;                               // samples per consumer thread
 constexpr int kTmaCons = kSlabSamples / kTS;         // 512 consumer threads: 4 warps per scheduler hide the dependent chains
 template <bool WANT_MASK>
-__global__ void __launch_bounds__(kTmaCons + 32, 1) call_filter_tma_kernel(CfTmaParams q) {
+__global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTmaParams q) {
     extern __shared__ __align__(128) unsigned char smem[];
     const CfParams& p = q.base;
     const int stages = q.stages;
@@ -264,16 +265,49 @@ __global__ void __launch_bounds__(kTmaCons + 32, 1) call_filter_tma_kernel(CfTma
     unsigned int* fcnt = (unsigned int*)(smem + (size_t)stages * stage_bytes);   // [n_specs][kTS][512] thread-private columns
     uint64_t* full = (uint64_t*)(fcnt + (size_t)max(p.n_specs, 1) * kSlabSamples);
     uint64_t* empty = full + kTmaMaxStages;
+    uint64_t* done = empty + kTmaMaxStages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&done[s], kTmaCons / 32);
         }
         mbar_fence_init();
     }
     __syncthreads();
 
+    if (warp == kTmaCons / 32 + 1) {
+        // ===== store warp: masked GT of every finished stage back to HBM, then the stage is free again =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int pending_stage = -1;      // stage whose GT is still being read by the previous bulk store
+            for (int64_t item = blockIdx.x; item < q.n_items; item += gridDim.x) {
+                const int64_t slab = item % q.n_slabs, chunk = item / q.n_slabs;
+                const int64_t s0 = slab * kSlabSamples;
+                const int64_t ns = min((int64_t)kSlabSamples, p.S - s0);
+                const uint32_t gt_bytes = (uint32_t)((ns * 6 + 15) & ~int64_t(15));
+                const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
+                for (int64_t l = l0; l < l1; l++) {
+                    mbar_wait(&done[stage], phase);
+                    tma_store_1d((char*)p.gt_out + (size_t)l * p.pitch + (size_t)s0 * 6, ring + (size_t)stage * stage_bytes, gt_bytes);
+                    tma_store_commit();
+                    if (pending_stage >= 0) {
+                        tma_store_wait_read<1>();        // the PREVIOUS store has finished reading its stage
+                        mbar_arrive(&empty[pending_stage]);
+                    }
+                    pending_stage = stage;
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+            if (pending_stage >= 0) {
+                tma_store_wait_read<0>();
+                mbar_arrive(&empty[pending_stage]);
+            }
+        }
+        return;
+    }
     if (warp == kTmaCons / 32) {
         // ===== producer =====
         if (lane == 0) {
@@ -304,7 +338,6 @@ __global__ void __launch_bounds__(kTmaCons + 32, 1) call_filter_tma_kernel(CfTma
     // ===== consumers: thread <-> kTS consecutive samples of the slab =====
     int stage = 0;
     uint32_t phase = 0;
-    int pending_stage = -1;      // thread 0: stage whose GT is still being read by the previous bulk store
     constexpr uint32_t kAll = (1u << kTS) - 1u;
     for (int64_t item = blockIdx.x; item < q.n_items; item += gridDim.x) {
         const int64_t slab = item % q.n_slabs, chunk = item / q.n_slabs;
@@ -464,17 +497,9 @@ __global__ void __launch_bounds__(kTmaCons + 32, 1) call_filter_tma_kernel(CfTma
                 gsrc[1] = make_uint2(w[2], w[3]);
                 gsrc[2] = make_uint2(w[4], w[5]);
             }
-            fence_proxy_async_smem();                 // generic-proxy writes -> visible to the bulk store
-            asm volatile("bar.sync 1, %0;" ::"n"(kTmaCons) : "memory");
-            if (tid == 0) {
-                tma_store_1d((char*)p.gt_out + (size_t)l * p.pitch + (size_t)s0 * 6, st, gt_bytes);
-                tma_store_commit();
-                if (pending_stage >= 0) {
-                    tma_store_wait_read<1>();        // the PREVIOUS store has finished reading its stage
-                    mbar_arrive(&empty[pending_stage]);
-                }
-                pending_stage = stage;
-            }
+            fence_proxy_async_smem();                 // generic-proxy writes -> visible to the store warp's bulk store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         // ---- flush the per-sample accumulators of this item -----------------------------------------
@@ -489,10 +514,6 @@ __global__ void __launch_bounds__(kTmaCons + 32, 1) call_filter_tma_kernel(CfTma
                 if (c) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + sb + j], (unsigned long long)c);
             }
         }
-    }
-    if (tid == 0 && pending_stage >= 0) {
-        tma_store_wait_read<0>();
-        mbar_arrive(&empty[pending_stage]);
     }
 }
 
@@ -720,7 +741,7 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
         if (tma_ok) {
             q.base = p;
             const size_t stage_bytes = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes;
-            const size_t fixed = (size_t)std::max(n_specs, 1) * kSlabSamples * 4 + 2 * kTmaMaxStages * 8 + 128;
+            const size_t fixed = (size_t)std::max(n_specs, 1) * kSlabSamples * 4 + 3 * kTmaMaxStages * 8 + 128;
             int stages = (int)(((size_t)ctx->max_smem_optin - fixed) / stage_bytes);
             stages = std::min(stages, kTmaMaxStages);
             if (stages < 3) tma_ok = false;
@@ -735,10 +756,10 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
                 const int grid = (int)std::min<int64_t>(q.n_items, ctx->sm_count);
                 if (p.call_mask) {
                     TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    call_filter_tma_kernel<true><<<grid, kTmaCons + 32, smem, ctx->stream>>>(q);
+                    call_filter_tma_kernel<true><<<grid, kTmaCons + 64, smem, ctx->stream>>>(q);
                 } else {
                     TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    call_filter_tma_kernel<false><<<grid, kTmaCons + 32, smem, ctx->stream>>>(q);
+                    call_filter_tma_kernel<false><<<grid, kTmaCons + 64, smem, ctx->stream>>>(q);
                 }
             }
         }

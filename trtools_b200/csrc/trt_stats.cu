@@ -10,6 +10,7 @@
 //   utils.GetHeterozygosity/GetEntropy/GetMean/GetMode/GetVariance  trtools/utils/utils.py:142-296
 //   utils.GetHardyWeinbergBinomialTest :298-338 -> scipy.stats.binomtest (two-sided, exact)
 #include <float.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include <algorithm>
@@ -449,6 +450,28 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
     if (n_out) TRT_CUDA(cudaMemcpyAsync(&bad, f + 12 * n_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
 #undef D2H
     TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad && getenv("TRT_DEBUG_BAD")) {
+        // diagnostics: which loci report out-of-range genotype entries, and what the scan counted for them
+        std::vector<long long> lcv(n_out * TRT_LC_N);
+        cudaMemcpy(lcv.data(), ctx->lc.p, n_out * TRT_LC_N * 8, cudaMemcpyDeviceToHost);
+        int shown = 0;
+        for (size_t i = 0; i < n_out && shown < 12; i++) {
+            if (!lcv[i * TRT_LC_N + 6]) continue;
+            const int64_t l = (int64_t)(i % L);
+            const int A = ctx->h_locus_off[l + 1] - ctx->h_locus_off[l];
+            std::vector<int16_t> rowv((size_t)S * (ctx->P + 1));
+            cudaMemcpy(rowv.data(), (const char*)ctx->d_gt_active + (size_t)l * ctx->gt_active_pitch, rowv.size() * 2, cudaMemcpyDeviceToHost);
+            long long truly = 0, first = -1;
+            for (int64_t s2 = 0; s2 < S; s2++)
+                for (int h = 0; h < ctx->P; h++) {
+                    const int a = rowv[(size_t)s2 * (ctx->P + 1) + h];
+                    if (a < -2 || a >= A) { truly++; if (first < 0) first = s2; }
+                }
+            fprintf(stderr, "[bad] locus %lld A=%d tier=%d n_full=%lld n_non=%lld n_pad=%lld n_bad=%lld | host recount of the row: %lld out-of-range entries (first at sample %lld)\n",
+                    (long long)l, A, scan_tier(A), lcv[i * TRT_LC_N + 0], lcv[i * TRT_LC_N + 1], lcv[i * TRT_LC_N + 2], lcv[i * TRT_LC_N + 6], truly, first);
+            shown++;
+        }
+    }
     if (bad)
         return trt_set_error(ctx, TRT_ERECORD,
                              "%lld genotype entries index an allele the record does not have (or are < -2)", (long long)bad);
