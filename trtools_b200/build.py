@@ -53,14 +53,14 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     inc, libdir, soname = _find_nccl()
-    cmd = [nvcc] + list(NVCC_FLAGS)
+    cmd = [nvcc] + list(NVCC_FLAGS) + os.environ.get("TRT_EXTRA_NVCC", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     if inc:
         cmd += ["-I", inc, "-L", libdir, "-l:" + soname, "-Xlinker", "-rpath=" + libdir]
     else:
         cmd += ["-lnccl"]
-    cmd += ["-o", LIB] + sources()
+    cmd += ["-o", os.environ.get("TRT_BUILD_OUT", LIB)] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -168,7 +168,11 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     const int nfull = (int)(p.S / kPChunkCalls);   // chunks whose calls are all real samples
     const unsigned trash = (unsigned)max_rows;     // extra row: calls beyond S in the last chunk land here
     // the non-blocking hand-off to warp 0 relies on the ring keeping the warps within one locus of each other
+#ifdef TRT_SCAN_BLOCKING_HANDOFF
+    const bool loose = false;
+#else
     const bool loose = nchunks > stages;
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
@@ -233,6 +237,13 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             }
             const uint4* sp = (const uint4*)(ring + (size_t)stage * kPChunkBytes + (size_t)tid * 48);
             const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
+#ifndef TRT_SCAN_EARLY_ARRIVE
+            // Release the slot only once this thread's loads have RETURNED (register dependency), not merely been issued:
+            // the refill is an async-proxy (TMA) write, which is not ordered after a generic-proxy read that is still in
+            // flight.  With the early arrive, cold first launches miscounted a handful of calls in ~1/3 of the runs
+            // (profiles/README.md, "ring WAR hazard").
+            asm volatile("" ::"r"(v0.x), "r"(v0.w), "r"(v1.x), "r"(v1.w), "r"(v2.x), "r"(v2.w) : "memory");
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->empty[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -460,6 +471,7 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
             mbar_wait(&hdr->full[stage], phase);
             const uint4* src = (const uint4*)(ring + (size_t)stage * kWChunkBytes + (size_t)tid * 48);
             const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+            asm volatile("" ::"r"(v0.x), "r"(v0.w), "r"(v1.x), "r"(v1.w), "r"(v2.x), "r"(v2.w) : "memory");   // loads returned (see above)
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->empty[stage]);
             const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
