@@ -544,6 +544,11 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
     TRT_CUDA(cudaMemsetAsync(ctx->lc.p, 0, (size_t)L * TRT_LC_N * 8 + 16, ctx->stream));
     TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
     if (L > 0) {
+        ctx->want_ac_part = true;
+        const bool all_samples = (n == S);
+        int rc = trt_run_scan(ctx, all_samples ? nullptr : (const uint8_t*)ctx->group_masks.p, 0, 1);
+        ctx->want_ac_part = false;
+        if (rc != TRT_OK) return rc;
         AssocParams ap;
         ap.gt = ctx->d_gt_active;
         ap.pitch = ctx->gt_active_pitch;
@@ -576,17 +581,8 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
                 ap.list = (const int32_t*)ctx->assoc_fast_tiles.p;
                 ap.n_list = (int64_t)generic_list.size();
             }
+            TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, ap.mom, ap.dd));
         }
-        if (need_generic) {
-            // allele counts over the design samples (and their partial-call share) via the scan; the fast path counts
-            // the alleles of the tested samples itself, so the scan only runs when some locus needs the generic kernels
-            ctx->want_ac_part = true;
-            const bool all_samples = (n == S);
-            int rc = trt_run_scan(ctx, all_samples ? nullptr : (const uint8_t*)ctx->group_masks.p, 0, 1);
-            ctx->want_ac_part = false;
-            if (rc != TRT_OK) return rc;
-        }
-        if (fast_ok) TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, ap.mom, ap.dd, (int32_t*)ctx->ac.p, (int32_t*)ctx->ac_part.p));
         const int64_t n_gen = ap.list ? ap.n_list : L;
         const int64_t ntiles = (n_gen + kTileLoci - 1) / kTileLoci;
         const size_t smem = (size_t)K * 256 * 8;

@@ -52,7 +52,6 @@ struct TileParams {
     const double* zt;               // [nchunks * 40][ZW] z-rows in VCF sample order (zeros outside the design)
     double* mom_part;               // [nseg][L][K + 3]
     uint32_t* masks;                // [n_tiles][nchunks][tile loci]: bit i = sample i of the chunk is an uncalled design sample
-    int32_t* ac;                    // [nA] allele counts (by index) over the TESTED samples, summed over segments (atomics)
     int stages;
 };
 
@@ -75,8 +74,7 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
     unsigned char* gt_ring = smem;                                            // [stages][kTGtBytes]
     unsigned char* z_ring = smem + (size_t)stages * kTGtBytes;                // [stages][kZBytes]
     double* table = (double*)(z_ring + (size_t)stages * kZBytes);             // [kTMaxD][kTLoci]
-    uint16_t* counts = (uint16_t*)(table + kTMaxD * kTLoci);                  // [kTMaxD][kTLoci] thread-private allele counters
-    uint64_t* full = (uint64_t*)(counts + kTMaxD * kTLoci);
+    uint64_t* full = (uint64_t*)(table + kTMaxD * kTLoci);
     uint64_t* empty = full + kTMaxStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -87,7 +85,6 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < kTMaxD * kTLoci / 2; i += kTThreads) ((uint32_t*)counts)[i] = 0u;
     __syncthreads();
     const int n_units = p.n_tiles * p.nseg;
 
@@ -119,7 +116,6 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     double* mytab = table + tid;
-    uint16_t* mycnt = counts + tid;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int tile = u / p.nseg;
         const int seg = u % p.nseg;
@@ -194,24 +190,14 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                         const int b = (k1 & 1) ? ((int)w[h][k1 >> 1] >> 16) : (int)(short)(w[h][k1 >> 1] & 0xffffu);
                         const unsigned da = (unsigned)(a + 2), db = (unsigned)(b + 2);
                         const double* t = mytab + h * kTCons;
-                        const unsigned ia = (da < D[h]) ? da : 1u, ib = (db < D[h]) ? db : 1u;
-                        const double la = t[ia * kTLoci];
-                        const double lb = t[ib * kTLoci];
+                        const double la = t[((da < D[h]) ? da : 1u) * kTLoci];
+                        const double lb = t[((db < D[h]) ? db : 1u) * kTLoci];
                         const double gs = la + lb;
                         const bool called = (gs == gs);             // an invalid locus has D = 2 and a NaN pad entry: never called
                         const bool ok = called & ind;
                         const double g = ok ? gs : 0.0;
                         if (ok) n[h]++;
                         if (ind & !called) mask[h] |= 1u << sidx;
-                        {   // allele counts of the tested samples: thread-private 16-bit cells; untested calls hit the no-call row
-                            uint16_t* cnt = mycnt + h * kTCons;
-                            uint16_t* pa = cnt + (ok ? ia : 1u) * kTLoci;
-                            uint16_t* pb = cnt + (ok ? ib : 1u) * kTLoci;
-                            const unsigned xa = *pa, xb = *pb;
-                            const unsigned e = (pa == pb) ? 2u : 1u;   // homozygote: both stores write x + 2
-                            *pa = (uint16_t)(xa + e);
-                            *pb = (uint16_t)(xb + e);
-                        }
                         sg[h] += g;
                         sgg[h] = fma(g, g, sgg[h]);      // explicit fma: the library builds with -fmad=false
 #pragma unroll
@@ -227,20 +213,9 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
         }
 #pragma unroll
         for (int h = 0; h < kNL; h++) {
-            uint16_t* cnt = mycnt + h * kTCons;
-            cnt[0] = 0;                       // pad digit and no-call row: not alleles
-            cnt[kTLoci] = 0;
             if (!valid[h]) continue;
-            const int64_t l = (int64_t)tile * kTLoci + h * kTCons + tid;
-            {
-                const int a0 = p.locus_off[l];
-                for (unsigned d = 2; d < D[h]; d++) {
-                    const unsigned v = cnt[d * kTLoci];
-                    cnt[d * kTLoci] = 0;
-                    if (v) atomicAdd(&p.ac[a0 + (int)d - 2], (int)v);
-                }
-            }
             // mom layout of the solve kernel: n, sum g', sum g'^2, g'.y, g'.c_1 .. g'.c_{K-1}
+            const int64_t l = (int64_t)tile * kTLoci + h * kTCons + tid;
             double* o = p.mom_part + ((size_t)seg * p.L + l) * (K + 3);
             o[0] = (double)n[h];
             o[1] = sg[h];
@@ -267,17 +242,6 @@ __global__ void assoc_ztable_kernel(const double* __restrict__ covars, const dou
         else if (k == K) v = 1.0;
     }
     zt[i] = v;
-}
-
-// the fast-path loci get their allele counts from the tile kernel: zero ac (atomics accumulate) and ac_part (the tile
-// kernel counts TESTED samples only, so there is no partial-call share to subtract)
-__global__ void assoc_clear_counts_kernel(const int32_t* __restrict__ locus_off, int64_t L, int32_t* __restrict__ ac,
-                                          int32_t* __restrict__ ac_part) {
-    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= L) return;
-    const int a0 = locus_off[l], A = locus_off[l + 1] - a0;
-    if (A > kAssocFastMaxAlleles) return;
-    for (int a = 0; a < A; a++) { ac[a0 + a] = 0; ac_part[a0 + a] = 0; }
 }
 
 __global__ void assoc_reduce_mom_kernel(const double* __restrict__ part, int nseg, int64_t n, double* __restrict__ mom,
@@ -422,7 +386,7 @@ template <int K>
 int launch_tile(trt_ctx* ctx, const CUtensorMap& tmap, TileParams& tp, int grid) {
     constexpr int ZW = (K + 2) & ~1;
     constexpr size_t zbytes = (size_t)kTChunk * ZW * 8;
-    const size_t fixed = (size_t)kTMaxD * kTLoci * (8 + 2) + 2 * kTMaxStages * 8 + 64;
+    const size_t fixed = (size_t)kTMaxD * kTLoci * 8 + 2 * kTMaxStages * 8 + 128;
     int stages = (int)(((size_t)ctx->max_smem_optin - fixed) / (kTGtBytes + zbytes));
     stages = std::min(stages, kTMaxStages);
     if (stages < 2) return trt_set_error(ctx, TRT_ENOMEM, "assoc tile kernel: not enough shared memory");
@@ -440,7 +404,7 @@ int trt_assoc_fast_zw(int K) { return (K + 2) & ~1; }
 
 // Moments (into mom [L][K+3]) and down-dates (into dd [L][K(K+1)/2]) of every locus with at most
 // kAssocFastMaxAlleles alleles; the others are left to the generic kernels.
-int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, double* dd, int32_t* ac, int32_t* ac_part) {
+int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, double* dd) {
     const int64_t L = ctx->L, S = ctx->S;
     const int K = ctx->K, nacc = K + 3, ZW = trt_assoc_fast_zw(K);
     if (L == 0) return TRT_OK;
@@ -451,15 +415,13 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     const int64_t S_pad = (int64_t)nchunks * kTChunk;
     // work units = tile x sample segment, sized so the persistent grid's last wave is >= 95% full
     const int sms = ctx->sm_count;
-    // a segment may hold at most 65535 / 2 calls per locus (16-bit allele counters in shared memory)
-    const int min_seg = (nchunks + (32000 / kTChunk) - 1) / (32000 / kTChunk);
-    int nseg = std::max(1, min_seg);
-    for (; nseg < std::max(16, min_seg); nseg++) {
+    int nseg = 1;
+    for (; nseg < 16; nseg++) {
         const int64_t units = (int64_t)n_tiles * nseg;
         const int64_t waves = (units + sms - 1) / sms;
         if ((double)units / (double)(waves * sms) >= 0.95 || nchunks / (nseg + 1) < 32) break;
     }
-    nseg = std::max(std::max(1, min_seg), std::min(nseg, nchunks));
+    nseg = std::max(1, std::min(nseg, nchunks));
     const int cps = (nchunks + nseg - 1) / nseg;
     nseg = (nchunks + cps - 1) / cps;
 
@@ -496,10 +458,7 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     tp.zt = (const double*)ctx->assoc_zt.p;
     tp.mom_part = (double*)ctx->assoc_mom_part.p;
     tp.masks = (uint32_t*)ctx->assoc_masks.p;
-    tp.ac = ac;
     tp.stages = 0;
-    assoc_clear_counts_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(tp.locus_off, L, ac, ac_part);
-    TRT_KERNEL_CHECK();
     const int grid = (int)std::min<int64_t>((int64_t)n_tiles * nseg, sms);
     switch (K) {
 #define CASE(KK) case KK: TRT_TRY(launch_tile<KK>(ctx, tmap, tp, grid)); break;

@@ -237,15 +237,11 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             }
             const uint4* sp = (const uint4*)(ring + (size_t)stage * kPChunkBytes + (size_t)tid * 48);
             const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
-#ifndef TRT_SCAN_EARLY_ARRIVE
-            // Release the slot only once this thread's loads have RETURNED (register dependency), not merely been issued:
-            // the refill is an async-proxy (TMA) write, which is not ordered after a generic-proxy read that is still in
-            // flight.  With the early arrive, cold first launches miscounted a handful of calls in ~1/3 of the runs
-            // (profiles/README.md, "ring WAR hazard").
-            asm volatile("" ::"r"(v0.x), "r"(v0.w), "r"(v1.x), "r"(v1.w), "r"(v2.x), "r"(v2.w) : "memory");
-#endif
+#ifdef TRT_SCAN_EARLY_ARRIVE
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+#endif
+            const int stage_used = stage;
             if (++stage == stages) { stage = 0; phase ^= 1u; }
             const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
             unsigned idx[8], dg0[8], dg1[8];
@@ -264,6 +260,17 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
 #pragma unroll
                 for (int j = 0; j < 8; j++) idx[j] = tri(max(dg0[j], dg1[j]), min(dg0[j], dg1[j]));
             }
+#ifndef TRT_SCAN_EARLY_ARRIVE
+            {
+                // Release the ring slot only after this warp's loads have RETURNED: the predicate below consumes every
+                // loaded word (it is always true, bins are < 2^16, but the compiler cannot prove it), so the arrive cannot
+                // issue while a generic-proxy read of the slot is still in flight — the refill is an async-proxy (TMA)
+                // write, which is not ordered behind such a read.
+                const unsigned any = idx[0] | idx[1] | idx[2] | idx[3] | idx[4] | idx[5] | idx[6] | idx[7];
+                const bool returned = __all_sync(0xffffffffu, any != 0xffffffffu);
+                if (lane == 0 && returned) mbar_arrive(&hdr->empty[stage_used]);
+            }
+#endif
             if (MASKED || c >= nfull) {
                 const int64_t sb0 = (int64_t)c * kPChunkCalls + (int64_t)tid * 8;
 #pragma unroll
@@ -471,9 +478,6 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
             mbar_wait(&hdr->full[stage], phase);
             const uint4* src = (const uint4*)(ring + (size_t)stage * kWChunkBytes + (size_t)tid * 48);
             const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
-            asm volatile("" ::"r"(v0.x), "r"(v0.w), "r"(v1.x), "r"(v1.w), "r"(v2.x), "r"(v2.w) : "memory");   // loads returned (see above)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hdr->empty[stage]);
             const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
             const int64_t s_base = (int64_t)c * kWChunkCalls + (int64_t)tid * 8;
 #pragma unroll
@@ -503,6 +507,13 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
                     h_len += ((ca >> 16) == (cb >> 16)) | (a == b);
                     h_seq += ((ca & 0xffffu) == (cb & 0xffffu)) | (a == b);
                 }
+            }
+            // release the slot after the chunk has been consumed (the counter updates above depend on every loaded
+            // word), never while a read of the slot may still be in flight: see scan_pairs_kernel
+            {
+                const unsigned any = w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7] | w[8] | w[9] | w[10] | w[11];
+                const bool returned = __all_sync(0xffffffffu, any != 0x7fff7fffu || n_full >= 0);
+                if (lane == 0 && returned) mbar_arrive(&hdr->empty[stage]);
             }
         }
         n_full = warp_sum(n_full); n_non = warp_sum(n_non); n_pad = warp_sum(n_pad);
