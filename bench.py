@@ -262,12 +262,13 @@ def run_gpu(args):
             dist.barrier()
         ctx.synchronize()
 
+    STAT_COLS = ("thresh", "het", "entropy", "mean", "mode", "var", "hwep")
+    plan = tdist.GatherPlan(dist, len(STAT_COLS), L) if dist is not None else None
+
     def gather_rows(st):
-        """NCCL gather of the fixed-width per-locus result rows (north_star: the only collective)."""
-        if dist is None:
-            return
-        rows = np.stack([st[k][0] for k in ("thresh", "het", "entropy", "mean", "mode", "var", "hwep")], axis=1)
-        tdist.gather_table(dist, rows)
+        """NCCL gather of the fixed-width per-locus result table on rank 0 (north_star: the only collective)."""
+        if plan is not None:
+            plan.gather([st[k][0] for k in STAT_COLS])
 
     for _ in range(max(args.warmup, 0)):
         gather_rows(step())

@@ -26,6 +26,18 @@ def main():
     dp_total = tdist.allreduce_sum(d, dp + rank)
     t = tdist.max_over_ranks(d, 10.0 + rank)
     ok = True
+    # fixed-shape plan (bench.py's per-step gather): 3 columns x 17 rows per rank, twice through the same buffers
+    plan = tdist.GatherPlan(d, 3, 17)
+    for rep in range(2):
+        cols = [np.arange(17, dtype=np.float64) + 100 * rank + rep, np.full(17, float(rank)), np.full(17, np.nan)]
+        got = plan.gather(cols)
+        if rank == 0:
+            ok = ok and got.shape == (world, 3, 17)
+            for r in range(world):
+                ok = ok and np.array_equal(got[r, 0], np.arange(17, dtype=np.float64) + 100 * r + rep)
+                ok = ok and np.all(got[r, 1] == r) and np.all(np.isnan(got[r, 2]))
+        else:
+            ok = ok and got is None
     if rank == 0:
         want = np.arange(L, dtype=np.float64)
         ok = ok and table.shape == (L, 3) and np.array_equal(table[:, 0], want) and np.array_equal(table[:, 1], want * want)

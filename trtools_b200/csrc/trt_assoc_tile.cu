@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
             const unsigned char* gts = gt_ring + (size_t)stage * kTGtBytes + (size_t)tid * kTRowBytes;
             const double2* zc = (const double2*)(z_ring + (size_t)stage * kZBytes);
             uint32_t mask[kNL];
+            unsigned dep = 0u;      // one word of every shared-memory load of the chunk's LAST sample (see the arrive below)
 #pragma unroll
             for (int h = 0; h < kNL; h++) mask[h] = 0u;
 #pragma unroll
@@ -183,6 +184,10 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                         z[2 * q + 1] = t.y;
                     }
                     const bool ind = z[K] != 0.0;
+                    if (grp == kTChunk / 8 - 1 && j == 7) {
+#pragma unroll
+                        for (int q = 0; q < NZ2; q++) dep ^= (unsigned)__double2loint(z[2 * q]);
+                    }
                     const int k0 = 3 * j, k1 = k0 + 1;
 #pragma unroll
                     for (int h = 0; h < kNL; h++) {
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                         const double* t = mytab + h * kTCons;
                         const double la = t[((da < D[h]) ? da : 1u) * kTLoci];
                         const double lb = t[((db < D[h]) ? db : 1u) * kTLoci];
+                        if (grp == kTChunk / 8 - 1 && j == 7) dep ^= (unsigned)__double2loint(la) ^ (unsigned)__double2loint(lb);
                         const double gs = la + lb;
                         const bool called = (gs == gs);             // an invalid locus has D = 2 and a NaN pad entry: never called
                         const bool ok = called & ind;
@@ -205,8 +211,15 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
+            {
+                // Release the stage only after every shared-memory load of the chunk has RETURNED.  Loads return in order,
+                // so a vote on a value built from the last sample's loads is enough; it is true unless all 32 lanes hold
+                // the constant.  Without the dependency ptxas hoists the arrive above the trailing DFMAs, and the refill
+                // (an async-proxy TMA write) is not ordered behind a generic-proxy read that is still in flight — the
+                // same hazard that made the GT scan miscount on cold launches (profiles/README.md).
+                const bool returned = __any_sync(0xffffffffu, dep != 0x9e3779b9u);
+                if (lane == 0 && returned) mbar_arrive(&empty[stage]);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
 #pragma unroll
             for (int h = 0; h < kNL; h++) mrow[(size_t)c * kTLoci + h * kTCons] = valid[h] ? mask[h] : 0u;

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kWThreads, 1) scan_wide_kernel(ScanParams p, i
             // word), never while a read of the slot may still be in flight: see scan_pairs_kernel
             {
                 const unsigned any = w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7] | w[8] | w[9] | w[10] | w[11];
-                const bool returned = __all_sync(0xffffffffu, any != 0x7fff7fffu || n_full >= 0);
+                const bool returned = __any_sync(0xffffffffu, any != 0x7fff7fffu);   // true unless ALL 32 lanes hold the constant
                 if (lane == 0 && returned) mbar_arrive(&hdr->empty[stage]);
             }
         }

@@ -68,6 +68,53 @@ def gather_table(dist, local: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
     return np.concatenate([o[:k].cpu().numpy() for o, k in zip(out, sizes)], axis=0)
 
 
+class GatherPlan:
+    """Repeated gather of a fixed-shape per-locus table: float64 [n_cols, n_rows] per rank -> [world, n_cols, n_rows] on
+    ``dst``.  Buffers (device send/receive tensors, pinned host result) are allocated once; a gather is then n_cols
+    host->device copies, ONE NCCL gather and one device->host copy — the only collective of the whole path."""
+
+    def __init__(self, dist, n_cols: int, n_rows: int, dst: int = 0):
+        import torch
+        self.dist, self.dst, self.n_cols, self.n_rows = dist, dst, n_cols, n_rows
+        self.world = 1 if dist is None else dist.get_world_size()
+        self.rank = 0 if dist is None else dist.get_rank()
+        if dist is None:
+            self.out = np.empty((1, n_cols, n_rows))
+            return
+        dev = _device(dist)
+        # every rank must bring the same shape (bench: weak scaling, fixed loci per rank)
+        shape = torch.tensor([n_cols, n_rows], dtype=torch.int64, device=dev)
+        lo, hi = shape.clone(), shape.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not (torch.equal(lo, shape) and torch.equal(hi, shape)):
+            raise ValueError("GatherPlan needs the same table shape on every rank; use gather_table for ragged tables")
+        self.send = torch.empty((n_cols, n_rows), dtype=torch.float64, device=dev)
+        self.recv = torch.empty((self.world, n_cols, n_rows), dtype=torch.float64, device=dev) if self.rank == dst else None
+        pin = dev.type == "cuda"
+        self.host = torch.empty((self.world, n_cols, n_rows), dtype=torch.float64, pin_memory=pin) if self.rank == dst else None
+        self.out = None if self.host is None else self.host.numpy()
+
+    def gather(self, columns):
+        """columns: n_cols float64 arrays of length n_rows (host).  Returns [world, n_cols, n_rows] on dst, else None."""
+        import torch
+        if self.dist is None:
+            for j, c in enumerate(columns):
+                self.out[0, j] = c
+            return self.out
+        for j, c in enumerate(columns):
+            self.send[j].copy_(torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)), non_blocking=True)
+        self.dist.gather(self.send, list(self.recv.unbind(0)) if self.rank == self.dst else None, dst=self.dst)
+        if self.rank != self.dst:
+            if self.send.is_cuda:
+                torch.cuda.current_stream().synchronize()     # the host columns may be reused by the caller now
+            return None
+        self.host.copy_(self.recv, non_blocking=True)
+        if self.recv.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        return self.out
+
+
 def allreduce_sum(dist, arr: np.ndarray) -> np.ndarray:
     """Sum an int64 / float64 array over ranks (dumpSTR per-sample accumulators; NaN poison propagates)."""
     if dist is None:
