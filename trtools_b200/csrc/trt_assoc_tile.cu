@@ -304,9 +304,13 @@ __global__ void __launch_bounds__(256, 2) assoc_downdate_mask_kernel(TileParams 
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+        uint32_t m_next = (lane < p.nchunks) ? mrow[(size_t)lane * kTLoci] : 0u;
         for (int cb = 0; cb < p.nchunks; cb += 32) {
-            const int c = cb + lane;
-            uint32_t m = (c < p.nchunks) ? mrow[(size_t)c * kTLoci] : 0u;
+            uint32_t m = m_next;
+            {   // the next window's masks are requested now: their latency hides under this window's work
+                const int cn = cb + 32 + lane;
+                m_next = (cn < p.nchunks) ? mrow[(size_t)cn * kTLoci] : 0u;
+            }
             const int cnt = __popc(m);
             int off = cnt;
 #pragma unroll

@@ -414,17 +414,26 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
                     } break;
                     case CFV_RATIO_FAST: {
                         // RN(raw/den) > thr decided without dividing when raw is clear of thr*den by 2^-50 relative
-                        // (thr > 0 finite, den > 0, raw >= 0); the exact float64 division otherwise (numpy int32/int32)
+                        // (thr > 0 finite, den > 0, raw >= 0); the exact float64 division (numpy int32/int32) only for
+                        // the calls that are not — one rare branch per thread instead of one per call
                         const double t = p.specs[f].thr;
+                        uint32_t slow = 0;
 #pragma unroll
                         for (int j = 0; j < kTS; j++) {
                             const double r = (double)raw[j];
                             const double prod = t * den[j];
                             const double hi = fma(prod, 0x1p-50, prod), lo = fma(prod, -0x1p-50, prod);
-                            bool h1;
-                            if (deni[j] > 0 && raw[j] >= 0 && (r > hi || r < lo)) h1 = r > hi;
-                            else h1 = (r / den[j]) > t;
-                            hit |= h1 ? (1u << j) : 0u;
+                            const bool clear = (deni[j] > 0) & (raw[j] >= 0) & ((r > hi) | (r < lo));
+                            hit |= (r > hi) ? (1u << j) : 0u;
+                            slow |= clear ? 0u : (1u << j);
+                        }
+                        if (slow) {
+#pragma unroll
+                            for (int j = 0; j < kTS; j++) {
+                                if (!((slow >> j) & 1u)) continue;
+                                const bool h1 = ((double)raw[j] / den[j]) > t;
+                                hit = (hit & ~(1u << j)) | (h1 ? (1u << j) : 0u);
+                            }
                         }
                     } break;
                     case CFV_RATIO_EXACT: {
@@ -457,15 +466,20 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
             if (q.acc_slot >= 0) {
                 const int4 a = *reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 16);
                 const int32_t dpv[kTS] = {a.x, a.y, a.z, a.w};
+                uint32_t negm = 0;
 #pragma unroll
                 for (int j = 0; j < kTS; j++) {
                     const bool ps = (pass >> j) & 1u;
                     const int dd = dpv[j];
-                    if (ps && dd < 0) {                       // rare: missing depth poisons, negative depth is an error
-                        if (dd == INT_MIN) poison |= 1u << j;
+                    negm |= (ps & (dd < 0)) ? (1u << j) : 0u;
+                    dps[j] += (ps & (dd >= 0)) ? (long long)dd : 0ll;
+                }
+                if (negm) {                                   // rare: missing depth poisons, negative depth is an error
+#pragma unroll
+                    for (int j = 0; j < kTS; j++) {
+                        if (!((negm >> j) & 1u)) continue;
+                        if (dpv[j] == INT_MIN) poison |= 1u << j;
                         else atomicMin(p.neg_dp_locus, (int)l);
-                    } else {
-                        dps[j] += ps ? (long long)dd : 0ll;
                     }
                 }
             }
