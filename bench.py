@@ -322,18 +322,34 @@ def run_gpu(args):
     blk_tables = [synth.allele_tables(loci, 0, min(Lb, L - b * Lb)) for b in range(nblk)]
     h2d = d2h = 0
 
+    # two contexts (own stream + device buffers each) ping-pong over the blocks: while one block's kernels and result
+    # copies run, the next block's host->device copy is already in flight on the other stream
+    ctxs = [ctx, _lib.Context(local_rank)]
+
     def e2e_step():
         nonlocal h2d, d2h
         h2d = d2h = 0
+
+        def finish(c):
+            nonlocal d2h
+            c.check(c.lib.trt_harmonize(c.h))
+            st_ = c.locus_stats(False, None, 0.01, pinned=True)
+            d2h += sum(v.nbytes for v in st_.values())
+            return st_
+
+        pending, st = None, None
         for b in range(nblk):
+            c = ctxs[b & 1]
             n = blk_tables[b][2].shape[0] - 1
-            ctx.block_begin(n, S, 2, "hipstr")
-            ctx.block_set_gt(host_gt[:n])
-            ctx.block_set_alleles(*blk_tables[b])
-            ctx.check(ctx.lib.trt_harmonize(ctx.h))
-            st = ctx.locus_stats(False, None, 0.01, pinned=True)
+            c.block_begin(n, S, 2, "hipstr")
+            c.block_set_gt(host_gt[:n])                       # asynchronous copy from the pinned block
+            c.block_set_alleles(*blk_tables[b])
             h2d += host_gt[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
-            d2h += sum(v.nbytes for v in st.values())
+            if pending is not None:
+                st = finish(pending)
+            pending = c
+        if pending is not None:
+            st = finish(pending)
         return st
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -347,6 +363,7 @@ def run_gpu(args):
     e2e_ms = tdist.max_over_ranks(dist, e2e_ms)
     e2e_value = world * L / (e2e_ms / 1000.0)
     ctx.free_pinned(host_gt)
+    ctxs[1].close()
 
     # ---- the other two tools of the metric on the same resident block (device-timed, results copied to host) ----
     tools = {}
@@ -427,7 +444,7 @@ def run_gpu(args):
                                    "GT int16 [L][S][3] generated in HBM".format(L, S),
                        "loci_per_gpu": L, "samples": S, "seed": SEED, "parallelism": "loci sharded x{}".format(world),
                        "l2": "inputs ({:.1f} GB) far larger than L2; no flush needed".format(algo_bytes / 1e9),
-                       "e2e": "one pinned {}-locus host block (loci 0..{}) streamed {}x per step; every copy is a real H2D".format(Lb, Lb - 1, nblk),
+                       "e2e": "one pinned {}-locus host block (loci 0..{}) streamed {}x per step through two ping-pong contexts; every copy is a real H2D".format(Lb, Lb - 1, nblk),
                        "device": info["name"], "sm_count": info["sm_count"]},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -242,3 +242,60 @@ def test_filter_classes_are_drop_in(ctx, golden_dir):
         assert (got is None) == (want is None), mine.filter_name()
         if got is not None:
             assert_close(got, want, mine.filter_name())
+
+
+@pytest.mark.parametrize("L,S", [(97, 4104), (20, 2048)])
+def test_call_filter_variants_tma_vs_legacy_vs_numpy(ctx, monkeypatch, L, S):
+    """Every comparison variant of the TMA call-filter kernel (int/float min/max, stutter ratio with zero and missing
+    depths, host-evaluated values) against the legacy kernel on the same block and against numpy."""
+    from trtools_b200 import _lib, synth
+    sl = synth.make_loci(L, seed=1000 + L)
+    calls = synth.fill_calls(sl, S)
+    rng = np.random.default_rng(L)
+    dp = calls.dp.copy()
+    dp[rng.random(dp.shape) < 0.01] = 0                      # 0/0 and x/0 ratios
+    dp[rng.random(dp.shape) < 0.01] = np.iinfo(np.int32).min  # missing depth
+    host = np.where(rng.random((L, S)) < 0.05, rng.random((L, S)) * 10, np.nan).astype(np.float32)
+    specs = [(_lib.CF_MAX, _lib.FMT_DP, 45), (_lib.CF_RATIO_GT, _lib.FMT_DSTUTTER, 0.1), (_lib.CF_MAX, _lib.FMT_Q, 0.9999),
+             (_lib.CF_MIN, _lib.FMT_DP, 12.5), (_lib.CF_HOST_VALUE, _lib.FMT_AUX0, 0.0)]
+
+    def run():
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt(calls.gt)
+        ctx.block_set_format(_lib.FMT_DP, dp)
+        ctx.block_set_format(_lib.FMT_DSTUTTER, calls.dstutter)
+        ctx.block_set_format(_lib.FMT_Q, calls.q)
+        ctx.block_set_format(_lib.FMT_AUX0, host)
+        ctx.block_set_alleles(*synth.allele_tables(sl))
+        counts = np.zeros((len(specs), S), np.int64)
+        numcalls = np.zeros(S, np.int64)
+        totaldp = np.zeros(S)
+        res = ctx.call_filters(specs, _lib.FMT_DP, counts, numcalls, totaldp, want_mask=True, want_trigger=False)
+        return res, counts, numcalls, totaldp
+
+    tma = run()
+    monkeypatch.setenv("TRT_CF_LEGACY", "1")
+    leg = run()
+    monkeypatch.delenv("TRT_CF_LEGACY")
+    for a, b in zip(tma[1:], leg[1:]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(tma[0]["call_mask"], leg[0]["call_mask"])
+    assert np.array_equal(tma[0]["gt_masked"], leg[0]["gt_masked"])
+    assert tma[0]["negative_dp_locus"] == leg[0]["negative_dp_locus"]
+    # numpy restatement (filters.py:327-484: int32 fields compare as float64, float32 fields in float32)
+    nocall = np.any(calls.gt[:, :, :2] == -1, axis=2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = [dp.astype(np.float64) > 45, (calls.dstutter / dp) > 0.1, calls.q > np.float32(0.9999),
+             dp.astype(np.float64) < 12.5, ~np.isnan(host)]
+    want_mask = np.zeros((L, S), np.uint32)
+    for i, fi in enumerate(f):
+        assert np.array_equal(tma[1][i], np.sum(fi & ~nocall, axis=0)), i
+        want_mask |= fi.astype(np.uint32) << i
+    want_mask |= nocall.astype(np.uint32) << 31
+    assert np.array_equal(tma[0]["call_mask"], want_mask)
+    passed = ~np.logical_or.reduce(f) & ~nocall
+    assert np.array_equal(tma[2], passed.sum(axis=0))
+    missing = passed & (dp == np.iinfo(np.int32).min)
+    want_dp = np.where(passed & (dp > 0), dp, 0).sum(axis=0).astype(float)
+    want_dp[missing.any(axis=0)] = np.nan
+    assert np.array_equal(tma[3], want_dp, equal_nan=True)
