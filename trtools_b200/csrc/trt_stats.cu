@@ -174,7 +174,7 @@ struct EpiParams {
     unsigned long long* n_bad;   // device-wide count of genotype entries outside [-2, A)
 };
 
-__global__ void __launch_bounds__(128) locus_epilogue_kernel(EpiParams p) {
+__global__ void __launch_bounds__(64, 11) locus_epilogue_kernel(EpiParams p) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.L * p.G) return;
     const int64_t g = idx / p.L, l = idx % p.L;
@@ -387,7 +387,7 @@ int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G
     ep.n_padded = (long long*)(f + 11 * n_out);
     ep.n_bad = (unsigned long long*)(f + 12 * n_out);
     TRT_CUDA(cudaMemsetAsync(ep.n_bad, 0, 8, ctx->stream));
-    locus_epilogue_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(ep);
+    locus_epilogue_kernel<<<(unsigned)((n_out + 63) / 64), 64, 0, ctx->stream>>>(ep);
     TRT_KERNEL_CHECK();
     return TRT_OK;
 }
