@@ -388,3 +388,44 @@ def test_many_loci_per_cta(ctx, L, S, seed):
             assert int(st["n_called"][0, j]) == want["numcalled"][0], j
             for stat in ("thresh", "hwep", "het", "entropy", "mean", "mode", "var"):
                 assert_close(st[stat][0, j], want[stat][0], "locus {} {}".format(j, stat), abs_tol=1e-300)
+
+
+@pytest.mark.parametrize("L,S", [(60, 4104), (33, 2048), (25, 1001)])
+def test_packed_length_genotype_tensor(ctx, monkeypatch, L, S):
+    """Packed int16 [L][S][P] tensor (device-side GetLengthGenotypes, tr_harmonizer.py:1210-1245): entry = rank of the
+    haplotype's length among the locus' distinct lengths, -1 / -2 sentinels kept.  Vectorised kernel vs the scalar one,
+    vs a numpy restatement, and round-tripped through the oracle's allele lengths."""
+    from oracle import trh as otrh
+    from oracle.records import synth_to_loci
+    from trtools_b200 import synth
+    sl = synth.make_loci(L, seed=400 + L)
+    calls = synth.fill_calls(sl, S)
+
+    def run():
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt(calls.gt)
+        ctx.block_set_alleles(*synth.allele_tables(sl))
+        h = ctx.harmonize()
+        return h, ctx.pack_length_genotypes()
+
+    h, packed = run()
+    monkeypatch.setenv("TRT_PACK_SCALAR", "1")
+    _, packed_scalar = run()
+    monkeypatch.delenv("TRT_PACK_SCALAR")
+    assert packed.shape == (L, S, 2) and packed.dtype == np.int16
+    assert np.array_equal(packed, packed_scalar)
+    off = ctx.locus_off
+    loci = synth_to_loci(sl, calls, with_fmt=False)
+    for l in range(L):
+        lens = h["allele_len"][off[l]:off[l + 1]]
+        uniq = np.unique(lens)
+        rank = np.searchsorted(uniq, lens).astype(np.int16)
+        gt = calls.gt[l, :, :2]
+        want = np.where(gt >= 0, rank[np.clip(gt, 0, len(lens) - 1)], gt)
+        assert np.array_equal(packed[l], want), l
+        if l % 7 == 0:      # length genotypes of the reference = table[packed]
+            oh = otrh.harmonize(loci[l])
+            ref_lens = np.array([oh.ref_allele_length] + list(oh.alt_allele_lengths))
+            lg = np.where(gt >= 0, ref_lens[np.clip(gt, 0, len(lens) - 1)], gt.astype(float))
+            got = np.where(packed[l] >= 0, uniq[np.clip(packed[l], 0, len(uniq) - 1)], packed[l].astype(float))
+            assert np.array_equal(got, lg), l

@@ -23,6 +23,11 @@ if "stat" in tools:
         t2 = time.perf_counter()
         print("statSTR harmonize wall %.3f ms, locus_stats wall %.3f ms (kernels %.3f, scan %.3f)" % (
             (t1 - t0) * 1e3, (t2 - t1) * 1e3, ctx.last_kernel_ms(), ctx.last_scan_ms()), flush=True)
+if "pack" in tools:
+    for i in range(reps):
+        ctx.check(ctx.lib.trt_pack_length_genotypes(ctx.h))
+        ctx.synchronize()
+        print("pack: kernels %.3f ms -> %.0f GB/s of 10 B/call" % (ctx.last_kernel_ms(), 10.0 * L * S / ctx.last_kernel_ms() / 1e6), flush=True)
 if "assoc" in tools:
     rng = np.random.default_rng(SEED)
     traits = np.hstack([rng.standard_normal((S, 1)), rng.standard_normal((S, 10))])

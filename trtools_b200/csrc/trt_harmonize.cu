@@ -15,6 +15,10 @@
 
 #include <algorithm>
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "trt_internal.cuh"
 
 namespace {
@@ -306,6 +310,68 @@ __global__ void pack_kernel(const int16_t* __restrict__ gt, size_t pitch, int64_
     }
 }
 
+// Vectorised pack (diploid, S % 4 == 0): a CTA moves 2048 calls at a time.  Loads are fully coalesced 16-byte
+// vectors into shared memory; a thread then owns 8 consecutive calls (3 x LDS.128 at a 48-byte stride: conflict-free),
+// maps the two alleles of each call through the locus' length-rank table (shared memory) and stages 32 bytes of
+// output, which leave as coalesced 16-byte stores.  10 algorithmic bytes per call (6 read, 4 written).
+constexpr int kPackThreads = 256;
+constexpr int kPackCalls = kPackThreads * 8;          // 2048 calls = 12288 B in, 8192 B out per iteration
+constexpr int kPackMaxRanks = 512;
+
+__global__ void __launch_bounds__(kPackThreads) pack_vec_kernel(const int16_t* __restrict__ gt, size_t pitch, int64_t L, int64_t S,
+                                                                const int32_t* __restrict__ locus_off,
+                                                                const int32_t* __restrict__ len_rank_of_allele,
+                                                                int16_t* __restrict__ out, int loci_per_block) {
+    __shared__ uint4 sin[3 * kPackThreads];
+    __shared__ uint4 sout[2 * kPackThreads];
+    __shared__ int16_t srank[kPackMaxRanks];
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * kPackCalls;          // first call (sample) of this CTA's slab
+    const int64_t ncalls = min((int64_t)kPackCalls, S - c0);
+    const int64_t in_vecs = (ncalls * 6 + 15) / 16;               // 16-byte vectors of the slab (row pitch covers the tail)
+    const int64_t out_vecs = ncalls * 4 / 16;                     // S % 4 == 0 on this path
+    const int64_t l_begin = (int64_t)blockIdx.y * loci_per_block, l_end = min(L, l_begin + loci_per_block);
+    for (int64_t l = l_begin; l < l_end; l++) {
+        const int a0 = locus_off[l];
+        const int A = locus_off[l + 1] - a0;
+        const bool ranks_in_smem = A <= kPackMaxRanks;
+        __syncthreads();                                           // previous iteration's sout / srank readers are done
+        if (ranks_in_smem)
+            for (int a = tid; a < A; a += kPackThreads) srank[a] = (int16_t)len_rank_of_allele[a0 + a];
+        const uint4* src = (const uint4*)((const char*)gt + (size_t)l * pitch + (size_t)c0 * 6);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int i = r * kPackThreads + tid;
+            if (i < in_vecs) sin[i] = src[i];
+        }
+        __syncthreads();
+        if ((int64_t)tid * 8 < ncalls) {
+            const uint4 v0 = sin[3 * tid], v1 = sin[3 * tid + 1], v2 = sin[3 * tid + 2];
+            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k0 = 3 * j, k1 = k0 + 1;
+                const int a = (k0 & 1) ? ((int)w[k0 >> 1] >> 16) : (int)(short)(w[k0 >> 1] & 0xffffu);
+                const int b = (k1 & 1) ? ((int)w[k1 >> 1] >> 16) : (int)(short)(w[k1 >> 1] & 0xffffu);
+                int ra = a, rb = b;                                // -1 / -2 sentinels pass through
+                if (a >= 0) ra = a < A ? (ranks_in_smem ? (int)srank[a] : len_rank_of_allele[a0 + a]) : -1;
+                if (b >= 0) rb = b < A ? (ranks_in_smem ? (int)srank[b] : len_rank_of_allele[a0 + b]) : -1;
+                o[j] = (uint32_t)(uint16_t)(int16_t)ra | ((uint32_t)(uint16_t)(int16_t)rb << 16);
+            }
+            sout[2 * tid] = make_uint4(o[0], o[1], o[2], o[3]);
+            sout[2 * tid + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        __syncthreads();
+        uint4* dst = (uint4*)(out + ((size_t)l * S + c0) * 2);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int i = r * kPackThreads + tid;
+            if (i < out_vecs) dst[i] = sout[i];
+        }
+    }
+}
+
 // rank of each allele's length class among the locus' distinct lengths (ascending)
 __global__ void len_rank_kernel(const int32_t* __restrict__ locus_off, const int32_t* __restrict__ len_order,
                                 const int32_t* __restrict__ len_class, int64_t L, int32_t* __restrict__ rank_out) {
@@ -426,10 +492,22 @@ int trt_pack_length_genotypes(trt_ctx* ctx) {
             (const int32_t*)ctx->locus_off.p, (const int32_t*)ctx->len_order.p, (const int32_t*)ctx->len_class.p, L,
             (int32_t*)ctx->stat_i32.p);
         TRT_KERNEL_CHECK();
-        dim3 grid((unsigned)std::min<int64_t>((S + 255) / 256, 64), (unsigned)std::min<int64_t>(L, 32768));
-        pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_gt_active, ctx->gt_active_pitch, L, S, ctx->P,
-                                                   (const int32_t*)ctx->locus_off.p, (const int32_t*)ctx->stat_i32.p,
-                                                   (int16_t*)ctx->packed.p);
+        if (ctx->P == 2 && S % 4 == 0 && (ctx->gt_active_pitch % 16) == 0 && ((uintptr_t)ctx->d_gt_active % 16) == 0 &&
+            !getenv("TRT_PACK_SCALAR")) {
+            const int64_t slabs = (S + kPackCalls - 1) / kPackCalls;
+            // enough CTAs to fill the machine several times; each walks a chunk of loci over its sample slab
+            int64_t per = std::max<int64_t>(1, (L * slabs) / ((int64_t)ctx->sm_count * 64));
+            per = std::min<int64_t>(per, 64);
+            dim3 grid((unsigned)slabs, (unsigned)((L + per - 1) / per));
+            pack_vec_kernel<<<grid, kPackThreads, 0, ctx->stream>>>(ctx->d_gt_active, ctx->gt_active_pitch, L, S,
+                                                                     (const int32_t*)ctx->locus_off.p,
+                                                                     (const int32_t*)ctx->stat_i32.p, (int16_t*)ctx->packed.p, (int)per);
+        } else {
+            dim3 grid((unsigned)std::min<int64_t>((S + 255) / 256, 64), (unsigned)std::min<int64_t>(L, 32768));
+            pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_gt_active, ctx->gt_active_pitch, L, S, ctx->P,
+                                                       (const int32_t*)ctx->locus_off.p, (const int32_t*)ctx->stat_i32.p,
+                                                       (int16_t*)ctx->packed.p);
+        }
         TRT_KERNEL_CHECK();
         trt_timer_end(ctx);
     }
