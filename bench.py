@@ -396,6 +396,17 @@ def run_gpu(args):
             ms_ = max(dev, wall) / steps
             return tdist.max_over_ranks(dist, ms_), float(np.mean(scan))
 
+        def pack_step():
+            ctx.check(ctx.lib.trt_pack_length_genotypes(ctx.h))
+            ctx.synchronize()
+            pack_step.kernel = ctx.last_kernel_ms()
+
+        ms_p, _ = timed(pack_step, 3, 1)
+        tools["pack"] = {"value": world * L / (ms_p / 1000.0), "unit": "loci/s", "ms_per_step": ms_p,
+                         "workload": "packed int16 [L][S][2] length-genotype tensor from the native GT rows (SURVEY.md 8d K1 without "
+                                     "the harmonize kernel); the statistics kernels do not need it (they read the native rows)",
+                         "kernel_ms": pack_step.kernel, "algorithmic_bytes_per_call": 10,
+                         "roofline_frac": (10.0 * L * S / (pack_step.kernel / 1000.0) / 1e9) / peak}
         ms_a, k_a = timed(lambda: ctx.assoc_ols(20.0, pinned=True), max(2, min(args.steps, 5)), 2)
         tools["associaTR"] = {"value": world * L / (ms_a / 1000.0), "unit": "loci/s", "ms_per_step": ms_a,
                               "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; allele-count scan + "
