@@ -531,246 +531,6 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Shared-memory staged variant (the default for diploid blocks with plain 4-byte [L][S] fields): many small CTAs
-// instead of one persistent CTA per SM.  A CTA owns a 2048-sample slab and walks a chunk of loci; per locus every
-// thread issues its coalesced 16-byte loads of GT and of the fields at once (7 independent loads in flight for two
-// fields), the slab is processed from shared memory (a thread owns 8 consecutive samples: per-sample counters in
-// registers / thread-private shared-memory columns), filtered calls are patched in place and the slab leaves as
-// coalesced 16-byte stores.  Same pattern as pack_vec_kernel (87 % of the measured copy peak).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kVS = 8;                     // samples per thread
-constexpr int kVecThreads = kSlabSamples / kVS;   // 256
-#ifndef TRT_CF_VEC_MINB
-#define TRT_CF_VEC_MINB 3
-#endif
-template <bool WANT_MASK>
-__global__ void __launch_bounds__(kVecThreads, TRT_CF_VEC_MINB) call_filter_vec_kernel(CfTmaParams q) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const CfParams& p = q.base;
-    unsigned char* sgt = smem;                                            // [12288] GT slab of the current locus
-    unsigned char* sfld = smem + kTmaGtBytes;                             // [n_fields][8192]
-    unsigned int* fcnt = (unsigned int*)(sfld + (size_t)q.n_fields * kTmaFieldBytes);   // [n_specs][8][256]
-    const int tid = threadIdx.x;
-    const int64_t slab = blockIdx.x, chunk = blockIdx.y;
-    const int64_t s0 = slab * kSlabSamples;
-    const int64_t ns = min((int64_t)kSlabSamples, p.S - s0);
-    const int gt_vecs = (int)((ns * 6 + 15) / 16);                        // the row pitch covers the tail
-    const int f_vecs = (int)(ns * 4 / 16);                                // S % 4 == 0 on this path
-    const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
-    const int64_t sb = s0 + (int64_t)tid * kVS;                           // first sample of this thread
-    constexpr uint32_t kAll = (1u << kVS) - 1u;
-    const uint32_t valid_mask = (sb + kVS <= p.S) ? kAll : (sb >= p.S ? 0u : ((1u << (int)(p.S - sb)) - 1u));
-    for (int f = 0; f < p.n_specs; f++)
-#pragma unroll
-        for (int j = 0; j < kVS; j++) fcnt[(f * kVS + j) * kVecThreads + tid] = 0;
-    int ncalls[kVS];
-    long long dps[kVS];
-    unsigned int poison = 0;
-#pragma unroll
-    for (int j = 0; j < kVS; j++) { ncalls[j] = 0; dps[j] = 0; }
-
-    for (int64_t l = l0; l < l1; l++) {
-        __syncthreads();                                                  // the previous locus' stores have read sgt
-        {
-            const uint4* g = (const uint4*)((const char*)p.gt + (size_t)l * p.pitch + (size_t)s0 * 6);
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const int i = r * kVecThreads + tid;
-                if (i < gt_vecs) ((uint4*)sgt)[i] = g[i];
-            }
-            for (int k = 0; k < q.n_fields; k++) {
-                const uint4* fsrc = (const uint4*)((const char*)p.fmt[q.field_of_slot[k]] + ((size_t)l * p.S + s0) * 4);
-                uint4* fdst = (uint4*)(sfld + (size_t)k * kTmaFieldBytes);
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const int i = r * kVecThreads + tid;
-                    if (i < f_vecs) fdst[i] = fsrc[i];
-                }
-            }
-        }
-        __syncthreads();
-        {
-            uint4* gsrc = reinterpret_cast<uint4*>(sgt + (size_t)tid * 48);
-            const uint4 v0 = gsrc[0], v1 = gsrc[1], v2 = gsrc[2];
-            uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            // bit j of the masks = call j of this thread
-            uint32_t nocall = 0;
-#pragma unroll
-            for (int j = 0; j < kVS; j++) {
-                const int k0 = 3 * j, k1 = k0 + 1;
-                const uint32_t a = (k0 & 1) ? (w[k0 >> 1] >> 16) : (w[k0 >> 1] & 0xffffu);
-                const uint32_t b = (k1 & 1) ? (w[k1 >> 1] >> 16) : (w[k1 >> 1] & 0xffffu);
-                nocall |= ((a == 0xffffu) | (b == 0xffffu)) ? (1u << j) : 0u;
-            }
-            uint32_t fired_any = 0;
-            uint32_t fired[kVS];
-            if (WANT_MASK) {
-#pragma unroll
-                for (int j = 0; j < kVS; j++) fired[j] = 0;
-            }
-            double den[kVS];
-            int32_t deni[kVS];
-            if (q.dp_slot >= 0) {
-                const int4* d4 = reinterpret_cast<const int4*>(sfld + (size_t)q.dp_slot * kTmaFieldBytes + (size_t)tid * 32);
-                const int4 a = d4[0], bb = d4[1];
-                deni[0] = a.x; deni[1] = a.y; deni[2] = a.z; deni[3] = a.w; deni[4] = bb.x; deni[5] = bb.y; deni[6] = bb.z; deni[7] = bb.w;
-#pragma unroll
-                for (int j = 0; j < kVS; j++) den[j] = (double)deni[j];
-            }
-            for (int f = 0; f < p.n_specs; f++) {
-                const int variant = p.specs[f].variant;
-                const int4* d4 = reinterpret_cast<const int4*>(sfld + (size_t)q.slot_of_spec[f] * kTmaFieldBytes + (size_t)tid * 32);
-                const int4 a = d4[0], bb = d4[1];
-                const int32_t raw[kVS] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
-                uint32_t hit = 0;
-                switch (variant) {      // uniform across the grid
-                    case CFV_MIN_I32: {
-                        const long long t = p.specs[f].thr_i64;
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) hit |= ((long long)raw[j] < t) ? (1u << j) : 0u;
-                    } break;
-                    case CFV_MAX_I32: {
-                        const long long t = p.specs[f].thr_i64;
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) hit |= ((long long)raw[j] > t) ? (1u << j) : 0u;
-                    } break;
-                    case CFV_MIN_F32: {
-                        const float t = p.specs[f].thr_f32;
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) hit |= (__int_as_float(raw[j]) < t) ? (1u << j) : 0u;
-                    } break;
-                    case CFV_MAX_F32: {
-                        const float t = p.specs[f].thr_f32;
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) hit |= (__int_as_float(raw[j]) > t) ? (1u << j) : 0u;
-                    } break;
-                    case CFV_RATIO_FAST: {
-                        // RN(raw/den) > thr decided without dividing when raw is clear of thr*den by 2^-50 relative
-                        // (thr > 0 finite, den > 0, raw >= 0); the exact float64 division (numpy int32/int32) only for
-                        // the calls that are not — one rare branch per thread instead of one per call
-                        const double t = p.specs[f].thr;
-                        uint32_t slow = 0;
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) {
-                            const double r = (double)raw[j];
-                            const double prod = t * den[j];
-                            const double hi = fma(prod, 0x1p-50, prod), lo = fma(prod, -0x1p-50, prod);
-                            const bool clear = (deni[j] > 0) & (raw[j] >= 0) & ((r > hi) | (r < lo));
-                            hit |= (r > hi) ? (1u << j) : 0u;
-                            slow |= clear ? 0u : (1u << j);
-                        }
-                        if (slow) {
-#pragma unroll
-                            for (int j = 0; j < kVS; j++) {
-                                if (!((slow >> j) & 1u)) continue;
-                                const bool h1 = ((double)raw[j] / den[j]) > t;
-                                hit = (hit & ~(1u << j)) | (h1 ? (1u << j) : 0u);
-                            }
-                        }
-                    } break;
-                    case CFV_RATIO_EXACT: {
-                        const double t = p.specs[f].thr;
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) hit |= (((double)raw[j] / den[j]) > t) ? (1u << j) : 0u;
-                    } break;
-                    case CFV_HOST: {
-#pragma unroll
-                        for (int j = 0; j < kVS; j++) hit |= !isnan(__int_as_float(raw[j])) ? (1u << j) : 0u;
-                    } break;
-                    default: break;
-                }
-                hit &= valid_mask;
-                fired_any |= hit;
-                const uint32_t cnt = hit & ~nocall;
-                if (cnt) {
-#pragma unroll
-                    for (int j = 0; j < kVS; j++)
-                        if ((cnt >> j) & 1u) fcnt[(f * kVS + j) * kVecThreads + tid] += 1;
-                }
-                if (WANT_MASK) {
-#pragma unroll
-                    for (int j = 0; j < kVS; j++) fired[j] |= ((hit >> j) & 1u) << f;
-                }
-            }
-            const uint32_t pass = ~fired_any & ~nocall & valid_mask;
-#pragma unroll
-            for (int j = 0; j < kVS; j++) ncalls[j] += (pass >> j) & 1u;
-            if (q.acc_slot >= 0) {
-                const int4* d4 = reinterpret_cast<const int4*>(sfld + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 32);
-                const int4 a = d4[0], bb = d4[1];
-                const int32_t dpv[kVS] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
-                uint32_t negm = 0;
-#pragma unroll
-                for (int j = 0; j < kVS; j++) {
-                    const bool ps = (pass >> j) & 1u;
-                    const int dd = dpv[j];
-                    negm |= (ps & (dd < 0)) ? (1u << j) : 0u;
-                    dps[j] += (ps & (dd >= 0)) ? (long long)dd : 0ll;
-                }
-                if (negm) {                                   // rare: missing depth poisons, negative depth is an error
-#pragma unroll
-                    for (int j = 0; j < kVS; j++) {
-                        if (!((negm >> j) & 1u)) continue;
-                        if (dpv[j] == INT_MIN) poison |= 1u << j;
-                        else atomicMin(p.neg_dp_locus, (int)l);
-                    }
-                }
-            }
-            if (WANT_MASK && sb < p.S) {
-                uint32_t* cm = p.call_mask + (size_t)l * p.S + sb;
-                uint32_t m[kVS];
-#pragma unroll
-                for (int j = 0; j < kVS; j++) m[j] = fired[j] | (((nocall >> j) & 1u) ? 0x80000000u : 0u);
-                if (sb + kVS <= p.S) {
-                    reinterpret_cast<uint4*>(cm)[0] = make_uint4(m[0], m[1], m[2], m[3]);
-                    reinterpret_cast<uint4*>(cm)[1] = make_uint4(m[4], m[5], m[6], m[7]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kVS; j++)
-                        if (sb + j < p.S) cm[j] = m[j];
-                }
-            }
-            const uint32_t filt = fired_any & ~nocall;       // filtered calls: every haplotype -> '.', unphased
-            if (filt) {
-#pragma unroll
-                for (int j = 0; j < kVS; j++) {
-                    if (!((filt >> j) & 1u)) continue;
-#pragma unroll
-                    for (int k = 3 * j; k < 3 * j + 3; k++) {
-                        const uint32_t val = (k == 3 * j + 2) ? 0u : 0xffffu;
-                        w[k >> 1] = (k & 1) ? ((w[k >> 1] & 0x0000ffffu) | (val << 16)) : ((w[k >> 1] & 0xffff0000u) | val);
-                    }
-                }
-                gsrc[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                gsrc[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                gsrc[2] = make_uint4(w[8], w[9], w[10], w[11]);
-            }
-        }
-        __syncthreads();
-        {
-            uint4* g = (uint4*)((char*)p.gt_out + (size_t)l * p.pitch + (size_t)s0 * 6);
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const int i = r * kVecThreads + tid;
-                if (i < gt_vecs) g[i] = ((const uint4*)sgt)[i];
-            }
-        }
-    }
-    // ---- flush the per-sample accumulators of this (slab, chunk) -----------------------------------
-#pragma unroll
-    for (int j = 0; j < kVS; j++) {
-        if (sb + j >= p.S) continue;
-        if (ncalls[j]) atomicAdd((unsigned long long*)&p.numcalls[sb + j], (unsigned long long)ncalls[j]);
-        if (dps[j]) atomicAdd((unsigned long long*)&p.dpsum[sb + j], (unsigned long long)dps[j]);
-        if ((poison >> j) & 1u) atomicOr(&p.dp_poison[sb + j], 1u);
-        for (int f = 0; f < p.n_specs; f++) {
-            const unsigned int c = fcnt[(f * kVS + j) * kVecThreads + tid];
-            if (c) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + sb + j], (unsigned long long)c);
-        }
-    }
-}
-
 // generic ploidy variant (P != 2): one thread per call, plain atomics; correctness path only
 __global__ void call_filter_generic_kernel(CfParams p, int P) {
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.L * p.S;
@@ -1008,21 +768,7 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
                 q.n_items = q.n_slabs * ((L + per - 1) / per);
                 const size_t smem = (size_t)stages * stage_bytes + fixed;
                 const int grid = (int)std::min<int64_t>(q.n_items, ctx->sm_count);
-                if (!getenv("TRT_CF_TMA")) {
-                    // default: shared-memory staged kernel, grid = slabs x locus chunks
-                    const size_t vsmem = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes +
-                                         (size_t)std::max(n_specs, 1) * kSlabSamples * 4;
-                    int64_t per_v = std::max<int64_t>(16, std::min<int64_t>(128, (L * q.n_slabs) / ((int64_t)ctx->sm_count * 32) + 1));
-                    q.loci_per_item = (int)per_v;
-                    dim3 vgrid((unsigned)q.n_slabs, (unsigned)((L + per_v - 1) / per_v));
-                    if (p.call_mask) {
-                        TRT_CUDA(cudaFuncSetAttribute(call_filter_vec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-                        call_filter_vec_kernel<true><<<vgrid, kVecThreads, vsmem, ctx->stream>>>(q);
-                    } else {
-                        TRT_CUDA(cudaFuncSetAttribute(call_filter_vec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-                        call_filter_vec_kernel<false><<<vgrid, kVecThreads, vsmem, ctx->stream>>>(q);
-                    }
-                } else if (p.call_mask) {
+                if (p.call_mask) {
                     TRT_CUDA(cudaFuncSetAttribute(call_filter_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     call_filter_tma_kernel<true><<<grid, kTmaCons + 64, smem, ctx->stream>>>(q);
                 } else {
