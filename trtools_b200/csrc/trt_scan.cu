@@ -110,6 +110,7 @@ constexpr int kPChunkBytes = kPT * 48;         // 24576 B = 4096 calls; thread t
 constexpr int kPChunkCalls = kPT * 8;
 constexpr int kPMaxStages = 6;
 constexpr int kPMinStages = 3;
+constexpr int kPDefaultSub = 1;                // chunks per ring stage (TRT_SCAN_NSUB overrides)
 constexpr int kPMaxDigits = kPairsMaxAlleles + 3;
 constexpr int kPMaxBins = kPMaxDigits * (kPMaxDigits + 1) / 2;   // unordered digit pairs of the largest tier
 constexpr int kPRowBytes = kPT * 2;            // one table row: 512 thread-private 16-bit cells
@@ -154,11 +155,13 @@ __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.
 // Per locus the bins are ORDERED digit pairs d0*D + d1 (one IMAD per call, D^2 rows) while D^2 <= kSquareRows,
 // otherwise UNORDERED pairs (D(D+1)/2 rows, ~4 more instructions per call).
 template <bool MASKED>
-__global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages) {
+__global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages, int nsub) {
+    // a ring stage holds nsub chunks of 24576 B and is filled by ONE bulk copy (fewer, larger TMA requests per SM)
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
-    PairHeader* hdr = (PairHeader*)(smem + (size_t)stages * kPChunkBytes);
-    uint16_t* table = (uint16_t*)(smem + (size_t)stages * kPChunkBytes + sizeof(PairHeader));   // [max_rows + 1][512]
+    const size_t stage_bytes = (size_t)nsub * kPChunkBytes;
+    PairHeader* hdr = (PairHeader*)(smem + (size_t)stages * stage_bytes);
+    uint16_t* table = (uint16_t*)(smem + (size_t)stages * stage_bytes + sizeof(PairHeader));   // [max_rows + 1][512]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -166,12 +169,13 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     const size_t copy_bytes = (row_bytes + 15) & ~size_t(15);
     const int nchunks = (int)((copy_bytes + kPChunkBytes - 1) / kPChunkBytes);
     const int nfull = (int)(p.S / kPChunkCalls);   // chunks whose calls are all real samples
+    const int nst = (nchunks + nsub - 1) / nsub;    // ring stages per locus
     const unsigned trash = (unsigned)max_rows;     // extra row: calls beyond S in the last chunk land here
     // the non-blocking hand-off to warp 0 relies on the ring keeping the warps within one locus of each other
 #ifdef TRT_SCAN_BLOCKING_HANDOFF
     const bool loose = false;
 #else
-    const bool loose = nchunks > stages;
+    const bool loose = nst > stages;
 #endif
 
     if (tid == 0) {
@@ -195,12 +199,12 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             for (int i = blockIdx.x; i < p.n_list; i += gridDim.x) {
                 const int64_t l = p.list[i];
                 const char* src = (const char*)p.gt + (size_t)l * p.pitch;
-                for (int c = 0; c < nchunks; c++) {
+                for (int st = 0; st < nst; st++) {
                     mbar_wait(&hdr->empty[stage], phase ^ 1u);
-                    const size_t off = (size_t)c * kPChunkBytes;
-                    const uint32_t bytes = (uint32_t)min((size_t)kPChunkBytes, copy_bytes - off);
+                    const size_t off = (size_t)st * stage_bytes;
+                    const uint32_t bytes = (uint32_t)min(stage_bytes, copy_bytes - off);
                     mbar_arrive_expect_tx(&hdr->full[stage], bytes);
-                    tma_load_1d(ring + (size_t)stage * kPChunkBytes, src + off, bytes, &hdr->full[stage]);
+                    tma_load_1d(ring + (size_t)stage * stage_bytes, src + off, bytes, &hdr->full[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -227,22 +231,28 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
 
         for (int c = 0; c < nchunks; c++) {
             const long long t0 = p.dbg ? clock64() : 0;
-            mbar_wait(&hdr->full[stage], phase);
+            const int sub = c % nsub;                       // chunk within its ring stage
+            const bool last_sub = (sub == nsub - 1) || (c == nchunks - 1);
+            if (sub == 0) mbar_wait(&hdr->full[stage], phase);
             if (p.dbg && tid == 32 && blockIdx.x == 0) dbg_wait += clock64() - t0;
             if (p.stream_only) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hdr->empty[stage]);
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                if (last_sub) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
                 continue;
             }
-            const uint4* sp = (const uint4*)(ring + (size_t)stage * kPChunkBytes + (size_t)tid * 48);
+            const uint4* sp = (const uint4*)(ring + (size_t)stage * stage_bytes + (size_t)sub * kPChunkBytes + (size_t)tid * 48);
             const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
 #ifdef TRT_SCAN_EARLY_ARRIVE
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+            if (last_sub) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+            }
 #endif
             const int stage_used = stage;
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            if (last_sub && ++stage == stages) { stage = 0; phase ^= 1u; }
             const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
             unsigned idx[8], dg0[8], dg1[8];
 #pragma unroll
@@ -266,9 +276,10 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 // loaded word (it is always true, bins are < 2^16, but the compiler cannot prove it), so the arrive cannot
                 // issue while a generic-proxy read of the slot is still in flight — the refill is an async-proxy (TMA)
                 // write, which is not ordered behind such a read.
+                // (loads return in order, so the last chunk of a stage vouches for the earlier ones)
                 const unsigned any = idx[0] | idx[1] | idx[2] | idx[3] | idx[4] | idx[5] | idx[6] | idx[7];
                 const bool returned = __all_sync(0xffffffffu, any != 0xffffffffu);
-                if (lane == 0 && returned) mbar_arrive(&hdr->empty[stage_used]);
+                if (last_sub && lane == 0 && returned) mbar_arrive(&hdr->empty[stage_used]);
             }
 #endif
             if (MASKED || c >= nfull) {
@@ -620,16 +631,23 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
         sp.n_list = n_tier[t];
         const int rows = rows_in_tier[t];
         const size_t table = (size_t)(rows + 1) * kPRowBytes;
-        int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
-        stages = std::max(kPMinStages, std::min(kPMaxStages, stages));
-        const size_t smem = (size_t)stages * kPChunkBytes + sizeof(PairHeader) + table;
+        // chunks per ring stage: one bulk copy per stage, so larger stages mean fewer TMA requests per byte
+        int nsub = getenv("TRT_SCAN_NSUB") ? atoi(getenv("TRT_SCAN_NSUB")) : kPDefaultSub;
+        nsub = std::max(1, std::min(nsub, 4));
+        int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / ((size_t)nsub * kPChunkBytes));
+        if (stages < 2) {
+            nsub = 1;
+            stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
+        }
+        stages = std::max(nsub > 1 ? 2 : kPMinStages, std::min(kPMaxStages, stages));
+        const size_t smem = (size_t)stages * nsub * kPChunkBytes + sizeof(PairHeader) + table;
         if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
         if (d_mask) {
             TRT_TRY(set_smem(ctx, scan_pairs_kernel<true>, smem));
-            scan_pairs_kernel<true><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
+            scan_pairs_kernel<true><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages, nsub);
         } else {
             TRT_TRY(set_smem(ctx, scan_pairs_kernel<false>, smem));
-            scan_pairs_kernel<false><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
+            scan_pairs_kernel<false><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages, nsub);
         }
         TRT_KERNEL_CHECK();
     }
