@@ -340,6 +340,28 @@ def test_trrecord_api_known_answers(ctx):
     lg = tr.GetLengthGenotypes()
     assert lg.dtype == np.float64 and np.array_equal(lg[:, :-1], [[3, 4], [4, 4], [4, 4], [4, 6], [6, 6], [3, -1]])
     assert np.array_equal(tr.GetDosages(), np.array([7, 8, 8, 10, 12, 3], dtype=np.float32))
+    # accessors around a same-length sequence variant and a lower-ploidy sample; expected values produced by the
+    # unmodified reference on the same record (string genotypes :963-1017, unique mappings :1049-1082, :1247-1273,
+    # ploidies :899-919, normalised dosages :1191-1205)
+    gts_b = [[0, 1], [1, 1], [1, 1], [1, 2], [2, 2], [0, -1], [2, -2]]
+    rec_b = DummyCyvcf2Record(gts_b, "CAGCAGCAG", ["CAGCAGCAGCAG", "CAGCAACAGCAG"])
+    trb = trh.TRRecord(rec_b, "CAGCAGCAG", ["CAGCAGCAGCAG", "CAGCAACAGCAG"], "CAG", "STR1", None)
+    sg = trb.GetStringGenotypes()
+    assert sg.tolist() == [['CAGCAGCAG', 'CAGCAGCAGCAG', '0'], ['CAGCAGCAGCAG', 'CAGCAGCAGCAG', '0'],
+                           ['CAGCAGCAGCAG', 'CAGCAGCAGCAG', '0'], ['CAGCAGCAGCAG', 'CAGCAACAGCAG', '0'],
+                           ['CAGCAACAGCAG', 'CAGCAACAGCAG', '0'], ['CAGCAGCAG', '.', '0'], ['CAGCAACAGCAG', ',', '0']]
+    assert trb.UniqueStringGenotypeMapping() == {0: 0, 1: 1, 2: 2} and trb.UniqueLengthGenotypeMapping() == {0: 0, 1: 1, 2: 1}
+    assert trb.UniqueStringGenotypes() == {0, 1, 2} and trb.UniqueLengthGenotypes() == {0, 1}
+    assert trb.GetSamplePloidies().tolist() == [2, 2, 2, 2, 2, 2, 1] and trb.GetMaxPloidy() == 2 and trb.GetNumSamples() == 7
+    assert np.array_equal(trb.GetDosages(), np.array([7, 8, 8, 8, 8, 3, 4], dtype=np.float32))
+    assert np.array_equal(trb.GetDosages(trh.TRDosageTypes.bestguess_norm),
+                          np.array([1, 2, 2, 2, 2, np.nan, np.nan], dtype=np.float32), equal_nan=True)
+    assert not trb.HasQualityScores()
+    assert trb.GetAlleleCounts() == {3: 2, 4: 10}
+    assert trb.GetAlleleCounts(uselength=False) == {"CAGCAACAGCAG": 4, "CAGCAGCAG": 2, "CAGCAGCAGCAG": 6}
+    assert trb.GetGenotypeCounts() == {(-2, 4): 1, (3, 4): 1, (4, 4): 4}
+    assert np.array_equal(trb.GetCalledSamples(), [True] * 5 + [False, True])
+    assert str(trb) == "STR1 CAG CAGCAGCAG CAGCAGCAGCAG,CAGCAACAGCAG"
     # fabricated alleles (length-only callers)
     rec2 = DummyCyvcf2Record(gts, "A", ["<STR4>", "<STR5.5>"])
     tr2 = trh.TRRecord(rec2, None, None, "CAG", "x", None, ref_allele_length=3, alt_allele_lengths=[4, 5.5])
