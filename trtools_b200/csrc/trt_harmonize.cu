@@ -392,30 +392,8 @@ __global__ void len_rank_kernel(const int32_t* __restrict__ locus_off, const int
 
 }  // namespace
 
-extern "C" {
-
-int trt_harmonize(trt_ctx* ctx) {
-    if (!ctx || !ctx->block_open || !ctx->have_alleles)
-        return trt_set_error(ctx, TRT_ESTATE, "trt_harmonize: call trt_block_begin and trt_block_set_alleles first");
-    TRT_CUDA(cudaSetDevice(ctx->device));
-    const int64_t L = ctx->L, nA = ctx->nA;
-    // motif offsets = exclusive prefix sum of max(period,0)
-    std::vector<int64_t> moff((size_t)L + 1, 0);
-    for (int64_t l = 0; l < L; l++) moff[l + 1] = moff[l] + (ctx->h_period[l] > 0 ? ctx->h_period[l] : 0);
-    ctx->motif_bytes = moff[L];
-    TRT_TRY(trt_ensure(ctx, ctx->motif_off, (size_t)(L + 1) * 8));
-    TRT_CUDA(cudaMemcpyAsync(ctx->motif_off.p, moff.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
-    TRT_TRY(trt_ensure(ctx, ctx->motif, (size_t)ctx->motif_bytes + 16));
-    TRT_TRY(trt_ensure(ctx, ctx->allele_len, (size_t)nA * 8));
-    TRT_TRY(trt_ensure(ctx, ctx->trim_off, (size_t)nA * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->trim_len, (size_t)nA * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->len_class, (size_t)nA * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->seq_class, (size_t)nA * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->len_order, (size_t)nA * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->seq_order, (size_t)nA * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->hrun, (size_t)L * 4));
-    TRT_TRY(trt_ensure(ctx, ctx->hflags, (size_t)L * 4));
+int trt_launch_harmonize(trt_ctx* ctx, cudaStream_t st) {
+    const int64_t L = ctx->L;
     HarmParams P;
     P.seqs = (const char*)ctx->seqs.p;
     P.allele_off = (const int64_t*)ctx->allele_off.p;
@@ -440,27 +418,68 @@ int trt_harmonize(trt_ctx* ctx) {
     P.flags = (int32_t*)ctx->hflags.p;
     P.motif = (char*)ctx->motif.p;
     if (L > 0) {
-        trt_timer_begin(ctx);
         // 8 lanes per locus unless the block has loci with many alleles (lanes stride over alleles / k-mers)
         if (ctx->maxA <= 16 && !getenv("TRT_HARMONIZE_WARP")) {
             const int64_t per = 128 / 8;
-            harmonize_kernel<8><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
+            harmonize_kernel<8><<<(unsigned)((L + per - 1) / per), 128, 0, st>>>(P);
         } else {
             const int64_t per = 128 / 32;
-            harmonize_kernel<32><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
+            harmonize_kernel<32><<<(unsigned)((L + per - 1) / per), 128, 0, st>>>(P);
         }
         TRT_KERNEL_CHECK();
-        trt_timer_end(ctx);
     }
-    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->harmonized = true;
-    ctx->have_packed = false;
     return TRT_OK;
 }
+
+int trt_flush_harmonize(trt_ctx* ctx) {
+    if (!ctx->harm_pending) return TRT_OK;
+    ctx->harm_pending = false;
+    return trt_launch_harmonize(ctx, ctx->stream);
+}
+
+extern "C" {
+
+int trt_harmonize(trt_ctx* ctx) {
+    if (!ctx || !ctx->block_open || !ctx->have_alleles)
+        return trt_set_error(ctx, TRT_ESTATE, "trt_harmonize: call trt_block_begin and trt_block_set_alleles first");
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    const int64_t L = ctx->L, nA = ctx->nA;
+    // motif offsets = exclusive prefix sum of max(period,0)
+    std::vector<int64_t> moff((size_t)L + 1, 0);
+    for (int64_t l = 0; l < L; l++) moff[l + 1] = moff[l] + (ctx->h_period[l] > 0 ? ctx->h_period[l] : 0);
+    ctx->motif_bytes = moff[L];
+    TRT_TRY(trt_ensure(ctx, ctx->motif_off, (size_t)(L + 1) * 8));
+    TRT_CUDA(cudaMemcpyAsync(ctx->motif_off.p, moff.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    TRT_TRY(trt_ensure(ctx, ctx->motif, (size_t)ctx->motif_bytes + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->allele_len, (size_t)nA * 8));
+    TRT_TRY(trt_ensure(ctx, ctx->trim_off, (size_t)nA * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->trim_len, (size_t)nA * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->len_class, (size_t)nA * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->seq_class, (size_t)nA * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->len_order, (size_t)nA * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->seq_order, (size_t)nA * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->hrun, (size_t)L * 4));
+    TRT_TRY(trt_ensure(ctx, ctx->hflags, (size_t)L * 4));
+    ctx->harmonized = true;
+    ctx->have_packed = false;
+    // Lazy: the kernel is launched by the first consumer of its outputs.  trt_locus_stats launches it on the side stream
+    // AFTER the GT scan of the pair-table tiers, so the two overlap (the scan leaves ~half of the issue slots idle and
+    // harmonize needs no shared memory); every other consumer runs it on the main stream first (trt_flush_harmonize).
+    ctx->harm_pending = (L > 0);
+    if (getenv("TRT_HARMONIZE_EAGER")) {
+        TRT_TRY(trt_flush_harmonize(ctx));
+        TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return TRT_OK;
+}
+
+
 
 int trt_get_harmonized(trt_ctx* ctx, trt_harmonize_out* out) {
     if (!ctx || !ctx->harmonized) return trt_set_error(ctx, TRT_ESTATE, "trt_get_harmonized: call trt_harmonize first");
     if (!out) return trt_set_error(ctx, TRT_EINVAL, "trt_get_harmonized: out is NULL");
+    TRT_TRY(trt_flush_harmonize(ctx));
     const int64_t L = ctx->L, nA = ctx->nA;
 #define D2H(dst, buf, bytes) \
     if ((dst) && (bytes)) TRT_CUDA(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream))
@@ -483,6 +502,7 @@ int trt_get_harmonized(trt_ctx* ctx, trt_harmonize_out* out) {
 int trt_pack_length_genotypes(trt_ctx* ctx) {
     if (!ctx || !ctx->harmonized || !ctx->have_gt)
         return trt_set_error(ctx, TRT_ESTATE, "trt_pack_length_genotypes: needs GT and trt_harmonize");
+    TRT_TRY(trt_flush_harmonize(ctx));
     const int64_t L = ctx->L, S = ctx->S;
     TRT_TRY(trt_ensure(ctx, ctx->stat_i32, (size_t)ctx->nA * 4 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->packed, (size_t)L * S * ctx->P * 2 + 16));
