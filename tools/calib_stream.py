@@ -1,5 +1,5 @@
 """Calibration helper (GPU): GT scan time vs the HBM-read ceiling of its own TMA ring (TRT_SCAN_STREAM_ONLY: the
-consumers only drain the ring), for 1..3 chunks of 24 KB per ring stage (TRT_SCAN_NSUB)."""
+consumers only drain the ring), (a 2-3 chunks-per-stage variant was measured with this tool and dropped)."""
 import sys, os, numpy as np
 sys.path.insert(0, '.')
 from trtools_b200 import _lib, synth
@@ -12,8 +12,7 @@ for maxa in [int(x) for x in os.environ.get("CAL_MAXA", "16,6").split(",")]:
     ctx.block_set_alleles(*synth.allele_tables(loci))
     ctx.check(ctx.lib.trt_harmonize(ctx.h))
     ref = None
-    for nsub in (1, 2, 3):
-        os.environ["TRT_SCAN_NSUB"] = str(nsub)
+    for nsub in (1,):
         for mode in ("normal", "stream"):
             os.environ.pop("TRT_SCAN_STREAM_ONLY", None)
             if mode == "stream":

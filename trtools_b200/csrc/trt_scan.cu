@@ -110,7 +110,6 @@ constexpr int kPChunkBytes = kPT * 48;         // 24576 B = 4096 calls; thread t
 constexpr int kPChunkCalls = kPT * 8;
 constexpr int kPMaxStages = 6;
 constexpr int kPMinStages = 3;
-constexpr int kPDefaultSub = 1;                // chunks per ring stage (TRT_SCAN_NSUB overrides)
 constexpr int kPMaxDigits = kPairsMaxAlleles + 3;
 constexpr int kPMaxBins = kPMaxDigits * (kPMaxDigits + 1) / 2;   // unordered digit pairs of the largest tier
 constexpr int kPRowBytes = kPT * 2;            // one table row: 512 thread-private 16-bit cells
@@ -155,8 +154,10 @@ __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.
 // Per locus the bins are ORDERED digit pairs d0*D + d1 (one IMAD per call, D^2 rows) while D^2 <= kSquareRows,
 // otherwise UNORDERED pairs (D(D+1)/2 rows, ~4 more instructions per call).
 template <bool MASKED>
-__global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages, int nsub) {
-    // a ring stage holds nsub chunks of 24576 B and is filled by ONE bulk copy (fewer, larger TMA requests per SM)
+__global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages) {
+    // a ring stage holds nsub chunks of 24576 B and is filled by ONE bulk copy; nsub > 1 was measured (2, 3): no gain in the
+    // ring-only ceiling nor in the scan, so it is a compile-time 1 (a runtime value costs a modulo per chunk)
+    constexpr int nsub = 1;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     const size_t stage_bytes = (size_t)nsub * kPChunkBytes;
@@ -662,23 +663,17 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase, i
         sp.n_list = n_tier[t];
         const int rows = rows_in_tier[t];
         const size_t table = (size_t)(rows + 1) * kPRowBytes;
-        // chunks per ring stage: one bulk copy per stage, so larger stages mean fewer TMA requests per byte
-        int nsub = getenv("TRT_SCAN_NSUB") ? atoi(getenv("TRT_SCAN_NSUB")) : kPDefaultSub;
-        nsub = std::max(1, std::min(nsub, 4));
-        int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / ((size_t)nsub * kPChunkBytes));
-        if (stages < 2) {
-            nsub = 1;
-            stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
-        }
-        stages = std::max(nsub > 1 ? 2 : kPMinStages, std::min(kPMaxStages, stages));
+        const int nsub = 1;
+        int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
+        stages = std::max(kPMinStages, std::min(kPMaxStages, stages));
         const size_t smem = (size_t)stages * nsub * kPChunkBytes + sizeof(PairHeader) + table;
         if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
         if (d_mask) {
             TRT_TRY(set_smem(ctx, scan_pairs_kernel<true>, smem));
-            scan_pairs_kernel<true><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages, nsub);
+            scan_pairs_kernel<true><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
         } else {
             TRT_TRY(set_smem(ctx, scan_pairs_kernel<false>, smem));
-            scan_pairs_kernel<false><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages, nsub);
+            scan_pairs_kernel<false><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
         }
         TRT_KERNEL_CHECK();
     }
