@@ -510,7 +510,6 @@ int trt_assoc_set_design(trt_ctx* ctx, const double* covars, const double* outco
 int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
     if (!ctx || !ctx->block_open || !ctx->have_gt || !ctx->harmonized)
         return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_ols: needs a block with GT and trt_harmonize");
-    TRT_TRY(trt_flush_harmonize(ctx));
     if (!ctx->have_design) return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_ols: call trt_assoc_set_design first");
     if (!out) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_ols: out is NULL");
     TRT_CUDA(cudaSetDevice(ctx->device));

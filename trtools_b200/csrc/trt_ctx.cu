@@ -96,9 +96,6 @@ int trt_init(int device_ordinal, trt_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&ctx->ev_h0, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&ctx->ev_h1, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_s0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_s1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_u0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_u1)) != cudaSuccess) {
@@ -118,7 +115,7 @@ void trt_destroy(trt_ctx* ctx) {
                       &ctx->start, &ctx->end, &ctx->period, &ctx->given_len, &ctx->motif_in, &ctx->allele_len, &ctx->trim_off,
                       &ctx->trim_len, &ctx->len_class, &ctx->seq_class, &ctx->len_order, &ctx->seq_order, &ctx->hrun,
                       &ctx->hflags, &ctx->motif, &ctx->motif_off, &ctx->packed, &ctx->ac, &ctx->ac_part, &ctx->lc, &ctx->group_masks,
-                      &ctx->stat_f64, &ctx->stat_i32, &ctx->work_counter, &ctx->scan_lists, &ctx->scan_pair_off, &ctx->scan_tpairs, &ctx->cf_specs, &ctx->call_mask, &ctx->trig,
+                      &ctx->stat_f64, &ctx->stat_i32, &ctx->work_counter, &ctx->scan_lists, &ctx->cf_specs, &ctx->call_mask, &ctx->trig,
                       &ctx->samp_counts, &ctx->samp_dp, &ctx->misc, &ctx->covars, &ctx->outcome, &ctx->sample_index,
                       &ctx->design_row_of_sample, &ctx->assoc_acc, &ctx->assoc_out, &ctx->assoc_tot, &ctx->assoc_zt, &ctx->assoc_fast_tiles,
                       &ctx->assoc_tile_fast, &ctx->assoc_masks, &ctx->assoc_mom_part, &ctx->dist_send,
@@ -127,10 +124,6 @@ void trt_destroy(trt_ctx* ctx) {
     for (int i = 0; i < TRT_FMT_NFIELDS; i++) trt_free_buf(ctx->fmt_buf[i]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
-    cudaStreamSynchronize(ctx->stream2);
-    cudaEventDestroy(ctx->ev_h0);
-    cudaEventDestroy(ctx->ev_h1);
-    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -211,7 +204,6 @@ int trt_block_begin(trt_ctx* ctx, int64_t n_loci, int64_t n_samples, int ploidy,
     ctx->have_alleles = false;
     ctx->scan_lists_valid = false;
     ctx->harmonized = false;
-    ctx->harm_pending = false;
     ctx->have_packed = false;
     ctx->d_gt = nullptr;
     ctx->d_gt_active = nullptr;
@@ -343,7 +335,6 @@ int trt_block_set_alleles(trt_ctx* ctx, const char* seqs, const int64_t* allele_
     ctx->have_alleles = true;
     ctx->scan_lists_valid = false;
     ctx->harmonized = false;
-    ctx->harm_pending = false;
     ctx->have_packed = false;
     return TRT_OK;
 }

@@ -844,7 +844,6 @@ int trt_locus_filters(trt_ctx* ctx, const trt_locus_filter_spec* specs, int n_sp
                       trt_locus_filter_out* out) {
     if (!ctx || !ctx->block_open || !ctx->have_gt || !ctx->harmonized)
         return trt_set_error(ctx, TRT_ESTATE, "trt_locus_filters: needs a block with GT and trt_harmonize");
-    TRT_TRY(trt_flush_harmonize(ctx));
     if (!out || n_specs < 0 || n_specs > 31 || (n_specs > 0 && !specs))
         return trt_set_error(ctx, TRT_EINVAL, "trt_locus_filters: bad arguments");
     TRT_CUDA(cudaSetDevice(ctx->device));

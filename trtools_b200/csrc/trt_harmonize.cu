@@ -392,51 +392,6 @@ __global__ void len_rank_kernel(const int32_t* __restrict__ locus_off, const int
 
 }  // namespace
 
-int trt_launch_harmonize(trt_ctx* ctx, cudaStream_t st) {
-    const int64_t L = ctx->L;
-    HarmParams P;
-    P.seqs = (const char*)ctx->seqs.p;
-    P.allele_off = (const int64_t*)ctx->allele_off.p;
-    P.locus_off = (const int32_t*)ctx->locus_off.p;
-    P.pos = (const int32_t*)ctx->pos.p;
-    P.start = (const int32_t*)ctx->start.p;
-    P.end = (const int32_t*)ctx->end.p;
-    P.period = (const int32_t*)ctx->period.p;
-    P.given_len = (const double*)ctx->given_len.p;
-    P.motif_in = ctx->have_motif_in ? (const char*)ctx->motif_in.p : nullptr;
-    P.motif_off = (const int64_t*)ctx->motif_off.p;
-    P.L = L;
-    P.vcftype = ctx->vcftype;
-    P.allele_len = (double*)ctx->allele_len.p;
-    P.trim_off = (int32_t*)ctx->trim_off.p;
-    P.trim_len = (int32_t*)ctx->trim_len.p;
-    P.len_class = (int32_t*)ctx->len_class.p;
-    P.seq_class = (int32_t*)ctx->seq_class.p;
-    P.len_order = (int32_t*)ctx->len_order.p;
-    P.seq_order = (int32_t*)ctx->seq_order.p;
-    P.hrun = (int32_t*)ctx->hrun.p;
-    P.flags = (int32_t*)ctx->hflags.p;
-    P.motif = (char*)ctx->motif.p;
-    if (L > 0) {
-        // 8 lanes per locus unless the block has loci with many alleles (lanes stride over alleles / k-mers)
-        if (ctx->maxA <= 16 && !getenv("TRT_HARMONIZE_WARP")) {
-            const int64_t per = 128 / 8;
-            harmonize_kernel<8><<<(unsigned)((L + per - 1) / per), 128, 0, st>>>(P);
-        } else {
-            const int64_t per = 128 / 32;
-            harmonize_kernel<32><<<(unsigned)((L + per - 1) / per), 128, 0, st>>>(P);
-        }
-        TRT_KERNEL_CHECK();
-    }
-    return TRT_OK;
-}
-
-int trt_flush_harmonize(trt_ctx* ctx) {
-    if (!ctx->harm_pending) return TRT_OK;
-    ctx->harm_pending = false;
-    return trt_launch_harmonize(ctx, ctx->stream);
-}
-
 extern "C" {
 
 int trt_harmonize(trt_ctx* ctx) {
@@ -461,25 +416,51 @@ int trt_harmonize(trt_ctx* ctx) {
     TRT_TRY(trt_ensure(ctx, ctx->seq_order, (size_t)nA * 4));
     TRT_TRY(trt_ensure(ctx, ctx->hrun, (size_t)L * 4));
     TRT_TRY(trt_ensure(ctx, ctx->hflags, (size_t)L * 4));
+    HarmParams P;
+    P.seqs = (const char*)ctx->seqs.p;
+    P.allele_off = (const int64_t*)ctx->allele_off.p;
+    P.locus_off = (const int32_t*)ctx->locus_off.p;
+    P.pos = (const int32_t*)ctx->pos.p;
+    P.start = (const int32_t*)ctx->start.p;
+    P.end = (const int32_t*)ctx->end.p;
+    P.period = (const int32_t*)ctx->period.p;
+    P.given_len = (const double*)ctx->given_len.p;
+    P.motif_in = ctx->have_motif_in ? (const char*)ctx->motif_in.p : nullptr;
+    P.motif_off = (const int64_t*)ctx->motif_off.p;
+    P.L = L;
+    P.vcftype = ctx->vcftype;
+    P.allele_len = (double*)ctx->allele_len.p;
+    P.trim_off = (int32_t*)ctx->trim_off.p;
+    P.trim_len = (int32_t*)ctx->trim_len.p;
+    P.len_class = (int32_t*)ctx->len_class.p;
+    P.seq_class = (int32_t*)ctx->seq_class.p;
+    P.len_order = (int32_t*)ctx->len_order.p;
+    P.seq_order = (int32_t*)ctx->seq_order.p;
+    P.hrun = (int32_t*)ctx->hrun.p;
+    P.flags = (int32_t*)ctx->hflags.p;
+    P.motif = (char*)ctx->motif.p;
+    if (L > 0) {
+        trt_timer_begin(ctx);
+        // 8 lanes per locus unless the block has loci with many alleles (lanes stride over alleles / k-mers)
+        if (ctx->maxA <= 16 && !getenv("TRT_HARMONIZE_WARP")) {
+            const int64_t per = 128 / 8;
+            harmonize_kernel<8><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
+        } else {
+            const int64_t per = 128 / 32;
+            harmonize_kernel<32><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
+        }
+        TRT_KERNEL_CHECK();
+        trt_timer_end(ctx);
+    }
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->harmonized = true;
     ctx->have_packed = false;
-    // Lazy: the kernel is launched by the first consumer of its outputs.  trt_locus_stats launches it on the side stream
-    // AFTER the GT scan of the pair-table tiers, so the two overlap (the scan leaves ~half of the issue slots idle and
-    // harmonize needs no shared memory); every other consumer runs it on the main stream first (trt_flush_harmonize).
-    ctx->harm_pending = (L > 0);
-    if (getenv("TRT_HARMONIZE_EAGER")) {
-        TRT_TRY(trt_flush_harmonize(ctx));
-        TRT_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
     return TRT_OK;
 }
-
-
 
 int trt_get_harmonized(trt_ctx* ctx, trt_harmonize_out* out) {
     if (!ctx || !ctx->harmonized) return trt_set_error(ctx, TRT_ESTATE, "trt_get_harmonized: call trt_harmonize first");
     if (!out) return trt_set_error(ctx, TRT_EINVAL, "trt_get_harmonized: out is NULL");
-    TRT_TRY(trt_flush_harmonize(ctx));
     const int64_t L = ctx->L, nA = ctx->nA;
 #define D2H(dst, buf, bytes) \
     if ((dst) && (bytes)) TRT_CUDA(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream))
@@ -502,7 +483,6 @@ int trt_get_harmonized(trt_ctx* ctx, trt_harmonize_out* out) {
 int trt_pack_length_genotypes(trt_ctx* ctx) {
     if (!ctx || !ctx->harmonized || !ctx->have_gt)
         return trt_set_error(ctx, TRT_ESTATE, "trt_pack_length_genotypes: needs GT and trt_harmonize");
-    TRT_TRY(trt_flush_harmonize(ctx));
     const int64_t L = ctx->L, S = ctx->S;
     TRT_TRY(trt_ensure(ctx, ctx->stat_i32, (size_t)ctx->nA * 4 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->packed, (size_t)L * S * ctx->P * 2 + 16));

@@ -19,8 +19,6 @@ struct trt_ctx {
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;      // side stream: the harmonize kernel overlapped with the GT scan (trt_locus_stats)
-    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr;
     double last_scan_ms = 0.0;
     std::string err;
@@ -55,7 +53,6 @@ struct trt_ctx {
 
     // harmonize outputs
     bool    harmonized = false;
-    bool    harm_pending = false;     // trt_harmonize was called but the kernel has not been launched yet (lazy)
     DevBuf  allele_len, trim_off, trim_len, len_class, seq_class, len_order, seq_order, hrun, hflags, motif, motif_off;
     int64_t motif_bytes = 0;
 
@@ -66,8 +63,6 @@ struct trt_ctx {
     // stats scratch (device)
     DevBuf  ac, ac_part, lc, group_masks, stat_f64, stat_i32, work_counter;
     DevBuf  scan_lists;              // per-tier locus lists of the current block (trt_scan.cu)
-    DevBuf  scan_pair_off, scan_tpairs;   // het allele-pair counts of the pair-table tiers (deferred class statistics)
-    int64_t scan_pairs_total = 0;
     bool    scan_lists_valid = false;
     int     scan_tier_off[8] = {0};   // list offsets per tier (+ end)
     bool    want_ac_part = false;
@@ -91,8 +86,6 @@ int  trt_ensure(trt_ctx* ctx, DevBuf& b, size_t bytes);
 void trt_free_buf(DevBuf& b);
 void trt_timer_begin(trt_ctx* ctx);
 void trt_timer_end(trt_ctx* ctx);
-int  trt_launch_harmonize(trt_ctx* ctx, cudaStream_t st);   // trt_harmonize.cu: the kernel launch alone
-int  trt_flush_harmonize(trt_ctx* ctx);                     // run a pending (lazy) harmonize on the main stream
 
 #define TRT_CUDA(call)                                                                          \
     do {                                                                                        \

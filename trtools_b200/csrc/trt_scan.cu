@@ -354,9 +354,8 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             int cl = -1, cq = -1;
             if (lane == 0) cl = cq = -2;
             else if (lane >= 2 && lane < A + 2) {
-                // deferred: every allele its own class here (hom = same index); the epilogue adds the class-equal pairs
-                cl = p.defer_classes ? lane : p.len_class[a0 + lane - 2];
-                cq = p.defer_classes ? lane : p.seq_class[a0 + lane - 2];
+                cl = p.len_class[a0 + lane - 2];
+                cq = p.seq_class[a0 + lane - 2];
             }
             __syncwarp();
             long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
@@ -374,8 +373,6 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 const bool vlo = (lo >= 2u) & (lo < Dm1), vhi = (hi >= 2u) & (hi < Dm1);
                 if (bad) n_bad += n;
                 if (vlo | vhi) n_non += n;
-                if (p.tpairs && vlo && vhi && lo != hi && b0 + lane < nb)      // heterozygous allele pair (lo-2) < (hi-2)
-                    p.tpairs[p.pair_off[l] + (int64_t)(hi - 2u) * (hi - 3u) / 2 + (lo - 2u)] = (int32_t)n;
                 if (!m1) {
                     n_full += n;
                     if (lo == 0u) n_pad += n;
@@ -569,7 +566,7 @@ int set_smem(trt_ctx* ctx, K kernel, size_t smem) {
 }  // namespace
 
 // run the scan (all tiers) for one group mask; results into ctx->ac / ctx->lc at group g
-int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase, int defer_classes) {
+int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     (void)G;
     const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
     ScanParams sp;
@@ -598,9 +595,6 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase, i
     }
     sp.list = nullptr;
     sp.n_list = 0;
-    sp.defer_classes = defer_classes;
-    sp.tpairs = nullptr;
-    sp.pair_off = nullptr;
     sp.stream_only = getenv("TRT_SCAN_STREAM_ONLY") ? 1 : 0;   // HBM-read ceiling of this access pattern (calibration)
     // which tiers occur in this block, and the locus list of each (cached per block: the allele table fixes them)
     int n_tier[TIER_COUNT] = {0};
@@ -628,37 +622,12 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase, i
         if (L) TRT_CUDA(cudaMemcpyAsync(ctx->scan_lists.p, lists.data(), (size_t)L * 4, cudaMemcpyHostToDevice, ctx->stream));
         TRT_CUDA(cudaStreamSynchronize(ctx->stream));   // `lists` is a local
         for (int t = 0; t <= TIER_COUNT; t++) ctx->scan_tier_off[t] = off[t];
-        // offsets of the per-locus heterozygous-pair tables (pair-table tiers only)
-        std::vector<int64_t> poff((size_t)L);
-        int64_t tot = 0;
-        for (int64_t l = 0; l < L; l++) {
-            const int A = ctx->h_locus_off[l + 1] - ctx->h_locus_off[l];
-            const int t = fast ? scan_tier(A) : TIER_GENERIC;
-            if (t == TIER_PAIRS_A || t == TIER_PAIRS_B) {
-                poff[(size_t)l] = tot;
-                tot += (int64_t)A * (A - 1) / 2;
-            } else {
-                poff[(size_t)l] = -1;
-            }
-        }
-        ctx->scan_pairs_total = tot;
-        TRT_TRY(trt_ensure(ctx, ctx->scan_pair_off, (size_t)L * 8 + 16));
-        if (L) TRT_CUDA(cudaMemcpyAsync(ctx->scan_pair_off.p, poff.data(), (size_t)L * 8, cudaMemcpyHostToDevice, ctx->stream));
-        TRT_CUDA(cudaStreamSynchronize(ctx->stream));   // `poff` is a local
         ctx->scan_lists_valid = true;
-    }
-    if (defer_classes) {
-        // zero-filled per call: pairs never seen keep a zero count
-        TRT_TRY(trt_ensure(ctx, ctx->scan_tpairs, (size_t)G * (size_t)std::max<int64_t>(ctx->scan_pairs_total, 1) * 4 + 16));
-        sp.tpairs = (int32_t*)ctx->scan_tpairs.p + (size_t)g * (size_t)ctx->scan_pairs_total;
-        sp.pair_off = (const int64_t*)ctx->scan_pair_off.p;
-        if ((phase & SCAN_PHASE_PAIRS) && ctx->scan_pairs_total)
-            TRT_CUDA(cudaMemsetAsync(sp.tpairs, 0, (size_t)ctx->scan_pairs_total * 4, ctx->stream));
     }
     const int grid_persist = (int)std::min<int64_t>(std::max<int64_t>(L, 1), ctx->sm_count);
     const size_t smem_limit = (size_t)ctx->max_smem_optin;
     for (int t = TIER_PAIRS_A; t <= TIER_PAIRS_B; t++) {
-        if (!n_tier[t] || !(phase & SCAN_PHASE_PAIRS)) continue;
+        if (!n_tier[t]) continue;
         sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[t];
         sp.n_list = n_tier[t];
         const int rows = rows_in_tier[t];
@@ -677,7 +646,7 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase, i
         }
         TRT_KERNEL_CHECK();
     }
-    if (n_tier[TIER_WIDE] && (phase & SCAN_PHASE_REST)) {
+    if (n_tier[TIER_WIDE]) {
         sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[TIER_WIDE];
         sp.n_list = n_tier[TIER_WIDE];
         const int amax = max_in_tier[TIER_WIDE];
@@ -698,7 +667,7 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase, i
         fprintf(stderr, "[scan dbg] wait=%llu proc(incl wait)=%llu end=%llu chunks=%llu  per-chunk wait=%.0f proc=%.0f\n", h[0], h[1], h[2], h[3],
                 h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0);
     }
-    if (n_tier[TIER_GENERIC] && (phase & SCAN_PHASE_REST)) {
+    if (n_tier[TIER_GENERIC]) {
         const int warps_per_block = 8;
         const int64_t blocks = std::min<int64_t>((L + warps_per_block - 1) / warps_per_block, (int64_t)ctx->sm_count * 8);
         scan_generic_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, ctx->stream>>>(sp);

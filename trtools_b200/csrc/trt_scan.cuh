@@ -22,12 +22,6 @@ struct ScanParams {
     int stream_only;       // calibration: consumers only drain the TMA ring (results are meaningless)
     const int32_t* list;   // loci of the tier this launch handles (built on the host per block)
     int n_list;
-    // deferred class statistics (trt_locus_stats with harmonize overlapped): the pair-table tiers do not read the
-    // length / sequence classes; they export the counts of heterozygous allele pairs instead and the epilogue adds the
-    // pairs whose alleles fall in one class to the homozygote counts
-    int defer_classes;
-    int32_t* tpairs;              // [scan_pairs_total]: locus l, alleles a < b at pair_off[l] + b(b-1)/2 + a
-    const int64_t* pair_off;      // [L] (-1: locus not in a pair-table tier)
 };
 
 enum { TIER_PAIRS_A = 0, TIER_PAIRS_B = 1, TIER_WIDE = 2, TIER_GENERIC = 3, TIER_COUNT = 4 };
@@ -47,7 +41,6 @@ __host__ __device__ __forceinline__ int pairs_rows(int A) {
     return pairs_square(A) ? D * D : D * (D + 1) / 2;
 }
 
-enum { SCAN_PHASE_PAIRS = 1, SCAN_PHASE_REST = 2, SCAN_PHASE_ALL = 3 };
-int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G, int phase = SCAN_PHASE_ALL, int defer_classes = 0);
+int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G);
 int trt_prepare_ranks(trt_ctx* ctx);
-int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G, int deferred = 0);
+int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G);

@@ -171,10 +171,6 @@ struct EpiParams {
     int32_t* nalleles;
     long long* n_hom;
     long long *n_called, *n_nonstrict, *n_padded;
-    // deferred class statistics: heterozygous allele-pair counts exported by the pair-table scan tiers
-    const int32_t* tpairs;     // [G][pairs_total] or null
-    const int64_t* pair_off;   // [L] (-1: the scan already applied the classes for this locus)
-    int64_t pairs_total;
     unsigned long long* n_bad;   // device-wide count of genotype entries outside [-2, A)
 };
 
@@ -280,16 +276,7 @@ __global__ void __launch_bounds__(64, 11) locus_epilogue_kernel(EpiParams p) {
     }
     // ---- HWE ---------------------------------------------------------------------------------
     const long long n_full = lc[TRT_LC_NFULL];
-    long long n_hom = p.use_length ? lc[TRT_LC_HOM_LEN] : lc[TRT_LC_HOM_SEQ];
-    if (p.tpairs && p.pair_off[l] >= 0) {
-        // the scan counted index-homozygotes only: add the heterozygous pairs whose alleles share a class
-        const int32_t* tp = p.tpairs + g * p.pairs_total + p.pair_off[l];
-        const int32_t* cls = (p.use_length ? p.len_class : p.seq_class) + a0;
-        n_hom = lc[TRT_LC_HOM_IDX];
-        for (int b = 1; b < A; b++)
-            for (int a = 0; a < b; a++)
-                if (cls[a] == cls[b]) n_hom += tp[b * (b - 1) / 2 + a];
-    }
+    const long long n_hom = p.use_length ? lc[TRT_LC_HOM_LEN] : lc[TRT_LC_HOM_SEQ];
     double hwep = NaN;
     if (total > 0 && lc[TRT_LC_NPAD] == 0 && p.P >= 2 && !isnan(het))
         hwep = binomtest_two_sided((double)n_hom, (double)n_full, sumsq);
@@ -373,7 +360,7 @@ int trt_prepare_ranks(trt_ctx* ctx) {
 
 // epilogue over ctx->ac / ctx->lc -> ctx->stat_f64 = [thresh|het|entropy|mean|mode|var|hwep|nalleles(i32)|n_hom(i64)|
 // n_called|n_called_nonstrict|n_padded (i64)] x G*L, then one u64 bad-entry counter
-int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G, int deferred) {
+int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G) {
     const int64_t L = ctx->L, nA = ctx->nA;
     const size_t n_out = (size_t)G * L;
     if (n_out == 0) return TRT_OK;
@@ -399,9 +386,6 @@ int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G
     ep.n_nonstrict = (long long*)(f + 10 * n_out);
     ep.n_padded = (long long*)(f + 11 * n_out);
     ep.n_bad = (unsigned long long*)(f + 12 * n_out);
-    ep.tpairs = deferred ? (const int32_t*)ctx->scan_tpairs.p : nullptr;
-    ep.pair_off = (const int64_t*)ctx->scan_pair_off.p;
-    ep.pairs_total = ctx->scan_pairs_total;
     TRT_CUDA(cudaMemsetAsync(ep.n_bad, 0, 8, ctx->stream));
     locus_epilogue_kernel<<<(unsigned)((n_out + 63) / 64), 64, 0, ctx->stream>>>(ep);
     TRT_KERNEL_CHECK();
@@ -426,39 +410,17 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
         TRT_CUDA(cudaMemcpyAsync(ctx->group_masks.p, group_masks, (size_t)G * S, cudaMemcpyHostToDevice, ctx->stream));
     }
     trt_timer_begin(ctx);
+    TRT_TRY(trt_prepare_ranks(ctx));
     TRT_CUDA(cudaMemsetAsync(ctx->ac.p, 0, (size_t)G * nA * 4 + 16, ctx->stream));
     TRT_CUDA(cudaMemsetAsync(ctx->lc.p, 0, (size_t)G * L * TRT_LC_N * 8 + 16, ctx->stream));
     if (L > 0) {
-        // A pending (lazy) harmonize is overlapped with the scan of the pair-table tiers: those launches do not read the
-        // allele classes (deferred to the epilogue), so the harmonize kernel goes to the side stream right AFTER them and
-        // fills the SM resources the persistent scan CTAs leave free.  Everything else waits for it.
-        const bool overlap = ctx->harm_pending && ctx->P == 2 && S >= kMinFastSamples && !getenv("TRT_HARMONIZE_NO_OVERLAP");
-        if (!overlap) {
-            TRT_TRY(trt_flush_harmonize(ctx));
-            TRT_TRY(trt_prepare_ranks(ctx));      // the generic tier reads the dense class ranks
-        }
-        if (overlap) TRT_CUDA(cudaEventRecord(ctx->ev_h0, ctx->stream));      // inputs of harmonize are uploaded before this point
         TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
         for (int g = 0; g < G; g++) {
             const uint8_t* m = group_masks ? (const uint8_t*)ctx->group_masks.p + (size_t)g * S : nullptr;
-            TRT_TRY(trt_run_scan(ctx, m, g, G, overlap ? SCAN_PHASE_PAIRS : SCAN_PHASE_ALL, overlap ? 1 : 0));
+            TRT_TRY(trt_run_scan(ctx, m, g, G));
         }
         TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
-        if (overlap) {
-            TRT_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_h0, 0));
-            ctx->harm_pending = false;
-            TRT_TRY(trt_launch_harmonize(ctx, ctx->stream2));
-            TRT_CUDA(cudaEventRecord(ctx->ev_h1, ctx->stream2));
-            TRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h1, 0));
-        }
-        if (overlap) {
-            TRT_TRY(trt_prepare_ranks(ctx));
-            for (int g = 0; g < G; g++) {
-                const uint8_t* m = group_masks ? (const uint8_t*)ctx->group_masks.p + (size_t)g * S : nullptr;
-                TRT_TRY(trt_run_scan(ctx, m, g, G, SCAN_PHASE_REST, 0));
-            }
-        }
-        TRT_TRY(trt_run_epilogue(ctx, use_length, nalleles_thresh, G, overlap ? 1 : 0));
+        TRT_TRY(trt_run_epilogue(ctx, use_length, nalleles_thresh, G));
     }
     trt_timer_end(ctx);
     ctx->last_scan_ms = 0.0;
