@@ -268,7 +268,7 @@ def run_gpu(args):
     def gather_rows(st):
         """NCCL gather of the fixed-width per-locus result table on rank 0 (north_star: the only collective)."""
         if plan is not None:
-            plan.gather([st[k][0] for k in STAT_COLS])
+            plan.gather([st[k][0] for k in STAT_COLS], wait=False)     # in flight under the next step's kernels
 
     for _ in range(max(args.warmup, 0)):
         gather_rows(step())
@@ -284,6 +284,8 @@ def run_gpu(args):
         scan_ms.append(ctx.last_scan_ms())
         gather_rows(st)
     ms = ctx.stopwatch_stop()
+    if plan is not None:
+        plan.wait()                                     # the last gather belongs to the timed region
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
     launches = ctx.launch_count() - launches0

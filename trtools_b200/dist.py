@@ -95,8 +95,10 @@ class GatherPlan:
         self.host = torch.empty((self.world, n_cols, n_rows), dtype=torch.float64, pin_memory=pin) if self.rank == dst else None
         self.out = None if self.host is None else self.host.numpy()
 
-    def gather(self, columns):
-        """columns: n_cols float64 arrays of length n_rows (host).  Returns [world, n_cols, n_rows] on dst, else None."""
+    def gather(self, columns, wait: bool = True):
+        """columns: n_cols float64 arrays of length n_rows (host).  Returns [world, n_cols, n_rows] on dst, else None.
+        With ``wait=False`` the NCCL gather and the device->host copy of the result stay in flight (call ``wait()``
+        before reading ``out``): the next step's kernels overlap them.  The host columns may be reused on return."""
         import torch
         if self.dist is None:
             for j, c in enumerate(columns):
@@ -104,15 +106,23 @@ class GatherPlan:
             return self.out
         for j, c in enumerate(columns):
             self.send[j].copy_(torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)), non_blocking=True)
+        if self.send.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            ev.synchronize()                                   # the host columns have been read
         self.dist.gather(self.send, list(self.recv.unbind(0)) if self.rank == self.dst else None, dst=self.dst)
-        if self.rank != self.dst:
-            if self.send.is_cuda:
-                torch.cuda.current_stream().synchronize()     # the host columns may be reused by the caller now
-            return None
-        self.host.copy_(self.recv, non_blocking=True)
-        if self.recv.is_cuda:
+        if self.rank == self.dst:
+            self.host.copy_(self.recv, non_blocking=True)
+        if wait:
+            return self.wait()
+        return None
+
+    def wait(self):
+        """Block until the last gather (and its copy to the pinned host table) has finished."""
+        import torch
+        if self.dist is not None and self.send.is_cuda:
             torch.cuda.current_stream().synchronize()
-        return self.out
+        return self.out if (self.dist is None or self.rank == self.dst) else None
 
 
 def allreduce_sum(dist, arr: np.ndarray) -> np.ndarray:
