@@ -241,6 +241,7 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from trtools_b200 import _lib, synth, dist as tdist
+    numa_cpus = tdist.bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa_bind) else None
     dist = tdist.init("nccl") if world > 1 else None
 
     ctx = _lib.Context(local_rank)
@@ -458,7 +459,8 @@ def run_gpu(args):
                        "loci_per_gpu": L, "samples": S, "seed": SEED, "parallelism": "loci sharded x{}".format(world),
                        "l2": "inputs ({:.1f} GB) far larger than L2; no flush needed".format(algo_bytes / 1e9),
                        "e2e": "one pinned {}-locus host block (loci 0..{}) streamed {}x per step through two ping-pong contexts; every copy is a real H2D".format(Lb, Lb - 1, nblk),
-                       "device": info["name"], "sm_count": info["sm_count"]},
+                       "device": info["name"], "sm_count": info["sm_count"],
+                       "numa_bound_cpus": numa_cpus},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms},
@@ -501,6 +503,7 @@ def main():
     ap.add_argument("--samples", type=int, default=50000)
     ap.add_argument("--e2e-block", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--statstr-only", action="store_true", help="skip the dumpSTR / associaTR measurements")
     args = ap.parse_args()
     if args.impl == "reference":
