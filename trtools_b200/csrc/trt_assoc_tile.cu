@@ -276,7 +276,9 @@ template <int NB>
 __global__ void __launch_bounds__(256, 2) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
     constexpr int kBlocks = NB * (NB + 1) / 2;
     constexpr int kG = 32 / kBlocks;             // samples processed concurrently by a warp
-    constexpr int kBatch = (kG >= 8) ? kG : (kG * 2 >= 8 ? kG * 2 : kG * 3);   // z-rows staged per round trip to L2
+    // z-rows staged per round trip to L2: a 32-chunk window holds ~15 uncalled samples at 2 % missingness, so ~20 slots
+    // cover a window in one trip
+    constexpr int kBatch = (kG >= 16) ? kG : ((20 + kG - 1) / kG) * kG;
     constexpr int kZS = 18;                      // staged row pitch in doubles (144 B: odd multiple of 16 B)
     __shared__ uint16_t lst_all[8][32 * kTChunk];   // uncalled samples of a 32-chunk window, relative to its first sample
     __shared__ __align__(16) double zs_all[8][kBatch][kZS];

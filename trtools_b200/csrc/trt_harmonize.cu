@@ -70,7 +70,43 @@ struct AlleleStr {
     __device__ __forceinline__ char at(int i) const { return mlen ? up(base[i % mlen]) : up(base[i]); }
 };
 
+// 8 upper-cased characters starting at p (any alignment): two aligned 64-bit loads and a funnel shift; bytes past
+// the string are garbage and must be masked by the caller (the sequence buffer has 16 bytes of slack)
+__device__ __forceinline__ unsigned long long load8_up(const char* p) {
+    const unsigned long long* base = (const unsigned long long*)((uintptr_t)p & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)((uintptr_t)p & 7) * 8u;
+    const unsigned long long lo = base[0], hi = base[1];
+    unsigned long long x = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+    // SWAR str.upper(): subtract 0x20 from the bytes in 'a'..'z'
+    const unsigned long long t = x & 0x7f7f7f7f7f7f7f7full;
+    const unsigned long long ge_a = t + 0x1f1f1f1f1f1f1f1full;      // bit 7 set: (byte & 0x7f) >= 'a'
+    const unsigned long long gt_z = t + 0x0505050505050505ull;      // bit 7 set: (byte & 0x7f) >  'z'
+    const unsigned long long lower = ge_a & ~gt_z & ~x & 0x8080808080808080ull;
+    return x - (lower >> 2);
+}
+
+// lexicographic compare of two real (non-fabricated) allele windows, 8 characters per step
+__device__ int str_cmp_real(const char* pa, int la, const char* pb, int lb) {
+    const int n = la < lb ? la : lb;
+    for (int i = 0; i < n; i += 8) {
+        unsigned long long x = load8_up(pa + i), y = load8_up(pb + i);
+        const int rem = n - i;
+        if (rem < 8) {
+            const unsigned long long m = (1ull << (8 * rem)) - 1ull;
+            x &= m;
+            y &= m;
+        }
+        if (x != y) {
+            const int byte = (__ffsll((long long)(x ^ y)) - 1) >> 3;     // first differing character (little endian)
+            const unsigned cx = (unsigned)(x >> (8 * byte)) & 0xffu, cy = (unsigned)(y >> (8 * byte)) & 0xffu;
+            return cx < cy ? -1 : 1;
+        }
+    }
+    return la == lb ? 0 : (la < lb ? -1 : 1);
+}
+
 __device__ int str_cmp(const AlleleStr& a, const AlleleStr& b) {
+    if (a.mlen == 0 && b.mlen == 0) return str_cmp_real(a.base, a.len, b.base, b.len);
     int n = a.len < b.len ? a.len : b.len;
     for (int i = 0; i < n; i++) {
         unsigned char x = (unsigned char)a.at(i), y = (unsigned char)b.at(i);
@@ -240,8 +276,14 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
                 // running count c_i of k-mer i among k-mers 0..i; the winner is the k-mer that first
                 // reaches the final maximum count (see oracle/trh.py::infer_repeat_sequence)
                 int best_c = 0, best_i = 0x7fffffff;
+                const unsigned long long kmask = period >= 8 ? ~0ull : ((1ull << (8 * period)) - 1ull);
                 for (int i = lane; i < K; i += GS) {
                     int c = 0;
+                    if (period <= 8) {
+                        // k-mers as 64-bit keys: one unaligned 8-byte read each
+                        const unsigned long long ki = load8_up(seq + (size_t)i * period) & kmask;
+                        for (int j = 0; j <= i; j++) c += ((load8_up(seq + (size_t)j * period) & kmask) == ki);
+                    } else
                     for (int j = 0; j <= i; j++) {
                         bool eq = true;
                         for (int t = 0; t < period; t++)
