@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     int stage = 0;
     uint32_t phase = 0;
     int parity = 0;
-    long long dbg_wait = 0, dbg_proc = 0, dbg_end = 0, dbg_chunks = 0;
     int A, a0, A_next = 0, a0_next = 0;
     int li = blockIdx.x;
     int64_t l = list_locus(p, li, A, a0);
@@ -231,11 +230,9 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
         const bool sq = pairs_square(A);
 
         for (int c = 0; c < nchunks; c++) {
-            const long long t0 = p.dbg ? clock64() : 0;
             const int sub = c % nsub;                       // chunk within its ring stage
             const bool last_sub = (sub == nsub - 1) || (c == nchunks - 1);
             if (sub == 0) mbar_wait(&hdr->full[stage], phase);
-            if (p.dbg && tid == 32 && blockIdx.x == 0) dbg_wait += clock64() - t0;
             if (p.stream_only) {
                 if (last_sub) {
                     __syncwarp();
@@ -295,9 +292,7 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             }
 #pragma unroll
             for (int j = 0; j < 8; j += 2) bump2(my, idx[j], idx[j + 1]);   // (four loads in flight + 6 compares measured 3 % slower)
-            if (p.dbg && tid == 32 && blockIdx.x == 0) { dbg_proc += clock64() - t0; dbg_chunks++; }
         }
-        const long long t_end0 = p.dbg ? clock64() : 0;
 
         // ---- each warp PAIR folds its own 64 threads' table columns (pair-local barrier only) ----------
         const int nrows = sq ? (int)(D * D) : (int)(D * (D + 1u) / 2u);
@@ -401,14 +396,10 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             __syncwarp();
             if (!loose) named_sync(2, kPT);
         }
-        if (p.dbg && tid == 32 && blockIdx.x == 0) dbg_end += clock64() - t_end0;
         parity ^= 1;
         l = l_next;
         A = A_next;
         a0 = a0_next;
-    }
-    if (p.dbg && tid == 32 && blockIdx.x == 0) {
-        p.dbg[0] = dbg_wait; p.dbg[1] = dbg_proc; p.dbg[2] = dbg_end; p.dbg[3] = dbg_chunks;
     }
 }
 
@@ -587,12 +578,6 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
     const bool fast = (ctx->P == 2 && S >= kMinFastSamples);
     sp.fast_enabled = fast ? 1 : 0;
-    sp.dbg = nullptr;
-    if (getenv("TRT_SCAN_DEBUG")) {
-        TRT_TRY(trt_ensure(ctx, ctx->work_counter, 64));
-        TRT_CUDA(cudaMemsetAsync(ctx->work_counter.p, 0, 64, ctx->stream));
-        sp.dbg = (unsigned long long*)ctx->work_counter.p;
-    }
     sp.list = nullptr;
     sp.n_list = 0;
     sp.stream_only = getenv("TRT_SCAN_STREAM_ONLY") ? 1 : 0;   // HBM-read ceiling of this access pattern (calibration)
@@ -659,13 +644,6 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
             scan_wide_kernel<false><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
         }
         TRT_KERNEL_CHECK();
-    }
-    if (sp.dbg) {
-        unsigned long long h[4];
-        TRT_CUDA(cudaMemcpyAsync(h, sp.dbg, 32, cudaMemcpyDeviceToHost, ctx->stream));
-        TRT_CUDA(cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "[scan dbg] wait=%llu proc(incl wait)=%llu end=%llu chunks=%llu  per-chunk wait=%.0f proc=%.0f\n", h[0], h[1], h[2], h[3],
-                h[3] ? (double)h[0] / h[3] : 0.0, h[3] ? (double)h[1] / h[3] : 0.0);
     }
     if (n_tier[TIER_GENERIC]) {
         const int warps_per_block = 8;

@@ -18,7 +18,6 @@ struct ScanParams {
     int32_t* ac_part;      // optional [nA], zero-initialised: alleles carried by PARTIALLY called samples (a/.)
     long long* lc;         // [L][TRT_LC_N]
     int fast_enabled;      // the TMA tiers are in use (diploid, enough samples)
-    unsigned long long* dbg;   // optional [4]: cycles waiting / processing / end-of-locus, chunks (warp 1 of CTA 0)
     int stream_only;       // calibration: consumers only drain the TMA ring (results are meaningless)
     const int32_t* list;   // loci of the tier this launch handles (built on the host per block)
     int n_list;
