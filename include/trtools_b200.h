@@ -290,6 +290,50 @@ int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset, int64_t n_
 int trt_block_get_gt(trt_ctx* ctx, int64_t locus0, int64_t n, int16_t* out_host /*[n][S][P+1]*/);
 int trt_block_get_format(trt_ctx* ctx, int field_id, int64_t locus0, int64_t n, void* out_host);
 
+/* ---- native block VCF ingest (host side; SURVEY.md §8f "next" row 1) ---------------------------
+ * Replaces the per-record cyvcf2/htslib pulls the reference makes in its record loop:
+ * `for record in vcf` + vcfrecord.genotype.array() (tr_harmonizer.py:829-862, 1761-1779) and
+ * vcfrecord.format(key) (tr_harmonizer.py:561-588; dumpSTR/filters.py:365,446).  BGZF members are
+ * inflated in parallel; a block of records is held as text and GT + the requested numeric
+ * FORMAT keys of all its records are parsed in one multi-threaded pass into the stacked arrays
+ * trt_block_set_gt / trt_block_set_format_* take (pass trt_host_alloc memory for pinned staging).
+ * Pure host code: no CUDA call, no trt_ctx.                                                      */
+typedef struct trt_vcf trt_vcf;
+typedef struct trt_vcf_block trt_vcf_block;
+/* plain text, gzip or BGZF; n_threads <= 0 = all hardware threads.  Reads the header.           */
+int         trt_vcf_open(const char* path, int n_threads, trt_vcf** out);
+void        trt_vcf_close(trt_vcf* v);
+/* message of the last failure on v (v == NULL: of the calling thread's last failed trt_vcf_open)  */
+const char* trt_vcf_last_error(const trt_vcf* v);
+/* every leading '#' line, verbatim (cyvcf2 VCF.raw_header)                                        */
+int         trt_vcf_header(trt_vcf* v, const char** text, int64_t* len);
+/* sample columns named by the #CHROM line                                                         */
+int64_t     trt_vcf_n_samples(const trt_vcf* v);
+/* restrict parsing to these sample columns (strictly increasing, 0-based; cyvcf2 VCF(samples=))   */
+int         trt_vcf_set_samples(trt_vcf* v, const int64_t* cols, int64_t n);
+/* next run of up to max_loci records / about max_bytes of text (<= 0: no byte cap; at least one
+ * record is returned).  *n_loci == 0 and *out == NULL at end of file.  The block owns its text
+ * and outlives the reader's later reads; free it with trt_vcf_block_free.                         */
+int         trt_vcf_read_block(trt_vcf* v, int64_t max_loci, int64_t max_bytes, trt_vcf_block** out, int64_t* n_loci);
+void        trt_vcf_block_free(trt_vcf_block* b);
+/* record text: record i is text[line_off[i] .. line_off[i+1]) (ends with '\n'); its first nine
+ * columns (CHROM..FORMAT) are the first fixed_len[i] bytes; fixed_len[i] < 0 = fewer than eight
+ * columns (the reference's reader fails on such a record)                                         */
+int         trt_vcf_block_text(const trt_vcf_block* b, const char** text, const int64_t** line_off,
+                               const int64_t** fixed_len);
+/* One pass over the block's sample columns.
+ *   gt_out (may be NULL): int16 [n][S][ploidy+1] in cyvcf2 layout (trt_block_set_gt's input)
+ *   keys[k] / key_is_float[k] / key_out[k]: numeric scalar FORMAT keys -> int32 or float32 [n][S]
+ *     (INT32_MIN / NaN for '.'); at most 32 keys per pass
+ *   present[n][n_keys]: 0 = the record's FORMAT lacks the key, 1 = parsed, 2 = the record has a
+ *     value this parser does not take (vector-valued, non-numeric): re-parse that record's key
+ *   rec_ploidy[n]: most alleles in one GT of the record (> ploidy: call again with that ploidy)
+ *   rec_status[n]: 0 ok, 1 malformed (< 8 columns), 2 = not handled natively (odd GT token, no GT
+ *     key, ragged sample columns): re-parse the record from its text                              */
+int         trt_vcf_block_parse(const trt_vcf_block* b, int ploidy, int16_t* gt_out, int n_keys,
+                                const char* const* keys, const int32_t* key_is_float, void* const* key_out,
+                                uint8_t* present, int32_t* rec_ploidy, uint8_t* rec_status);
+
 /* ---- multi-GPU: loci shard by contiguous ranges, one context per rank --------------------------
  * NCCL is used only to gather fixed-width per-locus result rows and to sum per-sample counters.  */
 int trt_dist_unique_id(void* out_128_bytes);

@@ -1,0 +1,449 @@
+"""
+CPU tests of the native block VCF ingest (csrc/trt_ingest.cpp behind trt_vcf_*).
+
+The checker is the pure-Python text reader ``cyvcf2_compat.TextVCF`` — the reader every golden-output CLI test
+of rounds 1 was pinned with (it follows cyvcf2's conventions).  The C++ reader must hand
+out the same arrays bit for bit (GT int16, Integer int32, Float float32 compared as raw bits), the same fixed
+columns, the same errors at the same record, and the same re-serialised text, on the reference's own example
+files (copies under tests/golden/data; the whole reference tree when it is present) and on edge cases built
+here: ploidy mixes, half calls, dropped trailing fields, vector values in scalar fields, odd tokens, ragged
+columns, CRLF, blank lines, unterminated last line, sample subsets, gzip / BGZF / plain, corrupt members.
+"""
+import glob
+import gzip
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from trtools_b200 import cyvcf2_compat as cc
+from trtools_b200.vcf_ingest import NativeVCF, NativeVariant
+
+from conftest import DATA
+
+REF_ROOT = "/root/reference"
+
+
+def _same(a, b):
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if a.dtype.kind == 'f':
+        return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    return np.array_equal(a, b)
+
+
+def _next(it):
+    try:
+        return next(it)
+    except StopIteration:
+        return None
+    except Exception as e:   # the error itself is compared
+        return e
+
+
+def _try(fn):
+    try:
+        return fn()
+    except Exception as e:
+        return (type(e).__name__, str(e))
+
+
+def _compare(path, max_records=None, block_loci=5, samples=None, threads=None, block_bytes=None):
+    """Walk both readers in lock step; returns the number of records compared."""
+    try:
+        t = cc.TextVCF(path, samples=samples)
+    except OSError:
+        with pytest.raises(OSError):
+            NativeVCF(path, samples=samples)
+        return 0
+    n = NativeVCF(path, samples=samples, threads=threads)
+    n._native_block_loci = block_loci
+    if block_bytes:
+        n._native_block_bytes = block_bytes
+    assert t.raw_header == n.raw_header
+    assert t.samples == n.samples
+    assert t.seqnames == n.seqnames
+    keys = list(t._format_types)
+    it, inn = iter(t), iter(n)
+    count = 0
+    while max_records is None or count < max_records:
+        a, b = _next(it), _next(inn)
+        if a is None or b is None:
+            assert a is None and b is None, (path, count, a, b)
+            break
+        if isinstance(a, Exception) or isinstance(b, Exception):
+            assert type(a) is type(b) and str(a) == str(b), (path, count, a, b)
+            break
+        where = (path, count, a.CHROM, a.POS)
+        assert (a.CHROM, a.POS, a.ID, a.REF, a.ALT, a.QUAL, a.FILTER, a.FORMAT) == \
+               (b.CHROM, b.POS, b.ID, b.REF, b.ALT, b.QUAL, b.FILTER, b.FORMAT), where
+        assert list(a.INFO) == list(b.INFO), where
+        if not t.samples:
+            assert a.genotype is None and b.genotype is None, where
+        else:
+            ga, gb = _try(lambda: a.genotype.array()), _try(lambda: b.genotype.array())
+            if isinstance(ga, tuple) or isinstance(gb, tuple):      # both readers fail alike (e.g. GT "0/x")
+                assert ga == gb, where + (ga, gb)
+                count += 1
+                continue
+            assert _same(ga, gb), where
+            assert a.ploidy == b.ploidy, where
+            assert a.genotypes == b.genotypes, where
+        for k in keys:
+            fa, fb = _try(lambda: a.format(k)), _try(lambda: b.format(k))
+            if isinstance(fa, tuple) or isinstance(fb, tuple):
+                assert fa == fb, where + (k, fa, fb)
+                continue
+            assert _same(fa, fb), where + (k, fa[:4], fb[:4])
+        assert str(a) == str(b), where
+        count += 1
+    t.close()
+    n.close()
+    return count
+
+
+# ---- the reference's own files ---------------------------------------------------------------
+
+FIXTURES = sorted(glob.glob(os.path.join(DATA, "*.vcf")) + glob.glob(os.path.join(DATA, "*.vcf.gz")))
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_native_reader_matches_text_reader_on_fixtures(path):
+    assert _compare(path, max_records=150, block_loci=16) > 0
+
+
+def test_fixture_trio_all_records_one_thread_vs_many():
+    path = os.path.join(DATA, "trio_chr21_hipstr.sorted.vcf.gz")
+    outs = []
+    for threads in (1, 8):
+        v = NativeVCF(path, threads=threads)
+        v._prefetch = ("DP", "Q", "DSTUTTER", "DFLANKINDEL")
+        gts, dps, qs = [], [], []
+        for r in v:
+            gts.append(r.genotype.array())
+            dps.append(r.format("DP"))
+            qs.append(r.format("Q"))
+        outs.append(gts + dps + qs)
+    assert len(outs[0]) == 3 * 9532          # BASELINE config 1
+    for a, b in zip(*outs):
+        assert _same(a, b)
+
+
+@pytest.mark.needs_reference
+def test_native_reader_matches_text_reader_on_reference_tree():
+    files = sorted(glob.glob(REF_ROOT + "/example-files/*.vcf*") +
+                   glob.glob(REF_ROOT + "/trtools/testsupport/sample_vcfs/**/*.vcf*", recursive=True))
+    files = [f for f in files if not f.endswith((".tbi", ".csi"))]
+    assert len(files) > 100
+    total = sum(_compare(f, max_records=12, block_loci=5) for f in files)
+    assert total > 1000
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+
+HEADER = (
+    "##fileformat=VCFv4.1\n"
+    "##command=HipSTR-test\n"
+    "##contig=<ID=1,length=1000000>\n"
+    '##INFO=<ID=START,Number=1,Type=Integer,Description="s">\n'
+    '##INFO=<ID=END,Number=1,Type=Integer,Description="e">\n'
+    '##INFO=<ID=PERIOD,Number=1,Type=Integer,Description="p">\n'
+    '##INFO=<ID=AF,Number=A,Type=Float,Description="vector info">\n'
+    '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n'
+    '##FORMAT=<ID=Q,Number=1,Type=Float,Description="q">\n'
+    '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="dp">\n'
+    '##FORMAT=<ID=DFLANKINDEL,Number=1,Type=Integer,Description="dfi">\n'
+    '##FORMAT=<ID=GB,Number=1,Type=String,Description="bp diffs">\n'
+    '##FORMAT=<ID=PL,Number=G,Type=Integer,Description="vector">\n'
+    '##FORMAT=<ID=QEXP,Number=3,Type=Float,Description="fixed-size vector">\n'
+)
+
+
+def _vcf_text(records, samples=("A", "B", "C", "D"), eol="\n", header=HEADER):
+    h = header + "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples) + "\n"
+    if not samples:
+        h = header + "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+    return h.replace("\n", eol) + "".join(r + eol for r in records)
+
+
+def _rec(pos, fmt, cols, ref="ACACAC", alt="ACAC,ACACACAC", info="START=%d;END=%d;PERIOD=2"):
+    fixed = ["1", str(pos), "STR_%d" % pos, ref, alt, ".", ".", info % (pos, pos + len(ref) - 1) if "%d" in info else info]
+    if fmt is None:
+        return "\t".join(fixed)
+    return "\t".join(fixed + [fmt] + list(cols))
+
+
+EDGE_RECORDS = [
+    _rec(100, "GT:Q:DP:DFLANKINDEL:GB", ["0|1:0.99:30:1:0|-2", "1/2:0.5:12:0:-2/2", ".:.:.:.:.", "./1:1:7:2:.|-2"]),
+    _rec(200, "GT:DP", ["0", "1", ".", "2"]),                                  # haploid record
+    _rec(300, "GT:DP", ["0/1/2", "1|1|0", "0/1", "."]),                        # triploid + diploid + missing
+    _rec(400, "GT:Q:DP", ["0/1", "1/1:0.25", "0/0:0.5:3", "2|0:.:4"]),         # trailing fields dropped
+    _rec(500, "GT:Q:DP", ["0/1:1e-3:5", "0/0:nan:6", "1/1:inf:-7", "0|2:-0.0:+8"]),
+    _rec(600, "GT:Q:DP", ["0/1:0.1234567890123456789:5", "0/0:.5:6", "1/1:5.:7", "0|2:123456789012345678901234567890:8"]),
+    _rec(700, "GT:DP:PL:QEXP", ["0/1:5:0,10,20:0.1,0.2,0.7", "0/0:6:.:.", "1/1:7:1,2,3:.,.,.", "0|2:8:5,6:1,0,0"]),
+    _rec(800, "GT:DP", ["0/1:1,2", "0/0:6", "1/1:7", "0|2:8"]),                # vector value in a scalar field
+    _rec(900, "GT:DP", ["0/x:1", "0/0:6", "1/1:7", "0|2:8"]),                  # odd GT token: Python int() decides
+    _rec(1000, "DP:Q", ["5:0.5", "6:0.25", "7:.", ".:."]),                     # no GT key
+    _rec(1100, "DP:GT:Q", ["5:0|1:0.5", "6:1/1:0.25", "7:.:.", ".:./.:1"]),    # GT not first
+    _rec(1200, "GT:DP", ["0/1:3", "0/0:6", "1/1:7"]),                          # a sample column short
+    _rec(1300, "GT:DP:DP", ["0/1:3:4", "0/0:6:7", "1/1:7:8", "0|2:8:9"]),      # duplicated key: first wins
+    _rec(1400, "GT:Q", ["0/1:1E+2", "0/0:-1.5e-10", "1/1:1e", "0|2:0x10"]),    # exponents; tokens float() rejects
+    _rec(1500, "GT:DP", ["40000/1:3", "0/0:6", "1/1:7", "0|2:8"]),             # allele index beyond int16
+    _rec(1600, "GT:DP", ["0/1:99999999999", "0/0:2147483647", "1/1:-2147483648", "0|2:-2147483647"]),
+    _rec(1700, "GT", ["0|0", "1|1", "2|2", "0|1"], info="START=1700;END=1705;PERIOD=2;AF=0.5,0.25;IMP"),
+    _rec(1800, "GT:DP", ["|1:3", "0/:6", "/:7", "0|2:"]),                      # empty allele / empty value tokens
+    _rec(1900, "GT:DP", ["0/1:3", "0/0:6", "1/1:7", "0|2:8", "0/0:1"]),        # a sample column too many
+]
+
+
+def _write(tmp_path, name, text, mode="plain"):
+    p = str(tmp_path / name)
+    data = text.encode()
+    if mode == "plain":
+        open(p, "wb").write(data)
+    elif mode == "gzip":
+        with gzip.open(p, "wb") as f:
+            f.write(data)
+    else:
+        open(p, "wb").write(_bgzf(data, member=int(mode)))
+    return p
+
+
+def _bgzf(data: bytes, member: int = 300) -> bytes:
+    """BGZF (SAM spec §4.1): gzip members with a 'BC' extra field carrying the member size, then the EOF member."""
+    out = []
+    for o in list(range(0, len(data), member)) + [None]:
+        chunk = b"" if o is None else data[o:o + member]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(body) + 8 - 1
+        out.append(struct.pack("<4BIBBH2BHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord('B'), ord('C'), 2, bsize))
+        out.append(body)
+        out.append(struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("mode", ["plain", "gzip", "300", "65280"])
+@pytest.mark.parametrize("block_loci", [1, 3, 512])
+def test_edge_records_match_text_reader(tmp_path, mode, block_loci):
+    p = _write(tmp_path, "edge.vcf" + ("" if mode == "plain" else ".gz"), _vcf_text(EDGE_RECORDS), mode)
+    assert _compare(p, block_loci=block_loci) == len(EDGE_RECORDS)
+
+
+def test_bgzf_written_here_is_valid_gzip(tmp_path):
+    p = _write(tmp_path, "x.vcf.gz", _vcf_text(EDGE_RECORDS), "300")
+    assert gzip.open(p, "rb").read().decode() == _vcf_text(EDGE_RECORDS)
+
+
+def test_flagged_records_are_reparsed_not_guessed(tmp_path):
+    p = _write(tmp_path, "edge.vcf", _vcf_text(EDGE_RECORDS))
+    v = NativeVCF(p)
+    recs = list(v)
+    blk = recs[0]._nblk
+    blk.parse(("DP", "Q"))
+    by_pos = {r.POS: i for i, r in enumerate(recs)}
+    assert blk.status[by_pos[100]] == 0 and blk.status[by_pos[300]] == 0
+    for pos in (900, 1000, 1200, 1500, 1900):       # odd token, no GT, ragged columns, int16 overflow
+        assert blk.status[by_pos[pos]] == 2, pos
+    assert blk.present["DP"][by_pos[800]] == 2       # "1,2" in a scalar field
+    assert blk.present["DP"][by_pos[1600]] == 2      # beyond int32
+    assert blk.present["Q"][by_pos[1400]] == 2       # "1e", "0x10"
+    assert blk.present["Q"][by_pos[200]] == 0        # key absent from FORMAT
+    assert blk.gt.shape == (len(recs), 4, 4)         # sized by the triploid record
+    assert list(blk.rec_ploidy[:3]) == [2, 1, 3]
+
+
+def test_crlf_blank_lines_and_unterminated_last_record(tmp_path):
+    text = _vcf_text(EDGE_RECORDS[:4], eol="\r\n")
+    p = _write(tmp_path, "crlf.vcf", text)
+    assert _compare(p) == 4
+    text = _vcf_text(EDGE_RECORDS[:2]) + "\n\n" + EDGE_RECORDS[2] + "\n\n" + EDGE_RECORDS[3]    # no final newline
+    p = _write(tmp_path, "blank.vcf", text)
+    assert _compare(p, block_loci=2) == 4
+
+
+def test_no_samples_and_header_only(tmp_path):
+    p = _write(tmp_path, "nosamp.vcf", _vcf_text([_rec(100, None, []), _rec(200, None, [])], samples=()))
+    assert _compare(p) == 2
+    p = _write(tmp_path, "empty.vcf", _vcf_text([]))
+    assert _compare(p) == 0
+    p = _write(tmp_path, "notvcf.txt", "hello\nworld\n")
+    with pytest.raises(OSError):
+        NativeVCF(p)
+    with pytest.raises(OSError):
+        NativeVCF(str(tmp_path / "does_not_exist.vcf"))
+
+
+def test_malformed_record_raises_when_reached(tmp_path):
+    text = _vcf_text(EDGE_RECORDS[:3] + ["1\t5000\tonly_three_columns"] + EDGE_RECORDS[3:5])
+    p = _write(tmp_path, "broken.vcf", text)
+    assert _compare(p, block_loci=512) == 3         # both readers raise ValueError at the 4th record
+    v = NativeVCF(p)
+    got = [next(v) for _ in range(3)]
+    assert [r.POS for r in got] == [100, 200, 300]
+    with pytest.raises(ValueError):
+        next(v)
+
+
+@pytest.mark.parametrize("keep", [["B"], ["A", "D"], ["D", "A", "zzz"], []])
+def test_sample_subsets(tmp_path, keep):
+    p = _write(tmp_path, "edge.vcf.gz", _vcf_text(EDGE_RECORDS), "300")
+    # record 1200 lacks its 4th sample column: picking "D" out of it fails (IndexError) in both readers
+    want = 11 if "D" in keep else len(EDGE_RECORDS)
+    assert _compare(p, samples=keep, block_loci=4) == want
+
+
+def test_region_query(tmp_path):
+    p = _write(tmp_path, "edge.vcf", _vcf_text(EDGE_RECORDS))
+    a = [r.POS for r in cc.TextVCF(p)("1:300-805")]
+    b = [r.POS for r in NativeVCF(p)("1:300-805")]
+    assert a == b and len(a) > 3
+
+
+def test_corrupt_and_truncated_bgzf_fail_loudly(tmp_path):
+    data = bytearray(_bgzf(_vcf_text(EDGE_RECORDS * 20).encode(), 4000))
+    bad = bytearray(data)
+    bad[len(bad) // 2] ^= 0x55
+    p = str(tmp_path / "bad.vcf.gz")
+    open(p, "wb").write(bytes(bad))
+    with pytest.raises(OSError):
+        list(NativeVCF(p))
+    p = str(tmp_path / "trunc.vcf.gz")
+    open(p, "wb").write(bytes(data[:len(data) // 2]))
+    with pytest.raises(OSError):
+        list(NativeVCF(p))
+
+
+def test_float_tokens_round_like_numpy(tmp_path):
+    """Float FORMAT values: decimal string -> nearest double -> float32, bit for bit as np.float32(str)."""
+    rng = np.random.default_rng(20261017)
+    toks = []
+    for i in range(6000):
+        kind = i % 6
+        if kind == 0:
+            toks.append("%.*f" % (int(rng.integers(0, 12)), rng.random()))
+        elif kind == 1:
+            toks.append(repr(float(np.float32(rng.normal() * 10 ** int(rng.integers(-8, 8))))))
+        elif kind == 2:
+            toks.append("%.17g" % (rng.random() * 10 ** int(rng.integers(-30, 30))))
+        elif kind == 3:
+            toks.append("%d" % rng.integers(-10 ** 9, 10 ** 9))
+        elif kind == 4:
+            # halfway cases between adjacent float32 values (double rounding matters here)
+            f = np.float32(rng.random())
+            mid = (float(f) + float(np.nextafter(f, np.float32(2)))) / 2
+            toks.append("%.25f" % mid)
+        else:
+            toks.append("%.*e" % (int(rng.integers(0, 20)), rng.normal() * 10 ** int(rng.integers(-40, 40))))
+    samples = ["S%d" % i for i in range(len(toks))]
+    rec = _rec(100, "GT:Q", ["0/1:" + t for t in toks])
+    p = _write(tmp_path, "floats.vcf", _vcf_text([rec], samples=samples))
+    v = NativeVCF(p)
+    r = next(v)
+    got = r.format("Q")[:, 0]
+    assert r._nblk.present["Q"][0] == 1              # all of them parsed natively
+    want = np.array([np.float32(t) for t in toks], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_wide_records_many_threads(tmp_path):
+    """A block of wide records (S = 3000) in several byte-capped runs, threads 1 vs 8, vs the text reader."""
+    rng = np.random.default_rng(7)
+    S, L = 3000, 24
+    samples = ["S%d" % i for i in range(S)]
+    recs = []
+    for l in range(L):
+        a = rng.integers(-1, 3, size=(S, 2))
+        dp = rng.integers(0, 80, size=S)
+        q = rng.random(S)
+        cols = []
+        for s in range(S):
+            if rng.random() < 0.02:
+                cols.append(".")
+                continue
+            g = "|".join("." if x < 0 else str(x) for x in a[s])
+            cols.append("%s:%d:%.6g" % (g, dp[s], q[s]))
+        recs.append(_rec(100 + 10 * l, "GT:DP:Q", cols))
+    p = _write(tmp_path, "wide.vcf.gz", _vcf_text(recs, samples=samples), "65280")
+    assert _compare(p, block_loci=7, block_bytes=200000, threads=8) == L
+    stacks = []
+    for threads in (1, 8):
+        v = NativeVCF(p, threads=threads)
+        v._prefetch = ("DP", "Q")
+        rr = list(v)
+        assert all(isinstance(r, NativeVariant) for r in rr)
+        stacks.append((np.stack([r.genotype.array() for r in rr]), np.stack([r.format("DP") for r in rr]),
+                       np.stack([r.format("Q") for r in rr])))
+    for a, b in zip(*stacks):
+        assert _same(a, b)
+
+
+# ---- the block hand-off: build_block takes the reader's stacked arrays as they are ----------------------
+
+
+class _RecordingCtx:
+    """Stands in for _lib.Context: records what a Block uploads (no GPU in the CPU suite)."""
+
+    def __init__(self):
+        self.calls = {}
+
+    def block_begin(self, L, S, P, vcftype):
+        self.calls["begin"] = (L, S, P, vcftype)
+
+    def block_set_gt(self, gt):
+        self.calls["gt"] = np.array(gt)
+        self.calls["gt_is_view"] = gt.base is not None
+
+    def block_set_alleles(self, *a):
+        self.calls["alleles"] = a
+
+    def block_set_format(self, slot, arr):
+        self.calls[("fmt", slot)] = np.array(arr).reshape(self.calls["begin"][0], self.calls["begin"][1], -1)
+
+    def harmonize(self):
+        return {"flags": np.zeros(self.calls["begin"][0], dtype=np.int32)}
+
+
+@pytest.mark.parametrize("path,vcftype,keys", [
+    (os.path.join(DATA, "trio_chr21_hipstr.sorted.vcf.gz"), "hipstr", ("DP", "Q", "DFLANKINDEL", "DSTUTTER")),
+    (os.path.join(DATA, "many_samples.vcf.gz"), "hipstr", ("DP", "Q")),
+    (os.path.join(DATA, "test_gangstr_head.vcf"), "gangstr", ("DP", "Q", "QEXP")),
+])
+def test_build_block_uploads_identical_arrays_from_both_readers(path, vcftype, keys):
+    from trtools_b200 import block as _block
+    uploads = []
+    for cls in (cc.TextVCF, NativeVCF):
+        v = cls(path)
+        if cls is NativeVCF:
+            v._prefetch = keys
+            v._native_block_loci = 64
+        recs = [r for _, r in zip(range(64), v)]
+        ctx = _RecordingCtx()
+        blk = _block.build_block(ctx, vcftype, recs, keys)
+        uploads.append((ctx.calls, blk))
+    (a, blk_a), (b, blk_b) = uploads
+    assert b["gt_is_view"]                                   # the reader's own slab, no per-record copy
+    assert a["begin"] == b["begin"]
+    assert _same(a["gt"], b["gt"])
+    fa = sorted(k for k in a if isinstance(k, tuple))
+    assert fa == sorted(k for k in b if isinstance(k, tuple)) and len(fa) == len(keys)
+    for k in fa:
+        assert _same(a[k], b[k]), k
+    assert blk_a.seqs == blk_b.seqs and np.array_equal(blk_a.allele_off, blk_b.allele_off)
+
+
+def test_format_arrays_are_private_copies():
+    """dumpSTR nulls filtered calls in the array format() returned; the block's stacked arrays must not change."""
+    v = NativeVCF(os.path.join(DATA, "many_samples.vcf.gz"))
+    v._prefetch = ("DP",)
+    r = next(v)
+    r.genotype.array()                       # first access parses the run (GT + the prefetch keys)
+    before = r._nblk.fmt["DP"].copy()
+    a = r.format("DP")
+    a[:] = -7
+    g = r.genotype.array()
+    g[:] = 9
+    assert np.array_equal(r._nblk.fmt["DP"], before)
+    assert not (r._nblk.gt[0] == 9).any()

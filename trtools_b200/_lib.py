@@ -37,6 +37,8 @@ EXPORTS = [
     "trt_synth_fill", "trt_block_get_gt", "trt_block_get_format",
     "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
     "trt_dist_allreduce_sum_f64", "trt_dist_barrier",
+    "trt_vcf_open", "trt_vcf_close", "trt_vcf_last_error", "trt_vcf_header", "trt_vcf_n_samples",
+    "trt_vcf_set_samples", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse",
 ]
 
 
@@ -145,6 +147,16 @@ def load():
         "trt_dist_allreduce_sum_i64": (i32, [vp, vp, i64]),
         "trt_dist_allreduce_sum_f64": (i32, [vp, vp, i64]),
         "trt_dist_barrier": (i32, [vp]),
+        "trt_vcf_open": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
+        "trt_vcf_close": (None, [vp]),
+        "trt_vcf_last_error": (C.c_char_p, [vp]),
+        "trt_vcf_header": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "trt_vcf_n_samples": (i64, [vp]),
+        "trt_vcf_set_samples": (i32, [vp, vp, i64]),
+        "trt_vcf_read_block": (i32, [vp, i64, i64, C.POINTER(vp), C.POINTER(i64)]),
+        "trt_vcf_block_free": (None, [vp]),
+        "trt_vcf_block_text": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "trt_vcf_block_parse": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

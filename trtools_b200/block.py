@@ -259,9 +259,40 @@ class Block:
         return self.h["motif"][o0:o1].decode("ascii")
 
 
+def _native_run(records):
+    """(native block, first index) if the records are a consecutive run of one block of the C++
+    reader (vcf_ingest) whose GT arrays are still the reader's own parse; else None."""
+    if not records or not hasattr(records[0], "native_slot"):
+        return None
+    first = records[0].native_slot()
+    if first is None:
+        return None
+    nblk, i0 = first
+    for j, r in enumerate(records):
+        slot = r.native_slot() if hasattr(r, "native_slot") else None
+        if slot is None or slot[0] is not nblk or slot[1] != i0 + j:
+            return None
+    if nblk.S == 0 or int(nblk.rec_ploidy[i0:i0 + len(records)].max()) != nblk.gt.shape[2] - 1:
+        return None
+    return nblk, i0
+
+
 def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[str] = ()) -> Block:
     """Stage a run of cyvcf2-like records (same ploidy) as one GPU block."""
     metas = [record_meta(vcftype, r) for r in records]
+    run = _native_run(records)
+    if run is not None:
+        # the C++ reader already parsed the whole run into stacked arrays: no per-record pulls
+        nblk, i0 = run
+        i1 = i0 + len(records)
+        nblk.parse(fmt_keys)
+        fmt = {}
+        for key in fmt_keys:
+            if key in nblk.fmt and bool((nblk.present[key][i0:i1] == 1).all()):
+                fmt[key] = nblk.fmt[key][i0:i1].reshape(len(records), nblk.S, 1)
+            elif all(key in r.FORMAT for r in records):
+                fmt[key] = np.stack([r.format(key) for r in records], axis=0)
+        return Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
     gts = []
     has_samples = True
     for r in records:

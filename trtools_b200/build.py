@@ -21,7 +21,8 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    """CUDA kernels + the host-side ingest (trt_ingest.cpp: zlib, threads; nvcc hands it to g++)."""
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def _find_nccl():
@@ -60,6 +61,7 @@ def build(force=False, verbose=False):
         cmd += ["-I", inc, "-L", libdir, "-l:" + soname, "-Xlinker", "-rpath=" + libdir]
     else:
         cmd += ["-lnccl"]
+    cmd += ["-lz", "-lpthread"]
     cmd += ["-o", os.environ.get("TRT_BUILD_OUT", LIB)] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

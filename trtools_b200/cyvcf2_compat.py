@@ -205,6 +205,16 @@ class Variant:
     def __init__(self, line: str, vcf: 'VCF'):
         self._vcf = vcf
         cols = line.rstrip('\n').rstrip('\r').split('\t')
+        self._init_fixed(cols)
+        if len(cols) > 8:
+            self._sample_cols = cols[9:]
+            if vcf._sample_idx is not None:
+                self._sample_cols = [self._sample_cols[i] for i in vcf._sample_idx]
+        else:
+            self._sample_cols = []
+
+    def _init_fixed(self, cols):
+        """CHROM..FORMAT from the first (up to) nine columns."""
         if len(cols) < 8:
             raise ValueError("malformed VCF line")
         self.CHROM = cols[0]
@@ -214,15 +224,8 @@ class Variant:
         self.ALT = [] if cols[4] == '.' else cols[4].split(',')
         self.QUAL = None if cols[5] == '.' else float(cols[5])
         self._filter_raw = cols[6]
-        self.INFO = _Info(cols[7], vcf._info_types)
-        if len(cols) > 8:
-            self.FORMAT = cols[8].split(':')
-            self._sample_cols = cols[9:]
-            if vcf._sample_idx is not None:
-                self._sample_cols = [self._sample_cols[i] for i in vcf._sample_idx]
-        else:
-            self.FORMAT = []
-            self._sample_cols = []
+        self.INFO = _Info(cols[7], self._vcf._info_types)
+        self.FORMAT = cols[8].split(':') if len(cols) > 8 else []
         self._split = None
         self._fmt_cache = {}
         self._gt_arr = None
@@ -395,8 +398,12 @@ class Variant:
         return '\t'.join(cols) + '\n'
 
 
-class VCF:
-    """Sequential text-VCF reader (``cyvcf2.VCF`` surface used by TRTools)."""
+class TextVCF:
+    """Sequential text-VCF reader in pure Python (``cyvcf2.VCF`` surface used by TRTools).
+
+    The drop-ins read through :class:`trtools_b200.vcf_ingest.NativeVCF` (exported below as ``VCF``),
+    which parses blocks of records in C++; this class is what it re-parses flagged records with, and
+    the reader the ingest parity tests compare against."""
 
     def __init__(self, fname, mode='r', gts012=False, lazy=False, strict_gt=False,
                  samples=None, threads=None):
@@ -416,9 +423,12 @@ class VCF:
                     break
         except (OSError, UnicodeDecodeError, EOFError):
             raise OSError("Error reading %s" % fname)
+        self._init_header(header_lines, samples)
+
+    def _init_header(self, header_lines, samples):
         if not header_lines or not header_lines[0].startswith('##fileformat'):
             if not any(l.startswith('#CHROM') for l in header_lines):
-                raise OSError("%s is not a VCF" % fname)
+                raise OSError("%s is not a VCF" % self.fname)
         self._header_lines = header_lines
         self._index_types()
         chrom_line = [l for l in header_lines if l.startswith('#CHROM')]
@@ -495,22 +505,27 @@ class VCF:
             line = self._fh.readline()
         return line
 
+    def _in_region(self, var) -> bool:
+        if self._region is None:
+            return True
+        chrom, start, end = self._region
+        if var.CHROM != chrom:
+            return False
+        vend = var.POS + len(var.REF) - 1
+        if start is not None and vend < start:
+            return False
+        if end is not None and var.POS > end:
+            return False
+        return True
+
     def __next__(self) -> Variant:
         while True:
             line = self._next_line()
             if not line:
                 raise StopIteration
             var = Variant(line, self)
-            if self._region is not None:
-                chrom, start, end = self._region
-                if var.CHROM != chrom:
-                    continue
-                vend = var.POS + len(var.REF) - 1
-                if start is not None and vend < start:
-                    continue
-                if end is not None and var.POS > end:
-                    continue
-            return var
+            if self._in_region(var):
+                return var
 
     def __call__(self, region: str):
         """Region query by linear scan (real cyvcf2 uses the tabix index)."""
@@ -537,7 +552,7 @@ class VCF:
 class Writer:
     """Text VCF writer (``cyvcf2.Writer`` surface used by dumpSTR)."""
 
-    def __init__(self, fname, tmpl: VCF, mode=None):
+    def __init__(self, fname, tmpl: 'TextVCF', mode=None):
         self.fname = str(fname)
         if self.fname.endswith('.gz'):
             self._fh = io.TextIOWrapper(gzip.open(self.fname, 'wb'), encoding='utf-8', newline='\n')
@@ -558,3 +573,15 @@ class Writer:
     def close(self):
         self.write_header()
         self._fh.close()
+
+
+# ``VCF`` is what the drop-ins open: the block reader of vcf_ingest (C++ inflate + FORMAT parse,
+# csrc/trt_ingest.cpp).  TRTOOLS_B200_INGEST=python selects the pure-Python reader instead.
+def __getattr__(name):
+    if name == "VCF":
+        import os
+        if os.environ.get("TRTOOLS_B200_INGEST", "native") == "python":
+            return TextVCF
+        from .vcf_ingest import NativeVCF
+        return NativeVCF
+    raise AttributeError(name)

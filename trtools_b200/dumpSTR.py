@@ -572,6 +572,11 @@ def main(args):
         loc_info[filt.filter_name()] = 0
 
     ctx = _lib.default_context()
+    if hasattr(invcf, "_prefetch"):
+        # C++ block reader: parse the call filters' numeric FORMAT keys in the same pass as GT,
+        # in runs of the GPU block length
+        invcf._prefetch = tuple(dict.fromkeys(_needed_fmt(call_filters) + ['DP', 'LC']))
+        invcf._native_block_loci = block_size
     harmonizer_idx = 1
     record_counter = 0
     done = False

@@ -564,6 +564,11 @@ class TRRecordHarmonizer:
         self._queue: List[Any] = []
         self._exhausted = False
         self._deferred_error = None
+        # the C++ block reader (vcf_ingest.NativeVCF) parses these keys together with GT, and reads
+        # runs of the same length as the GPU blocks so that a block is one run
+        if hasattr(vcffile, "_prefetch"):
+            vcffile._prefetch = tuple(dict.fromkeys(tuple(vcffile._prefetch) + self._fmt_keys))
+            vcffile._native_block_loci = self._block_size
 
     def MayHaveImpureRepeats(self) -> bool:
         return MayHaveImpureRepeats(self.vcftype)

@@ -1,0 +1,288 @@
+"""
+Native block VCF ingest (SURVEY.md §8f "next" row 1): the ``cyvcf2.VCF`` surface of
+:mod:`trtools_b200.cyvcf2_compat`, with the per-record text work moved into C++
+(``csrc/trt_ingest.cpp`` behind ``trt_vcf_*`` in ``include/trtools_b200.h``).
+
+The reference pulls ``genotype.array()`` and ``format(key)`` once per record through cyvcf2/htslib
+(trtools/utils/tr_harmonizer.py:829-862, 561-588).  Here the reader inflates BGZF members in
+parallel, keeps a run of records as text, and parses GT and the numeric scalar FORMAT keys of the
+whole run in one multi-threaded pass into stacked ``[L][S]`` arrays.  ``Variant`` objects are thin
+views: the first nine columns are decoded eagerly (INFO validation, allele strings), the sample
+columns only if something asks for a string-typed or vector-valued field.  ``block.build_block``
+takes the stacked arrays of a run as they are, without per-record copies.
+
+Whatever the C++ pass flags (odd GT tokens, vector-valued values in a scalar field, ragged sample
+columns) is re-parsed from the record's text by the pure-Python reader, so results are those of
+``cyvcf2_compat.TextVCF`` byte for byte (tests/test_ingest.py).
+"""
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from . import cyvcf2_compat as _compat
+
+_DEFAULT_BLOCK_LOCI = 512
+_DEFAULT_BLOCK_BYTES = 1 << 30
+
+
+class _NativeBlock:
+    """One run of records held by the C++ reader (``trt_vcf_block``) and its parsed arrays."""
+
+    def __init__(self, vcf: "NativeVCF", handle, n: int):
+        self.vcf = vcf
+        self.lib = vcf._lib
+        self.h = handle
+        self.n = n
+        text, off, fixed = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = self.lib.trt_vcf_block_text(self.h, C.byref(text), C.byref(off), C.byref(fixed))
+        if rc != _lib.TRT_OK:
+            raise OSError("trt_vcf_block_text failed")
+        self._text = text.value
+        self.line_off = np.ctypeslib.as_array((C.c_int64 * (n + 1)).from_address(off.value)).copy()
+        self.fixed_len = np.ctypeslib.as_array((C.c_int64 * n).from_address(fixed.value)).copy()
+        self.S = len(vcf.samples)
+        self.gt: Optional[np.ndarray] = None       # int16 [n][S][P+1]
+        self.rec_ploidy: Optional[np.ndarray] = None
+        self.status: Optional[np.ndarray] = None
+        self.fmt: Dict[str, np.ndarray] = {}       # key -> [n][S]
+        self.present: Dict[str, np.ndarray] = {}   # key -> uint8 [n]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.trt_vcf_block_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- text ----------------------------------------------------------------------------------
+    def prefix(self, i: int) -> str:
+        return C.string_at(self._text + int(self.line_off[i]), int(self.fixed_len[i])).decode('utf-8')
+
+    def line(self, i: int) -> str:
+        o0, o1 = int(self.line_off[i]), int(self.line_off[i + 1])
+        return C.string_at(self._text + o0, o1 - o0).decode('utf-8').split('\n', 1)[0]
+
+    # ---- arrays --------------------------------------------------------------------------------
+    def _native_key(self, key: str) -> Optional[int]:
+        """0 / 1 (is_float) if the header types the key as a numeric scalar, else None."""
+        hrec = self.vcf._format_types.get(key)
+        if not hrec or str(hrec.get('Number', '1')) != '1':
+            return None
+        typ = hrec.get('Type', 'String')
+        if typ == 'Integer':
+            return 0
+        if typ == 'Float':
+            return 1
+        return None
+
+    def parse(self, keys: Sequence[str] = ()):
+        """One C++ pass: GT (first time) + the numeric scalar keys not parsed yet."""
+        todo = [k for k in dict.fromkeys(keys) if k not in self.fmt and self._native_key(k) is not None][:32]
+        want_gt = self.gt is None
+        if not want_gt and not todo:
+            return
+        n, S = self.n, self.S
+        outs = [np.empty((n, S), dtype=np.float32 if self._native_key(k) else np.int32) for k in todo]
+        nk = len(todo)
+        c_keys = (C.c_char_p * max(nk, 1))(*[k.encode() for k in todo])
+        c_isf = (C.c_int32 * max(nk, 1))(*[int(self._native_key(k)) for k in todo])
+        c_out = (C.c_void_p * max(nk, 1))(*[o.ctypes.data for o in outs])
+        present = np.zeros((n, max(nk, 1)), dtype=np.uint8)
+        rec_ploidy = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint8)
+        P = 2
+        while True:
+            gt = np.empty((n, S, P + 1), dtype=np.int16) if want_gt else None
+            rc = self.lib.trt_vcf_block_parse(
+                self.h, P, None if gt is None else gt.ctypes.data_as(C.c_void_p), nk,
+                C.cast(c_keys, C.c_void_p), C.cast(c_isf, C.c_void_p), C.cast(c_out, C.c_void_p),
+                present.ctypes.data_as(C.c_void_p), rec_ploidy.ctypes.data_as(C.c_void_p),
+                status.ctypes.data_as(C.c_void_p))
+            if rc != _lib.TRT_OK:
+                raise OSError("trt_vcf_block_parse failed ({})".format(rc))
+            if not want_gt:
+                break
+            ok = status == 0
+            pmax = int(rec_ploidy[ok].max()) if ok.any() else 1
+            if pmax <= P:
+                break
+            P = pmax            # a call with more alleles than the array holds: size it and redo the pass
+        if want_gt:
+            self.gt = gt
+            self.rec_ploidy = np.maximum(rec_ploidy, 1)
+            self.status = status
+        for j, k in enumerate(todo):
+            self.fmt[k] = outs[j]
+            self.present[k] = present[:, j].copy()
+
+    def gt_of(self, i: int) -> Optional[np.ndarray]:
+        """cyvcf2-layout GT of record i ([S][p+1], p = the record's ploidy) or None if flagged."""
+        if self.gt is None:
+            self.parse(self.vcf._prefetch)
+        if self.status[i] != 0:
+            return None
+        P = self.gt.shape[2] - 1
+        p = int(self.rec_ploidy[i])
+        if p == P:
+            return self.gt[i]
+        return np.concatenate([self.gt[i, :, :p], self.gt[i, :, P:]], axis=1)
+
+    def numeric(self, key: str, i: int) -> Optional[np.ndarray]:
+        """[S][1] array of a numeric scalar FORMAT key of record i, or None (not handled natively)."""
+        if self._native_key(key) is None:
+            return None
+        if key not in self.fmt:
+            self.parse(tuple(self.vcf._prefetch) + (key,))
+        if self.present[key][i] != 1 or (self.status is not None and self.status[i] != 0):
+            return None
+        # a copy: callers own what format() returns (dumpSTR nulls filtered calls in place)
+        return self.fmt[key][i].reshape(self.S, 1).copy()
+
+
+class NativeVariant(_compat.Variant):
+    """A record of a native block: fixed columns decoded, sample columns parsed by the block."""
+
+    def __init__(self, blk: _NativeBlock, i: int, vcf: "NativeVCF"):
+        self._vcf = vcf
+        self._nblk = blk
+        self._nidx = i
+        self._cols_cache = None
+        self._gt_native = False
+        self._init_fixed(blk.prefix(i).split('\t'))
+
+    @property
+    def _sample_cols(self):
+        if self._cols_cache is None:
+            cols = self._nblk.line(self._nidx).rstrip('\r').split('\t')[9:]
+            if self._vcf._sample_idx is not None:
+                cols = [cols[j] for j in self._vcf._sample_idx]
+            self._cols_cache = cols
+        return self._cols_cache
+
+    def _gts(self):
+        if self._gt_arr is None:
+            arr = self._nblk.gt_of(self._nidx) if 'GT' in self.FORMAT else None
+            if arr is None:
+                return super()._gts()
+            self._gt_arr = arr
+            self._gt_native = True
+        return self._gt_arr
+
+    @property
+    def genotypes(self):
+        return _compat.Variant.genotypes.fget(self)
+
+    @genotypes.setter
+    def genotypes(self, gts):
+        _compat.Variant.genotypes.fset(self, gts)
+        self._gt_native = False
+
+    def format(self, key, vtype=None):
+        if key in self._fmt_cache:
+            return self._fmt_cache[key]
+        if key not in self.FORMAT:
+            raise KeyError(key)
+        arr = self._nblk.numeric(key, self._nidx)
+        if arr is None:
+            return super().format(key, vtype)
+        self._fmt_cache[key] = arr
+        return arr
+
+    def native_slot(self):
+        """(block, index) if this record's GT is still the block's own parse, else None."""
+        if self._gt_arr is not None and not self._gt_native:
+            return None
+        if self._nblk.gt is None:
+            self._nblk.parse(self._vcf._prefetch)
+        if self._nblk.status[self._nidx] != 0 or 'GT' not in self.FORMAT:
+            return None
+        return self._nblk, self._nidx
+
+
+class NativeVCF(_compat.TextVCF):
+    """``cyvcf2.VCF`` surface over the C++ block reader."""
+
+    def __init__(self, fname, mode='r', gts012=False, lazy=False, strict_gt=False, samples=None, threads=None):
+        self.fname = str(fname)
+        self._lib = _lib.load()
+        self._h = None
+        h = C.c_void_p()
+        rc = self._lib.trt_vcf_open(os.fsencode(self.fname), int(threads or 0), C.byref(h))
+        if rc != _lib.TRT_OK:
+            raise OSError("Error opening %s" % fname)
+        self._h = h
+        text, n = C.c_void_p(), C.c_int64()
+        self._lib.trt_vcf_header(self._h, C.byref(text), C.byref(n))
+        try:
+            raw = C.string_at(text.value, n.value).decode('utf-8') if n.value else ''
+        except UnicodeDecodeError:
+            raise OSError("Error reading %s" % fname)
+        header_lines = [l + '\n' for l in raw.split('\n') if l != ''] if raw else []
+        if raw and not raw.endswith('\n') and header_lines:
+            header_lines[-1] = header_lines[-1][:-1]
+        self._init_header(header_lines, samples)
+        if self._sample_idx is not None:
+            idx = np.asarray(self._sample_idx, dtype=np.int64)
+            rc = self._lib.trt_vcf_set_samples(self._h, idx.ctypes.data_as(C.c_void_p), len(idx))
+            if rc != _lib.TRT_OK:
+                raise OSError(self._err())
+        self._blk: Optional[_NativeBlock] = None
+        self._blk_i = 0
+        self._prefetch: Sequence[str] = ()
+        self._native_block_loci = _DEFAULT_BLOCK_LOCI
+        self._native_block_bytes = _DEFAULT_BLOCK_BYTES
+
+    def _err(self):
+        msg = self._lib.trt_vcf_last_error(self._h)
+        return msg.decode() if msg else "native VCF reader error"
+
+    def _next_block(self) -> bool:
+        blk, n = C.c_void_p(), C.c_int64()
+        rc = self._lib.trt_vcf_read_block(self._h, int(self._native_block_loci), int(self._native_block_bytes),
+                                          C.byref(blk), C.byref(n))
+        if rc != _lib.TRT_OK:
+            raise OSError("Error reading {}: {}".format(self.fname, self._err()))
+        if n.value == 0:
+            self._blk = None
+            return False
+        self._blk = _NativeBlock(self, blk, n.value)
+        self._blk_i = 0
+        return True
+
+    def __next__(self):
+        while True:
+            if self._blk is None or self._blk_i >= self._blk.n:
+                if self._h is None or not self._next_block():
+                    raise StopIteration
+            blk, i = self._blk, self._blk_i
+            self._blk_i += 1
+            if blk.fixed_len[i] < 0:
+                raise ValueError("malformed VCF line")
+            if self._sample_idx is not None:
+                # a sample subset of a ragged record fails in the text reader's constructor: same here
+                if blk.gt is None:
+                    blk.parse(self._prefetch)
+                if blk.status[i] == 2:
+                    var = _compat.Variant(blk.line(i), self)
+                    if self._in_region(var):
+                        return var
+                    continue
+            var = NativeVariant(blk, i, self)
+            if self._in_region(var):
+                return var
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.trt_vcf_close(self._h)
+            self._h = None
+        self._blk = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
