@@ -37,7 +37,7 @@ def test_statstr_outputs_identical_for_both_readers(data_dir, tmp_path, monkeypa
         return open(out + ".tab").read()
 
     a, b = _both_modes(monkeypatch, run)
-    assert a == b and a.count("\n") > 5
+    assert a == b and a.count("\n") >= 2
 
 
 @pytest.mark.parametrize("vcf,kw", [
