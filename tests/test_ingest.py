@@ -447,3 +447,48 @@ def test_format_arrays_are_private_copies():
     g[:] = 9
     assert np.array_equal(r._nblk.fmt["DP"], before)
     assert not (r._nblk.gt[0] == 9).any()
+
+
+@pytest.mark.parametrize("fname,limit", [("trio_chr21_hipstr.sorted.vcf.gz", 1500), ("many_samples.vcf.gz", 400)])
+def test_dumpstr_write_back_text_identical_for_both_readers(fname, limit):
+    """dumpSTR's record write-back (FORMAT:FILTER, nulling of filtered calls; reference dumpSTR.py:684-746) on
+    blocks cut like the CLI cuts them (runs of equal ploidy): the re-serialised record text must not depend on
+    the reader — including which untouched fields the writer passes through verbatim."""
+    import itertools
+    import types
+    from trtools_b200 import block as _block, dumpSTR, _lib
+
+    class MinDP:
+        name, gpu_kind, field, threshold = "HipSTRCallMinDepth10", _lib.CF_MIN, "DP", 10
+
+    keys = ["DP", "Q", "DFLANKINDEL", "DSTUTTER"]
+    outs = []
+    for cls in (cc.TextVCF, NativeVCF):
+        v = cls(os.path.join(DATA, fname))
+        if cls is NativeVCF:
+            v._prefetch = tuple(keys) + ("LC",)
+            v._native_block_loci = 300
+        it, texts, done = iter(v), [], False
+        rng = np.random.default_rng(1)
+        while not done and len(texts) < limit:
+            recs = []
+            while len(recs) < 300:
+                try:
+                    rec = next(it)
+                except StopIteration:
+                    done = True
+                    break
+                if recs and rec.ploidy != recs[0].ploidy:
+                    it = itertools.chain([rec], it)
+                    break
+                recs.append(rec)
+            if not recs:
+                break
+            blk = _block.build_block(_RecordingCtx(), "hipstr", recs, keys)
+            res = types.SimpleNamespace(call_mask=(rng.random((len(recs), blk.S)) < 0.3).astype(np.uint32),
+                                        host_values={})
+            for l, r in enumerate(recs):
+                dumpSTR._apply_to_record(r, blk, res, l, [MinDP()])
+                texts.append(str(r))
+        outs.append(texts)
+    assert len(outs[0]) >= limit and outs[0] == outs[1]

@@ -277,6 +277,20 @@ def _native_run(records):
     return nblk, i0
 
 
+def _stack_format(records, key):
+    """[L][S][n] stack of record.format(key), or None if a record lacks the key."""
+    cols = []
+    for r in records:
+        try:
+            v = r.format(key)
+        except KeyError:
+            return None
+        if v is None:
+            return None
+        cols.append(v)
+    return np.stack(cols, axis=0) if cols else None
+
+
 def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[str] = ()) -> Block:
     """Stage a run of cyvcf2-like records (same ploidy) as one GPU block."""
     metas = [record_meta(vcftype, r) for r in records]
@@ -290,8 +304,12 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
         for key in fmt_keys:
             if key in nblk.fmt and bool((nblk.present[key][i0:i1] == 1).all()):
                 fmt[key] = nblk.fmt[key][i0:i1].reshape(len(records), nblk.S, 1)
-            elif all(key in r.FORMAT for r in records):
-                fmt[key] = np.stack([r.format(key) for r in records], axis=0)
+                for j, r in enumerate(records):
+                    r.share_format(key, fmt[key][j])       # what r.format(key) would have cached
+            else:
+                stacked = _stack_format(records, key)
+                if stacked is not None:
+                    fmt[key] = stacked
         return Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
     gts = []
     has_samples = True
@@ -312,18 +330,7 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
             gt[i, :, P - 1] = g[:, p]
     fmt = {}
     for key in fmt_keys:
-        cols = []
-        ok = True
-        for r in records:
-            try:
-                v = r.format(key)
-            except KeyError:
-                ok = False
-                break
-            if v is None:
-                ok = False
-                break
-            cols.append(v)
-        if ok and cols:
-            fmt[key] = np.stack(cols, axis=0)
+        stacked = _stack_format(records, key)
+        if stacked is not None:
+            fmt[key] = stacked
     return Block(ctx, vcftype, metas, gt, fmt)

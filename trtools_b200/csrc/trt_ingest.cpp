@@ -19,6 +19,8 @@
 //
 // Host code only: no CUDA calls, usable (and tested) without a GPU.  It feeds the CUDA path; it is
 // not an alternative to it.
+#include <sys/types.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -131,6 +133,7 @@ struct trt_vcf {
     RawBuf text;                       // inflated bytes; [t_pos, t_end) not yet handed out
     size_t t_pos = 0, t_end = 0;
     bool eof = false;
+    int64_t plain_off = -1;            // PLAIN: file offset of the next unread byte when pread is usable
     std::string header;
     int64_t n_file_samples = 0;
     std::vector<int64_t> keep;
@@ -288,6 +291,41 @@ int fill_gzip(trt_vcf* v) {
 }
 
 int fill_plain(trt_vcf* v) {
+    // regular files: every host thread preads its own piece (page-cache copies scale with threads);
+    // anything pread refuses (pipes) goes through the FILE
+    constexpr size_t kPiece = size_t(8) << 20;
+    if (v->plain_off >= 0 && v->n_threads > 1) {
+        const int np = v->n_threads;
+        text_reserve(v, kPiece * np);
+        std::vector<ssize_t> got((size_t)np, 0);
+        char* base = v->text.data() + v->t_end;
+        const int fd = fileno(v->fh);
+        const off_t off0 = (off_t)v->plain_off;
+        parallel_for(np, np, [&](int64_t i) {
+            size_t done = 0;
+            while (done < kPiece) {
+                ssize_t r = pread(fd, base + i * kPiece + done, kPiece - done, off0 + (off_t)(i * kPiece + done));
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) { if (r < 0 && done == 0) got[i] = -1; break; }
+                done += (size_t)r;
+            }
+            if (got[i] == 0) got[i] = (ssize_t)done;
+        });
+        if (got[0] >= 0) {
+            size_t total = 0;
+            for (int i = 0; i < np; ++i) {
+                if (got[i] < 0) return fail(v, TRT_ERECORD, "read error: %s", strerror(errno));
+                total += (size_t)got[i];
+                if ((size_t)got[i] < kPiece) break;          // end of file inside this piece
+            }
+            v->plain_off += (int64_t)total;
+            v->t_end += total;
+            if (total == 0) v->eof = true;
+            return TRT_OK;
+        }
+        if (fseeko(v->fh, off0, SEEK_SET) != 0) v->plain_off = -1;   // not seekable: the FILE is where we left it
+        v->plain_off = -1;
+    }
     text_reserve(v, kCompressedChunk);
     size_t got = fread(v->text.data() + v->t_end, 1, kCompressedChunk, v->fh);
     v->t_end += got;
@@ -578,6 +616,8 @@ static int vcf_open_impl(const char* path, int n_threads, trt_vcf** out) {
         v->t_end = v->text.size();
         v->c_begin = v->c_end = 0;
         if (v->file_eof && v->t_end == 0) v->eof = true;
+        off_t at = ftello(fh);
+        v->plain_off = (at >= 0 && (size_t)at == v->t_end) ? (int64_t)at : -1;
     }
     // header: every leading line that starts with '#'
     for (;;) {

@@ -17,6 +17,7 @@ columns) is re-parsed from the record's text by the pure-Python reader, so resul
 """
 import ctypes as C
 import os
+import threading
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -152,6 +153,7 @@ class NativeVariant(_compat.Variant):
         self._nidx = i
         self._cols_cache = None
         self._gt_native = False
+        self._shared = set()
         self._init_fixed(blk.prefix(i).split('\t'))
 
     @property
@@ -181,8 +183,20 @@ class NativeVariant(_compat.Variant):
         _compat.Variant.genotypes.fset(self, gts)
         self._gt_native = False
 
+    def share_format(self, key, view):
+        """build_block took this key of the whole run from the block's arrays; keep the record's state as if
+        format(key) had been called (the writer re-serialises the keys a record has decoded), without a copy."""
+        if key not in self._fmt_cache:
+            self._fmt_cache[key] = view
+            self._shared.add(key)
+
     def format(self, key, vtype=None):
         if key in self._fmt_cache:
+            if key in self._shared:
+                # still the block's storage: the caller owns what format() returns (dumpSTR nulls filtered
+                # calls in place), so hand out a private copy from here on
+                self._shared.discard(key)
+                self._fmt_cache[key] = self._fmt_cache[key].copy()
             return self._fmt_cache[key]
         if key not in self.FORMAT:
             raise KeyError(key)
@@ -191,6 +205,10 @@ class NativeVariant(_compat.Variant):
             return super().format(key, vtype)
         self._fmt_cache[key] = arr
         return arr
+
+    def set_format(self, key, data):
+        self._shared.discard(key)
+        super().set_format(key, data)
 
     def native_slot(self):
         """(block, index) if this record's GT is still the block's own parse, else None."""
@@ -235,22 +253,53 @@ class NativeVCF(_compat.TextVCF):
         self._prefetch: Sequence[str] = ()
         self._native_block_loci = _DEFAULT_BLOCK_LOCI
         self._native_block_bytes = _DEFAULT_BLOCK_BYTES
+        # one run of read-ahead (TRTOOLS_B200_INGEST_READAHEAD=0 turns it off)
+        self._readahead = os.environ.get("TRTOOLS_B200_INGEST_READAHEAD", "1") != "0"
+        self._ra_thread = None
+        self._ra_result = None
 
     def _err(self):
         msg = self._lib.trt_vcf_last_error(self._h)
         return msg.decode() if msg else "native VCF reader error"
 
-    def _next_block(self) -> bool:
+    def _read_block(self) -> Optional[_NativeBlock]:
         blk, n = C.c_void_p(), C.c_int64()
         rc = self._lib.trt_vcf_read_block(self._h, int(self._native_block_loci), int(self._native_block_bytes),
                                           C.byref(blk), C.byref(n))
         if rc != _lib.TRT_OK:
             raise OSError("Error reading {}: {}".format(self.fname, self._err()))
         if n.value == 0:
-            self._blk = None
-            return False
-        self._blk = _NativeBlock(self, blk, n.value)
+            return None
+        return _NativeBlock(self, blk, n.value)
+
+    def _readahead_main(self):
+        """Worker thread: read and parse the next run while the caller works on the current one (the C++
+        calls release the GIL, so this overlaps with Python-side record handling and with GPU calls)."""
+        try:
+            blk = self._read_block()
+            if blk is not None:
+                blk.parse(self._prefetch)
+            self._ra_result = (blk, None)
+        except BaseException as e:      # handed to the consumer when it asks for this run
+            self._ra_result = (None, e)
+
+    def _next_block(self) -> bool:
+        if self._ra_thread is not None:
+            self._ra_thread.join()
+            self._ra_thread = None
+            blk, err = self._ra_result
+            self._ra_result = None
+            if err is not None:
+                raise err
+        else:
+            blk = self._read_block()
+        self._blk = blk
         self._blk_i = 0
+        if blk is None:
+            return False
+        if self._readahead:
+            self._ra_thread = threading.Thread(target=self._readahead_main, name="trt-vcf-readahead", daemon=True)
+            self._ra_thread.start()
         return True
 
     def __next__(self):
@@ -276,6 +325,10 @@ class NativeVCF(_compat.TextVCF):
                 return var
 
     def close(self):
+        if getattr(self, "_ra_thread", None) is not None:
+            self._ra_thread.join()
+            self._ra_thread = None
+            self._ra_result = None
         if getattr(self, "_h", None):
             self._lib.trt_vcf_close(self._h)
             self._h = None
