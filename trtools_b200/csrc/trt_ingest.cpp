@@ -22,6 +22,9 @@
 #include <sys/types.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <atomic>
 #include <cerrno>
@@ -349,58 +352,55 @@ struct KeySpec {
     void* out;          // int32 / float [n][S]
 };
 
-inline bool parse_i32(const char* p, const char* e, int32_t* out) {
-    // Python int() on the token, restricted to [-]digits (anything else -> caller flags the record)
-    bool neg = false;
-    if (p < e && (*p == '-' || *p == '+')) { neg = (*p == '-'); ++p; }
-    if (p == e || e - p > 10) return false;
-    int64_t x = 0;
-    for (; p < e; ++p) {
-        unsigned d = (unsigned char)*p - '0';
-        if (d > 9) return false;
-        x = x * 10 + d;
+inline bool is_delim(const char* q, const char* le) { return q >= le || *q == ':' || *q == '\t'; }
+
+// first ':' or '\t' at or after c (le if none), 16 bytes per step (SSE2 is baseline x86-64)
+inline const char* skip_field(const char* c, const char* le) {
+#if defined(__SSE2__)
+    const __m128i colon = _mm_set1_epi8(':'), tab = _mm_set1_epi8('\t');
+    while (le - c >= 16) {
+        __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c));
+        int m = _mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(v, colon), _mm_cmpeq_epi8(v, tab)));
+        if (m) return c + __builtin_ctz((unsigned)m);
+        c += 16;
     }
-    if (neg) x = -x;
-    if (x < INT32_MIN || x > INT32_MAX) return false;
-    *out = (int32_t)x;
-    return true;
+#endif
+    while (c < le && *c != ':' && *c != '\t') ++c;
+    return c;
+}
+
+// The field parsers scan and convert in one walk.  They return 1 = value parsed, 0 = missing ('.' or ''),
+// -1 = a token this parser does not take (the caller flags the record's key for the Python parser);
+// *end is the field's delimiter in every case.
+
+// Python int() on the token, restricted to [-+]digits within int32
+inline int field_i32(const char* a, const char* le, const char** end, int32_t* out) {
+    const char* q = a;
+    bool neg = false;
+    if (q < le && (*q == '-' || *q == '+')) { neg = (*q == '-'); ++q; }
+    const char* d0 = q;
+    uint64_t x = 0;
+    while (q < le && (unsigned)((unsigned char)*q - '0') <= 9u) { x = x * 10 + (unsigned)(*q - '0'); ++q; }
+    if (is_delim(q, le)) {
+        *end = q;
+        size_t nd = (size_t)(q - d0);
+        if (nd == 0) return q == a ? 0 : -1;
+        if (nd > 10) return -1;
+        int64_t v = neg ? -(int64_t)x : (int64_t)x;
+        if (v < INT32_MIN || v > INT32_MAX) return -1;
+        *out = (int32_t)v;
+        return 1;
+    }
+    *end = skip_field(q, le);
+    return (*end - a == 1 && *a == '.') ? 0 : -1;
 }
 
 const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
                            1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 
-inline bool parse_f32(const char* p, const char* e, float* out) {
-    // np.float32(str): the decimal string rounds to the nearest double, then to float32.
-    // Fast path (exact by Clinger's argument: mantissa < 2^53, |exp10| <= 22 -> one correctly rounded
-    // multiply/divide); everything else goes through strtod, which is correctly rounded as well.
-    const char* s = p;
-    bool neg = false;
-    if (s < e && (*s == '-' || *s == '+')) { neg = (*s == '-'); ++s; }
-    uint64_t m = 0;
-    int nd = 0, frac = 0;
-    bool seen_digit = false, seen_dot = false, simple = true;
-    const char* q = s;
-    for (; q < e; ++q) {
-        unsigned d = (unsigned char)*q - '0';
-        if (d <= 9) {
-            seen_digit = true;
-            if (m || d) { if (++nd > 15) { simple = false; break; } }
-            m = m * 10 + d;
-            if (seen_dot) ++frac;
-        } else if (*q == '.' && !seen_dot) {
-            seen_dot = true;
-        } else {
-            simple = false;
-            break;
-        }
-    }
-    if (simple && seen_digit && frac <= 22) {
-        double d = (double)m;
-        if (frac) d /= kPow10[frac];
-        *out = (float)(neg ? -d : d);
-        return true;
-    }
-    // general: exponents, long mantissas, inf/nan spellings Python accepts
+// exponents, long mantissas, inf/nan spellings: strtod (correctly rounded), on exactly the tokens both
+// Python float() and strtod accept
+bool parse_f32_general(const char* p, const char* e, float* out) {
     char tmp[64];
     size_t n = (size_t)(e - p);
     if (n == 0 || n >= sizeof tmp) return false;
@@ -410,19 +410,55 @@ inline bool parse_f32(const char* p, const char* e, float* out) {
         char ch = tmp[i];
         bool ok = (ch >= '0' && ch <= '9') || ch == '.' || ch == '-' || ch == '+' || ch == 'e' || ch == 'E';
         if (!ok) {
-            // only the exact spellings both Python float() and strtod agree on
             const char* t = tmp + ((tmp[0] == '-' || tmp[0] == '+') ? 1 : 0);
             if (!strcasecmp(t, "nan") || !strcasecmp(t, "inf") || !strcasecmp(t, "infinity")) break;
             return false;
         }
     }
-    if (tmp[0] == '.' && n == 1) return false;
     char* endp = nullptr;
-    errno = 0;
     double d = strtod(tmp, &endp);
     if (endp != tmp + n) return false;
     *out = (float)d;
     return true;
+}
+
+// np.float32(str): the decimal string rounds to the nearest double, then to float32.  Plain decimals with
+// <= 15 significant digits and <= 22 fractional digits are exact by Clinger's argument (mantissa < 2^53, one
+// correctly rounded division by an exactly representable power of ten).
+inline int field_f32(const char* a, const char* le, const char** end, float* out) {
+    const char* s = a;
+    bool neg = false;
+    if (s < le && (*s == '-' || *s == '+')) { neg = (*s == '-'); ++s; }
+    uint64_t m = 0;
+    int nd = 0, frac = 0;
+    bool seen_digit = false, seen_dot = false, simple = true;
+    const char* q = s;
+    for (; q < le; ++q) {
+        unsigned d = (unsigned char)*q - '0';
+        if (d <= 9) {
+            seen_digit = true;
+            if (m || d) { if (++nd > 15) { simple = false; break; } }
+            m = m * 10 + d;
+            if (seen_dot) ++frac;
+        } else if (*q == '.' && !seen_dot) {
+            seen_dot = true;
+        } else {
+            break;
+        }
+    }
+    if (simple && is_delim(q, le)) {
+        *end = q;
+        if (seen_digit && frac <= 22) {
+            double d = (double)m;
+            if (frac) d /= kPow10[frac];
+            *out = (float)(neg ? -d : d);
+            return 1;
+        }
+        if (q == a || (q - a == 1 && *a == '.')) return 0;
+        return parse_f32_general(a, q, out) ? 1 : -1;
+    }
+    *end = skip_field(q, le);
+    return parse_f32_general(a, *end, out) ? 1 : -1;
 }
 
 struct LineResult {
@@ -494,54 +530,52 @@ LineResult parse_line(const char* ls, const char* le, int64_t samp_off, const st
             uint32_t seen_mask_lo = 0;   // keys parsed for this sample (the ABI caps a pass at 32 keys)
             for (;;) {
                 const char* a = c;
-                while (c < le && *c != ':' && *c != '\t') ++c;
-                if (f < nfmt) {
-                    if (do_gt && f == gt_idx) {
-                        gt_seen = true;
-                        int16_t* g = gt_rec + (size_t)outi * (P + 1);
-                        int parts = 0;
-                        int phased = 0;
-                        const char* q = a;
-                        for (;;) {
-                            const char* ta = q;
-                            int32_t x = 0;
-                            bool digits = true;
-                            while (q < c && *q != '/' && *q != '|') {
-                                unsigned d = (unsigned char)*q - '0';
-                                if (d > 9) digits = false; else x = x * 10 + (int32_t)d;
-                                if (x > 32767) digits = false, x = 0;
-                                ++q;
-                            }
-                            int16_t val;
-                            if (q == ta || (q - ta == 1 && *ta == '.')) val = -1;
-                            else if (digits) val = (int16_t)x;
-                            else { r.status = 2; return r; }
-                            if (parts < P) g[parts] = val;
-                            ++parts;
-                            if (q >= c) break;
-                            if (parts == 1) phased = (*q == '|');
-                            ++q;
+                const bool is_gt = do_gt && f == gt_idx;
+                const int k = f < nfmt ? want[f] : -1;
+                if (is_gt) {
+                    gt_seen = true;
+                    int16_t* g = gt_rec + (size_t)outi * (P + 1);
+                    int parts = 0;
+                    int phased = 0;
+                    for (;;) {
+                        const char* ta = c;
+                        int32_t x = 0;
+                        bool digits = true;
+                        while (c < le && *c != '/' && *c != '|' && *c != ':' && *c != '\t') {
+                            unsigned d = (unsigned char)*c - '0';
+                            if (d > 9) digits = false; else x = x * 10 + (int32_t)d;
+                            if (x > 32767) digits = false, x = 0;
+                            ++c;
                         }
-                        for (int j = parts; j < P; ++j) g[j] = -2;
-                        g[P] = (int16_t)phased;
-                        if (parts > maxparts) maxparts = parts;
+                        int16_t val;
+                        if (c == ta || (c - ta == 1 && *ta == '.')) val = -1;
+                        else if (digits) val = (int16_t)x;
+                        else { r.status = 2; return r; }
+                        if (parts < P) g[parts] = val;
+                        ++parts;
+                        if (is_delim(c, le)) break;
+                        if (parts == 1) phased = (*c == '|');
+                        ++c;
                     }
-                    int k = want[f];
-                    if (k >= 0) {
-                        seen_mask_lo |= (1u << k);
-                        const KeySpec& ks = keys[k];
-                        size_t o = (size_t)rec * S + outi;
-                        bool missing = (c == a) || (c - a == 1 && *a == '.');
-                        if (ks.is_float) {
-                            float x = std::numeric_limits<float>::quiet_NaN();
-                            if (!missing && !parse_f32(a, c, &x)) present[k] = 2;
-                            ((float*)ks.out)[o] = x;
-                        } else {
-                            int32_t x = INT32_MIN;
-                            if (!missing && !parse_i32(a, c, &x)) present[k] = 2;
-                            ((int32_t*)ks.out)[o] = x;
-                        }
+                    for (int j = parts; j < P; ++j) g[j] = -2;
+                    g[P] = (int16_t)phased;
+                    if (parts > maxparts) maxparts = parts;
+                    if (k >= 0) { seen_mask_lo |= (1u << k); present[k] = 2; }    // GT asked for as a number
+                } else if (k >= 0) {
+                    seen_mask_lo |= (1u << k);
+                    const KeySpec& ks = keys[k];
+                    size_t o = (size_t)rec * S + outi;
+                    if (ks.is_float) {
+                        float x = std::numeric_limits<float>::quiet_NaN();
+                        if (field_f32(a, le, &c, &x) < 0) present[k] = 2;
+                        ((float*)ks.out)[o] = x;
+                    } else {
+                        int32_t x = INT32_MIN;
+                        if (field_i32(a, le, &c, &x) < 0) present[k] = 2;
+                        ((int32_t*)ks.out)[o] = x;
                     }
+                } else {
+                    c = skip_field(c, le);
                 }
                 ++f;
                 if (c >= le || *c == '\t') break;
