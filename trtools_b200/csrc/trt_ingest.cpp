@@ -430,25 +430,19 @@ inline int field_f32(const char* a, const char* le, const char** end, float* out
     bool neg = false;
     if (s < le && (*s == '-' || *s == '+')) { neg = (*s == '-'); ++s; }
     uint64_t m = 0;
-    int nd = 0, frac = 0;
-    bool seen_digit = false, seen_dot = false, simple = true;
     const char* q = s;
-    for (; q < le; ++q) {
-        unsigned d = (unsigned char)*q - '0';
-        if (d <= 9) {
-            seen_digit = true;
-            if (m || d) { if (++nd > 15) { simple = false; break; } }
-            m = m * 10 + d;
-            if (seen_dot) ++frac;
-        } else if (*q == '.' && !seen_dot) {
-            seen_dot = true;
-        } else {
-            break;
-        }
+    while (q < le && (unsigned)((unsigned char)*q - '0') <= 9u) { m = m * 10 + (unsigned)(*q - '0'); ++q; }
+    long nt = q - s, frac = 0;
+    if (q < le && *q == '.') {
+        ++q;
+        const char* f0 = q;
+        while (q < le && (unsigned)((unsigned char)*q - '0') <= 9u) { m = m * 10 + (unsigned)(*q - '0'); ++q; }
+        frac = q - f0;
+        nt += frac;
     }
-    if (simple && is_delim(q, le)) {
+    if (is_delim(q, le)) {
         *end = q;
-        if (seen_digit && frac <= 22) {
+        if (nt > 0 && nt <= 15) {          // <= 15 digits in all: mantissa < 2^53, frac <= 15 <= 22
             double d = (double)m;
             if (frac) d /= kPow10[frac];
             *out = (float)(neg ? -d : d);
@@ -537,6 +531,15 @@ LineResult parse_line(const char* ls, const char* le, int64_t samp_off, const st
                     int16_t* g = gt_rec + (size_t)outi * (P + 1);
                     int parts = 0;
                     int phased = 0;
+                    if (P == 2 && le - c >= 4 && (unsigned)((unsigned char)c[0] - '0') <= 9u && (c[1] == '|' || c[1] == '/') &&
+                        (unsigned)((unsigned char)c[2] - '0') <= 9u && (c[3] == ':' || c[3] == '\t')) {
+                        g[0] = (int16_t)(c[0] - '0');
+                        g[1] = (int16_t)(c[2] - '0');
+                        g[2] = (int16_t)(c[1] == '|');
+                        if (maxparts < 2) maxparts = 2;
+                        c += 3;
+                        goto gt_done;
+                    }
                     for (;;) {
                         const char* ta = c;
                         int32_t x = 0;
@@ -560,6 +563,7 @@ LineResult parse_line(const char* ls, const char* le, int64_t samp_off, const st
                     for (int j = parts; j < P; ++j) g[j] = -2;
                     g[P] = (int16_t)phased;
                     if (parts > maxparts) maxparts = parts;
+                gt_done:
                     if (k >= 0) { seen_mask_lo |= (1u << k); present[k] = 2; }    // GT asked for as a number
                 } else if (k >= 0) {
                     seen_mask_lo |= (1u << k);
@@ -599,7 +603,7 @@ LineResult parse_line(const char* ls, const char* le, int64_t samp_off, const st
                     return r;
                 }
             }
-            for (size_t k = 0; k < nk; ++k) {
+            if (f <= last_needed) for (size_t k = 0; k < nk; ++k) {
                 if (present[k] == 0) continue;
                 if (!((seen_mask_lo >> k) & 1u)) {
                     size_t o = (size_t)rec * S + outi;
