@@ -62,11 +62,16 @@ def build(force=False, verbose=False):
     else:
         cmd += ["-lnccl"]
     cmd += ["-lz", "-lpthread"]
-    cmd += ["-o", os.environ.get("TRT_BUILD_OUT", LIB)] + sources()
+    out = os.environ.get("TRT_BUILD_OUT", LIB)
+    tmp = out + ".tmp.%d" % os.getpid()          # link next to the target, then rename: never a half-written .so
+    cmd += ["-o", tmp] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libtrtools_b200.so")
+    os.replace(tmp, out)
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
     return LIB

@@ -166,14 +166,14 @@ void text_reserve(trt_vcf* v, size_t more) {
 }
 
 // pull more compressed bytes from the file behind whatever is left in cbuf
-size_t refill_compressed(trt_vcf* v) {
+size_t refill_compressed(trt_vcf* v, size_t chunk = kCompressedChunk) {
     if (v->c_begin > 0) {
         memmove(v->cbuf.data(), v->cbuf.data() + v->c_begin, v->c_end - v->c_begin);
         v->c_end -= v->c_begin;
         v->c_begin = 0;
     }
-    if (v->cbuf.size() < v->c_end + kCompressedChunk) v->cbuf.resize(v->c_end + kCompressedChunk);
-    size_t got = fread(v->cbuf.data() + v->c_end, 1, kCompressedChunk, v->fh);
+    if (v->cbuf.size() < v->c_end + chunk) v->cbuf.resize(v->c_end + chunk);
+    size_t got = fread(v->cbuf.data() + v->c_end, 1, chunk, v->fh);
     v->c_end += got;
     if (got == 0) v->file_eof = true;
     return got;
@@ -643,7 +643,7 @@ static int vcf_open_impl(const char* path, int n_threads, trt_vcf** out) {
         n_threads = hc ? (int)hc : 1;
     }
     v->n_threads = n_threads;
-    refill_compressed(v);
+    refill_compressed(v, size_t(1) << 20);      // enough for the header: opening a file only for its samples stays cheap
     size_t avail = v->c_end - v->c_begin;
     if (avail >= 2 && v->cbuf[0] == 0x1f && v->cbuf[1] == 0x8b) {
         size_t total, hdr;
