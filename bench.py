@@ -450,6 +450,9 @@ def run_gpu(args):
                        done, S, cores, wall)}
             if not args.statstr_only:
                 cpu["tools"] = cpu_other_tools(cores, S, cores)
+        ingest = None
+        if world == 1 and not args.no_cpu_baseline:
+            ingest = ingest_leg(S)
         out = {
             "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -464,13 +467,58 @@ def run_gpu(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "tools": tools,
+            "gpu_launches": int(launches), "clocks": clocks, "tools": tools, "ingest": ingest,
             "timing": {"device_ms_total": ms, "wall_ms_total": wall_ms},
         }
         emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ingest_leg(S, n_loci=32):
+    """The step before the path, reported beside it (not part of `value` / `e2e`, which start from arrays —
+    SURVEY.md 8d): a bounded sample of the workload written as VCF text, read back through the C++ block reader
+    (csrc/trt_ingest.cpp) into the arrays the kernels take, and checked against the generator's arrays.  Host work
+    only; never allowed to break the bench line."""
+    import shutil
+    import tempfile
+    import time
+    tmp = None
+    try:
+        from trtools_b200 import synth
+        from trtools_b200.vcf_ingest import NativeVCF
+        loci = synth.make_loci(n_loci, seed=SEED)
+        calls = synth.fill_calls(loci, S)
+        tmp = tempfile.mkdtemp(prefix="trt_bench_ingest_")
+        path = os.path.join(tmp, "sample.vcf")
+        synth.write_vcf(path, loci, calls)
+        nbytes = os.path.getsize(path)
+        best = None
+        ok = True
+        for _ in range(3):
+            t0 = time.time()
+            v = NativeVCF(path)
+            v._prefetch = ("DP", "DFLANKINDEL", "Q")
+            v._native_block_loci = n_loci
+            recs = list(v)
+            recs[0]._nblk.parse(v._prefetch)       # one pass: GT + the three keys of all records of the run
+            gt = recs[0]._nblk.gt
+            dt = time.time() - t0
+            ok = ok and gt is not None and gt.shape == calls.gt.shape and bool((gt == calls.gt).all()) and \
+                bool((recs[0]._nblk.fmt["DFLANKINDEL"][calls.gt[:, :, 1] != -2] ==
+                      calls.dflankindel[calls.gt[:, :, 1] != -2]).all())
+            v.close()
+            best = dt if best is None else min(best, dt)
+        return {"value": n_loci / best, "unit": "loci/s", "text_MB_per_s": nbytes / 1e6 / best,
+                "host_threads": os.cpu_count(), "arrays_equal_generator": ok,
+                "sample": "{} loci x {} samples as HipSTR VCF text ({:.0f} MB), GT+DP+DFLANKINDEL+Q -> int16/int32/float32 "
+                          "arrays, best of 3".format(n_loci, S, nbytes / 1e6)}
+    except Exception as e:      # pragma: no cover
+        return {"error": "{}: {}".format(type(e).__name__, e)}
+    finally:
+        if tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
 
 
 _REAL_STDOUT = None

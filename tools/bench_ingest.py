@@ -29,30 +29,6 @@ from trtools_b200.vcf_ingest import NativeVCF                      # noqa: E402
 KEYS = ("DP", "DFLANKINDEL", "Q")
 
 
-def write_vcf_fast(path, loci, calls):
-    """synth.write_vcf with the per-call formatting vectorised (same text)."""
-    S = calls.gt.shape[1]
-    names = ["S%06d" % i for i in range(S)]
-    with open(path, "w") as f:
-        f.write(synth.vcf_header(names))
-        for i in range(calls.gt.shape[0]):
-            info = "START={};END={};PERIOD={}".format(loci.start[i], loci.end[i], loci.period[i])
-            cols = [loci.chrom[i], str(loci.pos[i]), "STR_%d" % (i + loci.locus_offset), loci.ref[i],
-                    ",".join(loci.alts[i]) if loci.alts[i] else ".", ".", ".", info, "GT:Q:DP:DSTUTTER:DFLANKINDEL"]
-            gt = calls.gt[i]
-            a0 = np.where(gt[:, 0] < 0, ".", gt[:, 0].astype(str))
-            a1 = np.where(gt[:, 1] < 0, ".", gt[:, 1].astype(str))
-            sep = np.where(gt[:, 2] != 0, "|", "/")
-            q = np.array(["{:.8g}".format(x) for x in calls.q[i]])
-            body = np.char.add(np.char.add(np.char.add(a0, sep), a1), ":")
-            for arr in (q, calls.dp[i].astype(str), calls.dstutter[i].astype(str)):
-                body = np.char.add(np.char.add(body, arr), ":")
-            body = np.char.add(body, calls.dflankindel[i].astype(str))
-            nocall = (gt[:, 0] == -1) & (gt[:, 1] == -2)
-            body = np.where(nocall, ".", body)
-            f.write("\t".join(cols) + "\t" + "\t".join(body.tolist()) + "\n")
-
-
 def read_arrays(cls, path, limit=None, threads=None):
     t0 = time.time()
     v = cls(path) if cls is cc.TextVCF else cls(path, threads=threads)
@@ -86,7 +62,7 @@ def main():
     path = os.path.join(tmp, "synth.vcf")
     loci = synth.make_loci(a.loci)
     calls = synth.fill_calls(loci, a.samples)
-    write_vcf_fast(path, loci, calls)
+    synth.write_vcf(path, loci, calls)
     nbytes = os.path.getsize(path)
     res = {"workload": "synthetic HipSTR VCF text, %d loci x %d samples, %.1f MB, keys GT+%s" %
                        (a.loci, a.samples, nbytes / 1e6, "+".join(KEYS)),

@@ -243,7 +243,7 @@ def vcf_header(sample_names: List[str]) -> str:
 
 
 def write_vcf(path: str, loci: SynthLoci, calls: SynthCalls, sample_names: Optional[List[str]] = None):
-    """Write a (small) synthetic block as HipSTR-format VCF text."""
+    """Write a synthetic block as HipSTR-format VCF text (per-call formatting vectorised with np.char)."""
     S = calls.gt.shape[1]
     names = sample_names or ["S%06d" % i for i in range(S)]
     with open(path, "w") as f:
@@ -252,16 +252,16 @@ def write_vcf(path: str, loci: SynthLoci, calls: SynthCalls, sample_names: Optio
             info = "START={};END={};PERIOD={}".format(loci.start[i], loci.end[i], loci.period[i])
             cols = [loci.chrom[i], str(loci.pos[i]), "STR_%d" % (i + loci.locus_offset), loci.ref[i],
                     ",".join(loci.alts[i]) if loci.alts[i] else ".", ".", ".", info, "GT:Q:DP:DSTUTTER:DFLANKINDEL"]
-            for s in range(S):
-                a0, a1, ph = calls.gt[i, s]
-                if a0 == -1 and a1 == -2:
-                    cols.append(".")
-                    continue
-                sep = "|" if ph else "/"
-                g = ("." if a0 < 0 else str(a0)) + sep + ("." if a1 < 0 else str(a1))
-                cols.append("{}:{:.8g}:{}:{}:{}".format(g, calls.q[i, s], calls.dp[i, s],
-                                                        calls.dstutter[i, s], calls.dflankindel[i, s]))
-            f.write("\t".join(cols) + "\n")
+            gt = calls.gt[i]
+            a0 = np.where(gt[:, 0] < 0, ".", gt[:, 0].astype(str))
+            a1 = np.where(gt[:, 1] < 0, ".", gt[:, 1].astype(str))
+            body = np.char.add(np.char.add(np.char.add(a0, np.where(gt[:, 2] != 0, "|", "/")), a1), ":")
+            q = np.array(["{:.8g}".format(x) for x in calls.q[i]])
+            for arr in (q, calls.dp[i].astype(str), calls.dstutter[i].astype(str)):
+                body = np.char.add(np.char.add(body, arr), ":")
+            body = np.char.add(body, calls.dflankindel[i].astype(str))
+            body = np.where((gt[:, 0] == -1) & (gt[:, 1] == -2), ".", body)       # no call: a lone '.'
+            f.write("\t".join(cols) + "\t" + "\t".join(body.tolist()) + "\n")
 
 
 def allele_tables(loci: SynthLoci, lo: int = 0, hi: Optional[int] = None):
