@@ -311,6 +311,9 @@ int         trt_vcf_header(trt_vcf* v, const char** text, int64_t* len);
 int64_t     trt_vcf_n_samples(const trt_vcf* v);
 /* restrict parsing to these sample columns (strictly increasing, 0-based; cyvcf2 VCF(samples=))   */
 int         trt_vcf_set_samples(trt_vcf* v, const int64_t* cols, int64_t n);
+/* BGZF input only: continue reading at a virtual file offset from a tabix / CSI index (member at
+ * byte coffset of the file, uoffset bytes into its inflated data) — cyvcf2 VCF(region) queries    */
+int         trt_vcf_seek(trt_vcf* v, int64_t coffset, int32_t uoffset);
 /* next run of up to max_loci records / about max_bytes of text (<= 0: no byte cap; at least one
  * record is returned).  *n_loci == 0 and *out == NULL at end of file.  The block owns its text
  * and outlives the reader's later reads; free it with trt_vcf_block_free.                         */

@@ -546,3 +546,32 @@ def test_random_records_match_text_reader(tmp_path, seed):
     mode = ["plain", "gzip", "300", "65280"][seed % 4]
     p = _write(tmp_path, "fuzz.vcf" + ("" if mode == "plain" else ".gz"), _vcf_text(recs, samples=samples), mode)
     assert _compare(p, block_loci=int(rng.integers(1, 40))) == len(recs)
+
+
+@pytest.mark.parametrize("fname,regions", [
+    ("trio_chr21_hipstr.sorted.vcf.gz", ["chr21:9500000-9700000", "chr21:9489666-9489666", "chr21:1-9000000", "chr21",
+                                         "chr21:47000000-48000000", "chr21:48100000-48200000", "chr21:34000000-",
+                                         "chr21:20000000-20050000", "chr20:1-100", "chr21:9546720-9546780"]),
+    ("many_samples.vcf.gz", ["1:3000000-3200000", "1:1-1000", "1", "2:1-5", "1:3045000-3045500", "1:3060000-"]),
+])
+def test_region_queries_through_tabix_index_match_linear_scan(data_dir, fname, regions):
+    """vcf(region) with a .tbi (the reference's own index files): seek + early stop must serve exactly the records
+    the text reader's linear scan serves."""
+    from trtools_b200 import vcf_ingest
+    path = os.path.join(data_dir, fname)
+    assert os.path.isfile(path + ".tbi")
+    used_index = 0
+    for region in regions:
+        want = [(r.CHROM, r.POS, r.ID) for r in cc.TextVCF(path)(region)]
+        v = NativeVCF(path)
+        got_recs = list(v(region))
+        got = [(r.CHROM, r.POS, r.ID) for r in got_recs]
+        assert got == want, (region, len(got), len(want))
+        used_index += bool(v._region_stop or v._region_empty)
+        if got_recs:                               # arrays of a record reached through a seek
+            t = next(iter(cc.TextVCF(path)(region)))
+            assert _same(got_recs[0].genotype.array(), t.genotype.array()), region
+            assert _same(got_recs[0].format("DP"), t.format("DP")), region
+    assert used_index == len(regions)
+    # without the index: same answers by linear scan
+    assert vcf_ingest._tabix_start(path + ".nope.tbi", "1", 5) is None

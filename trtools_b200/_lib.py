@@ -38,7 +38,7 @@ EXPORTS = [
     "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
     "trt_dist_allreduce_sum_f64", "trt_dist_barrier",
     "trt_vcf_open", "trt_vcf_close", "trt_vcf_last_error", "trt_vcf_header", "trt_vcf_n_samples",
-    "trt_vcf_set_samples", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse",
+    "trt_vcf_set_samples", "trt_vcf_seek", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse",
 ]
 
 
@@ -153,6 +153,7 @@ def load():
         "trt_vcf_header": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "trt_vcf_n_samples": (i64, [vp]),
         "trt_vcf_set_samples": (i32, [vp, vp, i64]),
+        "trt_vcf_seek": (i32, [vp, i64, C.c_int32]),
         "trt_vcf_read_block": (i32, [vp, i64, i64, C.POINTER(vp), C.POINTER(i64)]),
         "trt_vcf_block_free": (None, [vp]),
         "trt_vcf_block_text": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),

@@ -722,6 +722,24 @@ int trt_vcf_set_samples(trt_vcf* v, const int64_t* cols, int64_t n) {
     return TRT_OK;
 }
 
+int trt_vcf_seek(trt_vcf* v, int64_t coffset, int32_t uoffset) {
+    // BGZF virtual file offset (tabix / CSI): member at byte coffset, uoffset bytes into its inflated data
+    if (!v || coffset < 0 || uoffset < 0 || uoffset > 65536) return TRT_EINVAL;
+    if (v->kind != trt_vcf::BGZF) return fail(v, TRT_ESTATE, "trt_vcf_seek: not a BGZF file");
+    if (fseeko(v->fh, (off_t)coffset, SEEK_SET) != 0) return fail(v, TRT_EINVAL, "trt_vcf_seek: %s", strerror(errno));
+    v->c_begin = v->c_end = 0;
+    v->file_eof = false;
+    v->t_pos = v->t_end = 0;
+    v->eof = false;
+    while (v->t_end < (size_t)uoffset && !v->eof) {
+        int rc = fill(v);
+        if (rc != TRT_OK) return rc;
+    }
+    if (v->t_end < (size_t)uoffset) return fail(v, TRT_EINVAL, "trt_vcf_seek: offset beyond the end of the file");
+    v->t_pos = (size_t)uoffset;
+    return TRT_OK;
+}
+
 static int vcf_read_block_impl(trt_vcf* v, int64_t max_loci, int64_t max_bytes, trt_vcf_block** out, int64_t* n_loci) {
     if (!v || !out || !n_loci || max_loci <= 0) return TRT_EINVAL;
     *out = nullptr;

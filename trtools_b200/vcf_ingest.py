@@ -29,6 +29,53 @@ _DEFAULT_BLOCK_LOCI = 512
 _DEFAULT_BLOCK_BYTES = 1 << 30
 
 
+def _tabix_start(tbi_path: str, chrom: str, start: Optional[int]) -> Optional[int]:
+    """Virtual file offset at which records overlapping ``chrom:start-`` can begin, from the linear index of a
+    tabix file (one offset per 16 kb window: the smallest offset of any record overlapping the window).
+    None: no usable index.  -1: the index shows there is nothing to read (contig absent / window past the end)."""
+    import gzip
+    import struct
+    if not os.path.isfile(tbi_path):
+        return None
+    with gzip.open(tbi_path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"TBI\x01":
+        return None
+    n_ref, fmt, col_seq, col_beg, col_end, meta, skip, l_nm = struct.unpack_from("<8i", data, 4)
+    names = data[36:36 + l_nm].split(b"\x00")[:n_ref]
+    if (fmt & 0xffff) != 2:              # not a VCF-preset index
+        return None
+    try:
+        tid = names.index(chrom.encode())
+    except ValueError:
+        return -1
+    o = 36 + l_nm
+    for r in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", data, o)
+        o += 4
+        for _ in range(n_bin):
+            _bin, n_chunk = struct.unpack_from("<Ii", data, o)
+            o += 8 + 16 * n_chunk
+        (n_intv,) = struct.unpack_from("<i", data, o)
+        o += 4
+        if r == tid:
+            if n_intv == 0:
+                return -1
+            w = max((start or 1) - 1, 0) >> 14
+            if w >= n_intv:
+                return -1
+            ioff = struct.unpack_from("<%dQ" % n_intv, data, o)
+            # gaps are stored as 0: the next filled window (or any earlier one) bounds the start from below
+            k = w
+            while k < n_intv and ioff[k] == 0:
+                k += 1
+            if k == n_intv:
+                return -1
+            return int(ioff[k])
+        o += 8 * n_intv
+    return None
+
+
 class _NativeBlock:
     """One run of records held by the C++ reader (``trt_vcf_block``) and its parsed arrays."""
 
@@ -257,6 +304,9 @@ class NativeVCF(_compat.TextVCF):
         self._readahead = os.environ.get("TRTOOLS_B200_INGEST_READAHEAD", "1") != "0"
         self._ra_thread = None
         self._ra_result = None
+        self._region_stop = False        # region query served through a tabix index: stop at the region's end
+        self._region_empty = False
+        self._seen_region_chrom = False
 
     def _err(self):
         msg = self._lib.trt_vcf_last_error(self._h)
@@ -302,8 +352,18 @@ class NativeVCF(_compat.TextVCF):
             self._ra_thread.start()
         return True
 
+    def _past_region(self, var) -> bool:
+        """Indexed (sorted) file: nothing after this record can be in the region."""
+        chrom, _, end = self._region
+        if var.CHROM != chrom:
+            return self._seen_region_chrom
+        self._seen_region_chrom = True
+        return end is not None and var.POS > end
+
     def __next__(self):
         while True:
+            if self._region_empty:
+                raise StopIteration
             if self._blk is None or self._blk_i >= self._blk.n:
                 if self._h is None or not self._next_block():
                     raise StopIteration
@@ -323,6 +383,37 @@ class NativeVCF(_compat.TextVCF):
             var = NativeVariant(blk, i, self)
             if self._in_region(var):
                 return var
+            if self._region_stop and self._past_region(var):
+                self._region_empty = True
+                raise StopIteration
+
+    # ---- region queries ------------------------------------------------------------------------------
+    def __call__(self, region: str):
+        """``vcf(region)``: with a tabix index next to a BGZF file, seek to the first 16 kb window of the region
+        and stop at its end (the file is sorted, or tabix would not have indexed it); otherwise the same linear
+        scan as the text reader."""
+        super().__call__(region)
+        self._region_stop = False
+        chrom, start, _ = self._region
+        try:
+            voff = _tabix_start(self.fname + ".tbi", chrom, start)
+        except Exception:
+            voff = None          # no / unreadable index: linear scan
+        if voff is None:
+            return self
+        if self._ra_thread is not None:
+            self._ra_thread.join()
+            self._ra_thread, self._ra_result = None, None
+        self._blk = None
+        if voff < 0:             # the index knows the contig is absent or the window is past its last record
+            self._region_empty = True
+            return self
+        if voff > 0:             # 0 = before any record of the file: keep reading where the header ended
+            rc = self._lib.trt_vcf_seek(self._h, voff >> 16, voff & 0xffff)
+            if rc != _lib.TRT_OK:
+                raise OSError("Error reading {}: {}".format(self.fname, self._err()))
+        self._region_stop = True
+        return self
 
     def close(self):
         if getattr(self, "_ra_thread", None) is not None:
