@@ -82,9 +82,15 @@ def main():
                      "gt_equals_generator": bool(gt_ok), "dp_equals_generator": bool(dp_ok)}
     if _lib.device_count() > 0:
         from trtools_b200 import statSTR
-        t0 = time.time()
-        assert statSTR.main(statstr_args(path, os.path.join(tmp, "native"))) == 0
-        t_e2e = time.time() - t0
+        # first run pays CUDA context creation and first-use allocations; the later runs are the steady state
+        runs = {}
+        for label, ra in (("cold", "1"), ("warm", "1"), ("warm_no_readahead", "0"), ("warm_again", "1")):
+            os.environ["TRTOOLS_B200_INGEST_READAHEAD"] = ra
+            t0 = time.time()
+            assert statSTR.main(statstr_args(path, os.path.join(tmp, "native"))) == 0
+            runs[label] = time.time() - t0
+        os.environ["TRTOOLS_B200_INGEST_READAHEAD"] = "1"
+        t_e2e = min(runs["warm"], runs["warm_again"])
         # the text reader on a prefix of the file
         prefix = os.path.join(tmp, "prefix.vcf")
         with open(path) as f, open(prefix, "w") as g:
@@ -102,6 +108,7 @@ def main():
         got = open(os.path.join(tmp, "native.tab")).read().splitlines()[:a.text_sample + 1]
         want = open(os.path.join(tmp, "text.tab")).read().splitlines()
         res["statSTR_e2e"] = {"native_loci_per_s": a.loci / t_e2e, "seconds": t_e2e,
+                              "seconds_by_run": runs,
                               "text_reader_loci_per_s": a.text_sample / t_txt_e2e,
                               "tab_identical_on_prefix": got == want}
     line = json.dumps(res)
