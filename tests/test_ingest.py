@@ -575,3 +575,41 @@ def test_region_queries_through_tabix_index_match_linear_scan(data_dir, fname, r
     assert used_index == len(regions)
     # without the index: same answers by linear scan
     assert vcf_ingest._tabix_start(path + ".nope.tbi", "1", 5) is None
+
+
+def test_refill_boundaries_small_chunks(tmp_path):
+    """Members, records and pread pieces straddling refill boundaries: the reader in a subprocess with 128 KiB fills
+    (TRTOOLS_B200_INGEST_CHUNK) over ~1.5 MB files, plain / gzip / BGZF, against the default 16 MiB fills."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(3)
+    S, L = 1500, 60
+    samples = ["S%d" % i for i in range(S)]
+    recs = []
+    for l in range(L):
+        a = rng.integers(0, 9, size=(S, 2))
+        dp = rng.integers(0, 99, size=S)
+        q = rng.random(S)
+        cols = ["%d|%d:%d:%.5g" % (a[s, 0], a[s, 1], dp[s], q[s]) for s in range(S)]
+        recs.append(_rec(100 + 10 * l, "GT:DP:Q", cols))
+    text = _vcf_text(recs, samples=samples)
+    script = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from trtools_b200.vcf_ingest import NativeVCF\n"
+        "v = NativeVCF(sys.argv[1], threads=4); v._prefetch = ('DP', 'Q'); v._native_block_loci = 7\n"
+        "h = hashlib.sha256()\n"
+        "n = 0\n"
+        "for r in v:\n"
+        "    h.update(r.genotype.array().tobytes()); h.update(r.format('DP').tobytes()); h.update(r.format('Q').tobytes())\n"
+        "    h.update(str(r.POS).encode()); n += 1\n"
+        "print(n, h.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = set()
+    for mode in ("plain", "gzip", "65280", "3000"):
+        p = _write(tmp_path, "chunks_%s.vcf%s" % (mode, "" if mode == "plain" else ".gz"), text, mode)
+        for chunk in ("131072", ""):
+            env = dict(os.environ, TRTOOLS_B200_INGEST_CHUNK=chunk)
+            res = subprocess.run([sys.executable, "-c", script, p], env=env, capture_output=True, text=True, timeout=300)
+            assert res.returncode == 0, res.stderr[-2000:]
+            outs.add(res.stdout.strip())
+    assert len(outs) == 1 and next(iter(outs)).startswith("%d " % L), outs

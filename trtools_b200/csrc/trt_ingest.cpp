@@ -46,7 +46,13 @@
 
 namespace {
 
-constexpr size_t kCompressedChunk = size_t(16) << 20;   // compressed bytes pulled per fill
+// file bytes pulled per fill (16 MiB; TRTOOLS_B200_INGEST_CHUNK overrides it so that the tests can put many
+// refill boundaries — members and records straddling them — into small files).  A BGZF member is at most 64 KiB.
+const size_t kCompressedChunk = [] {
+    const char* e = getenv("TRTOOLS_B200_INGEST_CHUNK");
+    long long n = e ? atoll(e) : 0;
+    return n >= (128 << 10) ? (size_t)n : size_t(16) << 20;
+}();
 constexpr int    kMaxFmtKeys = 256;                     // FORMAT keys per record handled natively
 
 void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t)>& fn) {
@@ -296,7 +302,7 @@ int fill_gzip(trt_vcf* v) {
 int fill_plain(trt_vcf* v) {
     // regular files: every host thread preads its own piece (page-cache copies scale with threads);
     // anything pread refuses (pipes) goes through the FILE
-    constexpr size_t kPiece = size_t(8) << 20;
+    const size_t kPiece = std::min(size_t(8) << 20, kCompressedChunk);
     if (v->plain_off >= 0 && v->n_threads > 1) {
         const int np = v->n_threads;
         text_reserve(v, kPiece * np);
