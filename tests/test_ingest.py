@@ -613,3 +613,59 @@ def test_refill_boundaries_small_chunks(tmp_path):
             assert res.returncode == 0, res.stderr[-2000:]
             outs.add(res.stdout.strip())
     assert len(outs) == 1 and next(iter(outs)).startswith("%d " % L), outs
+
+
+def test_vectorised_sample_text_equals_the_loop(tmp_path, monkeypatch):
+    """Record serialisation (the dumpSTR writer's path): the np.char version must produce the per-sample loop's text
+    byte for byte — untouched records, records whose numeric / string / vector fields were decoded, and records
+    after dumpSTR-style write-back (FILTER strings set, filtered calls nulled)."""
+    monkeypatch.setattr(cc, "_VEC_MIN_SAMPLES", 1)
+    rng = np.random.default_rng(5)
+    paths = list(FIXTURES) + [_write(tmp_path, "edge.vcf", _vcf_text(EDGE_RECORDS))]
+    checked = vectorised = 0
+    for path in paths:
+        for cls in (cc.TextVCF, NativeVCF):
+            v = cls(path)
+            it = iter(v)
+            for _ in range(60):
+                r = _next(it)
+                if r is None or isinstance(r, Exception):
+                    break
+                S = len(v.samples)
+                if S == 0 or isinstance(_try(lambda: r.genotype.array()), tuple) or len(r._sample_cols) != S:
+                    continue             # no samples / GT the readers reject / ragged record
+                for stage in range(3):
+                    if stage == 1:       # decode every field (numeric ones get re-serialised from their arrays)
+                        for k in list(r.FORMAT):
+                            _try(lambda: r.format(k))
+                    if stage == 2:       # dumpSTR write-back
+                        filtered = rng.random(S) < 0.4
+                        r.set_format("FILTER", np.char.encode(np.where(filtered, "HipSTRCallMinDepth10_3", "PASS")))
+                        gts = r.genotypes
+                        for i in np.nonzero(filtered)[0]:
+                            gts[i] = [-1] * r.ploidy + [False]
+                        r.genotypes = gts
+                        for k in list(r.FORMAT):
+                            if k in ("GT", "FILTER"):
+                                continue
+                            vals = _try(lambda: r.format(k))
+                            if isinstance(vals, tuple):
+                                continue
+                            if vals.dtype.kind == "U":
+                                vals[filtered] = "."
+                                vals = np.char.encode(vals)
+                            elif vals.dtype.kind == "f":
+                                vals[filtered] = np.nan
+                            else:
+                                vals[filtered] = cc.INT32_MISSING
+                            r.set_format(k, vals)
+                    want = _try(r._sample_text_loop)
+                    got = _try(r._sample_text)
+                    assert got == want, (path, cls.__name__, r.POS, stage)
+                    checked += 1
+                    # how often the np.char path itself (not its fallback to the loop) produced the text
+                    monkeypatch.setattr(cc.Variant, "_sample_text_loop", lambda self: None)
+                    vectorised += _try(r._sample_text) is not None
+                    monkeypatch.undo()
+                    monkeypatch.setattr(cc, "_VEC_MIN_SAMPLES", 1)
+    assert checked > 1500 and vectorised > 0.9 * checked, (checked, vectorised)

@@ -32,6 +32,7 @@ from typing import Dict, Iterator, List, Optional
 import numpy as np
 
 INT32_MISSING = -2147483648
+_VEC_MIN_SAMPLES = 64      # below this many samples the per-sample loop is as fast as the np.char path
 INT32_VECTOR_END = -2147483647
 
 _header_kv = re.compile(r'([A-Za-z0-9_]+)=("(?:[^"\\]|\\.)*"|[^,]*)')
@@ -357,7 +358,84 @@ class Variant:
             return '%g' % x
         return str(x)
 
+    # -- vectorised serialisation of the sample columns (np.char over all samples of a field at once; the loop
+    #    version below is the definition and the checker: tests/test_ingest.py compares the two byte for byte)
+    @staticmethod
+    def _gt_text_vec(arr):
+        p = arr.shape[1] - 1
+        if p < 1 or (arr[:, 0] == -2).any():
+            return None
+        sep = np.where(arr[:, p] != 0, '|', '/')
+        out = np.where(arr[:, 0] == -1, '.', arr[:, 0].astype(str))
+        for j in range(1, p):
+            a = arr[:, j]
+            nxt = np.char.add(np.char.add(out, sep), np.where(a == -1, '.', a.astype(str)))
+            out = np.where(a != -2, nxt, out)
+        return out
+
+    @staticmethod
+    def _column_text_vec(col):
+        """One column of a FORMAT array -> (strings, skip mask); skip = INT32_VECTOR_END entries."""
+        if col.dtype.kind in 'iu':
+            skip = (col == INT32_VECTOR_END) if col.dtype.itemsize >= 4 else np.zeros(col.shape, bool)
+            return np.where(col == INT32_MISSING, '.', col.astype(str)), skip
+        if col.dtype.kind == 'f':
+            nan = np.isnan(col)
+            txt = np.char.mod('%g', np.where(nan, 0, col).astype(col.dtype))
+            return np.where(nan, '.', txt), np.zeros(col.shape, bool)
+        if col.dtype.kind == 'U':
+            return col, np.zeros(col.shape, bool)
+        return None, None
+
+    @classmethod
+    def _array_text_vec(cls, data):
+        if data.dtype.kind not in 'iufU':
+            return None
+        if data.ndim == 1:
+            if data.dtype.kind in 'iu' and data.dtype.itemsize < 4:
+                return None
+            txt, _ = cls._column_text_vec(data)
+            return txt
+        if data.ndim != 2:
+            return None
+        if data.shape[1] == 0:
+            return np.full(data.shape[0], '.')
+        out, have = None, None
+        for j in range(data.shape[1]):
+            txt, skip = cls._column_text_vec(data[:, j])
+            if txt is None:
+                return None
+            if out is None:
+                out, have = np.where(skip, '', txt), ~skip
+            else:
+                joined = np.where(have, np.char.add(np.char.add(out, ','), txt), txt)
+                out = np.where(skip, out, joined)
+                have = have | ~skip
+        return np.where(have, out, '.')
+
     def _sample_text(self):
+        n = len(self._sample_cols)
+        if n == 0:
+            return []
+        if n < _VEC_MIN_SAMPLES:
+            return self._sample_text_loop()
+        fields = []
+        for key in self.FORMAT:
+            if key == 'GT':
+                txt = self._gt_text_vec(self._gts())
+            elif key in self._fmt_cache:
+                txt = self._array_text_vec(np.asarray(self._fmt_cache[key]))
+            else:
+                txt = np.array(self._raw_field(key), dtype=str)
+            if txt is None or txt.shape != (n,):
+                return self._sample_text_loop()
+            fields.append(txt)
+        out = fields[0]
+        for txt in fields[1:]:
+            out = np.char.add(np.char.add(out, ':'), txt)
+        return out.tolist()
+
+    def _sample_text_loop(self):
         n = len(self._sample_cols)
         if n == 0:
             return []
