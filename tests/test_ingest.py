@@ -669,3 +669,11 @@ def test_vectorised_sample_text_equals_the_loop(tmp_path, monkeypatch):
                     monkeypatch.undo()
                     monkeypatch.setattr(cc, "_VEC_MIN_SAMPLES", 1)
     assert checked > 1500 and vectorised > 0.9 * checked, (checked, vectorised)
+
+
+def test_bench_ingest_leg_small():
+    """bench.py's `ingest` key: the bounded VCF-text sample must come back equal to the generator's arrays."""
+    import bench
+    out = bench.ingest_leg(700, n_loci=6)
+    assert "error" not in out, out
+    assert out["arrays_equal_generator"] is True and out["value"] > 0 and out["unit"] == "loci/s"
