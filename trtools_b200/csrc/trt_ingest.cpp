@@ -17,6 +17,9 @@
 // allele tokens, vector-valued fields, ragged sample columns) is flagged per record / per key and the
 // Python side re-parses that record from its text: flagged, never guessed.
 //
+// Region queries: trt_vcf_seek continues at a BGZF virtual offset taken from a tabix index (the Python side reads
+// the .tbi); everything else about a region (overlap test, stopping) stays with the caller.
+//
 // Host code only: no CUDA calls, usable (and tested) without a GPU.  It feeds the CUDA path; it is
 // not an alternative to it.
 #include <sys/types.h>
