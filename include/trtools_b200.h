@@ -337,6 +337,22 @@ int         trt_vcf_block_parse(const trt_vcf_block* b, int ploidy, int16_t* gt_
                                 const char* const* keys, const int32_t* key_is_float, void* const* key_out,
                                 uint8_t* present, int32_t* rec_ploidy, uint8_t* rec_status);
 
+/* raw text of the field at position field_index of the record's FORMAT column, for every kept
+ * sample, as fixed-width NUL-padded byte strings [S][width] (String FORMAT keys: vcfrecord.format
+ * on HipSTR GB / ALLREADS, GangSTR RC / REPCI — dumpSTR/filters.py:573-757; and the writer's
+ * pass-through of fields nothing decoded).  *max_len = longest token; out is filled only when
+ * out != NULL and width >= *max_len (call once to size, once to fill).                           */
+int         trt_vcf_block_field(const trt_vcf_block* b, int64_t rec, int field_index, int32_t width, char* out,
+                                int32_t* max_len);
+/* Sample columns of one record as text (dumpSTR's record emission, trtools/dumpSTR/dumpSTR.py:1338
+ * vcf writer.write_record): per sample the fields joined by ':', samples joined by TAB.
+ *   kind[f]: 0 fixed-width byte strings [S] of ncol[f] bytes (NUL padded), 1 GT int16 [S][ncol]
+ *   (cyvcf2 layout), 2 int32 [S][ncol] (INT32_MIN prints '.', INT32_MIN+1 = vector end, skipped),
+ *   3 float32 / 4 float64 [S][ncol] ("%g", NaN prints '.')
+ * Returns the bytes written, or -(bytes needed) if cap is too small.                             */
+int64_t     trt_vcf_join_samples(int64_t n_samples, int n_fields, const int32_t* kind, const void* const* data,
+                                 const int32_t* ncol, char* out, int64_t cap);
+
 /* ---- multi-GPU: loci shard by contiguous ranges, one context per rank --------------------------
  * NCCL is used only to gather fixed-width per-locus result rows and to sum per-sample counters.  */
 int trt_dist_unique_id(void* out_128_bytes);

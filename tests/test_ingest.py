@@ -622,7 +622,7 @@ def test_vectorised_sample_text_equals_the_loop(tmp_path, monkeypatch):
     monkeypatch.setattr(cc, "_VEC_MIN_SAMPLES", 1)
     rng = np.random.default_rng(5)
     paths = list(FIXTURES) + [_write(tmp_path, "edge.vcf", _vcf_text(EDGE_RECORDS))]
-    checked = vectorised = 0
+    checked = vectorised = native = 0
     for path in paths:
         for cls in (cc.TextVCF, NativeVCF):
             v = cls(path)
@@ -663,12 +663,16 @@ def test_vectorised_sample_text_equals_the_loop(tmp_path, monkeypatch):
                     got = _try(r._sample_text)
                     assert got == want, (path, cls.__name__, r.POS, stage)
                     checked += 1
+                    nat = _try(r._sample_text_native)          # the C++ serialiser (trt_vcf_join_samples)
+                    if isinstance(want, list) and nat is not None:
+                        assert nat == "\t".join(want), (path, cls.__name__, r.POS, stage, "native")
+                        native += 1
                     # how often the np.char path itself (not its fallback to the loop) produced the text
                     monkeypatch.setattr(cc.Variant, "_sample_text_loop", lambda self: None)
                     vectorised += _try(r._sample_text) is not None
                     monkeypatch.undo()
                     monkeypatch.setattr(cc, "_VEC_MIN_SAMPLES", 1)
-    assert checked > 1500 and vectorised > 0.9 * checked, (checked, vectorised)
+    assert checked > 1500 and vectorised > 0.9 * checked and native > 0.9 * checked, (checked, vectorised, native)
 
 
 def test_bench_ingest_leg_small():

@@ -38,7 +38,7 @@ EXPORTS = [
     "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
     "trt_dist_allreduce_sum_f64", "trt_dist_barrier",
     "trt_vcf_open", "trt_vcf_close", "trt_vcf_last_error", "trt_vcf_header", "trt_vcf_n_samples",
-    "trt_vcf_set_samples", "trt_vcf_seek", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse",
+    "trt_vcf_set_samples", "trt_vcf_seek", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse", "trt_vcf_block_field", "trt_vcf_join_samples",
 ]
 
 
@@ -158,6 +158,8 @@ def load():
         "trt_vcf_block_free": (None, [vp]),
         "trt_vcf_block_text": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "trt_vcf_block_parse": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "trt_vcf_block_field": (i32, [vp, i64, i32, C.c_int32, vp, vp]),
+        "trt_vcf_join_samples": (i64, [i64, i32, vp, vp, vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

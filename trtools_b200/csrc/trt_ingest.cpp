@@ -890,6 +890,140 @@ static int vcf_block_parse_impl(const trt_vcf_block* b, int ploidy, int16_t* gt_
     return TRT_OK;
 }
 
+// Raw text of one FORMAT field (by position in the record's FORMAT column) of every kept sample of one record, as
+// fixed-width NUL-padded byte strings [S][width]; a sample column that ends before the field reads '.' (what the
+// text reader returns).  *max_len receives the longest token; nothing is written unless out != NULL and
+// width >= *max_len.  Returns TRT_OK, or TRT_ERECORD when the record's columns do not match the header.
+int trt_vcf_block_field(const trt_vcf_block* b, int64_t rec, int field_index, int32_t width, char* out,
+                        int32_t* max_len) {
+    if (!b || !max_len || rec < 0 || rec >= (int64_t)b->line_off.size() - 1 || field_index < 0) return TRT_EINVAL;
+    if (b->samp_off[rec] < 0) return TRT_ERECORD;
+    const char* t = b->text.data();
+    const char* ls = t + b->line_off[rec];
+    const char* le = (const char*)memchr(ls, '\n', (size_t)(t + b->line_off[rec + 1] - ls));
+    if (le > ls && le[-1] == '\r') --le;
+    const bool all = b->keep.empty();
+    const int64_t S = all ? b->n_file_samples : ((b->keep.size() == 1 && b->keep[0] < 0) ? 0 : (int64_t)b->keep.size());
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool fill = pass == 1;
+        if (fill && (!out || width < *max_len)) return TRT_OK;
+        if (fill) memset(out, 0, (size_t)S * (size_t)width);
+        int32_t longest = 1;
+        size_t kp = 0;
+        int64_t col = 0, outi = 0;
+        const char* p = ls + b->samp_off[rec];
+        while (p <= le) {
+            const void* tab = memchr(p, '\t', (size_t)(le - p));
+            const char* ce = tab ? (const char*)tab : le;
+            bool kept = all ? true : (kp < b->keep.size() && b->keep[kp] == col);
+            if (kept) {
+                if (outi >= S) return TRT_ERECORD;
+                const char* a = p;
+                int f = 0;
+                const char* c = a;
+                for (;;) {
+                    c = a;
+                    while (c < ce && *c != ':') ++c;
+                    if (f == field_index || c >= ce) break;
+                    ++f;
+                    a = c + 1;
+                }
+                const char* tok = a;
+                size_t n = (size_t)(c - a);
+                if (f != field_index) { tok = "."; n = 1; }
+                if ((int32_t)n > longest) longest = (int32_t)n;
+                if (fill) memcpy(out + (size_t)outi * (size_t)width, tok, n);
+                ++outi;
+                ++kp;
+            }
+            ++col;
+            if (!tab) break;
+            p = ce + 1;
+        }
+        if (col != b->n_file_samples || outi != S) return TRT_ERECORD;
+        if (!fill) *max_len = longest;
+    }
+    return TRT_OK;
+}
+
+// ---- record serialisation (the dumpSTR writer's inner loop; trtools/dumpSTR/dumpSTR.py:1338 write_record) ------
+// Sample columns of one record: per sample the fields joined by ':', samples joined by '\t'.  Field kinds:
+//   0 fixed-width byte strings [S] (numpy 'S', NUL padded)   1 GT int16 [S][ncol] (cyvcf2 layout, ncol = P+1)
+//   2 int32 [S][ncol] (INT32_MIN -> '.', INT32_MIN+1 = vector end, skipped)   3 float32 / 4 float64 [S][ncol]
+//   ('%g', NaN -> '.').  A vector prints its entries joined by ',', '.' if none is left.
+// Returns the bytes written, or -(bytes needed) when cap is too small (nothing useful is written then).
+int64_t trt_vcf_join_samples(int64_t n_samples, int n_fields, const int32_t* kind, const void* const* data,
+                             const int32_t* ncol, char* out, int64_t cap) {
+    if (n_samples < 0 || n_fields < 1 || !kind || !data || !ncol || (!out && cap > 0)) return 0;
+    int64_t w = 0;
+    char num[64];
+    auto put = [&](const char* p, size_t n) {
+        if (w + (int64_t)n <= cap) memcpy(out + w, p, n);
+        w += (int64_t)n;
+    };
+    auto putc_ = [&](char c) {
+        if (w < cap) out[w] = c;
+        ++w;
+    };
+    for (int64_t s = 0; s < n_samples; ++s) {
+        if (s) putc_('\t');
+        for (int f = 0; f < n_fields; ++f) {
+            if (f) putc_(':');
+            const int nc = ncol[f];
+            switch (kind[f]) {
+                case 0: {
+                    const char* p = (const char*)data[f] + (size_t)s * nc;
+                    put(p, strnlen(p, (size_t)nc));
+                    break;
+                }
+                case 1: {
+                    const int16_t* g = (const int16_t*)data[f] + (size_t)s * nc;
+                    const int P = nc - 1;
+                    const char sep = g[P] ? '|' : '/';
+                    int printed = 0;
+                    for (int j = 0; j < P; ++j) {
+                        if (g[j] == -2) continue;
+                        if (printed) putc_(sep);
+                        if (g[j] == -1) putc_('.');
+                        else put(num, (size_t)snprintf(num, sizeof num, "%d", (int)g[j]));
+                        ++printed;
+                    }
+                    if (!printed) putc_('.');
+                    break;
+                }
+                case 2: {
+                    const int32_t* v = (const int32_t*)data[f] + (size_t)s * nc;
+                    int printed = 0;
+                    for (int j = 0; j < nc; ++j) {
+                        if (v[j] == INT32_MIN + 1) continue;
+                        if (printed) putc_(',');
+                        if (v[j] == INT32_MIN) putc_('.');
+                        else put(num, (size_t)snprintf(num, sizeof num, "%d", (int)v[j]));
+                        ++printed;
+                    }
+                    if (!printed) putc_('.');
+                    break;
+                }
+                case 3:
+                case 4: {
+                    for (int j = 0; j < nc; ++j) {
+                        double x = kind[f] == 3 ? (double)((const float*)data[f])[(size_t)s * nc + j]
+                                                : ((const double*)data[f])[(size_t)s * nc + j];
+                        if (j) putc_(',');
+                        if (std::isnan(x)) putc_('.');
+                        else put(num, (size_t)snprintf(num, sizeof num, "%g", x));
+                    }
+                    if (nc == 0) putc_('.');
+                    break;
+                }
+                default:
+                    return 0;
+            }
+        }
+    }
+    return w <= cap ? w : -w;
+}
+
 // no exception crosses the ABI (allocation failures of multi-gigabyte blocks included)
 int trt_vcf_open(const char* path, int n_threads, trt_vcf** out) {
     try {

@@ -472,8 +472,75 @@ class Variant:
                 self._filter_raw, self.INFO.to_text()]
         if self.FORMAT:
             cols.append(':'.join(self.FORMAT))
+            if len(self._sample_cols) >= _VEC_MIN_SAMPLES:
+                joined = self._sample_text_native()
+                if joined is not None:
+                    return '\t'.join(cols) + '\t' + joined + '\n'
             cols.extend(self._sample_text())
         return '\t'.join(cols) + '\n'
+
+    def _sample_text_native(self):
+        """All sample columns as one TAB-joined string through trt_vcf_join_samples (csrc/trt_ingest.cpp), or
+        None when a field is of a kind the C++ serialiser does not take (the np.char / loop versions do)."""
+        import ctypes as C
+        try:
+            from . import _lib
+            lib = _lib.load()
+        except (ImportError, OSError, AttributeError):
+            return None
+        n = len(self._sample_cols)
+        kinds, ncols, arrays = [], [], []
+        est = 0
+        for key in self.FORMAT:
+            if key == 'GT':
+                a = np.ascontiguousarray(self._gts(), dtype=np.int16)
+                kind, nc, width = 1, a.shape[1], 7 * a.shape[1]
+            elif key in self._fmt_cache:
+                a = np.asarray(self._fmt_cache[key])
+                if a.ndim == 2 and a.shape[1] >= 1 and a.dtype in (np.int32, np.float32, np.float64):
+                    a = np.ascontiguousarray(a)
+                    kind = 2 if a.dtype == np.int32 else (3 if a.dtype == np.float32 else 4)
+                    nc, width = a.shape[1], (12 if kind == 2 else 26) * a.shape[1]
+                elif a.ndim == 1 and a.dtype.kind in 'US':
+                    try:
+                        a = np.ascontiguousarray(np.char.encode(a, 'utf-8') if a.dtype.kind == 'U' else a)
+                    except UnicodeError:
+                        return None
+                    kind, nc, width = 0, a.dtype.itemsize, a.dtype.itemsize
+                else:
+                    return None
+            else:
+                raw_bytes = getattr(self, '_raw_field_bytes', None)      # records of the C++ reader
+                a = raw_bytes(key) if raw_bytes is not None else None
+                if a is None:
+                    try:
+                        a = np.array(self._raw_field(key), dtype='S')
+                    except UnicodeError:
+                        return None
+                kind, nc, width = 0, a.dtype.itemsize, a.dtype.itemsize
+            if a.shape[0] != n:
+                return None
+            kinds.append(kind)
+            ncols.append(nc)
+            arrays.append(a)
+            est += width + 1
+        nf = len(kinds)
+        c_kind = (C.c_int32 * nf)(*kinds)
+        c_ncol = (C.c_int32 * nf)(*ncols)
+        c_data = (C.c_void_p * nf)(*[a.ctypes.data for a in arrays])
+        cap = n * est + 16
+        for _ in range(2):
+            buf = C.create_string_buffer(cap)
+            w = lib.trt_vcf_join_samples(n, nf, c_kind, c_data, c_ncol, buf, cap)
+            if w > 0:
+                try:
+                    return buf.raw[:w].decode('utf-8')
+                except UnicodeDecodeError:
+                    return None
+            if w == 0:
+                return None
+            cap = -w + 16
+        return None
 
 
 class TextVCF:

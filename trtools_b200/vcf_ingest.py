@@ -253,6 +253,26 @@ class NativeVariant(_compat.Variant):
         self._fmt_cache[key] = arr
         return arr
 
+    def _raw_field_bytes(self, key):
+        """Raw tokens of one FORMAT key for all samples as a numpy 'S' array (C++ walk of the record's text), or
+        None when the record is one the C++ reader flagged."""
+        if key not in self.FORMAT:
+            return None
+        blk = self._nblk
+        if blk.gt is None:
+            blk.parse(self._vcf._prefetch)
+        if blk.status[self._nidx] != 0:
+            return None
+        idx = self.FORMAT.index(key)
+        longest = C.c_int32(0)
+        rc = blk.lib.trt_vcf_block_field(blk.h, self._nidx, idx, 0, None, C.byref(longest))
+        if rc != _lib.TRT_OK:
+            return None
+        out = np.zeros(blk.S, dtype='S%d' % max(longest.value, 1))
+        rc = blk.lib.trt_vcf_block_field(blk.h, self._nidx, idx, out.dtype.itemsize, out.ctypes.data_as(C.c_void_p),
+                                         C.byref(longest))
+        return out if rc == _lib.TRT_OK else None
+
     def set_format(self, key, data):
         self._shared.discard(key)
         super().set_format(key, data)
