@@ -3,17 +3,23 @@
 bench.py — TR loci/sec of the hot path on a synthetic 100k-locus x 50k-sample HipSTR block.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--loci L] [--samples S]
+    python bench.py --tool associaTR --loci 1000000 --samples 500000 [--gpus N]      # BASELINE configs[4] (C5)
 
-A "step" is one pass of the hot path (harmonize kernel + GT scan + FP64 epilogue, results copied to
-the host) over the whole synthetic block, which is generated directly in HBM by ``trt_synth_fill``
-(30 GB of GT never crosses PCIe).  ``value`` = loci/s with the GT rows resident in HBM; ``e2e`` =
-the same pass through the C-ABI with HOST buffers (pinned staging block -> H2D -> kernels -> D2H).
-``--impl reference`` times the CPU restatement of the reference's algorithm (oracle port; the
-reference itself is pure Python and cannot travel to the GPU box) on a bounded locus sample.
+Default arm: a "step" is one statSTR pass of the hot path (harmonize kernel + GT scan + FP64 epilogue, all 11
+statistics, results copied to the host) over the whole synthetic block, which is generated directly in HBM by
+``trt_synth_fill`` (30 GB of GT never crosses PCIe).  ``value`` = loci/s with the GT rows resident in HBM; ``e2e`` =
+the same pass through the C-ABI with HOST buffers (pinned staging blocks -> H2D -> kernels -> D2H).  ``tools`` carries
+the associaTR and dumpSTR passes of the metric on the same block.  ``parity`` compares, in the same run, the GPU rows
+with the rows the unmodified reference computes for a sample of the same loci.
+
+``--impl reference`` times the UNMODIFIED reference (baseline/_ref; oracle port only if it is missing) on the box's
+host cores: statSTR (the headline ``value``), plus associaTR and dumpSTR under ``tools`` — same config / metric.
+
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement".
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,8 +33,9 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 SEED = 20261017
-STATS6 = ("afreq", "het", "hwep", "mean", "var", "entropy")      # BASELINE.json configs[1]
 METRIC = "TR loci/sec (statSTR all; associaTR OLS) 100k×50k samp, 1/2/4/8 GPU"
+STAT_F64 = ("thresh", "het", "entropy", "mean", "mode", "var", "hwep")       # order of TRT_REGION_STATS
+REL_TOL = 1e-6                                                              # north_star: floats within 1e-6 relative
 
 
 def load_peaks():
@@ -39,6 +46,19 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(L, S, world):
+    """The `config` object — identical on the GPU arm and the reference arm."""
+    return {
+        "workload": "statSTR all 11 statistics (thresh afreq acount nalleles hwep het entropy mean mode var numcalled; "
+                    "sequence grouping) on synthetic HipSTR, {} loci x {} samples per GPU; tools: associaTR (trait ~ TR length "
+                    "+ 10 PCs, non-major cutoff 20) and dumpSTR (min-call-DP 20, max-call-flank-indel 0.15, min-locus-hwep "
+                    "1e-4) on the same block".format(L, S),
+        "loci_per_gpu": L, "samples": S, "seed": SEED, "parallelism": "loci sharded x{}".format(world),
+        "layout": "cyvcf2 arrays: GT int16 [L][S][3], DP / DFLANKINDEL int32 [L][S]; VCF text parsing excluded on both arms",
+        "l2": "inputs ({:.1f} GB of GT per pass) far larger than the 126 MB L2; no flush needed".format(6.0 * L * S / 1e9),
+    }
 
 
 class ClockSampler:
@@ -93,158 +113,210 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's statSTR path on a bounded locus sample
+# CPU arm: the unmodified reference (oracle/ref_arm.py) on a bounded locus sample, one process per core
 # ---------------------------------------------------------------------------------------------------
-def _synth_sub(lo, hi, S, seed, with_fmt):
-    from oracle.records import synth_to_loci
-    from trtools_b200 import synth
-    sl = synth.make_loci(hi, seed=seed)
-    calls = synth.fill_calls(sl, S, slice(lo, hi))
-    sub = synth.SynthLoci(seed=sl.seed, n_loci=hi - lo, chrom=sl.chrom[lo:hi], pos=sl.pos[lo:hi], start=sl.start[lo:hi],
-                          end=sl.end[lo:hi], period=sl.period[lo:hi], ref=sl.ref[lo:hi], alts=sl.alts[lo:hi],
-                          n_alleles=sl.n_alleles[lo:hi], cum_freq=sl.cum_freq[lo:hi], locus_offset=lo)
-    return synth_to_loci(sub, calls, with_fmt=with_fmt)
+def cpu_arm(loci_tables, S, cores, tools=True, steps=1, warmup=0):
+    """-> dict(statSTR=..., associaTR=..., dumpSTR=...) each {value, unit, cores, kind, sample, rows}.  statSTR runs
+    `steps` times (mean loci/s); the other tools once.  One locus per core per run (~1.5 s / 0.6 s / 0.2 s per locus
+    at S = 50k on one core)."""
+    from oracle import ref_arm
+    ref_arm.set_loci(loci_tables)
+    kind = ref_arm.reference_kind()
+    n_sub = min(cores, loci_tables.n_loci)
+    out = {}
+    vals, walls, rows = [], [], None
+    for i in range(warmup + steps):
+        v, done, wall, res = ref_arm.run_pool(ref_arm.statstr_worker, n_sub, S, cores, kind)
+        if i >= warmup:
+            vals.append(v)
+            walls.append(wall)
+            rows = [r for part in res for r in part]
+    out["statSTR"] = {"value": float(np.mean(vals)), "unit": "loci/s", "cores": cores, "kind": kind,
+                      "sample": "{} loci x {} samples per step, {} processes, {:.1f} s per step".format(n_sub, S, cores, float(np.mean(walls))),
+                      "rows": rows, "seconds": float(np.sum(walls))}
+    if tools:
+        tp = ref_arm.save_traits(ref_arm.bench_traits(S, SEED))
+        try:
+            v, done, wall, res = ref_arm.run_pool(ref_arm.assoc_worker, n_sub, S, cores, kind, extra=(tp,))
+        finally:
+            os.remove(tp)
+        out["associaTR"] = {"value": v, "unit": "loci/s", "cores": cores, "kind": kind,
+                            "sample": "{} loci x {} samples, {} processes, {:.1f} s".format(done, S, cores, wall),
+                            "rows": [r for part in res for r in part]}
+        v, done, wall, res = ref_arm.run_pool(ref_arm.dumpstr_worker, n_sub, S, cores, kind)
+        out["dumpSTR"] = {"value": v, "unit": "loci/s", "cores": cores, "kind": kind,
+                          "sample": "{} loci x {} samples, {} processes, {:.1f} s".format(done, S, cores, wall),
+                          "parts": res}
+    return out
 
 
-def reference_kind():
-    """"reference" when the unmodified TRTools code is importable (baseline/_ref, see baseline/install_ref.py, or
-    /root/reference in the build container), else "port" (the oracle restatement)."""
-    from oracle import ref_import
-    return "reference" if ref_import.reference_code_available() else "port"
+def _strip(d):
+    return {k: v for k, v in d.items() if k not in ("rows", "parts", "seconds")}
 
 
-def _cpu_worker(args):
-    lo, hi, S, seed, kind = args
-    loci = _synth_sub(lo, hi, S, seed, False)
-    rows = []
-    if kind == "reference":
-        # the reference's own per-record loop body (trtools/statSTR/statSTR.py:576-630) on cyvcf2-layout records
-        from oracle import ref_import
-        from oracle.records import LocusAsVariant
-        ref_import.enable()
-        import trtools.utils.tr_harmonizer as rtrh
-        import trtools.statSTR.statSTR as rstat
-        recs = [LocusAsVariant(l) for l in loci]
-        t0 = time.perf_counter()
-        for rec in recs:
-            tr = rtrh.HarmonizeRecord(rtrh.VcfTypes.hipstr, rec)
-            items = [rec.CHROM, rec.POS, rec.POS + len(tr.ref_allele)]
-            items += rstat.GetAFreq(tr, [None], uselength=False)
-            for fn in (rstat.GetHet, rstat.GetHWEP):
-                items += fn(tr, [None], uselength=False)
-            items += rstat.GetMean(tr, [None]) + rstat.GetVariance(tr, [None])
-            items += rstat.GetEntropy(tr, [None], uselength=False)
-            rows.append("\t".join(str(x) for x in items))
-        return time.perf_counter() - t0, len(rows)
-    from oracle import stats as ostats, trh as otrh
-    t0 = time.perf_counter()
-    for l in loci:
-        h = otrh.harmonize(l)                                           # HarmonizeRecord
-        vals = ostats.locus_stats(h, l.gt, STATS6, [None], uselength=False)   # statSTR stat wrappers
-        rows.append(ostats.format_row(l.chrom, l.pos, h, vals))          # .tab row
-    return time.perf_counter() - t0, len(rows)
-
-
-def cpu_statstr(n_loci, S, cores, seed=SEED, kind=None):
-    """loci/s of the reference's statSTR path with one process per core on disjoint loci (wall clock of the
-    timed sections, data generation excluded)."""
-    import multiprocessing as mp
-    kind = kind or reference_kind()
-    per = max(1, n_loci // cores)
-    jobs = [(i * per, (i + 1) * per, S, seed, kind) for i in range(cores)]
-    ctxmp = mp.get_context("fork")
-    with ctxmp.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, jobs)
-    wall = max(r[0] for r in res)
-    done = sum(r[1] for r in res)
-    return done / wall, done, wall
-
-
-def _cpu_other_worker(args):
-    """oracle ports of the dumpSTR and associaTR per-locus paths on a few loci (seconds per locus on one core)."""
-    lo, hi, S, seed = args
-    from oracle import dumpstr as od, assoc as oassoc, trh as otrh
-    loci = _synth_sub(lo, hi, S, seed, True)
-    cf = [od.hipstr_flank_indels(0.15), od.min_value("HipSTRCallMinDepth", "DP", 20)]
-    lf = [od.LocusFilter("hwe", 1e-4, False)]
-    sinfo, linfo = od.new_sample_info(S, cf), od.new_loc_info(lf)
-    t0 = time.perf_counter()
-    for l in loci:
-        h = otrh.harmonize(l)
-        r = od.apply_call_filters(l, cf, sinfo)
-        od.apply_locus_filters(l, h, r.gt, lf, linfo)
-        od.recompute_info(h, r.gt, False)
-    t_dump = time.perf_counter() - t0
-    rng = np.random.default_rng(seed)
-    traits = np.hstack([rng.standard_normal((S, 1)), rng.standard_normal((S, 10))])
-    design = oassoc.prepare_design([traits], S, None)
-    t0 = time.perf_counter()
-    for l in loci:
-        h = otrh.harmonize(l)
-        oassoc.regress_locus(oassoc.load_locus(l, h, design.sample_filter.copy(), 20), design).to_text()
-    t_assoc = time.perf_counter() - t0
-    return t_dump, t_assoc, len(loci)
-
-
-def cpu_other_tools(n_loci, S, cores, seed=SEED):
-    import multiprocessing as mp
-    per = max(1, n_loci // cores)
-    jobs = [(i * per, (i + 1) * per, S, seed) for i in range(cores)]
-    with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_other_worker, jobs)
-    done = sum(r[2] for r in res)
-    return {"dumpSTR": {"value": done / max(r[0] for r in res), "unit": "loci/s", "cores": cores, "kind": "port",
-                        "sample": "{} loci x {} samples".format(done, S)},
-            "associaTR": {"value": done / max(r[1] for r in res), "unit": "loci/s", "cores": cores, "kind": "port",
-                          "sample": "{} loci x {} samples".format(done, S)}}
+REFERENCE_NOTE = ("the UNMODIFIED reference (trtools.utils.tr_harmonizer.HarmonizeRecord + trtools.statSTR.statSTR / "
+                  "trtools.dumpSTR.dumpSTR.ApplyCallFilters+ApplyLocusFilters / trtools.associaTR.associaTR.perform_gwas_helper "
+                  "over load_trs; baseline/_ref) on cyvcf2-layout records; loci/s extrapolates linearly (loci are independent)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from trtools_b200 import synth
     cores = os.cpu_count() or 1
-    kind = reference_kind()
     L, S = args.loci, args.samples
-    n_sub = cores * (1 if kind == "reference" else 4)      # ~1.5 s (reference) / ~0.9 s (port) per locus per core at S = 50k
-    vals = []
-    for _ in range(min(args.warmup, 1)):
-        cpu_statstr(cores, S, cores, kind=kind)
+    loci = synth.make_loci(L, seed=SEED)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v, done, wall = cpu_statstr(n_sub, S, cores, kind=kind)
-        vals.append(v)
+    res = cpu_arm(loci, S, cores, tools=not args.statstr_only, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
     total = time.perf_counter() - t0
-    value = float(np.mean(vals))
-    what = ("the UNMODIFIED reference (trtools.utils.tr_harmonizer.HarmonizeRecord + trtools.statSTR.statSTR stat functions, "
-            "baseline/_ref) on cyvcf2-layout records") if kind == "reference" else "oracle port of the reference's Python/numpy path"
-    sample = "{} loci x {} samples per step (of the {}-locus workload), {} processes".format(n_sub, S, L, cores)
+    st = res["statSTR"]
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1),
+        "impl": "reference", "metric": METRIC, "value": st["value"], "unit": "loci/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * st["seconds"] / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "statSTR --afreq --het --hwep --mean --var --entropy, synthetic HipSTR {}x{}".format(L, S),
-                   "loci": L, "samples": S, "note": what + "; VCF parsing excluded; loci/s extrapolates linearly "
-                   "(loci are independent)"},
-        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "config": workload_config(L, S, max(args.gpus, 1)),
+        "cpu_baseline": dict(_strip(st), note=REFERENCE_NOTE if st["kind"] == "reference" else "oracle port of the reference's numpy path"),
+        "tools": {k: _strip(v) for k, v in res.items() if k != "statSTR"},
+        "e2e": {"value": st["value"], "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
     }
     emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------
+# parity of the GPU rows against the reference rows of the same loci (same run)
+# ---------------------------------------------------------------------------------------------------
+class Parity:
+    def __init__(self):
+        self.max_rel = 0.0
+        self.int_mismatch = 0
+        self.n_float = 0
+        self.n_int = 0
+        self.worst = None
+
+    def f(self, got, want, what, abs_tol=0.0):
+        got, want = float(got), float(want)
+        self.n_float += 1
+        if math.isnan(got) or math.isnan(want):
+            rel = 0.0 if (math.isnan(got) and math.isnan(want)) else float("inf")
+        elif got == want:
+            rel = 0.0
+        elif abs(got - want) <= abs_tol:
+            rel = 0.0
+        else:
+            rel = abs(got - want) / max(abs(got), abs(want))
+        if rel > self.max_rel:
+            self.max_rel, self.worst = rel, what
+
+    def i(self, got, want, what):
+        self.n_int += 1
+        if got != want:
+            self.int_mismatch += 1
+            if self.worst is None or not str(self.worst).startswith("int"):
+                self.worst = "int " + what + ": {} vs {}".format(got, want)
+
+    def result(self, n_loci, kind):
+        return {"loci": n_loci, "max_rel": self.max_rel, "int_mismatch": self.int_mismatch, "floats_compared": self.n_float,
+                "ints_compared": self.n_int, "tolerance": REL_TOL, "ok": bool(self.max_rel <= REL_TOL and self.int_mismatch == 0),
+                "worst": self.worst, "against": kind}
+
+
+def parity_statstr(st, locus_off, rows, kind):
+    p = Parity()
+    for j, r in enumerate(rows):
+        for k in STAT_F64:
+            p.f(st[k][j], r[k], "statSTR {} locus {}".format(k, j), abs_tol=1e-300)
+        p.i(int(st["nalleles"][j]), r["nalleles"], "nalleles locus %d" % j)
+        p.i(int(st["n_called"][j]), r["numcalled"], "numcalled locus %d" % j)
+        p.i(st["ac"][locus_off[j]:locus_off[j + 1]].tolist(), r["ac"], "allele counts locus %d" % j)
+    return p.result(len(rows), kind)
+
+
+def parity_assoc(res, pheno_std, K, rows, kind):
+    import scipy.stats
+    from trtools_b200 import _lib
+    reasons = {_lib.AF_NO_CALLED: 'No called samples', _lib.AF_ONE_ALLELE: 'Only one called allele',
+               _lib.AF_NCOVARS: 'n covars >= n samples', _lib.AF_NON_MAJOR: 'non-major allele count<20'}
+    p = Parity()
+    for j, r in enumerate(rows):
+        p.i(int(res["n_tested"][j]), r["n_tested"], "n_tested locus %d" % j)
+        code = int(res["filter_code"][j])
+        p.i("False" if code == _lib.AF_OK else reasons[code], r["filtered"], "locus_filtered locus %d" % j)
+        if code != _lib.AF_OK or r["filtered"] != "False":
+            continue
+        p.f(res["coef"][j] * pheno_std, r["coef"], "assoc coef locus %d" % j)
+        p.f(res["se"][j] * pheno_std, r["se"], "assoc se locus %d" % j)
+        p.f(res["r2"][j], r["r2"], "assoc r2 locus %d" % j, abs_tol=1e-12)
+        # the reference prints p with 3 significant digits; its full-precision value is 2 T_df.sf(|coef/se|)
+        want_p = 2.0 * scipy.stats.t.sf(abs(r["coef"] / r["se"]), r["n_tested"] - K)
+        p.f(res["p"][j], want_p, "assoc p locus %d" % j, abs_tol=1e-300)
+        p.i("{:.2e}".format(res["p"][j]), r["p_text"], "printed p locus %d" % j)
+    return p.result(len(rows), kind)
+
+
+def parity_dumpstr(ctx, loci, S, lf, locus_off, parts, kind):
+    """per-locus values from the full-size pass (lf) + per-sample accumulators from a pass over the sampled loci only"""
+    from trtools_b200 import _lib, synth
+    p = Parity()
+    j = 0
+    for part in parts:
+        for r in part["per_locus"]:
+            names = []
+            if int(lf["flags"][j]) & 1:
+                names.append(part["locus_filter_names"][0])
+            if int(lf["flags"][j]) & 0x80000000:
+                names.append("NO_CALLS_REMAINING")
+            p.i(";".join(names) if names else "PASS", r["filter"], "FILTER locus %d" % j)
+            p.i(lf["ac"][locus_off[j]:locus_off[j + 1]].tolist(), r["AC"], "AC/REFAC locus %d" % j)
+            p.i(int(lf["n_called"][j]), r["n_called"], "n_called locus %d" % j)
+            p.i(int(lf["hrun"][j]), r["HRUN"], "HRUN locus %d" % j)
+            p.f(lf["het"][j], r["HET"], "INFO HET locus %d" % j)
+            p.f(lf["hwep"][j], r["HWEP"], "INFO HWEP locus %d" % j, abs_tol=1e-300)
+            j += 1
+    n = j
+    # per-sample counters of the sample log over exactly the sampled loci
+    ctx.block_begin(n, S, 2, "hipstr")
+    ctx.synth_fill(SEED, loci.locus_offset, loci.cum_freq[:n], loci.miss_thresh, loci.half_thresh, with_format=5)
+    ctx.block_set_alleles(*synth.allele_tables(loci, 0, n))
+    ctx.check(ctx.lib.trt_harmonize(ctx.h))
+    specs = [(_lib.CF_RATIO_GT, _lib.FMT_DFLANKINDEL, 0.15), (_lib.CF_MIN, _lib.FMT_DP, 20)]
+    counts = np.zeros((2, S), np.int64)
+    numcalls = np.zeros(S, np.int64)
+    totaldp = np.zeros(S)
+    ctx.call_filters(specs, _lib.FMT_DP, counts, numcalls, totaldp, want_mask=False, want_trigger=False, want_gt=False)
+    want_nc = sum(part["numcalls"] for part in parts)
+    want_dp = sum(part["totaldp"] for part in parts)
+    p.i(bool(np.array_equal(numcalls, want_nc)), True, "samplog numcalls")
+    p.i(bool(np.array_equal(totaldp, want_dp, equal_nan=True)), True, "samplog totaldp")
+    for f, key in enumerate(("HipSTRCallFlankIndels0.15", "HipSTRCallMinDepth20")):
+        want = sum(part["counts"][key] for part in parts)
+        p.i(bool(np.array_equal(counts[f], want)), True, "samplog " + key)
+    return p.result(n, kind)
+
+
+# ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+def _design(S, seed):
+    rng = np.random.default_rng(seed)
+    traits = np.hstack([rng.standard_normal((S, 1)), rng.standard_normal((S, 10))])
+    covars = np.hstack([np.full((S, 1), -1.0), traits])
+    pheno_std = float(np.std(covars[:, 1]))
+    covars = (covars - covars.mean(axis=0)) / np.maximum(covars.std(axis=0), 1e-300)
+    outcome = covars[:, 1].copy()
+    covars[:, 1] = 1.0
+    return covars, outcome, pheno_std
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from trtools_b200 import _lib, synth, dist as tdist
     numa_cpus = tdist.bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa_bind) else None
-    dist = tdist.init("nccl") if world > 1 else None
-
     ctx = _lib.Context(local_rank)
+    comm = tdist.init(ctx) if world > 1 else None
     info = ctx.device_info()
     L, S = args.loci, args.samples
     # weak scaling: every rank owns its own L loci (global locus ids rank*L .. rank*L+L-1)
@@ -253,26 +325,34 @@ def run_gpu(args):
     ctx.block_begin(L, S, 2, "hipstr")
     ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=False)
     ctx.block_set_alleles(*tables)
+    nA = ctx.nA
+    locus_off = ctx.locus_off.copy()
+
+    def barrier():
+        if comm is not None:
+            comm.barrier()
+        ctx.synchronize()
+
+    # ---- NCCL gather of the per-locus result table on rank 0: device buffers, no host bounce ------------------
+    # rows gathered per step: the seven float64 statistics + nalleles + n_hom + n_called (10 x 8 B x L) and the allele
+    # counts (int32 [nA]) — everything statSTR prints
+    gathered = None
+    if comm is not None:
+        sizes = comm.allgather_i64([10 * 8 * L, 4 * nA])
+        if rank == 0:
+            gathered = (ctx.pinned_empty((int(sizes[:, 0].sum()),), np.uint8), ctx.pinned_empty((int(sizes[:, 1].sum()),), np.uint8))
 
     def step():
         ctx.check(ctx.lib.trt_harmonize(ctx.h))
-        return ctx.locus_stats(False, None, 0.01, pinned=True)      # results land in page-locked host arrays
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        ctx.synchronize()
-
-    STAT_COLS = ("thresh", "het", "entropy", "mean", "mode", "var", "hwep")
-    plan = tdist.GatherPlan(dist, len(STAT_COLS), L) if dist is not None else None
-
-    def gather_rows(st):
-        """NCCL gather of the fixed-width per-locus result table on rank 0 (north_star: the only collective)."""
-        if plan is not None:
-            plan.gather([st[k][0] for k in STAT_COLS], wait=False)     # in flight under the next step's kernels
+        if comm is None:
+            return ctx.locus_stats(False, None, 0.01, pinned=True)      # results land in page-locked host arrays
+        ctx.locus_stats(False, None, 0.01, want=())                     # results stay in HBM ...
+        comm.gather_region(tdist.REGION_STATS, 0, 10 * 8 * L, sizes[:, 0], 0, None if gathered is None else gathered[0], wait=False)
+        comm.gather_region(tdist.REGION_ALLELE_COUNTS, 0, 4 * nA, sizes[:, 1], 0, None if gathered is None else gathered[1], wait=False)
+        return None                                                     # ... and travel to rank 0 under the next step
 
     for _ in range(max(args.warmup, 0)):
-        gather_rows(step())
+        step()
     sampler = ClockSampler(local_rank)
     scan_ms = []
     barrier()
@@ -280,23 +360,30 @@ def run_gpu(args):
     launches0 = ctx.launch_count()
     t_wall0 = time.perf_counter()
     ctx.stopwatch_start()
+    st = None
     for _ in range(args.steps):
         st = step()
         scan_ms.append(ctx.last_scan_ms())
-        gather_rows(st)
+    if comm is not None:
+        comm.wait()                                     # the last gather and its host copy belong to the timed region
     ms = ctx.stopwatch_stop()
-    if plan is not None:
-        plan.wait()                                     # the last gather belongs to the timed region
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
-    # the device stopwatch only spans this rank's stream; use the larger of device and wall time,
-    # then the max over ranks
-    ms = max(ms, 0.0)
+    # the device stopwatch only spans this rank's stream; use the larger of device and wall time, then the max over ranks
     step_ms = max(ms, wall_ms) / args.steps
-    step_ms = tdist.max_over_ranks(dist, step_ms)
+    step_ms = tdist.max_over_ranks(comm, step_ms)
     value = world * L / (step_ms / 1000.0)
+    if comm is not None:
+        # rank 0 now holds every rank's table; unpack its own share for the parity check below
+        st = ctx.locus_stats(False, None, 0.01, pinned=True)
+        if rank == 0:
+            own = np.frombuffer(gathered[0][:10 * 8 * L], dtype=np.float64).reshape(10, L)
+            assert np.array_equal(own[1], st["het"][0], equal_nan=True) and np.array_equal(own[6], st["hwep"][0], equal_nan=True)
+            last = np.frombuffer(gathered[0][-10 * 8 * L:], dtype=np.float64).reshape(10, L)
+            assert np.isfinite(last[3]).any()           # the last rank's rows arrived
+    st = {k: v[0].copy() for k, v in st.items()}
 
     # ---- roofline of the dominant kernel (GT scan): 6 algorithmic bytes per call ----------------
     peak, peak_src = load_peaks()
@@ -317,71 +404,17 @@ def run_gpu(args):
                 "kernel_share_of_step": scan / step_ms if step_ms > 0 else None}
 
     # ---- e2e through the C-ABI with HOST buffers (rank-local; max over ranks) -------------------
-    Lb = min(L, args.e2e_block)
-    nblk = (L + Lb - 1) // Lb
-    host_gt = ctx.pinned_empty((Lb, S, 3), np.int16)
-    host_gt[...] = ctx.block_get_gt(0, Lb)                     # untimed: fill the pinned staging block
-    # the pinned block holds loci [0, Lb): every streamed block re-sends it with its own allele tables
-    blk_tables = [synth.allele_tables(loci, 0, min(Lb, L - b * Lb)) for b in range(nblk)]
-    h2d = d2h = 0
-
-    # two contexts (own stream + device buffers each) ping-pong over the blocks: while one block's kernels and result
-    # copies run, the next block's host->device copy is already in flight on the other stream
-    ctxs = [ctx, _lib.Context(local_rank)]
-
-    def e2e_step():
-        nonlocal h2d, d2h
-        h2d = d2h = 0
-
-        def finish(c):
-            nonlocal d2h
-            c.check(c.lib.trt_harmonize(c.h))
-            st_ = c.locus_stats(False, None, 0.01, pinned=True)
-            d2h += sum(v.nbytes for v in st_.values())
-            return st_
-
-        pending, st = None, None
-        for b in range(nblk):
-            c = ctxs[b & 1]
-            n = blk_tables[b][2].shape[0] - 1
-            c.block_begin(n, S, 2, "hipstr")
-            c.block_set_gt(host_gt[:n])                       # asynchronous copy from the pinned block
-            c.block_set_alleles(*blk_tables[b])
-            h2d += host_gt[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
-            if pending is not None:
-                st = finish(pending)
-            pending = c
-        if pending is not None:
-            st = finish(pending)
-        return st
-
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()                                                 # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    ctx.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
-    e2e_ms = tdist.max_over_ranks(dist, e2e_ms)
-    e2e_value = world * L / (e2e_ms / 1000.0)
-    ctx.free_pinned(host_gt)
-    ctxs[1].close()
+    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier)
 
     # ---- the other two tools of the metric on the same resident block (device-timed, results copied to host) ----
-    tools = {}
+    tools, assoc_res, lf_res, pheno_std = {}, None, None, 1.0
     if not args.statstr_only:
-        from trtools_b200 import _lib as L_
+        L_ = _lib
         ctx.block_begin(L, S, 2, "hipstr")
         ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=5)   # DP + DFLANKINDEL
         ctx.block_set_alleles(*tables)
         ctx.check(ctx.lib.trt_harmonize(ctx.h))
-        rng = np.random.default_rng(SEED + rank)
-        traits = np.hstack([rng.standard_normal((S, 1)), rng.standard_normal((S, 10))])
-        covars = np.hstack([np.full((S, 1), -1.0), traits])
-        covars = (covars - covars.mean(axis=0)) / np.maximum(covars.std(axis=0), 1e-300)
-        outcome = covars[:, 1].copy()
-        covars[:, 1] = 1.0
+        covars, outcome, pheno_std = _design(S, SEED)
         ctx.assoc_set_design(covars, outcome, np.arange(S, dtype=np.int32))
 
         def timed(fn, steps, warm):
@@ -397,7 +430,7 @@ def run_gpu(args):
             dev = ctx.stopwatch_stop()
             wall = (time.perf_counter() - t0) * 1000.0
             ms_ = max(dev, wall) / steps
-            return tdist.max_over_ranks(dist, ms_), float(np.mean(scan))
+            return tdist.max_over_ranks(comm, ms_), float(np.mean(scan))
 
         def pack_step():
             ctx.check(ctx.lib.trt_pack_length_genotypes(ctx.h))
@@ -410,13 +443,16 @@ def run_gpu(args):
                                      "the harmonize kernel); the statistics kernels do not need it (they read the native rows)",
                          "kernel_ms": pack_step.kernel, "algorithmic_bytes_per_call": 10,
                          "roofline_frac": (10.0 * L * S / (pack_step.kernel / 1000.0) / 1e9) / peak}
-        ms_a, k_a = timed(lambda: ctx.assoc_ols(20.0, pinned=True), max(2, min(args.steps, 5)), 2)
+
+        def assoc_step():
+            assoc_step.res = ctx.assoc_ols(20.0, pinned=True)
+
+        ms_a, k_a = timed(assoc_step, max(2, min(args.steps, 5)), 2)
+        assoc_res = {k: v.copy() for k, v in assoc_step.res.items()}
         tools["associaTR"] = {"value": world * L / (ms_a / 1000.0), "unit": "loci/s", "ms_per_step": ms_a,
-                              "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; allele-count scan + "
-                                          "FP64 moments (thread-per-locus TMA tiles) + mask down-dates + solve, results to host",
+                              "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; FP64 moments "
+                                          "(thread-per-locus TMA tiles) + mask down-dates + solve, results to host",
                               "kernel_ms": k_a, "algorithmic_bytes_per_call": 6,
-                              "note": "one read of the native GT is the algorithmic minimum; the path reads it twice (scan + moments) "
-                                      "and the moments kernel is at the FP64 ridge (2*(K+2) flop per 6 B)",
                               "roofline_frac": (6.0 * L * S / (k_a / 1000.0) / 1e9) / peak if k_a > 0 else None}
         cf_specs = [(L_.CF_RATIO_GT, L_.FMT_DFLANKINDEL, 0.15), (L_.CF_MIN, L_.FMT_DP, 20)]
         counts = np.zeros((2, S), np.int64)
@@ -426,54 +462,230 @@ def run_gpu(args):
         def dump_step():
             ctx.call_filters(cf_specs, L_.FMT_DP, counts, numcalls, totaldp, want_mask=False, want_trigger=False, want_gt=False)
             k1 = ctx.last_scan_ms()
-            ctx.locus_filters([(L_.LF_HWE, 1e-4)], False, pinned=True)
+            dump_step.res = ctx.locus_filters([(L_.LF_HWE, 1e-4)], False, pinned=True)
             dump_step.kernel = k1 + ctx.last_scan_ms()
 
         ms_d, _ = timed(dump_step, max(2, min(args.steps, 5)), 2)
+        lf_res = {k: v.copy() for k, v in dump_step.res.items()}
         tools["dumpSTR"] = {"value": world * L / (ms_d / 1000.0), "unit": "loci/s", "ms_per_step": ms_d,
                             "workload": "call filters min-call-DP 20 + max-call-flank-indel 0.15 (masked GT written), locus filter "
                                         "HWE 1e-4 on the masked genotypes, sample/locus accumulators to host",
                             "kernel_ms": dump_step.kernel, "algorithmic_bytes_per_call": 20,
-                            "note": "GT 6 + DP 4 + DFLANKINDEL 4 read, masked GT 6 written; the locus statistics re-read the masked "
-                                    "GT (6 more bytes of actual traffic)",
+                            "note": "GT 6 + DP 4 + DFLANKINDEL 4 read, masked GT 6 written",
                             "roofline_frac": (20.0 * L * S / (dump_step.kernel / 1000.0) / 1e9) / peak}
 
     if rank == 0:
         cores = os.cpu_count() or 1
-        cpu = None
+        cpu, parity, ingest = None, None, None
         if world == 1 and not args.no_cpu_baseline:
-            kind = reference_kind()
-            n_sub = cores * (1 if kind == "reference" else 4)
-            v, done, wall = cpu_statstr(n_sub, S, cores, kind=kind)
-            cpu = {"value": v, "unit": "loci/s", "cores": cores, "kind": kind,
-                   "sample": "{} loci x {} samples, statSTR 6 stats (sequence grouping), {} processes, {:.1f} s".format(
-                       done, S, cores, wall)}
+            res = cpu_arm(loci, S, cores, tools=not args.statstr_only)
+            kind = res["statSTR"]["kind"]
+            cpu = dict(_strip(res["statSTR"]), note=REFERENCE_NOTE if kind == "reference" else "oracle port")
+            parity = parity_statstr(st, locus_off, res["statSTR"]["rows"], kind)
+            parity["tools"] = {}
             if not args.statstr_only:
-                cpu["tools"] = cpu_other_tools(cores, S, cores)
-        ingest = None
-        if world == 1 and not args.no_cpu_baseline:
+                cpu["tools"] = {k: _strip(v) for k, v in res.items() if k != "statSTR"}
+                parity["tools"]["associaTR"] = parity_assoc(assoc_res, pheno_std, 12, res["associaTR"]["rows"], kind)
+                parity["tools"]["dumpSTR"] = parity_dumpstr(ctx, loci, S, lf_res, locus_off, res["dumpSTR"]["parts"], kind)
+                parity["ok"] = bool(parity["ok"] and all(t["ok"] for t in parity["tools"].values()))
+                parity["max_rel"] = max([parity["max_rel"]] + [t["max_rel"] for t in parity["tools"].values()])
+                parity["int_mismatch"] += sum(t["int_mismatch"] for t in parity["tools"].values())
             ingest = ingest_leg(S)
+        cfg = workload_config(L, S, world)
         out = {
             "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "statSTR all 11 stats (sequence grouping) on synthetic HipSTR, {} loci x {} samples per GPU, "
-                                   "GT int16 [L][S][3] generated in HBM".format(L, S),
-                       "loci_per_gpu": L, "samples": S, "seed": SEED, "parallelism": "loci sharded x{}".format(world),
-                       "l2": "inputs ({:.1f} GB) far larger than L2; no flush needed".format(algo_bytes / 1e9),
-                       "e2e": "one pinned {}-locus host block (loci 0..{}) streamed {}x per step through two ping-pong contexts; every copy is a real H2D".format(Lb, Lb - 1, nblk),
-                       "device": info["name"], "sm_count": info["sm_count"],
-                       "numa_bound_cpus": numa_cpus},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "tools": tools, "ingest": ingest,
+            "device": {"name": info["name"], "sm_count": info["sm_count"], "numa_bound_cpus": numa_cpus},
+            "gather": None if comm is None else "per-locus rows (10 x 8 B x L + int32 allele counts) of every rank gathered on rank 0 "
+                      "with ncclSend/ncclRecv from device buffers on the context stream (trt_dist_gather_region), host copy on a side stream",
             "timing": {"device_ms_total": ms, "wall_ms_total": wall_ms},
         }
         emit(out)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.barrier()
+        comm.close()
+
+
+def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier):
+    """The statSTR pass through the C-ABI with HOST buffers: pinned host blocks of the workload's genotypes ->
+    trt_block_set_gt (H2D) -> kernels -> D2H of the statistics.  The host blocks hold DISTINCT loci of the workload
+    (copied out of the device-generated block before the clock starts), as many as fit the pinned budget; when the
+    budget is smaller than the workload the resident blocks are streamed round-robin (every copy is a real H2D)."""
+    from trtools_b200 import _lib, synth, dist as tdist
+    Lb = min(L, args.e2e_block)
+    nblk = (L + Lb - 1) // Lb
+    blk_bytes = Lb * S * 6
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    budget = min(args.e2e_host_gb * (1 << 30), 0.35 * avail / max(world, 1))
+    n_host = int(max(1, min(nblk, budget // blk_bytes)))
+    host_blocks = []
+    for b in range(n_host):
+        n = min(Lb, L - b * Lb)
+        hb = ctx.pinned_empty((Lb, S, 3), np.int16)
+        ctx.check(ctx.lib.trt_block_get_gt(ctx.h, b * Lb, n, hb.ctypes.data))       # untimed: distinct loci b*Lb .. b*Lb+n-1
+        host_blocks.append(hb)
+    blk_tables = [synth.allele_tables(loci, (b % n_host) * Lb, min((b % n_host) * Lb + min(Lb, L - b * Lb), L)) for b in range(nblk)]
+    counters = {"h2d": 0, "d2h": 0}
+    # two contexts (own stream + device buffers each) ping-pong over the blocks: while one block's kernels and result
+    # copies run, the next block's host->device copy is already in flight on the other stream
+    ctxs = [ctx, _lib.Context(local_rank)]
+
+    def e2e_step():
+        counters["h2d"] = counters["d2h"] = 0
+
+        def finish(c):
+            c.check(c.lib.trt_harmonize(c.h))
+            st_ = c.locus_stats(False, None, 0.01, pinned=True)
+            counters["d2h"] += sum(v.nbytes for v in st_.values())
+
+        pending = None
+        for b in range(nblk):
+            c = ctxs[b & 1]
+            n = blk_tables[b][2].shape[0] - 1
+            hb = host_blocks[b % n_host]
+            c.block_begin(n, S, 2, "hipstr")
+            c.block_set_gt(hb[:n])                            # asynchronous copy from the pinned block
+            c.block_set_alleles(*blk_tables[b])
+            counters["h2d"] += hb[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
+            if pending is not None:
+                finish(pending)
+            pending = c
+        if pending is not None:
+            finish(pending)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()                                                 # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
+    e2e_ms = tdist.max_over_ranks(comm, e2e_ms)
+    for hb in host_blocks:
+        ctx.free_pinned(hb)
+    ctxs[1].close()
+    return {"value": world * L / (e2e_ms / 1000.0), "unit": "loci/s", "h2d_bytes_per_step": int(counters["h2d"]),
+            "d2h_bytes_per_step": int(counters["d2h"]), "ms_per_step": e2e_ms,
+            "host_blocks": "{} pinned blocks of {} loci = {} distinct loci ({:.1f} GB) of the workload resident in host memory, "
+                           "streamed {} blocks per step through two ping-pong contexts".format(
+                               n_host, Lb, min(n_host * Lb, L), n_host * blk_bytes / 1e9, nblk)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[4] (C5): associaTR at biobank scale, loci sharded over the ranks, streamed in device-generated blocks
+# ---------------------------------------------------------------------------------------------------
+def run_assoc_stream(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from trtools_b200 import _lib, synth, dist as tdist
+    ctx = _lib.Context(local_rank)
+    comm = tdist.init(ctx) if world > 1 else None
+    info = ctx.device_info()
+    L, S, B = args.loci, args.samples, args.block_loci
+    lo, hi = tdist.locus_shard(L, rank, world)
+    # allele tables of ONE block (python-side generator: 0.13 ms per locus) reused by every block; the genotypes of
+    # block b are hashed from the GLOBAL locus ids, so every locus of the run has its own calls
+    tab = synth.make_loci(min(B, max(hi - lo, 1)), seed=SEED)
+    covars, outcome, pheno_std = _design(S, SEED)
+    ctx.assoc_set_design(covars, outcome, np.arange(S, dtype=np.int32))
+    blocks = [(b0, min(b0 + B, hi)) for b0 in range(lo, hi, B)]
+    row_bytes = 5 * 8          # p, coef, se, r2, std_g (f64) per locus: the fixed-width summary row
+    recv = None
+    n_rows = comm.allgather_i64([hi - lo])[:, 0] if comm is not None else np.array([hi - lo])
+    if rank == 0:
+        recv = ctx.pinned_empty((int(max(B * world * row_bytes, 16)),), np.uint8)
+    table = np.full((5, L), np.nan) if rank == 0 else None
+    nblk_max = int(tdist.max_over_ranks(comm, float(len(blocks))))
+
+    def run(timed):
+        hot_ms = gen_ms = 0.0
+        scan_ms = []
+        for i in range(nblk_max):
+            n = 0
+            if i < len(blocks):
+                b0, b1 = blocks[i]
+                n = b1 - b0
+                t0 = time.perf_counter()
+                ctx.block_begin(n, S, 2, "hipstr")
+                ctx.synth_fill(SEED, b0, tab.cum_freq[:n], tab.miss_thresh, tab.half_thresh, with_format=False)
+                ctx.block_set_alleles(*synth.allele_tables(tab, 0, n))
+                ctx.synchronize()
+                gen_ms += (time.perf_counter() - t0) * 1000.0
+                ctx.stopwatch_start()
+                ctx.check(ctx.lib.trt_harmonize(ctx.h))
+                res = ctx.assoc_ols(20.0, pinned=True) if comm is None else ctx.assoc_ols(20.0, want=())
+                scan_ms.append(ctx.last_scan_ms())
+            else:
+                ctx.stopwatch_start()
+            if comm is not None:
+                counts = comm.allgather_i64([n])[:, 0]
+                # the five float64 columns of this block's rows are contiguous per rank: [5][n] at the head of the region
+                comm.gather_region(tdist.REGION_ASSOC, 0, n * row_bytes, counts * row_bytes, 0, recv, wait=True)
+                if rank == 0 and timed:
+                    off = 0
+                    for r in range(world):
+                        c = int(counts[r])
+                        if c:
+                            g0 = tdist.locus_shard(L, r, world)[0] + i * B
+                            table[:, g0:g0 + c] = np.frombuffer(recv[off:off + c * row_bytes], dtype=np.float64).reshape(5, c)
+                        off += c * row_bytes
+            elif timed and n:
+                for k, key in enumerate(("p", "coef", "se", "r2", "std_g")):
+                    table[k, b0:b1] = res[key]
+            hot_ms += ctx.stopwatch_stop()
+        return hot_ms, gen_ms, scan_ms
+
+    run(False) if args.warmup > 0 and len(blocks) <= 2 else None      # tiny configurations only: warm the kernels
+    if comm is not None:
+        comm.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    hot_ms, gen_ms, scan_ms = run(True)
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    hot = tdist.max_over_ranks(comm, hot_ms)
+    kern = tdist.max_over_ranks(comm, float(np.sum(scan_ms)))
+    wall = tdist.max_over_ranks(comm, wall_s)
+    peak, peak_src = load_peaks()
+    if rank == 0:
+        n_ok = int(np.isfinite(table[0]).sum())
+        own_bytes = 6.0 * (hi - lo) * S
+        out = {
+            "metric": METRIC, "value": L / (hot / 1000.0), "unit": "loci/s", "n_gpus": world, "steps": 1, "warmup": 0,
+            "ms_per_step": hot, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "associaTR (trait ~ TR length + 10 PCs, cutoff 20) on {} loci x {} samples (BASELINE configs[4]) "
+                                   "sharded by locus over {} GPU(s), streamed in device-generated blocks of {} loci; per-locus summary "
+                                   "rows gathered on rank 0 with NCCL from device buffers".format(L, S, world, B),
+                       "loci": L, "samples": S, "block_loci": B, "seed": SEED,
+                       "l2": "each block ({:.1f} GB of GT) is far larger than L2".format(6.0 * min(B, hi - lo) * S / 1e9),
+                       "timed": "harmonize + associaTR kernels + NCCL gather + host copy of the rows per block (CUDA events on the "
+                                "context stream, summed over blocks, max over ranks); block generation (the stand-in for ingest) is "
+                                "reported separately as generation_ms"},
+            "roofline": {"bound": "hbm", "kernel": "assoc_tile_kernel (+ down-dates, solve)", "achieved": own_bytes / (kern / 1000.0) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": own_bytes / (kern / 1000.0) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": kern, "algorithmic_bytes_per_launch": own_bytes},
+            "rows_gathered": n_ok, "loci_tested_ok": n_ok, "generation_ms": tdist.max_over_ranks(None, gen_ms),
+            "wall_s": wall, "gpu_launches": int(launches), "clocks": clocks,
+            "device": {"name": info["name"], "sm_count": info["sm_count"]},
+            "e2e": None, "cpu_baseline": None,
+        }
+        emit(out)
+    if comm is not None:
+        comm.barrier()
+        comm.close()
 
 
 def ingest_leg(S, n_loci=32):
@@ -483,7 +695,6 @@ def ingest_leg(S, n_loci=32):
     only; never allowed to break the bench line."""
     import shutil
     import tempfile
-    import time
     tmp = None
     try:
         from trtools_b200 import synth
@@ -547,15 +758,21 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--tool", default="statSTR", choices=["statSTR", "associaTR"],
+                    help="associaTR: the streamed biobank-scale run of BASELINE configs[4]")
     ap.add_argument("--loci", type=int, default=100000)
     ap.add_argument("--samples", type=int, default=50000)
+    ap.add_argument("--block-loci", type=int, default=16384, help="--tool associaTR: loci per device-generated block")
     ap.add_argument("--e2e-block", type=int, default=4096)
+    ap.add_argument("--e2e-host-gb", type=float, default=32.0, help="pinned host memory holding distinct loci for the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--statstr-only", action="store_true", help="skip the dumpSTR / associaTR measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.tool == "associaTR":
+        run_assoc_stream(args)
     else:
         run_gpu(args)
 

@@ -360,7 +360,33 @@ int trt_dist_init(trt_ctx* ctx, int rank, int world, const void* unique_id_128_b
 int trt_dist_allgather_f64(trt_ctx* ctx, const double* send_host, int64_t count, double* recv_host /*[world*count]*/);
 int trt_dist_allreduce_sum_i64(trt_ctx* ctx, int64_t* inout_host, int64_t count);
 int trt_dist_allreduce_sum_f64(trt_ctx* ctx, double* inout_host, int64_t count);
+int trt_dist_allreduce_max_f64(trt_ctx* ctx, double* inout_host, int64_t count);
 int trt_dist_barrier(trt_ctx* ctx);
+/* Gather of per-locus result rows on rank dst, DEVICE buffers on both sides (no host bounce): every rank sends
+ * `nbytes` bytes starting `offset_bytes` into one of its device-resident result regions (the outputs of its most
+ * recent trt_locus_stats / trt_assoc_ols / trt_locus_filters call, which may be made with NULL host pointers);
+ * dst receives them in rank order (ragged sizes: nbytes_per_rank[world]) over NCCL on the context stream and copies the
+ * gathered table to host_out (pinned memory from trt_host_alloc for full speed) on a side stream, so the next block's
+ * kernels overlap the copy.  async != 0: returns without blocking the host; trt_dist_wait completes it.
+ * Region layouts (n = G*L rows of the call):
+ *   TRT_REGION_STATS          12 arrays of n 8-byte values: thresh, het, entropy, mean, mode, var, hwep (f64),
+ *                             nalleles (i32, first 4n bytes of its 8n slot), n_hom, n_called, n_called_nonstrict,
+ *                             n_padded (i64)
+ *   TRT_REGION_ALLELE_COUNTS  int32 [G][nA] allele counts by allele index
+ *   TRT_REGION_ASSOC          p, coef, se, r2, std_g (f64 [L] each), n_tested (i64 [L]), filter_code (i32 [L], padded
+ *                             to a multiple of 4 entries), ac_len (i32 [nA])
+ *   TRT_REGION_LOCUS_FILTERS  flags (u32 [L], padded to 16 bytes), het, hwep (f64 [L]), n_called (i64 [L])           */
+#define TRT_REGION_STATS          0
+#define TRT_REGION_ALLELE_COUNTS  1
+#define TRT_REGION_ASSOC          2
+#define TRT_REGION_LOCUS_FILTERS  3
+int trt_dist_gather_region(trt_ctx* ctx, int region, int64_t offset_bytes, int64_t nbytes, const int64_t* nbytes_per_rank,
+                           int dst, void* host_out /* dst only; may be NULL */, int async);
+/* same with host buffers on both sides (the CLIs' formatted output rows: ragged byte strings), blocking            */
+int trt_dist_gather_host(trt_ctx* ctx, const void* send_host, int64_t nbytes, const int64_t* nbytes_per_rank, int dst,
+                         void* recv_host);
+int trt_dist_wait(trt_ctx* ctx);
+int trt_dist_finalize(trt_ctx* ctx);
 
 #ifdef __cplusplus
 }

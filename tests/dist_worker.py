@@ -10,7 +10,7 @@ from trtools_b200 import dist as tdist  # noqa: E402
 
 def main():
     rank, world, _ = tdist.env_rank_world()
-    d = tdist.init("gloo")
+    d = tdist.init(backend="gloo")
     L = 1001
     lo, hi = tdist.locus_shard(L, rank, world)
     # every rank "computes" the rows of its own loci: row i = [i, i^2, nan for i % 7 == 0]
@@ -26,22 +26,18 @@ def main():
     dp_total = tdist.allreduce_sum(d, dp + rank)
     t = tdist.max_over_ranks(d, 10.0 + rank)
     ok = True
-    # fixed-shape plan (bench.py's per-step gather): 3 columns x 17 rows per rank, twice through the same buffers
-    plan = tdist.GatherPlan(d, 3, 17)
-    for rep in range(2):
-        cols = [np.arange(17, dtype=np.float64) + 100 * rank + rep, np.full(17, float(rank)), np.full(17, np.nan)]
-        if rep == 0:
-            got = plan.gather(cols)
-        else:                                      # the asynchronous form bench.py uses inside its timed loop
-            assert plan.gather(cols, wait=False) is None
-            got = plan.wait()
-        if rank == 0:
-            ok = ok and got.shape == (world, 3, 17)
-            for r in range(world):
-                ok = ok and np.array_equal(got[r, 0], np.arange(17, dtype=np.float64) + 100 * r + rep)
-                ok = ok and np.all(got[r, 1] == r) and np.all(np.isnan(got[r, 2]))
-        else:
-            ok = ok and got is None
+    # the CLIs' block dealing: every rank walks all 7 blocks, keeps the text of its own, rank 0 restores file order
+    sh = tdist.BlockSharder(d)
+    for b in range(7):
+        if sh.mine():
+            sh.add(("rank%d-block%d\n" % (rank, b)) * (b + 1))
+    merged = sh.finish()
+    if rank == 0:
+        ok = ok and merged == [(("rank%d-block%d\n" % (b % world, b)) * (b + 1)).encode() for b in range(7)]
+    else:
+        ok = ok and merged is None
+    sizes = d.allgather_i64([rank, 10 * rank + 1])
+    ok = ok and sizes.shape == (world, 2) and sizes[:, 1].tolist() == [10 * r + 1 for r in range(world)]
     if rank == 0:
         want = np.arange(L, dtype=np.float64)
         ok = ok and table.shape == (L, 3) and np.array_equal(table[:, 0], want) and np.array_equal(table[:, 1], want * want)
@@ -53,8 +49,7 @@ def main():
         expect[r::world] = r + 1
     ok = ok and np.array_equal(total, expect)
     ok = ok and np.isnan(dp_total[2]) and dp_total[0] == sum(range(world)) and t == 10.0 + world - 1
-    d.barrier()
-    d.destroy_process_group()
+    d.close()
     print("RANK{} {}".format(rank, "OK" if ok else "FAIL"), flush=True)
     sys.exit(0 if ok else 1)
 

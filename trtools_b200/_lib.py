@@ -36,7 +36,8 @@ EXPORTS = [
     "trt_locus_stats", "trt_genotype_counts", "trt_call_filters", "trt_locus_filters", "trt_assoc_set_design", "trt_assoc_ols",
     "trt_synth_fill", "trt_block_get_gt", "trt_block_get_format",
     "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
-    "trt_dist_allreduce_sum_f64", "trt_dist_barrier",
+    "trt_dist_allreduce_sum_f64", "trt_dist_allreduce_max_f64", "trt_dist_barrier", "trt_dist_gather_region",
+    "trt_dist_gather_host", "trt_dist_wait", "trt_dist_finalize",
     "trt_vcf_open", "trt_vcf_close", "trt_vcf_last_error", "trt_vcf_header", "trt_vcf_n_samples",
     "trt_vcf_set_samples", "trt_vcf_seek", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse", "trt_vcf_block_field", "trt_vcf_join_samples",
 ]
@@ -146,7 +147,12 @@ def load():
         "trt_dist_allgather_f64": (i32, [vp, vp, i64, vp]),
         "trt_dist_allreduce_sum_i64": (i32, [vp, vp, i64]),
         "trt_dist_allreduce_sum_f64": (i32, [vp, vp, i64]),
+        "trt_dist_allreduce_max_f64": (i32, [vp, vp, i64]),
         "trt_dist_barrier": (i32, [vp]),
+        "trt_dist_gather_region": (i32, [vp, i32, i64, i64, vp, i32, vp, i32]),
+        "trt_dist_gather_host": (i32, [vp, vp, i64, vp, i32, vp]),
+        "trt_dist_wait": (i32, [vp]),
+        "trt_dist_finalize": (i32, [vp]),
         "trt_vcf_open": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
         "trt_vcf_close": (None, [vp]),
         "trt_vcf_last_error": (C.c_char_p, [vp]),
@@ -406,12 +412,13 @@ class Context:
         assert cv.ndim == 2 and cv.shape[0] == oc.shape[0] == si.shape[0]
         self.check(self.lib.trt_assoc_set_design(self.h, _ptr(cv), _ptr(oc), _ptr(si), cv.shape[0], cv.shape[1]))
 
-    def assoc_ols(self, non_major_cutoff: float, pinned: bool = False) -> dict:
+    def assoc_ols(self, non_major_cutoff: float, pinned: bool = False, want=None) -> dict:
+        """``want=()``: leave the rows in device memory (multi-GPU runs gather them with trt_dist_gather_region)."""
         L, nA = self.L, self.nA
         r = lambda k, n_, dt: self._result(pinned, "assoc_" + k, (n_,), dt)
-        res = dict(filter_code=r("filter_code", L, np.int32), n_tested=r("n_tested", L, np.int64), p=r("p", L, np.float64),
-                   coef=r("coef", L, np.float64), se=r("se", L, np.float64), r2=r("r2", L, np.float64),
-                   std_g=r("std_g", L, np.float64), ac_len=r("ac_len", nA, np.int32))
+        spec = (("filter_code", L, np.int32), ("n_tested", L, np.int64), ("p", L, np.float64), ("coef", L, np.float64),
+                ("se", L, np.float64), ("r2", L, np.float64), ("std_g", L, np.float64), ("ac_len", nA, np.int32))
+        res = {k: r(k, n_, dt) for k, n_, dt in spec if want is None or k in want}
         out = AssocOut(**{k: _ptr(v) for k, v in res.items()})
         self.check(self.lib.trt_assoc_ols(self.h, float(non_major_cutoff), C.byref(out)))
         return res

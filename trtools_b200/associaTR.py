@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from . import __version__, _lib, block as _block
+from . import __version__, _lib, block as _block, dist as _dist
 from . import load_and_filter_genotypes
 from . import tr_harmonizer as trh
 from . import utils
@@ -146,11 +146,24 @@ def perform_gwas_helper(outfile, all_samples, get_genotype_iter, phenotype_name,
     ctx.assoc_set_design(covars, outcome, np.nonzero(sample_filter)[0].astype(np.int32))
     n_loci = 0
     start = time.time()
+    sharder = getattr(source, "sharder", None)
+    multi = sharder is not None and sharder.comm is not None
     for blk in source.blocks():
         blk._activate()
         res = ctx.assoc_ols(source.non_major_cutoff)
-        _write_block(outfile, blk, res, pheno_std, source.non_major_cutoff)
+        if multi:                                   # several GPUs: rank 0 gathers every rank's rows at the end
+            import io
+            buf = io.StringIO()
+            _write_block(buf, blk, res, pheno_std, source.non_major_cutoff)
+            sharder.add(buf.getvalue())
+        else:
+            _write_block(outfile, blk, res, pheno_std, source.non_major_cutoff)
         n_loci += blk.L
+    if multi:
+        merged = sharder.finish()
+        if merged is not None:
+            outfile.write(b"".join(merged).decode("utf-8"))
+            outfile.flush()
     total_time = time.time() - start
     if n_loci > 0:
         print("Done.\nTotal loci: {}\nTotal time: {}s\ntime/locus: {}s\n".format(n_loci, total_time, total_time / n_loci),
@@ -163,13 +176,21 @@ class _BlockSource:
     """Blocks of harmonized records of one VCF (the GPU counterpart of load_trs)."""
     detail_fields = ['motif', 'period', 'ref_len', 'allele_frequency']
 
-    def __init__(self, tr_vcf, region, non_major_cutoff, vcftype, period_check, block_size, ctx=None):
+    def __init__(self, tr_vcf, region, non_major_cutoff, vcftype, period_check, block_size, ctx=None, sharder=None):
         self.tr_vcf, self.region, self.non_major_cutoff = tr_vcf, region, non_major_cutoff
         self.vcftype, self.period_check, self.block_size = vcftype, period_check, block_size
         self.ctx = ctx or _lib.default_context()
+        self.sharder = sharder          # several GPUs: only the blocks this rank owns are built
+
+    def _build(self, vcftype, recs):
+        if self.sharder is not None and not self.sharder.mine():
+            return None
+        return _block.build_block(self.ctx, vcftype, recs)
 
     def blocks(self):
         vcf = cyvcf2.VCF(self.tr_vcf)
+        if hasattr(vcf, "_native_block_loci"):
+            vcf._native_block_loci = self.block_size     # one native run per GPU block (zero-copy hand-off)
         inferred = trh.InferVCFType(vcf, self.vcftype if self.vcftype else 'auto')
         region_start = None
         it = vcf
@@ -183,11 +204,15 @@ class _BlockSource:
             if self.period_check and record.INFO.get('PERIOD') is None:
                 continue
             if recs and (len(recs) >= self.block_size or record.ploidy != recs[0].ploidy):
-                yield _block.build_block(self.ctx, inferred.name, recs)
+                blk = self._build(inferred.name, recs)
+                if blk is not None:
+                    yield blk
                 recs = []
             recs.append(record)
         if recs:
-            yield _block.build_block(self.ctx, inferred.name, recs)
+            blk = self._build(inferred.name, recs)
+            if blk is not None:
+                yield blk
 
 
 def perform_gwas(outfname, tr_vcf, phenotype_name, traits_fnames, vcftype, same_samples, sample_fname, region,
@@ -195,16 +220,26 @@ def perform_gwas(outfname, tr_vcf, phenotype_name, traits_fnames, vcftype, same_
                  plot_phenotype_residuals, plotting_ci_alphas, imputed_ukb_strs_paper_period_check, block_size=512):
     """reference associaTR.py:424-470."""
     all_samples = cyvcf2.VCF(tr_vcf).samples
+    ctx = _lib.default_context()
+    comm = _dist.cli_comm(ctx)                 # several GPUs under torchrun: blocks dealt round-robin, rows gathered on rank 0
+    sharder = _dist.BlockSharder(comm) if comm is not None else None
     get_genotype_iter = lambda samples: _BlockSource(tr_vcf, region, non_major_cutoff, vcftype,
-                                                     imputed_ukb_strs_paper_period_check, block_size)
-    print("Writing output to {}.temp".format(outfname), flush=True)
-    with open(outfname + '.temp', 'w') as outfile:
+                                                     imputed_ukb_strs_paper_period_check, block_size, ctx, sharder)
+    rank0 = comm is None or comm.rank == 0
+    if rank0:
+        print("Writing output to {}.temp".format(outfname), flush=True)
+    import io
+    with (open(outfname + '.temp', 'w') if rank0 else io.StringIO()) as outfile:
         perform_gwas_helper(outfile, all_samples, get_genotype_iter, phenotype_name, traits_fnames, same_samples,
                             sample_fname, beagle_dosages, plotting_phenotype_fname, paired_genotype_plot,
                             plot_phenotype_residuals, plotting_ci_alphas)
-    print("Moving {}.temp to {}".format(outfname, outfname), flush=True)
-    shutil.move(outfname + '.temp', outfname)
-    print("Done.", flush=True)
+    if rank0:
+        print("Moving {}.temp to {}".format(outfname, outfname), flush=True)
+        shutil.move(outfname + '.temp', outfname)
+        print("Done.", flush=True)
+    if comm is not None:
+        comm.barrier()
+        comm.close()
 
 
 def run():  # pragma: no cover

@@ -111,6 +111,13 @@ void trt_destroy(trt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    trt_dist_finalize(ctx);
+    if (ctx->copy_stream) {
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->ev_gathered);
+        for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    for (int i = 0; i < 5; i++) trt_free_buf(ctx->dist_recv_r[i]);
     DevBuf* bufs[] = {&ctx->gt_buf, &ctx->gt_masked_buf, &ctx->seqs, &ctx->allele_off, &ctx->locus_off, &ctx->pos,
                       &ctx->start, &ctx->end, &ctx->period, &ctx->given_len, &ctx->motif_in, &ctx->allele_len, &ctx->trim_off,
                       &ctx->trim_len, &ctx->len_class, &ctx->seq_class, &ctx->len_order, &ctx->seq_order, &ctx->hrun,

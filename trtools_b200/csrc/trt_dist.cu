@@ -63,9 +63,128 @@ static int allreduce(trt_ctx* ctx, void* inout_host, int64_t count, ncclDataType
 int trt_dist_allreduce_sum_i64(trt_ctx* ctx, int64_t* inout_host, int64_t count) { return allreduce(ctx, inout_host, count, ncclInt64); }
 int trt_dist_allreduce_sum_f64(trt_ctx* ctx, double* inout_host, int64_t count) { return allreduce(ctx, inout_host, count, ncclDouble); }
 
+int trt_dist_allreduce_max_f64(trt_ctx* ctx, double* inout_host, int64_t count) {
+    TRT_TRY(need_comm(ctx));
+    TRT_TRY(trt_ensure(ctx, ctx->dist_send, (size_t)count * 8 + 16));
+    TRT_CUDA(cudaMemcpyAsync(ctx->dist_send.p, inout_host, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRT_NCCL(ncclAllReduce(ctx->dist_send.p, ctx->dist_send.p, (size_t)count, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    TRT_CUDA(cudaMemcpyAsync(inout_host, ctx->dist_send.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TRT_OK;
+}
+
 int trt_dist_barrier(trt_ctx* ctx) {
     int64_t one = 1;
     return trt_dist_allreduce_sum_i64(ctx, &one, 1);
+}
+
+// side stream + event for the device->host copy of a gathered table (so the next step's kernels overlap it)
+static int ensure_copy_stream(trt_ctx* ctx) {
+    if (!ctx->copy_stream) {
+        TRT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_gathered, cudaEventDisableTiming));
+        for (int i = 0; i < 5; i++) TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    }
+    return TRT_OK;
+}
+
+// rank -> dst gather of `nbytes` device bytes per rank (ragged: nbytes_per_rank) on the context stream; on dst the
+// gathered bytes land in ctx->dist_recv in rank order and, when host_out is given, are copied to the host on the side
+// stream.  Nothing blocks the host unless `async` is 0.
+static int gather_device(trt_ctx* ctx, int slot, const void* send_dev, int64_t nbytes, const int64_t* nbytes_per_rank, int dst,
+                         void* host_out, int async) {
+    TRT_TRY(need_comm(ctx));
+    if (dst < 0 || dst >= ctx->world || nbytes < 0 || !nbytes_per_rank || nbytes_per_rank[ctx->rank] != nbytes)
+        return trt_set_error(ctx, TRT_EINVAL, "trt_dist_gather: bad dst / byte counts");
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    TRT_TRY(ensure_copy_stream(ctx));
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    DevBuf& recv = ctx->dist_recv_r[slot];
+    int64_t total = 0;
+    for (int r = 0; r < ctx->world; r++) total += nbytes_per_rank[r];
+    if (ctx->rank == dst) {
+        // the previous gather's host copy must have left dist_recv before it is overwritten
+        TRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+        if ((size_t)total + 16 > recv.cap) {
+            TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            TRT_TRY(trt_ensure(ctx, recv, (size_t)total + 16));
+        }
+    }
+    TRT_NCCL(ncclGroupStart());
+    if (ctx->rank == dst) {
+        int64_t off = 0;
+        for (int r = 0; r < ctx->world; r++) {
+            if (r != dst && nbytes_per_rank[r] > 0)
+                TRT_NCCL(ncclRecv((char*)recv.p + off, (size_t)nbytes_per_rank[r], ncclChar, r, comm, ctx->stream));
+            off += nbytes_per_rank[r];
+        }
+    } else if (nbytes > 0) {
+        TRT_NCCL(ncclSend(send_dev, (size_t)nbytes, ncclChar, dst, comm, ctx->stream));
+    }
+    TRT_NCCL(ncclGroupEnd());
+    if (ctx->rank == dst) {
+        int64_t off = 0;
+        for (int r = 0; r < dst; r++) off += nbytes_per_rank[r];
+        if (nbytes > 0)
+            TRT_CUDA(cudaMemcpyAsync((char*)recv.p + off, send_dev, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        TRT_CUDA(cudaEventRecord(ctx->ev_gathered, ctx->stream));
+        TRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gathered, 0));
+        if (host_out && total > 0)
+            TRT_CUDA(cudaMemcpyAsync(host_out, recv.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        TRT_CUDA(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+    }
+    if (!async) {
+        TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->rank == dst) TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    }
+    return TRT_OK;
+}
+
+int trt_dist_gather_region(trt_ctx* ctx, int region, int64_t offset_bytes, int64_t nbytes, const int64_t* nbytes_per_rank,
+                           int dst, void* host_out, int async) {
+    if (!ctx) return TRT_EINVAL;
+    const DevBuf* b = nullptr;
+    switch (region) {
+        case TRT_REGION_STATS: b = &ctx->stat_f64; break;
+        case TRT_REGION_ALLELE_COUNTS: b = &ctx->ac; break;
+        case TRT_REGION_ASSOC: b = &ctx->assoc_out; break;
+        case TRT_REGION_LOCUS_FILTERS: b = &ctx->misc; break;
+        default: return trt_set_error(ctx, TRT_EINVAL, "trt_dist_gather_region: unknown region %d", region);
+    }
+    if (offset_bytes < 0 || nbytes < 0 || (size_t)(offset_bytes + nbytes) > b->cap)
+        return trt_set_error(ctx, TRT_EINVAL, "trt_dist_gather_region: [%lld, +%lld) is outside region %d (%zu bytes)",
+                             (long long)offset_bytes, (long long)nbytes, region, b->cap);
+    return gather_device(ctx, region, (const char*)b->p + offset_bytes, nbytes, nbytes_per_rank, dst, host_out, async);
+}
+
+int trt_dist_gather_host(trt_ctx* ctx, const void* send_host, int64_t nbytes, const int64_t* nbytes_per_rank, int dst,
+                         void* recv_host) {
+    TRT_TRY(need_comm(ctx));
+    if (nbytes < 0 || (nbytes > 0 && !send_host)) return trt_set_error(ctx, TRT_EINVAL, "trt_dist_gather_host: bad send buffer");
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    TRT_TRY(trt_ensure(ctx, ctx->dist_send, (size_t)nbytes + 16));
+    if (nbytes) TRT_CUDA(cudaMemcpyAsync(ctx->dist_send.p, send_host, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return gather_device(ctx, 4, ctx->dist_send.p, nbytes, nbytes_per_rank, dst, recv_host, 0);
+}
+
+int trt_dist_wait(trt_ctx* ctx) {
+    if (!ctx) return TRT_EINVAL;
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return TRT_OK;
+}
+
+int trt_dist_finalize(trt_ctx* ctx) {
+    if (!ctx) return TRT_EINVAL;
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        ncclCommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+        ctx->world = 1;
+        ctx->rank = 0;
+    }
+    return TRT_OK;
 }
 
 }  // extern "C"

@@ -79,6 +79,9 @@ struct trt_ctx {
     void*   nccl_comm = nullptr;
     int     rank = 0, world = 1;
     DevBuf  dist_send, dist_recv;
+    DevBuf  dist_recv_r[5];                 // receive buffer per result region (+ one for host-payload gathers)
+    cudaStream_t copy_stream = nullptr;     // device->host copies of gathered tables (overlap the next step's kernels)
+    cudaEvent_t  ev_gathered = nullptr, ev_copied[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 int  trt_set_error(trt_ctx* ctx, int code, const char* fmt, ...);

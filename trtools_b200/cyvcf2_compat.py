@@ -694,26 +694,84 @@ class TextVCF:
             pass
 
 
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+_BGZF_MAX = 0xff00          # uncompressed bytes per member (htslib's block size)
+
+
+class BgzfWriter:
+    """Blocked gzip as htslib / bgzip write it: members of <= 65 280 inflated bytes, each carrying its compressed
+    size in the ``BC`` extra field, then the empty EOF member — what ``tabix`` (dumpSTR ``--zip``, reference
+    dumpSTR.py:1347-1352) and the region seeks of csrc/trt_ingest.cpp need.  Plain ``gzip.open`` output is rejected
+    by both.  ``tell()`` is the BGZF virtual offset of the next byte (member offset << 16 | offset within it)."""
+
+    def __init__(self, path, level: int = 6):
+        self._fh = open(path, "wb")
+        self._buf = bytearray()
+        self._level = level
+        self._coffset = 0
+
+    def write(self, data: bytes):
+        self._buf += data
+        while len(self._buf) >= _BGZF_MAX:
+            self._flush_block(bytes(self._buf[:_BGZF_MAX]))
+            del self._buf[:_BGZF_MAX]
+
+    def tell(self) -> int:
+        return (self._coffset << 16) | len(self._buf)
+
+    def _flush_block(self, data: bytes):
+        import struct
+        import zlib
+        c = zlib.compressobj(self._level, zlib.DEFLATED, -15)
+        comp = c.compress(data) + c.flush()
+        if len(comp) + 26 > 65536:                      # incompressible input: store
+            c = zlib.compressobj(0, zlib.DEFLATED, -15)
+            comp = c.compress(data) + c.flush()
+        block = (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                 struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+        self._fh.write(block)
+        self._coffset += len(block)
+
+    def close(self):
+        if self._fh is None:
+            return
+        if self._buf:
+            self._flush_block(bytes(self._buf))
+            self._buf = bytearray()
+        self._fh.write(_BGZF_EOF)
+        self._fh.close()
+        self._fh = None
+
+
 class Writer:
-    """Text VCF writer (``cyvcf2.Writer`` surface used by dumpSTR)."""
+    """Text VCF writer (``cyvcf2.Writer`` surface used by dumpSTR); ``.gz`` names are written as BGZF."""
 
     def __init__(self, fname, tmpl: 'TextVCF', mode=None):
         self.fname = str(fname)
-        if self.fname.endswith('.gz'):
-            self._fh = io.TextIOWrapper(gzip.open(self.fname, 'wb'), encoding='utf-8', newline='\n')
+        self._bgzf = self.fname.endswith('.gz')
+        if self._bgzf:
+            self._fh = BgzfWriter(self.fname)
         else:
             self._fh = open(self.fname, 'w', encoding='utf-8', newline='\n')
         self._tmpl = tmpl
         self._header_written = False
 
+    def _write(self, text: str):
+        self._fh.write(text.encode('utf-8') if self._bgzf else text)
+
     def write_header(self):
         if not self._header_written:
-            self._fh.write(self._tmpl.raw_header)
+            self._write(self._tmpl.raw_header)
             self._header_written = True
 
     def write_record(self, variant: Variant):
         self.write_header()
-        self._fh.write(str(variant))
+        self._write(str(variant))
+
+    def write_text(self, text: str):
+        """Records already serialised (the multi-GPU dumpSTR gathers every rank's records as text on rank 0)."""
+        self.write_header()
+        self._write(text)
 
     def close(self):
         self.write_header()

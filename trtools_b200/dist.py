@@ -1,12 +1,29 @@
 """
-Multi-GPU plumbing: loci shard by contiguous ranges (one process per GPU, ``torch.distributed``); there is no
-data-path collective.  NCCL (or gloo on CPU boxes, for the tests) is used only to gather the fixed-width per-locus
-result tables on rank 0 and to sum dumpSTR's per-sample accumulators.
+Multi-GPU plumbing: loci shard by contiguous ranges, one process per GPU (launched by ``torchrun`` /
+``python -m torch.distributed.run``, which only supplies RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT).
+There is no data-path collective: NCCL only gathers the fixed-width per-locus result rows on rank 0 and
+sums dumpSTR's per-sample accumulators.
+
+Two communicators with the same interface:
+
+* :class:`NcclComm` — the product path: the library's own ``trt_dist_*`` entry points (csrc/trt_dist.cu) on the
+  context's stream.  Result tables are gathered from DEVICE buffers (no host bounce, no torch): every rank's kernels
+  leave their rows in HBM, ``ncclSend/ncclRecv`` moves them to rank 0 and one copy on a side stream brings the gathered
+  table to pinned host memory while the next block's kernels already run.  The 128-byte NCCL id travels over a plain
+  TCP socket (rank 0 listens on MASTER_PORT + 1 + TRT_RDZV_OFFSET).
+* :class:`GlooComm` — ``torch.distributed`` with the gloo backend, CPU only: lets the world-size-2 tests of the host
+  logic (sharding, gather order, NaN-poison-preserving sums) run on a box without GPUs.  It computes nothing.
 """
+import ctypes as C
 import os
-from typing import Optional, Tuple
+import socket
+import struct
+import time
+from typing import List, Optional, Tuple
 
 import numpy as np
+
+REGION_STATS, REGION_ALLELE_COUNTS, REGION_ASSOC, REGION_LOCUS_FILTERS = range(4)
 
 
 def env_rank_world() -> Tuple[int, int, int]:
@@ -43,124 +60,305 @@ def locus_shard(n_loci: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def init(backend: Optional[str] = None):
-    """Initialise torch.distributed from the torchrun environment; returns the module (or None when world == 1)."""
-    rank, world, local_rank = env_rank_world()
-    if world == 1:
-        return None
-    import torch
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
-        if backend == "nccl":
-            torch.cuda.set_device(local_rank)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+def block_owner(block_index: int, world: int) -> int:
+    """The CLIs deal locus BLOCKS round-robin (a file's record count is not known up front); rank 0 restores the
+    file order when it merges the ranks' rows (:func:`merge_round_robin`)."""
+    return block_index % world
+
+
+def merge_round_robin(per_rank: List[List[bytes]]) -> List[bytes]:
+    """per_rank[r] = the output chunks of the blocks rank r owned, in its own order (block r, r + world, ...).
+    Returns all chunks in block order."""
+    world = len(per_rank)
+    out = []
+    n = max((len(x) for x in per_rank), default=0)
+    for i in range(n):
+        for r in range(world):
+            if i < len(per_rank[r]):
+                out.append(per_rank[r][i])
+    return out
+
+
+class BlockSharder:
+    """How the CLIs (statSTR / dumpSTR / associaTR ``main``) use several GPUs: every rank reads the file, blocks of
+    records are dealt round-robin, each rank runs the kernels of its own blocks only and keeps the text it would have
+    written; ``finish`` gathers the chunks on rank 0 (NCCL, ragged byte gather) and returns them in file order."""
+
+    def __init__(self, comm):
+        self.comm = comm
+        self.rank = 0 if comm is None else comm.rank
+        self.world = 1 if comm is None else comm.world
+        self._next = 0
+        self._chunks: List[bytes] = []
+
+    def mine(self) -> bool:
+        """Call once per block, in file order, on every rank."""
+        own = block_owner(self._next, self.world) == self.rank
+        self._next += 1
+        return own
+
+    def add(self, text) -> None:
+        self._chunks.append(text.encode("utf-8") if isinstance(text, str) else bytes(text))
+
+    def finish(self) -> Optional[List[bytes]]:
+        if self.comm is None:
+            return list(self._chunks)
+        payload = b"".join(struct.pack("<q", len(c)) + c for c in self._chunks)
+        parts = self.comm.gather_bytes(payload, 0)
+        if parts is None:
+            return None
+        per_rank = []
+        for p in parts:
+            lst, off = [], 0
+            while off < len(p):
+                n = struct.unpack_from("<q", p, off)[0]
+                lst.append(p[off + 8:off + 8 + n])
+                off += 8 + n
+            per_rank.append(lst)
+        return merge_round_robin(per_rank)
+
+
+def cli_comm(ctx):
+    """Communicator for a CLI run under torchrun (WORLD_SIZE > 1), else None."""
+    return init(ctx) if env_rank_world()[1] > 1 else None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rendezvous of the 128-byte NCCL unique id over TCP
+# ---------------------------------------------------------------------------------------------------------------
+def _rdzv_addr():
+    host = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(os.environ.get("MASTER_PORT", "29500")) + 1 + int(os.environ.get("TRT_RDZV_OFFSET", "0"))
+    return host, port
+
+
+def _recv_exact(conn, n):
+    buf = b""
+    while len(buf) < n:
+        chunk = conn.recv(n - len(buf))
+        if not chunk:
+            raise ConnectionError("rendezvous peer closed the connection")
+        buf += chunk
+    return buf
+
+
+def exchange_unique_id(rank: int, world: int, make_id, timeout: float = 120.0) -> bytes:
+    """rank 0 creates the id and serves it to the world - 1 other ranks; they retry until rank 0 listens."""
+    host, port = _rdzv_addr()
+    if rank == 0:
+        uid = make_id()
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((host if host in ("127.0.0.1", "localhost") else "", port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        served = set()
+        try:
+            while len(served) < world - 1:
+                conn, _ = srv.accept()
+                with conn:
+                    peer = struct.unpack("<i", _recv_exact(conn, 4))[0]
+                    conn.sendall(uid)
+                    served.add(peer)
+        finally:
+            srv.close()
+        return uid
+    deadline = time.time() + timeout
+    while True:
+        try:
+            with socket.create_connection((host, port), timeout=5.0) as conn:
+                conn.sendall(struct.pack("<i", rank))
+                return _recv_exact(conn, 128)
+        except (ConnectionError, OSError):
+            if time.time() > deadline:
+                raise
+            time.sleep(0.05)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# communicators
+# ---------------------------------------------------------------------------------------------------------------
+class NcclComm:
+    """NCCL communicator owned by a ``trt_ctx`` (one per GPU / process)."""
+
+    backend = "nccl"
+
+    def __init__(self, ctx, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        lib = ctx.lib
+
+        def make_id():
+            buf = C.create_string_buffer(128)
+            ctx.check(lib.trt_dist_unique_id(buf))
+            return buf.raw
+
+        uid = exchange_unique_id(rank, world, make_id)
+        ctx.check(lib.trt_dist_init(ctx.h, rank, world, C.create_string_buffer(uid, 128)))
+
+    # -- small host-value collectives ---------------------------------------------------------------------------
+    def barrier(self):
+        self.ctx.check(self.ctx.lib.trt_dist_barrier(self.ctx.h))
+
+    def allreduce_sum(self, arr: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(arr).copy()
+        if a.dtype == np.int64:
+            fn = self.ctx.lib.trt_dist_allreduce_sum_i64
+        elif a.dtype == np.float64:
+            fn = self.ctx.lib.trt_dist_allreduce_sum_f64
         else:
-            dist.init_process_group(backend)
-    return dist
+            raise TypeError("allreduce_sum takes int64 or float64 arrays")
+        self.ctx.check(fn(self.ctx.h, a.ctypes.data_as(C.c_void_p), a.size))
+        return a
 
+    def max(self, value: float) -> float:
+        a = np.array([value], dtype=np.float64)
+        self.ctx.check(self.ctx.lib.trt_dist_allreduce_max_f64(self.ctx.h, a.ctypes.data_as(C.c_void_p), 1))
+        return float(a[0])
 
-def _device(dist):
-    import torch
-    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    def allgather_i64(self, values) -> np.ndarray:
+        """[world, len(values)] int64 (ranks agree on shapes / byte counts with this before a ragged gather)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)          # exact for |x| < 2^53
+        out = np.empty((self.world, v.size), np.float64)
+        self.ctx.check(self.ctx.lib.trt_dist_allgather_f64(self.ctx.h, v.ctypes.data_as(C.c_void_p), v.size,
+                                                          out.ctypes.data_as(C.c_void_p)))
+        return out.astype(np.int64)
 
-
-def gather_table(dist, local: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
-    """Gather per-locus rows float64 [n_local, C] of every rank on ``dst`` in rank order (row counts may differ)."""
-    local = np.ascontiguousarray(local, dtype=np.float64)
-    if dist is None:
-        return local
-    import torch
-    dev = _device(dist)
-    world, rank = dist.get_world_size(), dist.get_rank()
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(x.item()) for x in sizes]
-    cols = local.shape[1] if local.ndim == 2 else 1
-    pad = max(sizes) if sizes else 0
-    buf = torch.zeros((pad, cols), dtype=torch.float64, device=dev)
-    if local.shape[0]:
-        buf[:local.shape[0]] = torch.from_numpy(local.reshape(local.shape[0], cols)).to(dev)
-    out = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, out, dst=dst)
-    if rank != dst:
-        return None
-    return np.concatenate([o[:k].cpu().numpy() for o, k in zip(out, sizes)], axis=0)
-
-
-class GatherPlan:
-    """Repeated gather of a fixed-shape per-locus table: float64 [n_cols, n_rows] per rank -> [world, n_cols, n_rows] on
-    ``dst``.  Buffers (device send/receive tensors, pinned host result) are allocated once; a gather is then n_cols
-    host->device copies, ONE NCCL gather and one device->host copy — the only collective of the whole path."""
-
-    def __init__(self, dist, n_cols: int, n_rows: int, dst: int = 0):
-        import torch
-        self.dist, self.dst, self.n_cols, self.n_rows = dist, dst, n_cols, n_rows
-        self.world = 1 if dist is None else dist.get_world_size()
-        self.rank = 0 if dist is None else dist.get_rank()
-        if dist is None:
-            self.out = np.empty((1, n_cols, n_rows))
-            return
-        dev = _device(dist)
-        # every rank must bring the same shape (bench: weak scaling, fixed loci per rank)
-        shape = torch.tensor([n_cols, n_rows], dtype=torch.int64, device=dev)
-        lo, hi = shape.clone(), shape.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if not (torch.equal(lo, shape) and torch.equal(hi, shape)):
-            raise ValueError("GatherPlan needs the same table shape on every rank; use gather_table for ragged tables")
-        self.send = torch.empty((n_cols, n_rows), dtype=torch.float64, device=dev)
-        self.recv = torch.empty((self.world, n_cols, n_rows), dtype=torch.float64, device=dev) if self.rank == dst else None
-        pin = dev.type == "cuda"
-        self.host = torch.empty((self.world, n_cols, n_rows), dtype=torch.float64, pin_memory=pin) if self.rank == dst else None
-        self.out = None if self.host is None else self.host.numpy()
-
-    def gather(self, columns, wait: bool = True):
-        """columns: n_cols float64 arrays of length n_rows (host).  Returns [world, n_cols, n_rows] on dst, else None.
-        With ``wait=False`` the NCCL gather and the device->host copy of the result stay in flight (call ``wait()``
-        before reading ``out``): the next step's kernels overlap them.  The host columns may be reused on return."""
-        import torch
-        if self.dist is None:
-            for j, c in enumerate(columns):
-                self.out[0, j] = c
-            return self.out
-        for j, c in enumerate(columns):
-            self.send[j].copy_(torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)), non_blocking=True)
-        if self.send.is_cuda:
-            ev = torch.cuda.Event()
-            ev.record()
-            ev.synchronize()                                   # the host columns have been read
-        self.dist.gather(self.send, list(self.recv.unbind(0)) if self.rank == self.dst else None, dst=self.dst)
-        if self.rank == self.dst:
-            self.host.copy_(self.recv, non_blocking=True)
-        if wait:
-            return self.wait()
-        return None
+    # -- result tables --------------------------------------------------------------------------------------------
+    def gather_region(self, region: int, offset: int, nbytes: int, nbytes_per_rank, dst: int = 0,
+                      host_out: Optional[np.ndarray] = None, wait: bool = True):
+        """Device-to-device gather of a result region (see include/trtools_b200.h); ``host_out``: uint8 array of
+        sum(nbytes_per_rank) bytes on dst (pinned for full copy speed)."""
+        counts = np.ascontiguousarray(nbytes_per_rank, dtype=np.int64)
+        ptr = None if host_out is None else host_out.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.ctx.lib.trt_dist_gather_region(self.ctx.h, int(region), int(offset), int(nbytes),
+                                                           counts.ctypes.data_as(C.c_void_p), int(dst), ptr, 0 if wait else 1))
 
     def wait(self):
-        """Block until the last gather (and its copy to the pinned host table) has finished."""
+        self.ctx.check(self.ctx.lib.trt_dist_wait(self.ctx.h))
+
+    def gather_bytes(self, payload: bytes, dst: int = 0) -> Optional[List[bytes]]:
+        """Ragged gather of host byte strings (the CLIs' formatted rows) -> list per rank on dst."""
+        n = len(payload)
+        counts = self.allgather_i64([n])[:, 0].copy()
+        send = np.frombuffer(payload, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+        recv = np.empty(max(int(counts.sum()), 1), np.uint8) if self.rank == dst else None
+        self.ctx.check(self.ctx.lib.trt_dist_gather_host(
+            self.ctx.h, send.ctypes.data_as(C.c_void_p), n, counts.ctypes.data_as(C.c_void_p), int(dst),
+            None if recv is None else recv.ctypes.data_as(C.c_void_p)))
+        if self.rank != dst:
+            return None
+        out, off = [], 0
+        for c in counts:
+            out.append(recv[off:off + int(c)].tobytes())
+            off += int(c)
+        return out
+
+    def gather_table(self, local: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        cols = local.shape[1] if local.ndim == 2 else 1
+        parts = self.gather_bytes(local.tobytes(), dst)
+        if parts is None:
+            return None
+        return np.concatenate([np.frombuffer(p, dtype=np.float64).reshape(-1, cols) for p in parts], axis=0)
+
+    def close(self):
+        self.ctx.check(self.ctx.lib.trt_dist_finalize(self.ctx.h))
+
+
+class GlooComm:
+    """torch.distributed (gloo) on CPU — test double of :class:`NcclComm` for the host logic."""
+
+    backend = "gloo"
+
+    def __init__(self):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def allreduce_sum(self, arr: np.ndarray) -> np.ndarray:
         import torch
-        if self.dist is not None and self.send.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        return self.out if (self.dist is None or self.rank == self.dst) else None
+        t = torch.from_numpy(np.ascontiguousarray(arr).copy())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.numpy()
+
+    def max(self, value: float) -> float:
+        import torch
+        t = torch.tensor([value], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allgather_i64(self, values) -> np.ndarray:
+        import torch
+        v = torch.tensor(list(values), dtype=torch.int64)
+        out = [torch.zeros_like(v) for _ in range(self.world)]
+        self.dist.all_gather(out, v)
+        return np.stack([o.numpy() for o in out])
+
+    def gather_bytes(self, payload: bytes, dst: int = 0) -> Optional[List[bytes]]:
+        import torch
+        counts = self.allgather_i64([len(payload)])[:, 0]
+        pad = int(max(counts.max(), 1))
+        buf = torch.zeros(pad, dtype=torch.uint8)
+        if payload:
+            buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+        out = [torch.zeros_like(buf) for _ in range(self.world)] if self.rank == dst else None
+        self.dist.gather(buf, out, dst=dst)
+        if self.rank != dst:
+            return None
+        return [o[:int(c)].numpy().tobytes() for o, c in zip(out, counts)]
+
+    def gather_table(self, local: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        cols = local.shape[1] if local.ndim == 2 else 1
+        parts = self.gather_bytes(local.tobytes(), dst)
+        if parts is None:
+            return None
+        return np.concatenate([np.frombuffer(p, dtype=np.float64).reshape(-1, cols) for p in parts], axis=0)
+
+    def wait(self):
+        pass
+
+    def close(self):
+        self.dist.barrier()
+        self.dist.destroy_process_group()
 
 
-def allreduce_sum(dist, arr: np.ndarray) -> np.ndarray:
+def init(ctx=None, backend: Optional[str] = None):
+    """Communicator of this process from the torchrun environment, or None when world == 1.  ``ctx`` (a
+    ``_lib.Context`` on this rank's GPU) selects the NCCL path; without it (CPU tests) gloo is used."""
+    rank, world, _ = env_rank_world()
+    if world == 1:
+        return None
+    if backend is None:
+        backend = "nccl" if ctx is not None else "gloo"
+    if backend == "nccl":
+        if ctx is None:
+            raise ValueError("the NCCL communicator needs a trtools_b200 context")
+        return NcclComm(ctx, rank, world)
+    return GlooComm()
+
+
+# ---- helpers that accept ``None`` (single process) ---------------------------------------------------------------
+def gather_table(comm, local: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
+    """Gather per-locus rows float64 [n_local, C] of every rank on ``dst`` in rank order (row counts may differ)."""
+    if comm is None:
+        return np.ascontiguousarray(local, dtype=np.float64)
+    return comm.gather_table(local, dst)
+
+
+def allreduce_sum(comm, arr: np.ndarray) -> np.ndarray:
     """Sum an int64 / float64 array over ranks (dumpSTR per-sample accumulators; NaN poison propagates)."""
-    if dist is None:
-        return arr
-    import torch
-    t = torch.from_numpy(np.ascontiguousarray(arr)).to(_device(dist))
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t.cpu().numpy()
+    return arr if comm is None else comm.allreduce_sum(arr)
 
 
-def max_over_ranks(dist, value: float) -> float:
-    if dist is None:
-        return value
-    import torch
-    t = torch.tensor([value], dtype=torch.float64, device=_device(dist))
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+def max_over_ranks(comm, value: float) -> float:
+    return value if comm is None else comm.max(value)
+
+
+def gather_bytes(comm, payload: bytes, dst: int = 0) -> Optional[List[bytes]]:
+    return [payload] if comm is None else comm.gather_bytes(payload, dst)

@@ -20,7 +20,7 @@ from typing import Dict, List
 
 import numpy as np
 
-from . import __version__, _lib, block as _block, common
+from . import __version__, _lib, block as _block, common, dist as _dist
 from . import filters as filters
 from . import tr_harmonizer as trh
 from . import utils
@@ -553,9 +553,19 @@ def main(args):
         common.WARNING("At most 16 call-level filters can be combined")
         return 1
 
+    ctx = _lib.default_context()
+    # several GPUs (torchrun): blocks are dealt round-robin; rank 0 gathers the records' text (NCCL) and writes the
+    # VCF, the per-sample accumulators and locus counters are summed over ranks (NaN poison preserved, dumpSTR.py:710-713)
+    comm = _dist.cli_comm(ctx)
+    sharder = _dist.BlockSharder(comm)
     suffix = '.vcf.gz' if args.zip else '.vcf'
-    outvcf = MakeWriter(args.out + suffix, invcf, " ".join(sys.argv))
-    if outvcf is None:
+    outvcf = None
+    if sharder.rank == 0:
+        outvcf = MakeWriter(args.out + suffix, invcf, " ".join(sys.argv))
+    failed = np.array([1 if (sharder.rank == 0 and outvcf is None) else 0], dtype=np.int64)
+    if int(_dist.allreduce_sum(comm, failed)[0]):
+        if comm is not None:
+            comm.close()
         return 1
 
     n_samples = len(invcf.samples)
@@ -571,7 +581,6 @@ def main(args):
     for filt in locus_filters:
         loc_info[filt.filter_name()] = 0
 
-    ctx = _lib.default_context()
     if hasattr(invcf, "_prefetch"):
         # C++ block reader: parse the call filters' numeric FORMAT keys in the same pass as GT,
         # in runs of the GPU block length
@@ -619,7 +628,10 @@ def main(args):
                     break
                 raise
         recs = good
+        if recs and not sharder.mine():
+            recs = []
         if recs:
+            chunk = []
             if args.verbose:
                 for r in recs:
                     common.MSG("Processing %s:%s" % (r.CHROM, r.POS), debug=True)
@@ -665,14 +677,33 @@ def main(args):
                     rec.INFO['HWEP'] = -1
                 rec.INFO['AC'] = ",".join(str(int(x)) for x in ac[1:]) if len(ac) > 1 else 0
                 rec.INFO['REFAC'] = int(ac[0])
-                outvcf.write_record(rec)
-        if bad_message is not None:
-            common.WARNING("Could not parse VCF.\n" + bad_message)
-            return 1
-        if parse_error is not None:
-            common.WARNING("Could not parse VCF.\n" + parse_error)
+                if comm is None:
+                    outvcf.write_record(rec)
+                else:
+                    chunk.append(str(rec))
+            if comm is not None:
+                sharder.add("".join(chunk))
+        if bad_message is not None or parse_error is not None:      # every rank reads every record: all ranks stop here
+            if sharder.rank == 0:
+                common.WARNING("Could not parse VCF.\n" + (bad_message if bad_message is not None else parse_error))
+            if comm is not None:
+                comm.close()
             return 1
     invcf.close()
+    if comm is not None:
+        merged = sharder.finish()
+        if merged is not None:
+            outvcf.write_text(b"".join(merged).decode("utf-8"))
+        for k in list(sample_info.keys()):
+            sample_info[k] = _dist.allreduce_sum(comm, np.ascontiguousarray(sample_info[k]))
+        keys = list(loc_info.keys())
+        tot = _dist.allreduce_sum(comm, np.array([loc_info[k] for k in keys], dtype=np.int64))
+        for k, v in zip(keys, tot):
+            loc_info[k] = int(v)
+        comm.barrier()
+        comm.close()
+        if sharder.rank != 0:
+            return 0
     outvcf.close()
     WriteSampLog(sample_info, invcf.samples, args.out + ".samplog.tab")
     WriteLocLog(loc_info, args.out + ".loclog.tab")

@@ -15,7 +15,7 @@ from typing import Any, List
 
 import numpy as np
 
-from . import __version__, _lib, block as _block, common
+from . import __version__, _lib, block as _block, common, dist as _dist
 from . import tr_harmonizer as trh
 from . import utils
 
@@ -254,15 +254,24 @@ def main(args):
             return 1
     ctx = _lib.default_context()
     block_size = int(getattr(args, "block_size", 2048) or 2048)
+    if hasattr(invcf, "_native_block_loci"):
+        invcf._native_block_loci = block_size        # one native run per GPU block: zero-copy hand-off of the arrays
+    # several GPUs (torchrun): blocks are dealt round-robin, rank 0 gathers the rows (NCCL) and writes the file
+    comm = _dist.cli_comm(ctx)
+    sharder = _dist.BlockSharder(comm)
     outf = None
     try:
-        outf = sys.stdout if args.out == "stdout" else open(args.out + ".tab", "w")
-        outf.write("\t".join(header) + "\n")
+        if sharder.rank == 0:
+            outf = sys.stdout if args.out == "stdout" else open(args.out + ".tab", "w")
+            outf.write("\t".join(header) + "\n")
         region = invcf(args.region) if args.region else invcf
         start_time = time.time()
         nrecords = 0
         use_length = bool(args.use_length)
         for recs in _blocks(region, block_size):
+            if not sharder.mine():
+                nrecords += len(recs)
+                continue
             blk = _block.build_block(ctx, vcftype.name, recs)
             flags = blk.h["flags"]
             if np.any(flags & _lib.HF_MOTIF_NONACGT):
@@ -311,15 +320,25 @@ def main(args):
                     for g in range(G):
                         row.append("\t" + str(int(st["n_called"][g, l]) if st is not None else 0))
                 lines.append("".join(row) + "\n")
-            outf.write("".join(lines))
-            outf.flush()
-            if args.out != "stdout" and nrecords:
+            if comm is None:
+                outf.write("".join(lines))
+                outf.flush()
+            else:
+                sharder.add("".join(lines))
+            if args.out != "stdout" and nrecords and sharder.rank == 0:
                 print("Finished {} records, time/record={:.5}sec".format(
                     nrecords, (time.time() - start_time) / nrecords), flush=True, end="\r")
+        if comm is not None:
+            merged = sharder.finish()
+            if merged is not None:
+                outf.write(b"".join(merged).decode("utf-8"))
     finally:
         if outf is not None and args.out != "stdout":
             outf.close()
-    if args.out != "stdout":
+        if comm is not None:
+            comm.barrier()
+            comm.close()
+    if args.out != "stdout" and sharder.rank == 0:
         print("\nDone", flush=True)
     return 0
 
