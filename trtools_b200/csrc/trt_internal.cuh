@@ -65,6 +65,7 @@ struct trt_ctx {
     DevBuf  scan_lists;              // per-tier locus lists of the current block (trt_scan.cu)
     bool    scan_lists_valid = false;
     int     scan_tier_off[8] = {0};   // list offsets per tier (+ end)
+    int     scan_n_tier[8] = {0}, scan_max_in_tier[8] = {0}, scan_rows_in_tier[8] = {0}, scan_lists_fast = -1;
     bool    want_ac_part = false;
     // dumpSTR scratch
     DevBuf  cf_specs, call_mask, trig, samp_counts, samp_dp, misc;

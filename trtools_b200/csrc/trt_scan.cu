@@ -104,39 +104,59 @@ __global__ void __launch_bounds__(256) scan_generic_kernel(ScanParams p) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPT = 512;                       // consumer threads (16 warps: 4 per scheduler hide the RMW latency)
 constexpr int kPWarps = kPT / 32;
-constexpr int kPPairs = kPWarps / 2;
-constexpr int kPThreads = kPT + 32;            // + producer warp
+constexpr int kPThreads = kPT + 64;            // + producer warp + epilogue warp
 constexpr int kPChunkBytes = kPT * 48;         // 24576 B = 4096 calls; thread t owns bytes [48t, 48t+48) = 8 calls
 constexpr int kPChunkCalls = kPT * 8;
-constexpr int kPMaxStages = 6;
+constexpr int kPMaxStages = 8;
 constexpr int kPMinStages = 3;
 constexpr int kPMaxDigits = kPairsMaxAlleles + 3;
 constexpr int kPMaxBins = kPMaxDigits * (kPMaxDigits + 1) / 2;   // unordered digit pairs of the largest tier
-constexpr int kPRowBytes = kPT * 2;            // one table row: 512 thread-private 16-bit cells
+constexpr int kPMaxGroups = 8;                 // fold groups: warp pairs (16-bit cells) or warp quads (8-bit cells)
+constexpr int kPMaxChunks8 = 31;               // 8-bit cells hold 8 calls x 31 chunks = 248 <= 255 per (thread, bin)
 
-// Table cell of (bin b, thread t): 16-bit, at halfword  b*512 + 64*(t/64) + 2*(t%32) + ((t/32)&1).
-// The two warps of a warp PAIR share 32-bit words (low / high half), so within one warp the 32 lanes
-// always touch 32 different banks whatever bins they address: conflict-free without 32-bit cells.
+// Thread-private count cells, one table row per bin.  A row is 512 cells; within one warp the 32 lanes always touch 32
+// different banks whatever bins they address, because the warps that share a 32-bit word own different BYTES of it:
+//   16-bit cells (row = 1 KB): halfword  64*(t/64) + 2*(t%32) + ((t/32)&1)      — a warp PAIR shares words
+//    8-bit cells (row = 512 B): byte     128*(w/4) + 4*(t%32) + (w%4), w = t/32 — a warp QUAD shares words
+// 8-bit cells halve the table (more ring stages fit: the ring depth is what bounds the stream) and are used whenever a
+// locus has at most 31 chunks (S <= 126 976).  The warps sharing words form a fold group: they reduce and zero their
+// own 128-byte slice of every row behind a group-local named barrier.
+template <typename CELL> struct CellTraits;
+template <> struct CellTraits<uint16_t> {
+    static constexpr int kGroupWarps = 2;
+    __device__ static __forceinline__ int cell_index(int warp, int lane) { return 64 * (warp >> 1) + 2 * lane + (warp & 1); }
+    __device__ static __forceinline__ unsigned sum4(const uint4& x) {
+        return (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) + (x.w & 0xffffu) + (x.w >> 16);
+    }
+};
+template <> struct CellTraits<uint8_t> {
+    static constexpr int kGroupWarps = 4;
+    __device__ static __forceinline__ int cell_index(int warp, int lane) { return 128 * (warp >> 2) + 4 * lane + (warp & 3); }
+    __device__ static __forceinline__ unsigned sum4(const uint4& x) {
+        return (unsigned)__dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+    }
+};
+
 struct __align__(16) PairHeader {
     uint64_t full[kPMaxStages];
     uint64_t empty[kPMaxStages];
-    unsigned int partial[2][kPPairs][kPMaxBins];   // per-warp-pair sums, double buffered by locus parity
-    unsigned int T[kPMaxBins];                     // warp 0's CTA-wide pair table
+    uint64_t part_free[2];                              // the epilogue warp has consumed partial[parity]
+    unsigned int partial[2][kPMaxGroups][kPMaxBins];    // per-group sums, double buffered by locus parity
+    unsigned int T[kPMaxBins];                          // the epilogue warp's CTA-wide pair table
 };
 
-// digit of a haplotype: pad(-2) -> 0, no-call(-1) -> 1, allele a -> a+2, anything else -> D-1 ("bad")
-__device__ __forceinline__ unsigned digit(int a, unsigned Dm1) { return min((unsigned)(a + 2), Dm1); }
 // bin of an UNORDERED digit pair (genotypes are unphased for every statistic): tri(hi, lo), lo <= hi
 __device__ __forceinline__ unsigned tri(unsigned hi, unsigned lo) { return ((hi * (hi + 1u)) >> 1) + lo; }
 
 // two thread-private increments with both loads in flight; equal bins both store x + 2
-__device__ __forceinline__ void bump2(uint16_t* my, unsigned i0, unsigned i1) {
-    uint16_t* p0 = my + (size_t)i0 * kPT;
-    uint16_t* p1 = my + (size_t)i1 * kPT;
+template <typename CELL>
+__device__ __forceinline__ void bump2(CELL* my, unsigned i0, unsigned i1) {
+    CELL* p0 = my + (size_t)i0 * kPT;
+    CELL* p1 = my + (size_t)i1 * kPT;
     const unsigned x0 = *p0, x1 = *p1;
     const unsigned e = (i0 == i1) ? 2u : 1u;
-    *p0 = (uint16_t)(x0 + e);
-    *p1 = (uint16_t)(x1 + e);
+    *p0 = (CELL)(x0 + e);
+    *p1 = (CELL)(x1 + e);
 }
 
 // metadata of the i-th locus of this launch's tier list (or L past the end)
@@ -151,18 +171,24 @@ __device__ __forceinline__ int64_t list_locus(const ScanParams& p, int i, int& A
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Per locus the bins are ORDERED digit pairs d0*D + d1 (one IMAD per call, D^2 rows) while D^2 <= kSquareRows,
-// otherwise UNORDERED pairs (D(D+1)/2 rows, ~4 more instructions per call).
-template <bool MASKED>
+// Warp roles: 16 consumer warps, one producer warp (one elected lane feeds the ring), one epilogue warp (turns the
+// fold groups' partial sums of a finished locus into every per-locus output while the consumers are already streaming
+// the next locus: no consumer ever leaves the stream, so the ring never loses depth to a lagging warp).
+// A digit of a haplotype: pad(-2) -> 0, no-call(-1) -> 1, allele a -> a+2, anything else -> D-1 ("bad").  Both digits of
+// a call come from ONE add-and-min on the packed int16 pair (VIADDMNMX.U16x2) and the bin from ONE dot product
+// (IDP.2A: d0*D + d1) while D^2 <= kSquareRows rows; wider loci use UNORDERED pairs (D(D+1)/2 rows).
+template <bool MASKED, typename CELL>
 __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages) {
-    // a ring stage holds nsub chunks of 24576 B and is filled by ONE bulk copy; nsub > 1 was measured (2, 3): no gain in the
-    // ring-only ceiling nor in the scan, so it is a compile-time 1 (a runtime value costs a modulo per chunk)
-    constexpr int nsub = 1;
+    using CT = CellTraits<CELL>;
+    constexpr int kGW = CT::kGroupWarps;                  // warps per fold group
+    constexpr int kGT = kGW * 32;                         // threads per fold group
+    constexpr int kGroups = kPWarps / kGW;
+    constexpr int kRowWords = kPT * (int)sizeof(CELL) / 4;    // 32-bit words per table row
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
-    const size_t stage_bytes = (size_t)nsub * kPChunkBytes;
+    constexpr size_t stage_bytes = kPChunkBytes;
     PairHeader* hdr = (PairHeader*)(smem + (size_t)stages * stage_bytes);
-    uint16_t* table = (uint16_t*)(smem + (size_t)stages * stage_bytes + sizeof(PairHeader));   // [max_rows + 1][512]
+    CELL* table = (CELL*)(smem + (size_t)stages * stage_bytes + sizeof(PairHeader));   // [max_rows + 1][512]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -170,24 +196,19 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     const size_t copy_bytes = (row_bytes + 15) & ~size_t(15);
     const int nchunks = (int)((copy_bytes + kPChunkBytes - 1) / kPChunkBytes);
     const int nfull = (int)(p.S / kPChunkCalls);   // chunks whose calls are all real samples
-    const int nst = (nchunks + nsub - 1) / nsub;    // ring stages per locus
     const unsigned trash = (unsigned)max_rows;     // extra row: calls beyond S in the last chunk land here
-    // the non-blocking hand-off to warp 0 relies on the ring keeping the warps within one locus of each other
-#ifdef TRT_SCAN_BLOCKING_HANDOFF
-    const bool loose = false;
-#else
-    const bool loose = nst > stages;
-#endif
 
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
             mbar_init(&hdr->full[s], 1);
             mbar_init(&hdr->empty[s], kPWarps);
         }
+        mbar_init(&hdr->part_free[0], 1);
+        mbar_init(&hdr->part_free[1], 1);
         mbar_fence_init();
     }
     {
-        const int words = (max_rows + 1) * kPRowBytes / 4;
+        const int words = (max_rows + 1) * kRowWords;
         for (int i = tid; i < words; i += kPThreads) ((uint32_t*)table)[i] = 0u;
     }
     __syncthreads();
@@ -200,7 +221,7 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             for (int i = blockIdx.x; i < p.n_list; i += gridDim.x) {
                 const int64_t l = p.list[i];
                 const char* src = (const char*)p.gt + (size_t)l * p.pitch;
-                for (int st = 0; st < nst; st++) {
+                for (int st = 0; st < nchunks; st++) {
                     mbar_wait(&hdr->empty[stage], phase ^ 1u);
                     const size_t off = (size_t)st * stage_bytes;
                     const uint32_t bytes = (uint32_t)min(stage_bytes, copy_bytes - off);
@@ -213,138 +234,15 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
         return;
     }
 
-    // ===== consumers =====
-    const int pair = warp >> 1, half = warp & 1;
-    uint16_t* my = table + 64 * pair + 2 * lane + half;
-    int stage = 0;
-    uint32_t phase = 0;
-    int parity = 0;
-    int A, a0, A_next = 0, a0_next = 0;
-    int li = blockIdx.x;
-    int64_t l = list_locus(p, li, A, a0);
-    while (l < p.L) {
-        // metadata of the following locus is fetched now so its latency hides under this locus' stream
-        li += gridDim.x;
-        const int64_t l_next = list_locus(p, li, A_next, a0_next);
-        const unsigned D = (unsigned)A + 3u, Dm1 = D - 1u;
-        const bool sq = pairs_square(A);
-
-        for (int c = 0; c < nchunks; c++) {
-            const int sub = c % nsub;                       // chunk within its ring stage
-            const bool last_sub = (sub == nsub - 1) || (c == nchunks - 1);
-            if (sub == 0) mbar_wait(&hdr->full[stage], phase);
-            if (p.stream_only) {
-                if (last_sub) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&hdr->empty[stage]);
-                    if (++stage == stages) { stage = 0; phase ^= 1u; }
-                }
-                continue;
-            }
-            const uint4* sp = (const uint4*)(ring + (size_t)stage * stage_bytes + (size_t)sub * kPChunkBytes + (size_t)tid * 48);
-            const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
-#ifdef TRT_SCAN_EARLY_ARRIVE
-            if (last_sub) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hdr->empty[stage]);
-            }
-#endif
-            const int stage_used = stage;
-            if (last_sub && ++stage == stages) { stage = 0; phase ^= 1u; }
-            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            unsigned idx[8], dg0[8], dg1[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k0 = 3 * j, k1 = k0 + 1;      // half-word indices of the call's two alleles
-                const int a = (k0 & 1) ? ((int)w[k0 >> 1] >> 16) : (int)(short)(w[k0 >> 1] & 0xffffu);
-                const int b = (k1 & 1) ? ((int)w[k1 >> 1] >> 16) : (int)(short)(w[k1 >> 1] & 0xffffu);
-                dg0[j] = digit(a, Dm1);
-                dg1[j] = digit(b, Dm1);
-            }
-            if (sq) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) idx[j] = dg0[j] * D + dg1[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) idx[j] = tri(max(dg0[j], dg1[j]), min(dg0[j], dg1[j]));
-            }
-#ifndef TRT_SCAN_EARLY_ARRIVE
-            {
-                // Release the ring slot only after this warp's loads have RETURNED: the predicate below consumes every
-                // loaded word (it is always true, bins are < 2^16, but the compiler cannot prove it), so the arrive cannot
-                // issue while a generic-proxy read of the slot is still in flight — the refill is an async-proxy (TMA)
-                // write, which is not ordered behind such a read.
-                // (loads return in order, so the last chunk of a stage vouches for the earlier ones)
-                const unsigned any = idx[0] | idx[1] | idx[2] | idx[3] | idx[4] | idx[5] | idx[6] | idx[7];
-                const bool returned = __all_sync(0xffffffffu, any != 0xffffffffu);
-                if (last_sub && lane == 0 && returned) mbar_arrive(&hdr->empty[stage_used]);
-            }
-#endif
-            if (MASKED || c >= nfull) {
-                const int64_t sb0 = (int64_t)c * kPChunkCalls + (int64_t)tid * 8;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int64_t s = sb0 + j;
-                    bool live = s < p.S;
-                    if (MASKED) live = live && p.mask[live ? s : 0] != 0;
-                    idx[j] = live ? idx[j] : trash;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) bump2(my, idx[j], idx[j + 1]);   // (four loads in flight + 6 compares measured 3 % slower)
-        }
-
-        // ---- each warp PAIR folds its own 64 threads' table columns (pair-local barrier only) ----------
-        const int nrows = sq ? (int)(D * D) : (int)(D * (D + 1u) / 2u);
-        named_sync(3 + pair, 64);
-        unsigned int* part = hdr->partial[parity][pair];
-        for (int b0 = half * 32; b0 < nrows; b0 += 64) {
-            const int b = b0 + lane;
-            if (b < nrows) {
-                // this pair's 64 cells of row b = 128 B = 8 x 16 B; lanes own different rows (same bank offset), so each
-                // rotates its 16-byte slot: the 8 lanes of a quarter-warp hit 8 different bank groups (conflict-free)
-                uint4* rowp = (uint4*)((uint32_t*)table + (size_t)b * (kPT / 2) + pair * 32);
-                unsigned sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int kk = (k + lane) & 7;
-                    const uint4 x = rowp[kk];
-                    rowp[kk] = make_uint4(0u, 0u, 0u, 0u);
-                    sum += (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) +
-                           (x.w & 0xffffu) + (x.w >> 16);
-                }
-                part[b] = sum;
-            }
-        }
-        // the words just folded/zeroed hold BOTH warps' cells: neither may start the next locus earlier
-        named_sync(3 + pair, 64);
-        // hand the partials to warp 0; the other warps only signal and move on to the next locus
-        if (warp != 0) {
-            if (loose) {
-                named_arrive(1 + parity, kPT);
-            } else {
-                named_sync(1, kPT);
-                named_sync(2, kPT);
-            }
-        } else {
-            named_sync(loose ? 1 + parity : 1, kPT);
-            // ---- warp 0: CTA-wide table of UNORDERED pairs, then every per-locus output -----------------
-            const int nb = (int)(D * (D + 1u) / 2u);
-            unsigned int* T = hdr->T;
-            for (int b = lane; b < nb; b += 32) {
-                unsigned hi = (unsigned)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
-                while (tri(hi + 1u, 0u) <= (unsigned)b) hi++;
-                while (tri(hi, 0u) > (unsigned)b) hi--;
-                const unsigned lo = (unsigned)b - tri(hi, 0u);
-                unsigned t = 0;
-#pragma unroll
-                for (int w2 = 0; w2 < kPPairs; w2++) {
-                    const unsigned int* pp = hdr->partial[parity][w2];
-                    if (sq) t += pp[hi * D + lo] + ((lo != hi) ? pp[lo * D + hi] : 0u);
-                    else t += pp[b];
-                }
-                T[b] = t;
-            }
+    if (warp == kPWarps + 1) {
+        // ===== epilogue warp: CTA-wide table of UNORDERED pairs, then every per-locus output =====
+        int parity = 0;
+        int A, a0;
+        for (int li = blockIdx.x;; li += gridDim.x) {
+            const int64_t l = list_locus(p, li, A, a0);
+            if (l >= p.L) break;
+            const unsigned D = (unsigned)A + 3u, Dm1 = D - 1u;
+            const bool sq = pairs_square(A);
             // class of digit `lane` (pad digit: -2; no-call / bad: -1), exchanged by shuffles below
             int cl = -1, cq = -1;
             if (lane == 0) cl = cq = -2;
@@ -352,7 +250,9 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 cl = p.len_class[a0 + lane - 2];
                 cq = p.seq_class[a0 + lane - 2];
             }
-            __syncwarp();
+            named_sync(1 + parity, kPT + 32);            // the fold groups' partials of this locus are complete
+            const int nb = (int)(D * (D + 1u) / 2u);
+            unsigned int* T = hdr->T;
             long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
             for (int b0 = 0; b0 < nb; b0 += 32) {
                 const int b = min(b0 + lane, nb - 1);
@@ -360,9 +260,17 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 while (tri(hi + 1u, 0u) <= (unsigned)b) hi++;
                 while (tri(hi, 0u) > (unsigned)b) hi--;
                 const unsigned lo = (unsigned)b - tri(hi, 0u);
+                unsigned t = 0;
+#pragma unroll
+                for (int g = 0; g < kGroups; g++) {
+                    const unsigned int* pp = hdr->partial[parity][g];
+                    if (sq) t += pp[hi * D + lo] + ((lo != hi) ? pp[lo * D + hi] : 0u);
+                    else t += pp[b];
+                }
+                if (b0 + lane < nb) T[b] = t;
                 const int cl_lo = __shfl_sync(0xffffffffu, cl, lo), cl_hi = __shfl_sync(0xffffffffu, cl, hi);
                 const int cq_lo = __shfl_sync(0xffffffffu, cq, lo), cq_hi = __shfl_sync(0xffffffffu, cq, hi);
-                const long long n = (b0 + lane < nb) ? (long long)T[b] : 0;
+                const long long n = (b0 + lane < nb) ? (long long)t : 0;
                 const bool bad = (hi == Dm1);                        // lo <= hi
                 const bool m1 = (lo == 1u) | (hi == 1u) | bad;
                 const bool vlo = (lo >= 2u) & (lo < Dm1), vhi = (hi >= 2u) & (hi < Dm1);
@@ -376,6 +284,8 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                     if (cq_lo == cq_hi) h_seq += n;
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->part_free[parity]);     // partial[parity] may be refilled (locus + 2)
             n_full = warp_sum_ll(n_full); n_non = warp_sum_ll(n_non); n_pad = warp_sum_ll(n_pad);
             h_idx = warp_sum_ll(h_idx); h_len = warp_sum_ll(h_len); h_seq = warp_sum_ll(h_seq);
             n_bad = warp_sum_ll(n_bad);
@@ -394,9 +304,106 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 if (p.ac_part) p.ac_part[a0 + a] = (int)(T[tri(d, 1u)] + T[tri(Dm1, d)]);   // partner '.' or invalid
             }
             __syncwarp();
-            if (!loose) named_sync(2, kPT);
+            parity ^= 1;
         }
+        return;
+    }
+
+    // ===== consumers =====
+    const int group = warp / kGW, gwarp = warp % kGW;
+    CELL* my = table + CT::cell_index(warp, lane);
+    int stage = 0;
+    uint32_t phase = 0;
+    int parity = 0;
+    unsigned n_locus = 0;                 // loci this CTA has finished (uses of partial[] = n_locus >> 1 per parity)
+    int A, a0, A_next = 0, a0_next = 0;
+    int li = blockIdx.x;
+    int64_t l = list_locus(p, li, A, a0);
+    const int s_rel0 = tid * 8;           // first sample of this thread within a chunk
+    while (l < p.L) {
+        // metadata of the following locus is fetched now so its latency hides under this locus' stream
+        li += gridDim.x;
+        const int64_t l_next = list_locus(p, li, A_next, a0_next);
+        const unsigned D = (unsigned)A + 3u, Dm1 = D - 1u;
+        const bool sq = pairs_square(A);
+        const unsigned dm2 = Dm1 | (Dm1 << 16);
+        const int dot = (int)(D | (1u << 8));           // IDP.2A: lo16 * byte0 + hi16 * byte1 = d0 * D + d1
+
+        for (int c = 0; c < nchunks; c++) {
+            mbar_wait(&hdr->full[stage], phase);
+            if (p.stream_only) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                continue;
+            }
+            const uint4* sp = (const uint4*)(ring + (size_t)stage * stage_bytes + (size_t)tid * 48);
+            const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
+            const int stage_used = stage;
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            // packed (a, b) int16 pairs of the 8 calls: even calls sit in one word, odd calls straddle two
+            const uint32_t pr[8] = {v0.x, __byte_perm(v0.y, v0.z, 0x5432), v0.w, __byte_perm(v1.x, v1.y, 0x5432),
+                                    v1.z, __byte_perm(v1.w, v2.x, 0x5432), v2.y, __byte_perm(v2.z, v2.w, 0x5432)};
+            unsigned idx[8], dg[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) dg[j] = __vminu2(__vadd2(pr[j], 0x00020002u), dm2);     // both digits: one VIADDMNMX.U16x2
+            if (sq) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) idx[j] = (unsigned)__dp2a_lo((int)dg[j], dot, 0);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned d0 = dg[j] & 0xffffu, d1 = dg[j] >> 16;
+                    idx[j] = tri(max(d0, d1), min(d0, d1));
+                }
+            }
+            {
+                // Release the ring slot only after this warp's loads have RETURNED: the predicate below consumes every
+                // loaded word (it is always true, bins are < 2^16, but the compiler cannot prove it), so the arrive cannot
+                // issue while a generic-proxy read of the slot is still in flight — the refill is an async-proxy (TMA)
+                // write, which is not ordered behind such a read.
+                const unsigned any = idx[0] | idx[1] | idx[2] | idx[3] | idx[4] | idx[5] | idx[6] | idx[7];
+                const bool returned = __all_sync(0xffffffffu, any != 0xffffffffu);
+                if (lane == 0 && returned) mbar_arrive(&hdr->empty[stage_used]);
+            }
+            if (MASKED || c >= nfull) {
+                const int left = (int)min((int64_t)kPChunkCalls, p.S - (int64_t)c * kPChunkCalls) - s_rel0;   // live calls of this thread
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    bool live = j < left;
+                    if (MASKED) live = live && p.mask[live ? (int64_t)c * kPChunkCalls + s_rel0 + j : 0] != 0;
+                    idx[j] = live ? idx[j] : trash;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) bump2<CELL>(my, idx[j], idx[j + 1]);
+        }
+
+        // ---- each fold GROUP reduces and zeroes its own 128-byte slice of every row (group-local barrier only) ------
+        const int nrows = sq ? (int)(D * D) : (int)(D * (D + 1u) / 2u);
+        named_sync(3 + group, kGT);
+        // partial[parity] was last used two loci ago: wait until the epilogue warp has consumed it
+        if (n_locus >= 2u) mbar_wait(&hdr->part_free[parity], ((n_locus >> 1) - 1u) & 1u);
+        unsigned int* part = hdr->partial[parity][group];
+        for (int b = gwarp * 32 + lane; b < nrows; b += kGT) {
+            // this group's cells of row b = 128 B = 8 x 16 B; lanes own different rows (same bank offset), so each
+            // rotates its 16-byte slot: the 8 lanes of a quarter-warp hit 8 different bank groups (conflict-free)
+            uint4* rowp = (uint4*)((uint32_t*)table + (size_t)b * kRowWords + group * 32);
+            unsigned sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int kk = (k + lane) & 7;
+                const uint4 x = rowp[kk];
+                rowp[kk] = make_uint4(0u, 0u, 0u, 0u);
+                sum += CT::sum4(x);
+            }
+            part[b] = sum;
+        }
+        // the words just folded/zeroed hold every group warp's cells: none may start the next locus earlier
+        named_sync(3 + group, kGT);
+        named_arrive(1 + parity, kPT + 32);              // hand the partials to the epilogue warp and move on
         parity ^= 1;
+        n_locus++;
         l = l_next;
         A = A_next;
         a0 = a0_next;
@@ -581,18 +588,19 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     sp.list = nullptr;
     sp.n_list = 0;
     sp.stream_only = getenv("TRT_SCAN_STREAM_ONLY") ? 1 : 0;   // HBM-read ceiling of this access pattern (calibration)
-    // which tiers occur in this block, and the locus list of each (cached per block: the allele table fixes them)
-    int n_tier[TIER_COUNT] = {0};
-    int max_in_tier[TIER_COUNT] = {0};
-    int rows_in_tier[TIER_COUNT] = {0};
-    for (int64_t l = 0; l < L; l++) {
-        const int A = ctx->h_locus_off[l + 1] - ctx->h_locus_off[l];
-        const int t = fast ? scan_tier(A) : TIER_GENERIC;
-        n_tier[t]++;
-        max_in_tier[t] = std::max(max_in_tier[t], A);
-        rows_in_tier[t] = std::max(rows_in_tier[t], pairs_rows(A));
-    }
-    if (!ctx->scan_lists_valid) {
+    // which tiers occur in this block, and the locus list of each: computed once per block (the allele table fixes them)
+    int* n_tier = ctx->scan_n_tier;
+    int* max_in_tier = ctx->scan_max_in_tier;
+    int* rows_in_tier = ctx->scan_rows_in_tier;
+    if (!ctx->scan_lists_valid || ctx->scan_lists_fast != (fast ? 1 : 0)) {
+        for (int t = 0; t < TIER_COUNT; t++) n_tier[t] = max_in_tier[t] = rows_in_tier[t] = 0;
+        for (int64_t l = 0; l < L; l++) {
+            const int A = ctx->h_locus_off[l + 1] - ctx->h_locus_off[l];
+            const int t = fast ? scan_tier(A) : TIER_GENERIC;
+            n_tier[t]++;
+            max_in_tier[t] = std::max(max_in_tier[t], A);
+            rows_in_tier[t] = std::max(rows_in_tier[t], pairs_rows(A));
+        }
         std::vector<int32_t> lists((size_t)L);
         int off[TIER_COUNT + 1];
         off[0] = 0;
@@ -608,27 +616,36 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
         TRT_CUDA(cudaStreamSynchronize(ctx->stream));   // `lists` is a local
         for (int t = 0; t <= TIER_COUNT; t++) ctx->scan_tier_off[t] = off[t];
         ctx->scan_lists_valid = true;
+        ctx->scan_lists_fast = fast ? 1 : 0;
     }
     const int grid_persist = (int)std::min<int64_t>(std::max<int64_t>(L, 1), ctx->sm_count);
     const size_t smem_limit = (size_t)ctx->max_smem_optin;
+    const size_t row_bytes_gt = (((size_t)S * 6 + 15) & ~size_t(15));
+    const int nchunks_p = (int)((row_bytes_gt + kPChunkBytes - 1) / kPChunkBytes);
+    const bool cells8 = nchunks_p <= kPMaxChunks8 && !getenv("TRT_SCAN_CELLS16");
     for (int t = TIER_PAIRS_A; t <= TIER_PAIRS_B; t++) {
         if (!n_tier[t]) continue;
         sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[t];
         sp.n_list = n_tier[t];
         const int rows = rows_in_tier[t];
-        const size_t table = (size_t)(rows + 1) * kPRowBytes;
-        const int nsub = 1;
+        const size_t table = (size_t)(rows + 1) * kPT * (cells8 ? 1 : 2);
         int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
         stages = std::max(kPMinStages, std::min(kPMaxStages, stages));
-        const size_t smem = (size_t)stages * nsub * kPChunkBytes + sizeof(PairHeader) + table;
+        if (const char* e = getenv("TRT_SCAN_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
+        const size_t smem = (size_t)stages * kPChunkBytes + sizeof(PairHeader) + table;
         if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
+        const int grid = std::min(grid_persist, n_tier[t]);
+#define LAUNCH_PAIRS(M, C)                                                                        \
+    do {                                                                                          \
+        TRT_TRY(set_smem(ctx, scan_pairs_kernel<M, C>, smem));                                    \
+        scan_pairs_kernel<M, C><<<grid, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);     \
+    } while (0)
         if (d_mask) {
-            TRT_TRY(set_smem(ctx, scan_pairs_kernel<true>, smem));
-            scan_pairs_kernel<true><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
+            if (cells8) LAUNCH_PAIRS(true, uint8_t); else LAUNCH_PAIRS(true, uint16_t);
         } else {
-            TRT_TRY(set_smem(ctx, scan_pairs_kernel<false>, smem));
-            scan_pairs_kernel<false><<<std::min(grid_persist, n_tier[t]), kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);
+            if (cells8) LAUNCH_PAIRS(false, uint8_t); else LAUNCH_PAIRS(false, uint16_t);
         }
+#undef LAUNCH_PAIRS
         TRT_KERNEL_CHECK();
     }
     if (n_tier[TIER_WIDE]) {
