@@ -305,7 +305,9 @@ int fill_gzip(trt_vcf* v) {
 int fill_plain(trt_vcf* v) {
     // regular files: every host thread preads its own piece (page-cache copies scale with threads);
     // anything pread refuses (pipes) goes through the FILE
-    const size_t kPiece = std::min(size_t(8) << 20, kCompressedChunk);
+    // (at most 64 MiB per fill whatever the thread count: a fill is handed out block by block afterwards)
+    const int np_cap = std::max(1, v->n_threads);
+    const size_t kPiece = std::max(size_t(256) << 10, std::min(std::min(size_t(8) << 20, kCompressedChunk), (size_t(64) << 20) / (size_t)np_cap));
     if (v->plain_off >= 0 && v->n_threads > 1) {
         const int np = v->n_threads;
         text_reserve(v, kPiece * np);
@@ -755,11 +757,10 @@ static int vcf_read_block_impl(trt_vcf* v, int64_t max_loci, int64_t max_bytes, 
     *n_loci = 0;
     if (max_bytes <= 0) max_bytes = std::numeric_limits<int64_t>::max();
     std::vector<int64_t> off;
-    if (v->t_pos > 0) {     // only after the header: every later block leaves the buffer starting at 0
-        memmove(v->text.data(), v->text.data() + v->t_pos, v->t_end - v->t_pos);
-        v->t_end -= v->t_pos;
-        v->t_pos = 0;
-    }
+    // [t_pos, t_end) of the reader's buffer is unread text.  Nothing is moved per call: the consumed prefix is only
+    // compacted away when it is at least as large as what is left (amortised O(1) per byte), and a block that is
+    // small next to the unread tail gets a copy of ITS bytes instead of taking the buffer (the tail stays put) —
+    // files of many short records (few samples) used to pay a copy of the whole 16+ MiB fill per block.
     size_t scan = v->t_pos;
     size_t first = v->t_pos;
     // drop blank lines in front (the text reader skips them)
@@ -786,24 +787,42 @@ static int vcf_read_block_impl(trt_vcf* v, int64_t max_loci, int64_t max_bytes, 
             }
             break;
         }
+        {
+            // make room for the refill: drop the consumed prefix once it outweighs the unread text
+            const size_t keep_from = off.empty() ? scan : first;
+            if (keep_from > 0 && keep_from >= v->t_end - keep_from) {
+                memmove(v->text.data(), v->text.data() + keep_from, v->t_end - keep_from);
+                v->t_end -= keep_from;
+                scan -= keep_from;
+                first -= std::min(first, keep_from);
+                v->t_pos = 0;
+            }
+        }
         int rc = fill(v);
         if (rc != TRT_OK) return rc;
     }
     if (off.empty()) {
-        v->t_pos = v->t_end;
+        v->t_pos = v->t_end = 0;
         return TRT_OK;
     }
     trt_vcf_block* b = new trt_vcf_block();
     size_t nbytes = scan - first;
     size_t tail = v->t_end - scan;
-    // the block takes the reader's buffer; the unread tail is copied into a fresh one
-    RawBuf rest(std::max(tail + kCompressedChunk, size_t(1) << 20));
-    memcpy(rest.data(), v->text.data() + scan, tail);
-    b->text.swap(v->text);
-    v->text.swap(rest);
-    v->t_pos = 0;
-    v->t_end = tail;
-    if (first > 0) memmove(b->text.data(), b->text.data() + first, nbytes);
+    if (nbytes + 1 < tail) {
+        // small block, long tail: the block copies its own records
+        b->text.resize(nbytes + 1);
+        memcpy(b->text.data(), v->text.data() + first, nbytes);
+        v->t_pos = scan;
+    } else {
+        // the block takes the reader's buffer; the (shorter) unread tail is copied into a fresh one
+        RawBuf rest(std::max(tail + kCompressedChunk, size_t(1) << 20));
+        memcpy(rest.data(), v->text.data() + scan, tail);
+        b->text.swap(v->text);
+        v->text.swap(rest);
+        v->t_pos = 0;
+        v->t_end = tail;
+        if (first > 0) memmove(b->text.data(), b->text.data() + first, nbytes);
+    }
     bool unterminated = b->text[nbytes - 1] != '\n';
     b->text.resize(nbytes + (unterminated ? 1 : 0));
     if (unterminated) b->text[nbytes] = '\n';

@@ -79,6 +79,12 @@ __device__ double binom_pmf(double x, double n, double pr) {
     return exp(lc - 0.5 * lf);
 }
 
+// Tail sums.  Consecutive terms differ by a rational factor, t' = t * a / b; dividing per term makes every locus a chain
+// of ~2 sqrt(n) dependent FP64 divisions (the epilogue was bound by exactly that latency).  Instead kTailBlock terms are
+// accumulated over their common denominator — acc / Pd = sum over the block of prod(a) / prod(b) — with ONE reciprocal
+// per block.  a, b <= ~1e10 so eight factors stay far inside the FP64 range.
+constexpr int kTailBlock = 8;
+
 // P(X <= k): terms summed outward from k (decreasing away from the mode)
 __device__ double binom_cdf(double k, double n, double pr) {
     if (k < 0.0) return 0.0;
@@ -88,11 +94,21 @@ __device__ double binom_cdf(double k, double n, double pr) {
     if (q == 0.0) return 0.0;
     double t = binom_pmf(k, n, pr), sum = t;
     const double r = q / pr;
-    for (double i = k; i >= 1.0; i -= 1.0) {
-        const double ratio = i / (n - i + 1.0) * r;
-        t *= ratio;
-        sum += t;
-        if (ratio < 1.0 && t < sum * 1e-18) break;
+    double i = k;
+    while (i >= 1.0) {
+        double Pn = 1.0, Pd = 1.0, acc = 0.0;
+        bool falling = false;
+        for (int c = 0; c < kTailBlock && i >= 1.0; c++, i -= 1.0) {
+            const double a = i * r, b = n - i + 1.0;      // t_{i-1} = t_i * a / b
+            Pn *= a;
+            Pd *= b;
+            acc = fma(acc, b, Pn);
+            falling = a < b;
+        }
+        const double inv = 1.0 / Pd;
+        sum += t * (acc * inv);
+        t *= Pn * inv;
+        if (falling && t < sum * 1e-18) break;
     }
     return sum;
 }
@@ -106,11 +122,21 @@ __device__ double binom_upper(double k, double n, double pr) {
     if (q == 0.0) return 1.0;
     double t = binom_pmf(k, n, pr), sum = t;
     const double r = pr / q;
-    for (double i = k; i < n; i += 1.0) {
-        const double ratio = (n - i) / (i + 1.0) * r;
-        t *= ratio;
-        sum += t;
-        if (ratio < 1.0 && t < sum * 1e-18) break;
+    double i = k;
+    while (i < n) {
+        double Pn = 1.0, Pd = 1.0, acc = 0.0;
+        bool falling = false;
+        for (int c = 0; c < kTailBlock && i < n; c++, i += 1.0) {
+            const double a = (n - i) * r, b = i + 1.0;     // t_{i+1} = t_i * a / b
+            Pn *= a;
+            Pd *= b;
+            acc = fma(acc, b, Pn);
+            falling = a < b;
+        }
+        const double inv = 1.0 / Pd;
+        sum += t * (acc * inv);
+        t *= Pn * inv;
+        if (falling && t < sum * 1e-18) break;
     }
     return sum;
 }
