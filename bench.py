@@ -523,7 +523,8 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier):
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 64 << 30
-    budget = min(args.e2e_host_gb * (1 << 30), 0.35 * avail / max(world, 1))
+    # several ranks share one host: keep the sum of the pinned blocks well inside its memory
+    budget = min(args.e2e_host_gb * (1 << 30) / (1 if world == 1 else 4), 0.2 * avail / max(world, 1))
     n_host = int(max(1, min(nblk, budget // blk_bytes)))
     host_blocks = []
     for b in range(n_host):
@@ -644,7 +645,8 @@ def run_assoc_stream(args):
             hot_ms += ctx.stopwatch_stop()
         return hot_ms, gen_ms, scan_ms
 
-    run(False) if args.warmup > 0 and len(blocks) <= 2 else None      # tiny configurations only: warm the kernels
+    if args.warmup > 0 and nblk_max <= 2:       # tiny configurations only: warm the kernels (same decision on every rank)
+        run(False)
     if comm is not None:
         comm.barrier()
     sampler = ClockSampler(local_rank)

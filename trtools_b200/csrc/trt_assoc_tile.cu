@@ -51,7 +51,10 @@ struct TileParams {
     int nseg, chunks_per_seg;       // sample-axis segments (work unit = tile x segment)
     const double* zt;               // [nchunks * 40][ZW] z-rows in VCF sample order (zeros outside the design)
     double* mom_part;               // [nseg][L][K + 3]
-    uint32_t* masks;                // [n_tiles][nchunks][tile loci]: bit i = sample i of the chunk is an uncalled design sample
+    uint32_t* masks;                // [n_tiles][nwin][tile loci][32]: word (c & 31) of window c >> 5 of a locus holds chunk c's mask
+                                    // (bit i = sample i of the chunk is an uncalled design sample): the tile kernel writes one
+                                    // word per (locus, chunk), the down-date kernel reads a locus' window as ONE 128-byte line
+    int nwin;                       // ceil(nchunks / 32)
     int stages;
 };
 
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
             sg[h] = sgg[h] = 0.0;
             n[h] = 0;
         }
-        uint32_t* mrow = p.masks + ((size_t)tile * p.nchunks) * kTLoci + tid;
+        uint32_t* mrow = p.masks + ((size_t)tile * p.nwin * kTLoci + tid) * 32;
         for (int c = c0; c < c1; c++) {
             mbar_wait(&full[stage], phase);
             const unsigned char* gts = gt_ring + (size_t)stage * kTGtBytes + (size_t)tid * kTRowBytes;
@@ -222,7 +225,8 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
             }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
 #pragma unroll
-            for (int h = 0; h < kNL; h++) mrow[(size_t)c * kTLoci + h * kTCons] = valid[h] ? mask[h] : 0u;
+            for (int h = 0; h < kNL; h++)
+                mrow[((size_t)(c >> 5) * kTLoci + h * kTCons) * 32 + (c & 31)] = valid[h] ? mask[h] : 0u;
         }
 #pragma unroll
         for (int h = 0; h < kNL; h++) {
@@ -300,18 +304,18 @@ __global__ void __launch_bounds__(256, 2) assoc_downdate_mask_kernel(TileParams 
         if (p.locus_off[l + 1] - p.locus_off[l] > kAssocFastMaxAlleles) continue;   // generic-path locus
         const int64_t tile = l / kTLoci;
         const int tl = (int)(l % kTLoci);
-        const uint32_t* mrow = p.masks + ((size_t)tile * p.nchunks) * kTLoci + tl;
+        const uint32_t* mrow = p.masks + ((size_t)tile * p.nwin * kTLoci + tl) * 32 + lane;   // + window * kTLoci * 32
         double acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-        uint32_t m_next = (lane < p.nchunks) ? mrow[(size_t)lane * kTLoci] : 0u;
+        uint32_t m_next = (lane < p.nchunks) ? mrow[0] : 0u;
         for (int cb = 0; cb < p.nchunks; cb += 32) {
             uint32_t m = m_next;
             {   // the next window's masks are requested now: their latency hides under this window's work
                 const int cn = cb + 32 + lane;
-                m_next = (cn < p.nchunks) ? mrow[(size_t)cn * kTLoci] : 0u;
+                m_next = (cn < p.nchunks) ? mrow[(size_t)((cb >> 5) + 1) * kTLoci * 32] : 0u;
             }
             const int cnt = __popc(m);
             int off = cnt;
@@ -445,7 +449,8 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     nseg = (nchunks + cps - 1) / cps;
 
     TRT_TRY(trt_ensure(ctx, ctx->assoc_zt, (size_t)S_pad * ZW * 8 + 64));
-    TRT_TRY(trt_ensure(ctx, ctx->assoc_masks, (size_t)n_tiles * nchunks * kTLoci * 4 + 64));
+    const int nwin = (nchunks + 31) / 32;
+    TRT_TRY(trt_ensure(ctx, ctx->assoc_masks, (size_t)n_tiles * nwin * kTLoci * 32 * 4 + 64));
     TRT_TRY(trt_ensure(ctx, ctx->assoc_mom_part, (size_t)nseg * L * nacc * 8 + 64));
     {
         const int64_t n = S_pad * ZW;
@@ -472,6 +477,7 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     tp.allele_len = (const double*)ctx->allele_len.p;
     tp.n_tiles = n_tiles;
     tp.nchunks = nchunks;
+    tp.nwin = nwin;
     tp.nseg = nseg;
     tp.chunks_per_seg = cps;
     tp.zt = (const double*)ctx->assoc_zt.p;

@@ -39,8 +39,12 @@ struct CfSpec {
     float thr_f32;  // threshold rounded to float32 (numpy weak-scalar comparison for float32 arrays)
     int variant;    // CFV_*: the comparison the TMA kernel runs for this filter (kind x dtype, resolved on the host)
     long long thr_i64;   // int32 fields: value < thr <=> value < ceil(thr); value > thr <=> value > floor(thr)
+    int thr_i32;         // the same threshold when it lies inside the int32 range (else the variant is ALWAYS / NEVER)
+    int ratio_slot;      // CFV_RATIO_TABLE: which cut table of CfTmaParams::ratio_cut this filter reads
+    int hit_missing;     // CFV_RATIO_TABLE: INT32_MIN / INT32_MIN = 1.0 > thr  (a call whose depth fields are both '.')
 };
-enum { CFV_NEVER = 0, CFV_MIN_I32, CFV_MAX_I32, CFV_MIN_F32, CFV_MAX_F32, CFV_RATIO_FAST, CFV_RATIO_EXACT, CFV_HOST };
+enum { CFV_NEVER = 0, CFV_MIN_I32, CFV_MAX_I32, CFV_MIN_F32, CFV_MAX_F32, CFV_RATIO_TABLE, CFV_RATIO_EXACT, CFV_HOST, CFV_ALWAYS };
+constexpr int kRatioTable = 256;     // depths 0 .. 255 decide field/DP > thr with one table lookup
 
 struct CfParams {
     const int16_t* gt;
@@ -239,6 +243,8 @@ struct CfTmaParams {
     int slot_of_spec[kMaxSpecs];        // slot the filter reads (numerator for RATIO_GT)
     int dp_slot;                        // slot of TRT_FMT_DP for ratio filters (-1: none)
     int acc_slot;                       // slot of the depth field summed into totaldp (-1: none)
+    int n_ratio;                        // ratio filters with a cut table
+    const int32_t* ratio_cut;           // [n_ratio][kRatioTable]: field / depth > thr  <=>  field > cut[depth]  (0 <= depth < 256)
     int stages;
     int loci_per_item;
     int64_t n_slabs, n_items;
@@ -262,8 +268,11 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
     const int stages = q.stages;
     const size_t stage_bytes = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes;
     unsigned char* ring = smem;
-    unsigned int* fcnt = (unsigned int*)(smem + (size_t)stages * stage_bytes);   // [n_specs][kTS][512] thread-private columns
-    uint64_t* full = (uint64_t*)(fcnt + (size_t)max(p.n_specs, 1) * kSlabSamples);
+    // [n_specs][512] thread-private words: four 8-bit counters (one per call of the thread) of the calls each filter
+    // removed in the current item; then the ratio filters' cut tables
+    unsigned int* fcnt = (unsigned int*)(smem + (size_t)stages * stage_bytes);
+    int* cut_tab = (int*)(fcnt + (size_t)max(p.n_specs, 1) * kTmaCons);          // [n_ratio][kRatioTable]
+    uint64_t* full = (uint64_t*)(cut_tab + (size_t)q.n_ratio * kRatioTable + ((q.n_ratio * kRatioTable) & 1));
     uint64_t* empty = full + kTmaMaxStages;
     uint64_t* done = empty + kTmaMaxStages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -275,6 +284,7 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
         }
         mbar_fence_init();
     }
+    for (int i = tid; i < q.n_ratio * kRatioTable; i += kTmaCons + 64) cut_tab[i] = q.ratio_cut[i];
     __syncthreads();
 
     if (warp == kTmaCons / 32 + 1) {
@@ -336,25 +346,24 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
     }
 
     // ===== consumers: thread <-> kTS consecutive samples of the slab =====
+    // Bit j of every mask below = call j of this thread.  Everything per call is branch-free; the per-sample counters of
+    // the sample log are 8-bit fields of packed words (an item is at most 255 loci), spread from the bit masks with one
+    // multiply:  (m * 0x00204081) & 0x01010101  puts bit j of m into byte j.
     int stage = 0;
     uint32_t phase = 0;
     constexpr uint32_t kAll = (1u << kTS) - 1u;
     for (int64_t item = blockIdx.x; item < q.n_items; item += gridDim.x) {
         const int64_t slab = item % q.n_slabs, chunk = item / q.n_slabs;
         const int64_t s0 = slab * kSlabSamples;
-        const int64_t ns = min((int64_t)kSlabSamples, p.S - s0);
-        const uint32_t gt_bytes = (uint32_t)((ns * 6 + 15) & ~int64_t(15));
         const int64_t l0 = chunk * q.loci_per_item, l1 = min(p.L, l0 + q.loci_per_item);
         const int64_t sb = s0 + (int64_t)tid * kTS;          // first sample of this thread
         const uint32_t valid_mask = (sb + kTS <= p.S) ? kAll : (sb >= p.S ? 0u : ((1u << (int)(p.S - sb)) - 1u));
-        for (int f = 0; f < p.n_specs; f++)
-#pragma unroll
-            for (int j = 0; j < kTS; j++) fcnt[(f * kTS + j) * kTmaCons + tid] = 0;
-        int ncalls[kTS];
-        long long dps[kTS];
+        for (int f = 0; f < p.n_specs; f++) fcnt[f * kTmaCons + tid] = 0u;
+        uint32_t ncalls4 = 0u;               // packed: calls of each sample that passed every filter
+        uint32_t dps[kTS];                   // depth of the passing calls (an item cannot overflow 32 bits: see `big`)
         unsigned int poison = 0;
 #pragma unroll
-        for (int j = 0; j < kTS; j++) { ncalls[j] = 0; dps[j] = 0; }
+        for (int j = 0; j < kTS; j++) dps[j] = 0u;
 
         for (int64_t l = l0; l < l1; l++) {
             mbar_wait(&full[stage], phase);
@@ -363,28 +372,23 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
             uint2* gsrc = reinterpret_cast<uint2*>(st + (size_t)tid * (kTS * 6));
             const uint2 v0 = gsrc[0], v1 = gsrc[1], v2 = gsrc[2];
             uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-            // bit j of the masks = call j of this thread
+            // no-call = some haplotype is -1.  Both haplotypes of a call as one packed int16 pair (even calls sit in one
+            // word, odd calls straddle two), digits min(h + 2, 2) = {0 pad, 1 no-call, 2 allele} by one VIADDMNMX.U16x2
+            const uint32_t pr[kTS] = {w[0], __byte_perm(w[1], w[2], 0x5432), w[3], __byte_perm(w[4], w[5], 0x5432)};
             uint32_t nocall = 0;
 #pragma unroll
-            for (int j = 0; j < kTS; j++) {
-                const int k0 = 3 * j, k1 = k0 + 1;
-                const uint32_t a = (k0 & 1) ? (w[k0 >> 1] >> 16) : (w[k0 >> 1] & 0xffffu);
-                const uint32_t b = (k1 & 1) ? (w[k1 >> 1] >> 16) : (w[k1 >> 1] & 0xffffu);
-                nocall |= ((a == 0xffffu) | (b == 0xffffu)) ? (1u << j) : 0u;
-            }
+            for (int j = 0; j < kTS; j++)
+                nocall |= (__vminu2(__vadd2(pr[j], 0x00020002u), 0x00020002u) & 0x00010001u) ? (1u << j) : 0u;
             uint32_t fired_any = 0;
             uint32_t fired[kTS];
             if (WANT_MASK) {
 #pragma unroll
                 for (int j = 0; j < kTS; j++) fired[j] = 0;
             }
-            double den[kTS];
-            int32_t deni[kTS];
+            int32_t deni[kTS] = {0, 0, 0, 0};
             if (q.dp_slot >= 0) {
                 const int4 a = *reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.dp_slot * kTmaFieldBytes + (size_t)tid * 16);
                 deni[0] = a.x; deni[1] = a.y; deni[2] = a.z; deni[3] = a.w;
-#pragma unroll
-                for (int j = 0; j < kTS; j++) den[j] = (double)deni[j];
             }
             for (int f = 0; f < p.n_specs; f++) {
                 const int variant = p.specs[f].variant;
@@ -393,14 +397,14 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
                 uint32_t hit = 0;
                 switch (variant) {      // uniform across the grid
                     case CFV_MIN_I32: {
-                        const long long t = p.specs[f].thr_i64;
+                        const int t = p.specs[f].thr_i32;
 #pragma unroll
-                        for (int j = 0; j < kTS; j++) hit |= ((long long)raw[j] < t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= (raw[j] < t) ? (1u << j) : 0u;
                     } break;
                     case CFV_MAX_I32: {
-                        const long long t = p.specs[f].thr_i64;
+                        const int t = p.specs[f].thr_i32;
 #pragma unroll
-                        for (int j = 0; j < kTS; j++) hit |= ((long long)raw[j] > t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= (raw[j] > t) ? (1u << j) : 0u;
                     } break;
                     case CFV_MIN_F32: {
                         const float t = p.specs[f].thr_f32;
@@ -412,72 +416,82 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
 #pragma unroll
                         for (int j = 0; j < kTS; j++) hit |= (__int_as_float(raw[j]) > t) ? (1u << j) : 0u;
                     } break;
-                    case CFV_RATIO_FAST: {
-                        // RN(raw/den) > thr decided without dividing when raw is clear of thr*den by 2^-50 relative
-                        // (thr > 0 finite, den > 0, raw >= 0); the exact float64 division (numpy int32/int32) only for
-                        // the calls that are not — one rare branch per thread instead of one per call
-                        const double t = p.specs[f].thr;
-                        uint32_t slow = 0;
+                    case CFV_RATIO_TABLE: {
+                        // numpy: int32 / int32 -> float64, filtered when the quotient > thr.  For depths 0 .. 255 the host has
+                        // tabulated, with that very float64 division, the largest numerator that is NOT filtered, so the
+                        // test is one shared-memory lookup and an integer compare.  A call whose two depth fields are both
+                        // '.' (INT32_MIN / INT32_MIN = 1.0) is resolved on the host as well; anything else (negative or
+                        // huge depths) takes the exact division, one rare branch per thread.
+                        const int* cut = cut_tab + p.specs[f].ratio_slot * kRatioTable;
+                        const uint32_t miss_hit = p.specs[f].hit_missing ? kAll : 0u;
+                        uint32_t slow = 0, missing = 0;
 #pragma unroll
                         for (int j = 0; j < kTS; j++) {
-                            const double r = (double)raw[j];
-                            const double prod = t * den[j];
-                            const double hi = fma(prod, 0x1p-50, prod), lo = fma(prod, -0x1p-50, prod);
-                            const bool clear = (deni[j] > 0) & (raw[j] >= 0) & ((r > hi) | (r < lo));
-                            hit |= (r > hi) ? (1u << j) : 0u;
-                            slow |= clear ? 0u : (1u << j);
+                            const bool fastp = (unsigned)deni[j] < (unsigned)kRatioTable;
+                            const int c = cut[fastp ? deni[j] : 0];
+                            hit |= (fastp & (raw[j] > c)) ? (1u << j) : 0u;
+                            const bool ms = (deni[j] == INT_MIN) & (raw[j] == INT_MIN);
+                            missing |= ms ? (1u << j) : 0u;
+                            slow |= (fastp | ms) ? 0u : (1u << j);
                         }
+                        hit |= missing & miss_hit;
                         if (slow) {
+                            const double t = p.specs[f].thr;
 #pragma unroll
                             for (int j = 0; j < kTS; j++) {
                                 if (!((slow >> j) & 1u)) continue;
-                                const bool h1 = ((double)raw[j] / den[j]) > t;
-                                hit = (hit & ~(1u << j)) | (h1 ? (1u << j) : 0u);
+                                if (((double)raw[j] / (double)deni[j]) > t) hit |= 1u << j;
                             }
                         }
                     } break;
                     case CFV_RATIO_EXACT: {
                         const double t = p.specs[f].thr;
 #pragma unroll
-                        for (int j = 0; j < kTS; j++) hit |= (((double)raw[j] / den[j]) > t) ? (1u << j) : 0u;
+                        for (int j = 0; j < kTS; j++) hit |= (((double)raw[j] / (double)deni[j]) > t) ? (1u << j) : 0u;
                     } break;
                     case CFV_HOST: {
 #pragma unroll
                         for (int j = 0; j < kTS; j++) hit |= !isnan(__int_as_float(raw[j])) ? (1u << j) : 0u;
                     } break;
+                    case CFV_ALWAYS: hit = kAll; break;
                     default: break;
                 }
                 hit &= valid_mask;
                 fired_any |= hit;
-                const uint32_t cnt = hit & ~nocall;
-                if (cnt) {
-#pragma unroll
-                    for (int j = 0; j < kTS; j++)
-                        if ((cnt >> j) & 1u) fcnt[(f * kTS + j) * kTmaCons + tid] += 1;
-                }
+                fcnt[f * kTmaCons + tid] += ((hit & ~nocall) * 0x00204081u) & 0x01010101u;
                 if (WANT_MASK) {
 #pragma unroll
                     for (int j = 0; j < kTS; j++) fired[j] |= ((hit >> j) & 1u) << f;
                 }
             }
             const uint32_t pass = ~fired_any & ~nocall & valid_mask;
-#pragma unroll
-            for (int j = 0; j < kTS; j++) ncalls[j] += (pass >> j) & 1u;
+            ncalls4 += (pass * 0x00204081u) & 0x01010101u;
             if (q.acc_slot >= 0) {
                 const int4 a = *reinterpret_cast<const int4*>(st + kTmaGtBytes + (size_t)q.acc_slot * kTmaFieldBytes + (size_t)tid * 16);
                 const int32_t dpv[kTS] = {a.x, a.y, a.z, a.w};
-                uint32_t negm = 0;
+                int32_t neg = 0;
+                uint32_t big = 0;
+                uint32_t val[kTS];
 #pragma unroll
                 for (int j = 0; j < kTS; j++) {
-                    const bool ps = (pass >> j) & 1u;
-                    const int dd = dpv[j];
-                    negm |= (ps & (dd < 0)) ? (1u << j) : 0u;
-                    dps[j] += (ps & (dd >= 0)) ? (long long)dd : 0ll;
+                    const int32_t m = (int32_t)(pass << (31 - j)) >> 31;      // all ones iff call j passed
+                    neg |= dpv[j] & m;                                        // sign bit: a passing call with a negative depth
+                    val[j] = (uint32_t)(max(dpv[j], 0) & m);
+                    big |= val[j];
                 }
-                if (negm) {                                   // rare: missing depth poisons, negative depth is an error
+                if ((big >> 23) == 0u) {
+                    // 255 loci x 2^23 < 2^31: the item's 32-bit sums cannot wrap
+#pragma unroll
+                    for (int j = 0; j < kTS; j++) dps[j] += val[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kTS; j++)
+                        if (val[j]) atomicAdd((unsigned long long*)&p.dpsum[sb + j], (unsigned long long)val[j]);
+                }
+                if (neg < 0) {                                // rare: missing depth poisons, negative depth is an error
 #pragma unroll
                     for (int j = 0; j < kTS; j++) {
-                        if (!((negm >> j) & 1u)) continue;
+                        if (!((pass >> j) & 1u) || dpv[j] >= 0) continue;
                         if (dpv[j] == INT_MIN) poison |= 1u << j;
                         else atomicMin(p.neg_dp_locus, (int)l);
                     }
@@ -520,11 +534,12 @@ __global__ void __launch_bounds__(kTmaCons + 64, 1) call_filter_tma_kernel(CfTma
 #pragma unroll
         for (int j = 0; j < kTS; j++) {
             if (sb + j >= p.S) continue;
-            if (ncalls[j]) atomicAdd((unsigned long long*)&p.numcalls[sb + j], (unsigned long long)ncalls[j]);
+            const unsigned nc = (ncalls4 >> (8 * j)) & 0xffu;
+            if (nc) atomicAdd((unsigned long long*)&p.numcalls[sb + j], (unsigned long long)nc);
             if (dps[j]) atomicAdd((unsigned long long*)&p.dpsum[sb + j], (unsigned long long)dps[j]);
             if ((poison >> j) & 1u) atomicOr(&p.dp_poison[sb + j], 1u);
             for (int f = 0; f < p.n_specs; f++) {
-                const unsigned int c = fcnt[(f * kTS + j) * kTmaCons + tid];
+                const unsigned int c = (fcnt[f * kTmaCons + tid] >> (8 * j)) & 0xffu;
                 if (c) atomicAdd((unsigned long long*)&p.filter_counts[(size_t)f * p.S + sb + j], (unsigned long long)c);
             }
         }
@@ -682,16 +697,28 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
             CfSpec& c = p.specs[f];
             const double t = s.threshold;
             c.thr_i64 = 0;
+            c.thr_i32 = 0;
+            c.ratio_slot = -1;
+            c.hit_missing = 0;
             c.variant = CFV_NEVER;
             if (s.kind == TRT_CF_HOST_VALUE) c.variant = CFV_HOST;
-            else if (s.kind == TRT_CF_RATIO_GT) c.variant = (t > 0.0 && std::isfinite(t)) ? CFV_RATIO_FAST : CFV_RATIO_EXACT;
+            else if (s.kind == TRT_CF_RATIO_GT) c.variant = (t >= 0.0 && std::isfinite(t)) ? CFV_RATIO_TABLE : CFV_RATIO_EXACT;
             else if (s.kind == TRT_CF_MIN || s.kind == TRT_CF_MAX) {
                 if (c.is_float) c.variant = (s.kind == TRT_CF_MIN) ? CFV_MIN_F32 : CFV_MAX_F32;   // NaN threshold: never true
                 else if (!std::isnan(t)) {
+                    // int32 value v:  v < t <=> v < ceil(t);  v > t <=> v > floor(t)  (exact in integers)
                     const double lim = 4.0e18;
                     const double e = (s.kind == TRT_CF_MIN) ? ceil(t) : floor(t);
                     c.thr_i64 = (long long)std::max(-lim, std::min(lim, e));
-                    c.variant = (s.kind == TRT_CF_MIN) ? CFV_MIN_I32 : CFV_MAX_I32;
+                    if (s.kind == TRT_CF_MIN) {
+                        if (c.thr_i64 > (long long)INT_MAX) c.variant = CFV_ALWAYS;
+                        else if (c.thr_i64 <= (long long)INT_MIN) c.variant = CFV_NEVER;
+                        else { c.variant = CFV_MIN_I32; c.thr_i32 = (int)c.thr_i64; }
+                    } else {
+                        if (c.thr_i64 >= (long long)INT_MAX) c.variant = CFV_NEVER;
+                        else if (c.thr_i64 < (long long)INT_MIN) c.variant = CFV_ALWAYS;
+                        else { c.variant = CFV_MAX_I32; c.thr_i32 = (int)c.thr_i64; }
+                    }
                 }
             }
         }
@@ -755,7 +782,34 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
         if (tma_ok) {
             q.base = p;
             const size_t stage_bytes = (size_t)kTmaGtBytes + (size_t)q.n_fields * kTmaFieldBytes;
-            const size_t fixed = (size_t)std::max(n_specs, 1) * kSlabSamples * 4 + 3 * kTmaMaxStages * 8 + 128;
+            // cut tables of the ratio filters (see CFV_RATIO_TABLE): largest numerator NOT filtered, per depth 0 .. 255,
+            // decided with the float64 division numpy performs
+            std::vector<int32_t> cuts;
+            for (int f = 0; f < n_specs; f++) {
+                CfSpec& c = p.specs[f];
+                if (c.variant != CFV_RATIO_TABLE) continue;
+                c.ratio_slot = q.n_ratio++;
+                c.hit_missing = (1.0 > c.thr) ? 1 : 0;
+                for (int den = 0; den < kRatioTable; den++) {
+                    long long r = 0;
+                    if (den > 0) {
+                        const double guess = floor(c.thr * (double)den);
+                        r = (long long)std::max(0.0, std::min(guess, 2147483646.0));
+                        while (r < 2147483647LL && !((double)(r + 1) / (double)den > c.thr)) r++;
+                        while (r > 0 && ((double)r / (double)den > c.thr)) r--;
+                    }
+                    cuts.push_back((int32_t)r);
+                }
+            }
+            if (q.n_ratio) {
+                TRT_TRY(trt_ensure(ctx, ctx->cf_specs, cuts.size() * 4 + 16));
+                TRT_CUDA(cudaMemcpyAsync(ctx->cf_specs.p, cuts.data(), cuts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                TRT_CUDA(cudaStreamSynchronize(ctx->stream));      // `cuts` is a local
+                q.ratio_cut = (const int32_t*)ctx->cf_specs.p;
+            }
+            q.base = p;
+            const size_t fixed = (size_t)std::max(n_specs, 1) * kTmaCons * 4 + (size_t)q.n_ratio * kRatioTable * 4 + 8 +
+                                 3 * kTmaMaxStages * 8 + 128;
             int stages = (int)(((size_t)ctx->max_smem_optin - fixed) / stage_bytes);
             stages = std::min(stages, kTmaMaxStages);
             if (stages < 3) tma_ok = false;
@@ -763,7 +817,7 @@ int trt_call_filters(trt_ctx* ctx, const trt_call_filter_spec* specs, int n_spec
                 q.stages = stages;
                 q.n_slabs = (S + kSlabSamples - 1) / kSlabSamples;
                 // items small enough to balance 148 persistent CTAs, large enough to amortise the counter flush
-                int64_t per = std::max<int64_t>(32, std::min<int64_t>(256, (L * q.n_slabs) / ((int64_t)ctx->sm_count * 24) + 1));
+                int64_t per = std::max<int64_t>(32, std::min<int64_t>(255, (L * q.n_slabs) / ((int64_t)ctx->sm_count * 24) + 1));   // <= 255: 8-bit counters
                 q.loci_per_item = (int)per;
                 q.n_items = q.n_slabs * ((L + per - 1) / per);
                 const size_t smem = (size_t)stages * stage_bytes + fixed;
