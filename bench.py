@@ -600,26 +600,50 @@ def run_assoc_stream(args):
     ctx.assoc_set_design(covars, outcome, np.arange(S, dtype=np.int32))
     blocks = [(b0, min(b0 + B, hi)) for b0 in range(lo, hi, B)]
     row_bytes = 5 * 8          # p, coef, se, r2, std_g (f64) per locus: the fixed-width summary row
-    recv = None
-    n_rows = comm.allgather_i64([hi - lo])[:, 0] if comm is not None else np.array([hi - lo])
-    if rank == 0:
-        recv = ctx.pinned_empty((int(max(B * world * row_bytes, 16)),), np.uint8)
+    # every rank knows every rank's block sizes (contiguous shards, fixed block length): no size exchange per block
+    shards = [tdist.locus_shard(L, r, world) for r in range(world)]
+    nblk_max = max((h_ - l_ + B - 1) // B for l_, h_ in shards)
+
+    def counts_of(i):
+        return np.array([max(0, min(B, h_ - (l_ + i * B))) for l_, h_ in shards], dtype=np.int64)
+
+    recv = [ctx.pinned_empty((int(max(B * world * row_bytes, 16)),), np.uint8) for _ in range(2)] if rank == 0 else [None, None]
     table = np.full((5, L), np.nan) if rank == 0 else None
-    nblk_max = int(tdist.max_over_ranks(comm, float(len(blocks))))
+
+    def unpack(i, buf):
+        counts = counts_of(i)
+        off = 0
+        for r in range(world):
+            c = int(counts[r])
+            if c:
+                g0 = shards[r][0] + i * B
+                table[:, g0:g0 + c] = np.frombuffer(buf[off:off + c * row_bytes], dtype=np.float64).reshape(5, c)
+            off += c * row_bytes
+
+    tables_of = {}
+
+    def gen_block(i):
+        b0, b1 = blocks[i]
+        n = b1 - b0
+        if n not in tables_of:
+            tables_of[n] = synth.allele_tables(tab, 0, n)
+        ctx.block_begin(n, S, 2, "hipstr")
+        ctx.synth_fill(SEED, b0, tab.cum_freq[:n], tab.miss_thresh, tab.half_thresh, with_format=False)
+        ctx.block_set_alleles(*tables_of[n])
+        ctx.synchronize()
+        return n
 
     def run(timed):
+        """Per block: [generate] -> harmonize + associaTR kernels -> NCCL gather of the rows (device buffers) whose copy
+        to the host runs on the side stream under the NEXT block's generation and kernels."""
         hot_ms = gen_ms = 0.0
         scan_ms = []
+        pending = None                                  # (block index, host buffer) of the gather still in flight
         for i in range(nblk_max):
             n = 0
             if i < len(blocks):
-                b0, b1 = blocks[i]
-                n = b1 - b0
                 t0 = time.perf_counter()
-                ctx.block_begin(n, S, 2, "hipstr")
-                ctx.synth_fill(SEED, b0, tab.cum_freq[:n], tab.miss_thresh, tab.half_thresh, with_format=False)
-                ctx.block_set_alleles(*synth.allele_tables(tab, 0, n))
-                ctx.synchronize()
+                n = gen_block(i)
                 gen_ms += (time.perf_counter() - t0) * 1000.0
                 ctx.stopwatch_start()
                 ctx.check(ctx.lib.trt_harmonize(ctx.h))
@@ -628,25 +652,30 @@ def run_assoc_stream(args):
             else:
                 ctx.stopwatch_start()
             if comm is not None:
-                counts = comm.allgather_i64([n])[:, 0]
-                # the five float64 columns of this block's rows are contiguous per rank: [5][n] at the head of the region
-                comm.gather_region(tdist.REGION_ASSOC, 0, n * row_bytes, counts * row_bytes, 0, recv, wait=True)
-                if rank == 0 and timed:
-                    off = 0
-                    for r in range(world):
-                        c = int(counts[r])
-                        if c:
-                            g0 = tdist.locus_shard(L, r, world)[0] + i * B
-                            table[:, g0:g0 + c] = np.frombuffer(recv[off:off + c * row_bytes], dtype=np.float64).reshape(5, c)
-                        off += c * row_bytes
+                if pending is not None:                 # the previous block's rows have long arrived: bank them
+                    comm.wait()
+                    if rank == 0 and timed:
+                        unpack(*pending)
+                comm.gather_region(tdist.REGION_ASSOC, 0, n * row_bytes, counts_of(i) * row_bytes, 0, recv[i & 1], wait=False)
+                pending = (i, recv[i & 1])
             elif timed and n:
+                b0, b1 = blocks[i]
                 for k, key in enumerate(("p", "coef", "se", "r2", "std_g")):
                     table[k, b0:b1] = res[key]
             hot_ms += ctx.stopwatch_stop()
+        if comm is not None and pending is not None:
+            t0 = time.perf_counter()
+            comm.wait()
+            hot_ms += (time.perf_counter() - t0) * 1000.0
+            if rank == 0 and timed:
+                unpack(*pending)
         return hot_ms, gen_ms, scan_ms
 
-    if args.warmup > 0 and nblk_max <= 2:       # tiny configurations only: warm the kernels (same decision on every rank)
-        run(False)
+    # warm-up: one untimed block (first-use allocations of the 1.4 GB mask / moment buffers, kernel module loading)
+    if args.warmup > 0 and blocks:
+        gen_block(0)
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        ctx.assoc_ols(20.0, want=())
     if comm is not None:
         comm.barrier()
     sampler = ClockSampler(local_rank)

@@ -330,6 +330,8 @@ def main():
         section_synth()
     if want("edge"):
         section_edge()
+    if want("dosage"):
+        section_dosage()
 
 
 def section_many():
@@ -455,6 +457,116 @@ def section_assoc():
         json.dump(assoc, fh)
     print("associatr", {k: v.count("\n") for k, v in assoc.items()})
 
+
+
+def section_dosage():
+    # ---- 7. Beagle allele-probability dosages: GetDosages + the --beagle-dosages branch ----
+    AS = os.path.join(SV, "associaTR")
+    bi_d = copy_data(os.path.join(AS, "many_samples_biallelic_dosages.vcf.gz"))
+    multi_d = copy_data(os.path.join(AS, "many_samples_multiallelic_dosages.vcf.gz"))
+    t0 = copy_data(os.path.join(AS, "traits_0.npy"))
+    t1 = copy_data(os.path.join(AS, "traits_1.npy"))
+    s640 = copy_data(os.path.join(AS, "samples_6_to_45.txt"))
+    for fn in ("single_dosages.plink2.trait_0.glm.linear", "single_40_dosages.plink2.trait_0.glm.linear"):
+        copy_data(os.path.join(AS, fn))
+    out = dict(
+        single_dosages=associatr_cli(bi_d, [t0], beagle_dosages=True),
+        single_40_dosages=associatr_cli(bi_d, [t0], sample_list=s640, beagle_dosages=True),
+        combined_dosages_cutoff_20=associatr_cli(bi_d, [t0, t1], beagle_dosages=True, non_major_cutoff=20),
+        multi_dosages=associatr_cli(multi_d, [t0], beagle_dosages=True),
+        multi_dosages_cutoff_10=associatr_cli(multi_d, [t0], beagle_dosages=True, non_major_cutoff=10),
+        multi_dosages_cutoff_20=associatr_cli(multi_d, [t0], beagle_dosages=True, non_major_cutoff=20),
+        multi_dosages_cutoff_38=associatr_cli(multi_d, [t0], beagle_dosages=True, non_major_cutoff=38),
+    )
+    with open(os.path.join(HERE, "associatr_dosage.json"), "w") as fh:
+        json.dump(out, fh)
+    print("associatr dosage", {k: v.count("\n") for k, v in out.items()})
+
+    # function level: GetDosages on real records and on synthetic AP blocks (incl. invalid AP fields)
+    def dos(tr, kind, strict):
+        try:
+            d = tr.GetDosages(getattr(trh.TRDosageTypes, kind), strict=strict)
+            return dict(values=[f(x) for x in d])
+        except ValueError as e:
+            return dict(error=str(e))
+
+    def pack(loci):
+        rows = []
+        for l in loci:
+            tr = trh.HarmonizeRecord(l.vcftype, LocusAsVariant(l))
+            rows.append({k + ("" if strict else "_lenient"): dos(tr, k, strict)
+                         for k in ("bestguess", "bestguess_norm", "beagleap", "beagleap_norm") for strict in (True, False)})
+        return rows
+
+    vcf = cyvcf2.VCF(multi_d)
+    loci = [locus_from_variant(rec, "hipstr", numeric_fmt={"AP1", "AP2", "DP", "Q"}) for rec in vcf]
+    vcf = cyvcf2.VCF(bi_d)
+    for i, rec in enumerate(vcf):
+        if i >= 40:
+            break
+        loci.append(locus_from_variant(rec, "hipstr", numeric_fmt={"AP1", "AP2", "DP", "Q"}))
+    save_loci(os.path.join(HERE, "dosage_real.npz"), loci, extra=dict(dosages=pack(loci)), info_keys=INFO_KEYS)
+    # synthetic: HipSTR loci with Beagle-like AP fields consistent with (a noisy version of) the hard calls
+    rng = np.random.default_rng(20261017)
+    sl = synth.make_loci(24, seed=31)
+    calls = synth.fill_calls(sl, 301)
+    sloci = synth_to_loci(sl, calls, with_fmt=False)
+    for j, l in enumerate(sloci):
+        S, nalt = l.gt.shape[0], len(l.alts)
+        for p in (1, 2):
+            ap = np.zeros((S, nalt), dtype=np.float32)
+            hap = l.gt[:, p - 1].astype(int)
+            for s_ in range(S):
+                w = rng.dirichlet(np.full(nalt + 1, 0.3))
+                a = hap[s_] if hap[s_] >= 0 else int(rng.integers(0, nalt + 1))
+                w = 0.15 * w
+                w[a] += 0.85
+                ap[s_] = np.round(w[1:], 2).astype(np.float32)
+            l.fmt["AP%d" % p] = ap
+        if j == 5:
+            l.fmt["AP1"][7, 0] = np.float32(1.5)         # sums to more than 1.1
+        if j == 9:
+            l.fmt["AP2"][3, 0] = np.float32(-0.25)       # negative
+        if j == 11:
+            del l.fmt["AP2"]                             # field missing
+    traits = synth.make_traits(sl, calls.gt[0], 301, n_covars=3)
+    mask = rng.random(301) < 0.8
+    extra = dict(dosages=pack(sloci), traits=traits.tolist(), sample_mask=mask.tolist())
+    good = [l for j, l in enumerate(sloci) if j not in (11,)]
+    extra["good_index"] = [j for j in range(len(sloci)) if j not in (11,)]
+    extra["assoc_dosage"] = associatr_dosage_loci(good, [traits], non_major_cutoff=5)
+    extra["assoc_dosage_subset"] = associatr_dosage_loci(good, [traits], non_major_cutoff=20, sample_mask=mask)
+    save_loci(os.path.join(HERE, "dosage_synth.npz"), sloci, extra=extra, info_keys=INFO_KEYS)
+    print("dosage fixtures", len(loci), len(sloci))
+
+
+def associatr_dosage_loci(loci, trait_arrays, non_major_cutoff=20, sample_mask=None):
+    """Unmodified perform_gwas_helper over the unmodified load_trs (beagle_dosages=True), the records coming from
+    the shim's in-memory VCF source."""
+    samples = ["%d" % i for i in range(loci[0].gt.shape[0])]
+    key = "golden_dosage_%d" % id(loci)
+    cyvcf2.register_memory_vcf(key, [LocusAsVariant(l) for l in loci],
+                               "##fileformat=VCFv4.1\n##command=HipSTR-synthetic\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\n", samples)
+
+    def get_genotype_iter(sample_filter):
+        return rlafg.load_trs("mem://" + key, sample_filter, None, non_major_cutoff, True, "hipstr")
+
+    with tempfile.TemporaryDirectory() as td:
+        fns = []
+        for i, arr in enumerate(trait_arrays):
+            fn = os.path.join(td, "t%d.npy" % i)
+            np.save(fn, arr)
+            fns.append(fn)
+        sample_fname = None
+        if sample_mask is not None:
+            sample_fname = os.path.join(td, "samples.txt")
+            with open(sample_fname, "w") as fh:
+                fh.write("\n".join(s for s, m in zip(samples, sample_mask) if m) + "\n")
+        out = io.StringIO()
+        with contextlib.redirect_stdout(io.StringIO()):
+            rassoc.perform_gwas_helper(out, samples, get_genotype_iter, "test_pheno", fns, True, sample_fname, True,
+                                       None, False, False, [])
+        return out.getvalue()
 
 
 def section_synth():

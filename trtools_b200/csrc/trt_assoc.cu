@@ -504,6 +504,7 @@ int trt_assoc_set_design(trt_ctx* ctx, const double* covars, const double* outco
     ctx->n_design = n_design;
     ctx->K = K;
     ctx->have_design = true;
+    ctx->design_checked_S = -1;
     return TRT_OK;
 }
 
@@ -523,13 +524,14 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
     TRT_TRY(trt_ensure(ctx, ctx->lc, (size_t)L * TRT_LC_N * 8 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->assoc_acc, ((size_t)L * (nacc + ne)) * 8 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->assoc_out, (size_t)L * (5 * 8 + 8 + 4) + (size_t)nA * 4 + 64));
-    {
-        // validate the sample indices against this block (host copy is gone; check the max on the device side cheaply)
+    if (ctx->design_checked_S != S) {
+        // validate the sample indices against this block's sample axis (once per design and sample count)
         std::vector<int32_t> idx((size_t)n);
         if (n) TRT_CUDA(cudaMemcpyAsync(idx.data(), ctx->sample_index.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         TRT_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int64_t i = 0; i < n; i++)
             if (idx[i] < 0 || idx[i] >= S) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_ols: design row %lld maps to sample %d outside [0,%lld)", (long long)i, idx[i], (long long)S);
+        ctx->design_checked_S = S;
     }
     trt_timer_begin(ctx);
     TRT_CUDA(cudaMemsetAsync(ctx->group_masks.p, 0, (size_t)S + 16, ctx->stream));

@@ -75,6 +75,7 @@ struct trt_ctx {
     int64_t n_design = 0;
     int     K = 0;
     bool    have_design = false;
+    int64_t design_checked_S = -1;   // sample count the design's sample indices were last validated against
 
     // NCCL (opaque here)
     void*   nccl_comm = nullptr;
