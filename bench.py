@@ -671,11 +671,16 @@ def run_assoc_stream(args):
                 unpack(*pending)
         return hot_ms, gen_ms, scan_ms
 
-    # warm-up: one untimed block (first-use allocations of the 1.4 GB mask / moment buffers, kernel module loading)
-    if args.warmup > 0 and blocks:
-        gen_block(0)
-        ctx.check(ctx.lib.trt_harmonize(ctx.h))
-        ctx.assoc_ols(20.0, want=())
+    # warm-up: block 0 through the whole per-block path, untimed — first-use allocations of the 1.4 GB mask / moment
+    # buffers, kernel module loading, and NCCL's lazy peer-to-peer connection set-up of the first gather
+    if args.warmup > 0:
+        n0 = 0
+        if blocks:
+            n0 = gen_block(0)
+            ctx.check(ctx.lib.trt_harmonize(ctx.h))
+            ctx.assoc_ols(20.0, want=())
+        if comm is not None:
+            comm.gather_region(tdist.REGION_ASSOC, 0, n0 * row_bytes, counts_of(0) * row_bytes, 0, recv[0], wait=True)
     if comm is not None:
         comm.barrier()
     sampler = ClockSampler(local_rank)

@@ -280,6 +280,44 @@ typedef struct {
  * associaTR.py:246-291 (statsmodels OLS on called rows: params, bse, pvalues, rsquared).          */
 int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out);
 
+/* ---- dosages ----------------------------------------------------------------
+ * Beagle allele probabilities of the block: FORMAT AP1 / AP2 exactly as cyvcf2 returns them per record — float32
+ * [S][A_l - 1] — stacked over loci (locus l starts S * (alternate alleles of the loci before it) floats in).
+ * has_ap (may be NULL = all): [L] bytes, 0 = the record carries no AP1 / AP2 (its rows are skipped: zero alts' worth).   */
+int trt_block_set_ap(trt_ctx* ctx, const float* ap1_host, const float* ap2_host, const uint8_t* has_ap_host);
+/* TRRecord.GetDosages tr_harmonizer.py:1098-1208 for every locus of the block -> float32 [L][S] (the tensor annotaTR
+ * writes, annotaTR.py:673-703).  error_out [L]: record-level validation result; the dosages of an invalid record are
+ * not meaningful (the reference raises ValueError, or warns and returns NaN when strict=False).                          */
+#define TRT_DOSAGE_BESTGUESS       0
+#define TRT_DOSAGE_BEAGLEAP        1
+#define TRT_DOSAGE_BESTGUESS_NORM  2
+#define TRT_DOSAGE_BEAGLEAP_NORM   3
+#define TRT_DE_OK            0
+#define TRT_DE_NO_AP         1   /* 'Requested Beagle dosages ... but AP1/AP2 fields not found'      :1132-1140 */
+#define TRT_DE_AP_SUM        2   /* 'AP1 or AP2 field summing to more than 1 detected'               :1162-1168 */
+#define TRT_DE_AP_NEGATIVE   3   /* 'Negative AP1 or AP2 fields detected'                            :1169-1175 */
+#define TRT_DE_NORM_RANGE    4   /* 'Error normalizing dosages: value >=2.1 or <=-0.1 detected'      :1199-1205 */
+int trt_dosages(trt_ctx* ctx, int dosage_type, float* dosage_out /*[L][S]*/, int32_t* error_out /*[L]*/);
+
+/* associaTR --beagle-dosages: load_trs' dosage branch lafg.py:175-214 + the regression on the summed dosage
+ * associaTR.py:266-291.  Per allele a of the block the caller passes the length class it belongs to after rounding to
+ * two decimals (cls[a] = index within the locus of the first allele with the same rounded length), that rounded length
+ * (python round) and the numpy-rounded length used for the best-guess comparison (np.around).                          */
+typedef struct {
+    int64_t* n_tested;      /* [L] called samples among the design rows                                                */
+    double*  p;             /* [L] as trt_assoc_out (regression of the outcome on the summed dosage)                     */
+    double*  coef;
+    double*  se;
+    double*  r2;
+    double*  std_g;
+    int32_t* ncovars_code;  /* [L] TRT_AF_NCOVARS when the design has at least as many columns as tested samples, else 0 */
+    double*  class_stats;   /* [nA][4] at class representatives: sum d, sum d^2, #(best guess in class), sum d[best guess in class] */
+    double*  length_stats;  /* [L][5]: sum x, sum x^2, sum y, sum y^2, sum xy over the 2 n haplotype entries (x best-guess
+                               length, y expected length) for r2_length_dosages_vs_best_guess_lengths                   */
+} trt_assoc_dosage_out;
+int trt_assoc_dosage_ols(trt_ctx* ctx, const int32_t* cls /*[nA]*/, const double* len_round /*[nA]*/,
+                         const double* len_around /*[nA]*/, trt_assoc_dosage_out* out);
+
 /* ---- synthetic blocks (bench / parity at sizes that do not fit through PCIe) ------------------
  * Device twin of trtools_b200/synth.py::fill_calls — bit-identical arrays.                        */
 int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset, int64_t n_loci, int64_t n_samples,

@@ -275,3 +275,61 @@ def test_known_answers_utils():
     assert otrh.canonical_one_strand("CAG") == 'AGC'
     assert otrh.homopolymer_run("AATAAAATAAAAAT") == 5
     assert otrh.fabricate_allele("ACG", 2.4) == "ACGACGA"
+
+
+# ---- Beagle allele-probability dosages -----------------------------------------------------------
+def _dosage_fixture(golden_dir, name):
+    loci, extra, _ = load_loci(os.path.join(golden_dir, name + ".npz"))
+    for l in loci:
+        for k in ("AP1", "AP2"):
+            if k in l.fmt:
+                l.fmt[k] = np.ascontiguousarray(l.fmt[k][:, :len(l.alts)], dtype=np.float32)
+    return loci, extra
+
+
+@pytest.mark.parametrize("name", ["dosage_real", "dosage_synth"])
+def test_oracle_beagle_dosages_match_reference(golden_dir, name):
+    """oracle.dosage.beagle_dosages == the unmodified reference's GetDosages(beagleap[_norm]) on real Beagle records and
+    on synthetic AP blocks, including the three validation errors."""
+    import numpy as np
+    from oracle import dosage as odos, trh as otrh
+    loci, extra = _dosage_fixture(golden_dir, name)
+    n_err = 0
+    for i, (l, w) in enumerate(zip(loci, extra["dosages"])):
+        h = otrh.harmonize(l)
+        for kind, norm in (("beagleap", False), ("beagleap_norm", True)):
+            ww = w[kind]
+            try:
+                got = odos.beagle_dosages(h, l, norm=norm, strict=True)
+            except odos.DosageError as e:
+                assert ww.get("error") == str(e), (i, kind)
+                n_err += 1
+                assert np.isnan(odos.beagle_dosages(h, l, norm=norm, strict=False)).all()
+                continue
+            assert "values" in ww, (i, kind)
+            assert np.array_equal(np.array(ww["values"], dtype=np.float32), got, equal_nan=True), (i, kind)
+        want_bg = np.array(w["bestguess"]["values"], dtype=np.float32)
+        assert np.array_equal(otrh.dosages_bestguess(h, l.gt), want_bg)
+    assert n_err == (6 if name == "dosage_synth" else 0)
+
+
+@pytest.mark.parametrize("key,cutoff,use_mask", [("assoc_dosage", 5, False), ("assoc_dosage_subset", 20, True)])
+def test_oracle_assoc_dosage_rows_match_reference(golden_dir, key, cutoff, use_mask):
+    """oracle load_dosage_locus + regress_dosage_locus reproduce the rows the unmodified perform_gwas_helper over the
+    unmodified load_trs(beagle_dosages=True) wrote for the synthetic AP block (text columns exact, numbers to 1e-9)."""
+    import numpy as np
+    from oracle import assoc as oassoc, dosage as odos, trh as otrh
+    loci, extra = _dosage_fixture(golden_dir, "dosage_synth")
+    good = [loci[j] for j in extra["good_index"]]
+    traits = np.array(extra["traits"], dtype=float)
+    S = good[0].gt.shape[0]
+    design = oassoc.prepare_design([traits], S, np.array(extra["sample_mask"], dtype=bool) if use_mask else None)
+    want = extra[key].splitlines()[1:]
+    for i, l in enumerate(good):
+        h = otrh.harmonize(l)
+        row = odos.regress_dosage_locus(odos.load_dosage_locus(l, h, design.sample_filter.copy(), cutoff), design)
+        g, w = row.to_text().rstrip("\n").split("\t"), want[i].split("\t")
+        assert g[:6] == w[:6] and g[9:] == w[9:], (i, g, w)
+        if w[5] != "nan":
+            for c in (6, 7, 8):
+                assert abs(float(g[c]) - float(w[c])) <= 1e-9 * abs(float(w[c])), (i, c)

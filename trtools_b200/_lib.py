@@ -34,6 +34,7 @@ EXPORTS = [
     "trt_block_set_format_f32", "trt_block_set_format_device", "trt_block_set_alleles",
     "trt_harmonize", "trt_get_harmonized", "trt_pack_length_genotypes", "trt_get_packed_gt",
     "trt_locus_stats", "trt_genotype_counts", "trt_call_filters", "trt_locus_filters", "trt_assoc_set_design", "trt_assoc_ols",
+    "trt_block_set_ap", "trt_dosages", "trt_assoc_dosage_ols",
     "trt_synth_fill", "trt_block_get_gt", "trt_block_get_format",
     "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
     "trt_dist_allreduce_sum_f64", "trt_dist_allreduce_max_f64", "trt_dist_barrier", "trt_dist_gather_region",
@@ -94,6 +95,14 @@ class AssocOut(C.Structure):
                 ("se", C.c_void_p), ("r2", C.c_void_p), ("std_g", C.c_void_p), ("ac_len", C.c_void_p)]
 
 
+class AssocDosageOut(C.Structure):
+    _fields_ = [("n_tested", C.c_void_p), ("p", C.c_void_p), ("coef", C.c_void_p), ("se", C.c_void_p), ("r2", C.c_void_p),
+                ("std_g", C.c_void_p), ("ncovars_code", C.c_void_p), ("class_stats", C.c_void_p), ("length_stats", C.c_void_p)]
+
+
+DOSAGE_TYPES = {"bestguess": 0, "beagleap": 1, "bestguess_norm": 2, "beagleap_norm": 3}
+DE_OK, DE_NO_AP, DE_AP_SUM, DE_AP_NEGATIVE, DE_NORM_RANGE = range(5)
+
 _lib = None
 
 
@@ -139,6 +148,9 @@ def load():
         "trt_locus_filters": (i32, [vp, C.POINTER(LocusFilterSpec), i32, i32, C.POINTER(LocusFilterOut)]),
         "trt_assoc_set_design": (i32, [vp, vp, vp, vp, i64, i32]),
         "trt_assoc_ols": (i32, [vp, f64, C.POINTER(AssocOut)]),
+        "trt_block_set_ap": (i32, [vp, vp, vp, vp]),
+        "trt_dosages": (i32, [vp, i32, vp, vp]),
+        "trt_assoc_dosage_ols": (i32, [vp, vp, vp, vp, C.POINTER(AssocDosageOut)]),
         "trt_synth_fill": (i32, [vp, u64, i64, i64, i64, vp, u32, u32, i32]),
         "trt_block_get_gt": (i32, [vp, i64, i64, vp]),
         "trt_block_get_format": (i32, [vp, i32, i64, i64, vp]),
@@ -421,6 +433,34 @@ class Context:
         res = {k: r(k, n_, dt) for k, n_, dt in spec if want is None or k in want}
         out = AssocOut(**{k: _ptr(v) for k, v in res.items()})
         self.check(self.lib.trt_assoc_ols(self.h, float(non_major_cutoff), C.byref(out)))
+        return res
+
+    def block_set_ap(self, ap1: np.ndarray, ap2: np.ndarray, has_ap: Optional[np.ndarray] = None):
+        """Beagle FORMAT AP1 / AP2 of the block: float32, the records' [S][A-1] arrays concatenated."""
+        a1, a2 = _c(ap1, np.float32).reshape(-1), _c(ap2, np.float32).reshape(-1)
+        n = self.S * (self.nA - self.L)
+        assert a1.size == n and a2.size == n, (a1.size, a2.size, n)
+        h = None if has_ap is None else _c(has_ap, np.uint8)
+        self.check(self.lib.trt_block_set_ap(self.h, _ptr(a1), _ptr(a2), _ptr(h)))
+
+    def dosages(self, dosage_type) -> tuple:
+        """TRRecord.GetDosages for every locus: (float32 [L, S], int32 [L] record-level validation codes DE_*)."""
+        t = DOSAGE_TYPES[dosage_type] if isinstance(dosage_type, str) else int(dosage_type)
+        out = np.empty((self.L, self.S), np.float32)
+        err = np.zeros(self.L, np.int32)
+        self.check(self.lib.trt_dosages(self.h, t, _ptr(out), _ptr(err)))
+        return out, err
+
+    def assoc_dosage_ols(self, cls: np.ndarray, len_round: np.ndarray, len_around: np.ndarray) -> dict:
+        """associaTR --beagle-dosages on the current block (see include/trtools_b200.h trt_assoc_dosage_ols)."""
+        L, nA = self.L, self.nA
+        c, lr, la = _c(cls, np.int32), _c(len_round, np.float64), _c(len_around, np.float64)
+        assert c.size == nA and lr.size == nA and la.size == nA
+        res = dict(n_tested=np.empty(L, np.int64), p=np.empty(L), coef=np.empty(L), se=np.empty(L), r2=np.empty(L),
+                   std_g=np.empty(L), ncovars_code=np.empty(L, np.int32), class_stats=np.empty((nA, 4)),
+                   length_stats=np.empty((L, 5)))
+        out = AssocDosageOut(**{k: _ptr(v) for k, v in res.items()})
+        self.check(self.lib.trt_assoc_dosage_ols(self.h, _ptr(c), _ptr(lr), _ptr(la), C.byref(out)))
         return res
 
     def synth_fill(self, seed, locus_offset, cum_freq, miss_thresh, half_thresh, with_format=True):

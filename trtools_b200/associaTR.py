@@ -131,33 +131,124 @@ def _write_block(outfile, blk, res, pheno_std, non_major_cutoff):
     outfile.flush()
 
 
+def dosage_classes(blk):
+    """Per allele of a block: (class representative, python-rounded length, numpy-rounded length) — the keys the
+    reference's dosage branch groups alleles by (lafg.py:171-172 ``round``) and compares best guesses with
+    (lafg.py:199 ``np.around``)."""
+    lens = blk.h["allele_len"]
+    prec = load_and_filter_genotypes.allele_len_precision
+    len_round = np.array([round(float(x), prec) for x in lens], dtype=np.float64)
+    len_around = np.around(lens.astype(np.float64), prec)
+    cls = np.zeros(len(lens), np.int32)
+    for l in range(blk.L):
+        sl = blk.allele_slice(l)
+        first = {}
+        for j, v in enumerate(len_round[sl]):
+            cls[sl.start + j] = first.setdefault(v, j)
+    return cls, len_round, len_around
+
+
+def _r2(n, sx, sxx, sy, syy, sxy):
+    """np.corrcoef(x, y)[0, 1] ** 2 from the sums over n entries (NaN when either side is constant)."""
+    with np.errstate(divide='ignore', invalid='ignore'):
+        n = np.float64(n)
+        cov = np.float64(sxy) - np.float64(sx) * np.float64(sy) / n
+        vx = np.float64(sxx) - np.float64(sx) * np.float64(sx) / n
+        vy = np.float64(syy) - np.float64(sy) * np.float64(sy) / n
+        if not (vx > 0 and vy > 0):
+            return np.float64(np.nan)
+        r = cov / np.sqrt(vx * vy)
+        return np.float64(min(max(r, -1.0), 1.0)) ** 2
+
+
+def _write_dosage_block(outfile, blk, res, meta, pheno_std, non_major_cutoff):
+    """TSV rows of one GPU block with --beagle-dosages (reference associaTR.py:252-304, lafg.py:175-238)."""
+    cls, len_round, _ = meta
+    lafg = load_and_filter_genotypes
+    lines = []
+    for l in range(blk.L):
+        sl = blk.allele_slice(l)
+        lr = len_round[sl]
+        n = int(res["n_tested"][l])
+        alleles = ','.join(list(np.unique(lr).astype(str)))
+        cs = res["class_stats"][sl]
+        reps = [j for j in range(len(lr)) if cls[sl.start + j] == j]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            freq = {float(lr[j]): np.float64(cs[j, 0]) / (2 * n) for j in sorted(reps, key=lambda j: lr[j])}
+        r2 = {}
+        for j in range(len(lr)):                 # dict order of the reference: first occurrence among the alleles
+            key = float(lr[j])
+            if key not in r2:
+                c = int(cls[sl.start + j])
+                r2[key] = _r2(2 * n, cs[c, 2], cs[c, 2], cs[c, 0], cs[c, 1], cs[c, 3])
+        ls = res["length_stats"][l]
+        length_r2 = _r2(2 * n, ls[0], ls[1], ls[2], ls[3], ls[4])
+        m = blk.metas[l]
+        motif = blk.motif(l)
+        details = [motif, str(len(motif)), str(round(float(blk.h["allele_len"][sl.start]), lafg.allele_len_precision)),
+                   lafg.dict_str({k: '{:.2g}'.format(v) for k, v in freq.items()}),
+                   lafg.dict_str(lafg.round_vals(r2, lafg.r2_precision)), str(round(length_r2, lafg.r2_precision))]
+        pos = m.harmonized_pos if m.harmonized_pos is not None else m.vcf_pos
+        head = "{}\t{}\t{}\t{}\t".format(m.chrom, pos, alleles, n)
+        reason = lafg.locus_filter_reason(freq, n, non_major_cutoff, True)
+        if not reason and int(res["ncovars_code"][l]) == _lib.AF_NCOVARS:
+            reason = _REASONS[_lib.AF_NCOVARS]
+        if reason:
+            lines.append(head + '{}\tnan\tnan\tnan\tnan\t'.format(reason) + '\t'.join(details) + '\n')
+            continue
+        coef = res["coef"][l] * pheno_std
+        se = res["se"][l] * pheno_std
+        lines.append(head + 'False\t' + ("{:." + str(pval_precision) + "e}\t{}\t{}\t{}\t").format(
+            res["p"][l], coef, se, res["r2"][l]) + '\t'.join(details) + '\n')
+    outfile.write(''.join(lines))
+    outfile.flush()
+
+
 def perform_gwas_helper(outfile, all_samples, get_genotype_iter, phenotype_name, trait_fnames, same_samples,
                         sample_fname, beagle_dosages, plotting_phenotype_fname, paired_genotype_plot,
                         plot_phenotype_residuals, plotting_ci_alphas):
     """The reference's injected-generator seam (associaTR.py:117-422).  ``get_genotype_iter(sample_mask)`` must
     return an object with a ``blocks()`` generator of GPU blocks (see ``perform_gwas``) — the per-locus numpy
     generator protocol of the reference is served by ``load_and_filter_genotypes.load_trs`` for user scripts."""
-    if beagle_dosages or plotting_phenotype_fname:
-        raise NotImplementedError("dosage / plotting-phenotype branches are outside the accelerated path")
+    if plotting_phenotype_fname:
+        raise NotImplementedError("the plotting-phenotype columns are outside the accelerated path")
     covars, outcome, pheno_std, sample_filter = prepare_design(all_samples, trait_fnames, same_samples, sample_fname)
     source = get_genotype_iter(sample_filter.copy())
-    outfile.write(_header(phenotype_name, source.detail_fields))
+    fields = list(source.detail_fields)
+    if beagle_dosages:
+        fields += ['dosage_estimated_r2_per_length_allele', 'r2_length_dosages_vs_best_guess_lengths']
+    outfile.write(_header(phenotype_name, fields))
     ctx = source.ctx
     ctx.assoc_set_design(covars, outcome, np.nonzero(sample_filter)[0].astype(np.int32))
     n_loci = 0
     start = time.time()
     sharder = getattr(source, "sharder", None)
     multi = sharder is not None and sharder.comm is not None
+    first_block = True
     for blk in source.blocks():
         blk._activate()
-        res = ctx.assoc_ols(source.non_major_cutoff)
+        if beagle_dosages:
+            if first_block and "AP1" not in (blk._records[0].FORMAT or []):      # reference lafg.py:139-146
+                print("--beagle-dosages specified, missing required field AP1 for the TR")
+                if "GP" in (blk._records[0].FORMAT or []):
+                    print("We could support the GP field, but currently only support the AP fields")
+                print("Erroring out")
+                sys.exit(1)
+            blk.ensure_ap()
+            meta = dosage_classes(blk)
+            res = ctx.assoc_dosage_ols(*meta)
+            write = lambda f: _write_dosage_block(f, blk, res, meta, pheno_std, source.non_major_cutoff)
+        else:
+            res = ctx.assoc_ols(source.non_major_cutoff)
+            write = lambda f: _write_block(f, blk, res, pheno_std, source.non_major_cutoff)
+        first_block = False
         if multi:                                   # several GPUs: rank 0 gathers every rank's rows at the end
             import io
             buf = io.StringIO()
-            _write_block(buf, blk, res, pheno_std, source.non_major_cutoff)
+            write(buf)
             sharder.add(buf.getvalue())
         else:
-            _write_block(outfile, blk, res, pheno_std, source.non_major_cutoff)
+            write(outfile)
         n_loci += blk.L
     if multi:
         merged = sharder.finish()

@@ -178,6 +178,9 @@ class Block:
         if len(bad):
             raise ValueError("Record {}:{} has a non-positive period".format(metas[bad[0]].chrom, metas[bad[0]].vcf_pos))
         self._stats = {}
+        self._dosages = {}
+        self._records = None          # set by build_block: the AP1 / AP2 arrays are pulled lazily (Beagle dosages only)
+        self._ap = None
         ctx._current_block = self
 
     # ---- cached block-level statistics (one GPU pass per (use_length)) --------------------------
@@ -232,7 +235,58 @@ class Block:
                                        self.period, self.given_len, self.motifs_in)
             self._upload_fmt()
             self.ctx.harmonize()
+            if self._ap is not None:
+                self.ctx.block_set_ap(*self._ap)
         self.ctx._current_block = self
+
+    # ---- Beagle allele probabilities / dosages -------------------------------------------------
+    def ensure_ap(self):
+        """Pull FORMAT AP1 / AP2 (float32 [S][A-1] per record, as cyvcf2 returns them) of every record, stack them and
+        upload them.  Records without the fields get zero rows and has_ap = 0 (GetDosages reports them)."""
+        self._activate()
+        if self._ap is not None:
+            return self._ap
+        if self._records is None:
+            raise ValueError("this block was not built from records: AP1/AP2 are not available")
+        parts1, parts2 = [], []
+        has = np.ones(self.L, np.uint8)
+        for l, rec in enumerate(self._records):
+            nalt = int(self.locus_off[l + 1] - self.locus_off[l]) - 1
+            ap = []
+            for key in ("AP1", "AP2"):
+                arr = None
+                try:
+                    if key in (rec.FORMAT or []):
+                        arr = rec.format(key)
+                except KeyError:
+                    arr = None
+                if arr is None:
+                    has[l] = 0
+                    ap.append(np.zeros((self.S, nalt), np.float32))
+                    continue
+                arr = np.asarray(arr, dtype=np.float32).reshape(self.S, -1)
+                if arr.shape[1] != nalt:
+                    fixed = np.zeros((self.S, nalt), np.float32)
+                    k = min(nalt, arr.shape[1])
+                    fixed[:, :k] = arr[:, :k]
+                    arr = fixed
+                ap.append(arr)
+            parts1.append(ap[0].reshape(-1))
+            parts2.append(ap[1].reshape(-1))
+        cat = lambda p: np.concatenate(p) if p else np.zeros(0, np.float32)
+        self._ap = (cat(parts1), cat(parts2), has)
+        self.ctx.block_set_ap(*self._ap)
+        return self._ap
+
+    def dosages(self, kind: str):
+        """(float32 [L, S], int32 [L] validation codes) of TRRecord.GetDosages(kind) for the whole block, cached."""
+        if kind not in self._dosages:
+            if kind.startswith("beagleap"):
+                self.ensure_ap()
+            else:
+                self._activate()
+            self._dosages[kind] = self.ctx.dosages(kind)
+        return self._dosages[kind]
 
     # ---- per-locus views ---------------------------------------------------------------------------
     def allele_slice(self, l: int) -> slice:
@@ -310,7 +364,9 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
                 stacked = _stack_format(records, key)
                 if stacked is not None:
                     fmt[key] = stacked
-        return Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
+        blk = Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
+        blk._records = list(records)
+        return blk
     gts = []
     has_samples = True
     for r in records:
@@ -333,4 +389,6 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
         stacked = _stack_format(records, key)
         if stacked is not None:
             fmt[key] = stacked
-    return Block(ctx, vcftype, metas, gt, fmt)
+    blk = Block(ctx, vcftype, metas, gt, fmt)
+    blk._records = list(records)
+    return blk

@@ -312,6 +312,7 @@ struct SolveParams {
     const double* dd;         // [L][K(K+1)/2]
     const double* mom;        // [L][K+3]
     double cutoff;
+    int dosage_mode;          // the allele-frequency filters are the caller's (dosage frequencies): only 'n covars >= n samples'
     int32_t* filter_code;
     long long* n_tested;
     double *pval, *coef, *se, *r2, *std_g;
@@ -334,14 +335,15 @@ __global__ void __launch_bounds__(64) assoc_solve_kernel(SolveParams p) {
     const double NaN = nan("");
     // ---- allele frequencies over the tested samples, by length rounded to 2 decimals (lafg.py:37-45,174) ----
     long long total = 0;
-    for (int a = 0; a < A; a++) {
-        const int c = p.ac[a0 + a] - p.ac_part[a0 + a];
-        if (p.ac_len) p.ac_len[a0 + a] = c;
-        total += c;
-    }
+    if (!p.dosage_mode)
+        for (int a = 0; a < A; a++) {
+            const int c = p.ac[a0 + a] - p.ac_part[a0 + a];
+            if (p.ac_len) p.ac_len[a0 + a] = c;
+            total += c;
+        }
     const long long n = (long long)llrint(mom[0]);
     int code = TRT_AF_OK;
-    {
+    if (!p.dosage_mode) {
         // classes in ascending length; keys equal after rounding to 2 dp are merged (consecutive in this order).
         // pass 0: number of classes and the position of the FIRST maximum frequency (np.argmax);
         // pass 1: sum of the other frequencies in dictionary order (af.pop(argmax); np.sum(af)).
@@ -462,6 +464,153 @@ __global__ void __launch_bounds__(64) assoc_solve_kernel(SolveParams p) {
     p.se[l] = se;
     p.r2[l] = r2;
     p.std_g[l] = sdg;
+}
+
+
+// ---- associaTR --beagle-dosages -----------------------------------------------------------------
+// load_trs' dosage branch (lafg.py:175-214): per tested sample and haplotype h the dosage of every LENGTH CLASS c
+// (alleles whose lengths agree after rounding to two decimals) is d_hc = sum of AP_h over the class' alleles, the
+// reference allele taking max(0, 1 - sum(AP_h)) (float32, like numpy); the regressor is g = sum_c len_c (d_1c + d_2c)
+// (associaTR.py:266-270).  One warp per locus, lanes stride the sample axis, everything accumulates in FP64.
+constexpr int kDosClassBatch = 16;
+
+struct DosageAssocParams {
+    AssocParams a;
+    const float* ap1;
+    const float* ap2;
+    const int32_t* cls;          // [nA] class representative (index within the locus) of every allele
+    const int32_t* order;        // [nA] per locus: the class representatives in ascending rounded length, then -1
+    const double* len_round;     // [nA] python round(length, 2)
+    const double* len_around;    // [nA] np.around(length, 2): what the best-guess comparison uses
+    double* class_stats;         // [nA][4]
+    double* length_stats;        // [L][5]
+};
+
+__device__ float np_sum_f32_assoc(const float* a, int n) {
+    // np.sum over the contiguous last axis of a float32 array: first element + pairwise_sum of the rest
+    if (n <= 0) return 0.0f;
+    const float* b = a + 1;
+    const int m = n - 1;
+    float res;
+    if (m < 8) {
+        res = 0.0f;
+        for (int i = 0; i < m; i++) res = __fadd_rn(res, b[i]);
+    } else {
+        float r[8];
+        for (int j = 0; j < 8; j++) r[j] = b[j];
+        int i = 8;
+        for (; i < m - (m % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], b[i + j]);
+        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < m; i++) res = __fadd_rn(res, b[i]);
+    }
+    return __fadd_rn(a[0], res);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(128) assoc_dosage_kernel(DosageAssocParams q) {
+    const AssocParams& p = q.a;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int K = p.K, nacc = K + 3;
+    for (int64_t l = warp; l < p.L; l += nwarps) {
+        const int a0 = p.locus_off[l];
+        const int A = p.locus_off[l + 1] - a0;
+        const int nalt = A - 1;
+        const int16_t* row = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch);
+        const size_t ap_base = (size_t)p.S * (size_t)(a0 - l);
+        const int32_t* cls = q.cls + a0;
+        const int32_t* order = q.order + a0;
+        const double* lr = q.len_round + a0;
+        const double* la = q.len_around + a0;
+        int ncls = 0;
+        while (ncls < A && order[ncls] >= 0) ncls++;
+        const double goff = 2.0 * lr[0];                        // conditioning shift (the intercept absorbs it)
+        for (int b0 = 0; b0 < ncls || b0 == 0; b0 += kDosClassBatch) {
+            const bool first = (b0 == 0);
+            double acc[KP + 3], cs[4][kDosClassBatch], ls[5];
+#pragma unroll
+            for (int k = 0; k < KP + 3; k++) acc[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) ls[k] = 0.0;
+            for (int i = 0; i < kDosClassBatch; i++) cs[0][i] = cs[1][i] = cs[2][i] = cs[3][i] = 0.0;
+            for (int64_t sb = 0; sb < p.S; sb += 32) {
+                const int64_t s = sb + lane;
+                if (s >= p.S) continue;
+                const int r = p.row_of_sample[s];
+                if (r < 0) continue;
+                const int h1 = row[s * 3], h2 = row[s * 3 + 1];
+                const bool ok1 = (h1 >= 0 && h1 < A) || h1 == -2, ok2 = (h2 >= 0 && h2 < A) || h2 == -2;
+                if (!(ok1 && ok2)) continue;
+                const float* r1 = q.ap1 + ap_base + (size_t)s * nalt;
+                const float* r2 = q.ap2 + ap_base + (size_t)s * nalt;
+                const float ref1 = fmaxf(0.0f, __fsub_rn(1.0f, np_sum_f32_assoc(r1, nalt)));
+                const float ref2 = fmaxf(0.0f, __fsub_rn(1.0f, np_sum_f32_assoc(r2, nalt)));
+                const double x1 = (h1 >= 0) ? p.allele_len[a0 + h1] : -2.0, x2 = (h2 >= 0) ? p.allele_len[a0 + h2] : -2.0;
+                const double xr1 = (h1 >= 0) ? la[h1] : -2.0, xr2 = (h2 >= 0) ? la[h2] : -2.0;
+                double y1 = 0.0, y2 = 0.0, g = 0.0;
+                for (int ci = 0; ci < ncls; ci++) {
+                    const int c = order[ci];
+                    double d1 = 0.0, d2 = 0.0;
+                    for (int a = c; a < A; a++) {
+                        if (cls[a] != c) continue;
+                        d1 += (a == 0) ? (double)ref1 : (double)r1[a - 1];
+                        d2 += (a == 0) ? (double)ref2 : (double)r2[a - 1];
+                    }
+                    const double lenc = lr[c];
+                    y1 += lenc * d1;
+                    y2 += lenc * d2;
+                    g += lenc * (d1 + d2);
+                    const int j = ci - b0;
+                    if (j >= 0 && j < kDosClassBatch) {
+                        const double e1 = (xr1 == lenc) ? 1.0 : 0.0, e2 = (xr2 == lenc) ? 1.0 : 0.0;
+                        cs[0][j] += d1 + d2;
+                        cs[1][j] += d1 * d1 + d2 * d2;
+                        cs[2][j] += e1 + e2;
+                        cs[3][j] += e1 * d1 + e2 * d2;
+                    }
+                }
+                if (first) {
+                    ls[0] += x1 + x2;
+                    ls[1] += x1 * x1 + x2 * x2;
+                    ls[2] += y1 + y2;
+                    ls[3] += y1 * y1 + y2 * y2;
+                    ls[4] += x1 * y1 + x2 * y2;
+                    const double gp = g - goff;
+                    const double yv = p.outcome[r];
+                    acc[0] += 1.0;
+                    acc[1] += gp;
+                    acc[2] += gp * gp;
+                    acc[3] += gp * yv;
+#pragma unroll
+                    for (int k = 0; k < KP - 1; k++)
+                        if (k < K - 1) acc[4 + k] += gp * p.covars[(int64_t)r * K + k + 1];
+                }
+            }
+            if (first) {
+#pragma unroll
+                for (int k = 0; k < KP + 3; k++) {
+                    if (k < nacc) {
+                        const double v = warp_sum_d(acc[k]);
+                        if (lane == 0) p.mom[l * nacc + k] = v;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const double v = warp_sum_d(ls[k]);
+                    if (lane == 0) q.length_stats[l * 5 + k] = v;
+                }
+            }
+            for (int j = 0; j < kDosClassBatch && b0 + j < ncls; j++) {
+                const int c = order[b0 + j];
+                for (int k = 0; k < 4; k++) {
+                    const double v = warp_sum_d(cs[k][j]);
+                    if (lane == 0) q.class_stats[(size_t)(a0 + c) * 4 + k] = v;
+                }
+            }
+        }
+    }
 }
 
 __global__ void fill_rows_kernel(int32_t* row_of_sample, int64_t S) {
@@ -628,6 +777,7 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
         sp.mom = (const double*)ctx->assoc_acc.p;
         sp.dd = sp.mom + (size_t)L * nacc;
         sp.cutoff = non_major_cutoff;
+        sp.dosage_mode = 0;
         sp.filter_code = o_code; sp.n_tested = o_n; sp.pval = o_p; sp.coef = o_coef; sp.se = o_se; sp.r2 = o_r2;
         sp.std_g = o_sd; sp.ac_len = o_ac;
         if (K <= 8) assoc_solve_kernel<8><<<(unsigned)((L + 63) / 64), 64, 0, ctx->stream>>>(sp);
@@ -651,6 +801,147 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
     D2H(out->n_tested, o_n, (size_t)L * 8);
     D2H(out->filter_code, o_code, (size_t)L * 4);
     D2H(out->ac_len, o_ac, (size_t)nA * 4);
+#undef D2H
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TRT_OK;
+}
+
+
+int trt_assoc_dosage_ols(trt_ctx* ctx, const int32_t* cls, const double* len_round, const double* len_around,
+                         trt_assoc_dosage_out* out) {
+    if (!ctx || !ctx->block_open || !ctx->have_gt || !ctx->harmonized)
+        return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_dosage_ols: needs a block with GT and trt_harmonize");
+    if (!ctx->have_design) return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_dosage_ols: call trt_assoc_set_design first");
+    if (!ctx->have_ap) return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_dosage_ols: call trt_block_set_ap first");
+    if (ctx->P != 2) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_dosage_ols: Beagle AP1/AP2 dosages are diploid");
+    if (!out || !cls || !len_round || !len_around) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_dosage_ols: NULL argument");
+    TRT_CUDA(cudaSetDevice(ctx->device));
+    const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA, n = ctx->n_design;
+    const int K = ctx->K, ne = tri_entries(K), nacc = K + 3;
+    // class order per locus: representatives in ascending rounded length (np.unique of the rounded lengths), then -1
+    std::vector<int32_t> order((size_t)nA, -1);
+    for (int64_t l = 0; l < L; l++) {
+        const int a0 = ctx->h_locus_off[l], A = ctx->h_locus_off[l + 1] - a0;
+        std::vector<int> reps;
+        for (int a = 0; a < A; a++) {
+            if (cls[a0 + a] < 0 || cls[a0 + a] > a) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_dosage_ols: cls[%d] of locus %lld is not a class representative", a, (long long)l);
+            if (cls[a0 + a] == a) reps.push_back(a);
+        }
+        std::sort(reps.begin(), reps.end(), [&](int x, int y) { return len_round[a0 + x] < len_round[a0 + y]; });
+        for (size_t i = 0; i < reps.size(); i++) order[(size_t)a0 + i] = reps[i];
+    }
+    const size_t meta_bytes = (size_t)nA * (4 + 4 + 8 + 8) + 64;
+    TRT_TRY(trt_ensure(ctx, ctx->dos_meta, meta_bytes));
+    char* mb = (char*)ctx->dos_meta.p;
+    double* d_lr = (double*)mb;
+    double* d_la = d_lr + nA;
+    int32_t* d_cls = (int32_t*)(d_la + nA);
+    int32_t* d_order = d_cls + nA;
+    if (nA) {
+        TRT_CUDA(cudaMemcpyAsync(d_lr, len_round, (size_t)nA * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRT_CUDA(cudaMemcpyAsync(d_la, len_around, (size_t)nA * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRT_CUDA(cudaMemcpyAsync(d_cls, cls, (size_t)nA * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRT_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)nA * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));          // the caller's arrays and `order` are free again
+    TRT_TRY(trt_ensure(ctx, ctx->design_row_of_sample, (size_t)S * 4 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->group_masks, (size_t)S + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->assoc_acc, ((size_t)L * (nacc + ne)) * 8 + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->assoc_out, (size_t)L * (5 * 8 + 8 + 4) + (size_t)nA * 4 + 64));
+    TRT_TRY(trt_ensure(ctx, ctx->dos_out, ((size_t)nA * 4 + (size_t)L * 5) * 8 + 64));
+    trt_timer_begin(ctx);
+    TRT_CUDA(cudaMemsetAsync(ctx->group_masks.p, 0, (size_t)S + 16, ctx->stream));
+    TRT_CUDA(cudaMemsetAsync(ctx->dos_out.p, 0, ((size_t)nA * 4 + (size_t)L * 5) * 8 + 64, ctx->stream));
+    if (S) fill_rows_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>((int32_t*)ctx->design_row_of_sample.p, S);
+    if (n) scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        (const int32_t*)ctx->sample_index.p, n, (int32_t*)ctx->design_row_of_sample.p, (uint8_t*)ctx->group_masks.p);
+    ctx->launches += 2;
+    char* ob = (char*)ctx->assoc_out.p;
+    double* o_p = (double*)ob;
+    double* o_coef = o_p + L;
+    double* o_se = o_coef + L;
+    double* o_r2 = o_se + L;
+    double* o_sd = o_r2 + L;
+    long long* o_n = (long long*)(o_sd + L);
+    int32_t* o_code = (int32_t*)(o_n + L);
+    double* d_cs = (double*)ctx->dos_out.p;
+    double* d_ls = d_cs + (size_t)nA * 4;
+    TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
+    if (L > 0) {
+        DosageAssocParams q;
+        AssocParams& ap = q.a;
+        ap.gt = ctx->d_gt_active;
+        ap.pitch = ctx->gt_active_pitch;
+        ap.L = L; ap.S = S; ap.P = ctx->P;
+        ap.locus_off = (const int32_t*)ctx->locus_off.p;
+        ap.allele_len = (const double*)ctx->allele_len.p;
+        ap.row_of_sample = (const int32_t*)ctx->design_row_of_sample.p;
+        ap.covars = (const double*)ctx->covars.p;
+        ap.outcome = (const double*)ctx->outcome.p;
+        ap.K = K;
+        ap.mom = (double*)ctx->assoc_acc.p;
+        ap.dd = ap.mom + (size_t)L * nacc;
+        ap.list = nullptr;
+        ap.n_list = 0;
+        q.ap1 = (const float*)ctx->ap1.p;
+        q.ap2 = (const float*)ctx->ap2.p;
+        q.cls = d_cls;
+        q.order = d_order;
+        q.len_round = d_lr;
+        q.len_around = d_la;
+        q.class_stats = d_cs;
+        q.length_stats = d_ls;
+        const int64_t wblocks = std::max<int64_t>(1, std::min<int64_t>((L + 3) / 4, (int64_t)ctx->sm_count * 16));
+        const int64_t dblocks = std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)ctx->sm_count * 8));
+#define LAUNCH_DOSAGE(KP)                                                                  \
+    do {                                                                                   \
+        assoc_dosage_kernel<KP><<<(unsigned)wblocks, 128, 0, ctx->stream>>>(q);            \
+        TRT_KERNEL_CHECK();                                                                \
+        assoc_downdate_kernel<KP><<<(unsigned)dblocks, 256, 0, ctx->stream>>>(ap);         \
+        TRT_KERNEL_CHECK();                                                                \
+    } while (0)
+        if (K <= 8) LAUNCH_DOSAGE(8);
+        else if (K <= 16) LAUNCH_DOSAGE(16);
+        else LAUNCH_DOSAGE(32);
+#undef LAUNCH_DOSAGE
+        SolveParams sp;
+        sp.L = L; sp.K = K; sp.P = ctx->P;
+        sp.locus_off = (const int32_t*)ctx->locus_off.p;
+        sp.allele_len = (const double*)ctx->allele_len.p;
+        sp.len_class = (const int32_t*)ctx->len_class.p;
+        sp.len_order = (const int32_t*)ctx->len_order.p;
+        sp.ac = nullptr;
+        sp.ac_part = nullptr;
+        sp.tot = (const double*)ctx->assoc_tot.p;
+        sp.mom = (const double*)ctx->assoc_acc.p;
+        sp.dd = sp.mom + (size_t)L * nacc;
+        sp.cutoff = 0.0;
+        sp.dosage_mode = 1;
+        sp.filter_code = o_code; sp.n_tested = o_n; sp.pval = o_p; sp.coef = o_coef; sp.se = o_se; sp.r2 = o_r2;
+        sp.std_g = o_sd; sp.ac_len = nullptr;
+        if (K <= 8) assoc_solve_kernel<8><<<(unsigned)((L + 63) / 64), 64, 0, ctx->stream>>>(sp);
+        else if (K <= 16) assoc_solve_kernel<16><<<(unsigned)((L + 63) / 64), 64, 0, ctx->stream>>>(sp);
+        else assoc_solve_kernel<32><<<(unsigned)((L + 63) / 64), 64, 0, ctx->stream>>>(sp);
+        TRT_KERNEL_CHECK();
+    }
+    TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
+    trt_timer_end(ctx);
+    {
+        float ms = 0.f;
+        TRT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1));
+        ctx->last_scan_ms = ms;
+    }
+#define D2H(dst, src, bytes) \
+    if ((dst) && (bytes)) TRT_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+    D2H(out->p, o_p, (size_t)L * 8);
+    D2H(out->coef, o_coef, (size_t)L * 8);
+    D2H(out->se, o_se, (size_t)L * 8);
+    D2H(out->r2, o_r2, (size_t)L * 8);
+    D2H(out->std_g, o_sd, (size_t)L * 8);
+    D2H(out->n_tested, o_n, (size_t)L * 8);
+    D2H(out->ncovars_code, o_code, (size_t)L * 4);
+    D2H(out->class_stats, d_cs, (size_t)nA * 4 * 8);
+    D2H(out->length_stats, d_ls, (size_t)L * 5 * 8);
 #undef D2H
     TRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return TRT_OK;

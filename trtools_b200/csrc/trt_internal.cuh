@@ -60,6 +60,10 @@ struct trt_ctx {
     DevBuf  packed;
     bool    have_packed = false;
 
+    // Beagle allele probabilities (FORMAT AP1 / AP2) and the dosage tensor (trt_dosage.cu)
+    DevBuf  ap1, ap2, has_ap, dosage, dosage_err, dos_meta, dos_out;
+    bool    have_ap = false;
+
     // stats scratch (device)
     DevBuf  ac, ac_part, lc, group_masks, stat_f64, stat_i32, work_counter;
     DevBuf  scan_lists;              // per-tier locus lists of the current block (trt_scan.cu)

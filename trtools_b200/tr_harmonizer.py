@@ -403,33 +403,35 @@ class TRRecord:
         return len_gts
 
     def GetDosages(self, dosagetype: TRDosageTypes = TRDosageTypes.bestguess, strict: bool = True):
-        """reference :1098-1208 (bestguess variants; Beagle AP dosages are an adjacent path)."""
+        """reference :1098-1208.  One ``trt_dosages`` pass per (block, dosage type) yields the float32 [L][S] tensor;
+        this record's row is a view of it.  Record-level validation failures come back as a code per locus and are
+        raised (or, when not strict, reported and answered with NaN) here, with the reference's messages."""
         if self.GetNumSamples() == 0:
             return None
-        if dosagetype in (TRDosageTypes.beagleap, TRDosageTypes.beagleap_norm):
-            raise NotImplementedError("Beagle AP dosages are outside the accelerated path (SURVEY.md §8f)")
-        lengts = self.GetLengthGenotypes()
-        if dosagetype == TRDosageTypes.bestguess_norm:
-            lengts[lengts == -1] = np.nan
-            lengts[lengts == -2] = np.nan
-        elif dosagetype == TRDosageTypes.bestguess:
-            lengts[lengts == -1] = 0
-            lengts[lengts == -2] = 0
-        else:
+        if not isinstance(dosagetype, TRDosageTypes):
             raise ValueError("Unsupported dosagetype")
-        unnorm = lengts[:, :-1].sum(axis=1).astype(np.float32)
-        if dosagetype == TRDosageTypes.bestguess:
-            return unnorm
-        if self.min_allele_length == self.max_allele_length:
-            return np.zeros(self.GetNumSamples(), dtype=np.float32)
-        dosages = (unnorm - 2 * self.min_allele_length) / (self.max_allele_length - self.min_allele_length)
-        if np.any(dosages >= 2.1) or np.any(dosages <= -0.1):
-            msg = "{}:{} Error normalizing dosages: value >=2.1 or <=-0.1 detected".format(self.chrom, self.pos)
+        n = self.GetNumSamples()
+
+        def fail(msg, raised=None):
             if strict:
-                raise ValueError(msg)
+                raise ValueError(raised or msg)
             common.WARNING(msg)
-            return np.array([np.nan] * self.GetNumSamples())
-        return np.clip(dosages, 0, 2)
+            return np.array([np.nan] * n)
+
+        beagle = dosagetype in (TRDosageTypes.beagleap, TRDosageTypes.beagleap_norm)
+        if beagle and self._blk.P != 2:
+            return fail("{}:{} Beagle AP1/AP2 dosages need diploid genotypes".format(self.chrom, self.pos))
+        values, codes = self._blk.dosages(dosagetype.value)
+        code = int(codes[self._l])
+        if code == _lib.DE_NO_AP:
+            return fail("Requested Beagle dosages for record at {}:{} but AP1/AP2 fields not found.".format(self.chrom, self.pos))
+        if code == _lib.DE_AP_SUM:
+            return fail("{}:{} AP1 or AP2 field summing to more than 1 detected".format(self.chrom, self.pos))
+        if code == _lib.DE_AP_NEGATIVE:
+            return fail("{}:{} Negative AP1 or AP2 fields detected".format(self.chrom, self.pos), "Negative AP1 or AP2 fields detected")
+        if code == _lib.DE_NORM_RANGE:
+            return fail("{}:{} Error normalizing dosages: value >=2.1 or <=-0.1 detected".format(self.chrom, self.pos))
+        return values[self._l].copy()
 
     def HasFullStringGenotypes(self) -> bool:
         return self.full_alleles is not None
