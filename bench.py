@@ -404,7 +404,16 @@ def run_gpu(args):
                 "kernel_share_of_step": scan / step_ms if step_ms > 0 else None}
 
     # ---- e2e through the C-ABI with HOST buffers (rank-local; max over ranks) -------------------
-    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier)
+    # headline: the packed transfer form the library's own block reader parses VCF text into (2 B/call across PCIe);
+    # beside it the same pass from cyvcf2-layout int16 arrays (6 B/call), the form a cyvcf2 caller holds
+    def regen():        # the e2e legs stream small blocks through this context: restore the full synthetic block first
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=False)
+        ctx.block_set_alleles(*tables)
+
+    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True)
+    regen()
+    e2e["cyvcf2_layout"] = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=False)
 
     # ---- the other two tools of the metric on the same resident block (device-timed, results copied to host) ----
     tools, assoc_res, lf_res, pheno_std = {}, None, None, 1.0
@@ -509,15 +518,16 @@ def run_gpu(args):
         comm.close()
 
 
-def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier):
+def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True):
     """The statSTR pass through the C-ABI with HOST buffers: pinned host blocks of the workload's genotypes ->
-    trt_block_set_gt (H2D) -> kernels -> D2H of the statistics.  The host blocks hold DISTINCT loci of the workload
-    (copied out of the device-generated block before the clock starts), as many as fit the pinned budget; when the
-    budget is smaller than the workload the resident blocks are streamed round-robin (every copy is a real H2D)."""
+    trt_block_set_gt_packed / trt_block_set_gt (H2D) -> kernels -> D2H of the statistics.  The host blocks hold DISTINCT
+    loci of the workload (copied out of the device-generated block before the clock starts), as many as fit the pinned
+    budget; when the budget is smaller than the workload the resident blocks are streamed round-robin (every copy is a
+    real H2D).  ``packed``: uint8 [L][S][2] blocks (what trt_vcf_block_parse_packed emits) instead of int16 [L][S][3]."""
     from trtools_b200 import _lib, synth, dist as tdist
     Lb = min(L, args.e2e_block)
     nblk = (L + Lb - 1) // Lb
-    blk_bytes = Lb * S * 6
+    blk_bytes = Lb * S * (2 if packed else 6)
     try:
         import psutil
         avail = psutil.virtual_memory().available
@@ -529,8 +539,12 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier):
     host_blocks = []
     for b in range(n_host):
         n = min(Lb, L - b * Lb)
-        hb = ctx.pinned_empty((Lb, S, 3), np.int16)
-        ctx.check(ctx.lib.trt_block_get_gt(ctx.h, b * Lb, n, hb.ctypes.data))       # untimed: distinct loci b*Lb .. b*Lb+n-1
+        if packed:
+            hb = ctx.pinned_empty((Lb, S, 2), np.uint8)
+            ctx.check(ctx.lib.trt_block_get_gt_packed(ctx.h, b * Lb, n, hb.ctypes.data, None))
+        else:
+            hb = ctx.pinned_empty((Lb, S, 3), np.int16)
+            ctx.check(ctx.lib.trt_block_get_gt(ctx.h, b * Lb, n, hb.ctypes.data))   # untimed: distinct loci b*Lb .. b*Lb+n-1
         host_blocks.append(hb)
     blk_tables = [synth.allele_tables(loci, (b % n_host) * Lb, min((b % n_host) * Lb + min(Lb, L - b * Lb), L)) for b in range(nblk)]
     counters = {"h2d": 0, "d2h": 0}
@@ -552,7 +566,10 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier):
             n = blk_tables[b][2].shape[0] - 1
             hb = host_blocks[b % n_host]
             c.block_begin(n, S, 2, "hipstr")
-            c.block_set_gt(hb[:n])                            # asynchronous copy from the pinned block
+            if packed:
+                c.block_set_gt_packed(hb[:n])                 # asynchronous copy from the pinned block + expansion kernel
+            else:
+                c.block_set_gt(hb[:n])
             c.block_set_alleles(*blk_tables[b])
             counters["h2d"] += hb[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
             if pending is not None:
@@ -575,6 +592,9 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier):
     ctxs[1].close()
     return {"value": world * L / (e2e_ms / 1000.0), "unit": "loci/s", "h2d_bytes_per_step": int(counters["h2d"]),
             "d2h_bytes_per_step": int(counters["d2h"]), "ms_per_step": e2e_ms,
+            "transfer_form": ("packed: uint8 [L][S][2] allele codes (trt_block_set_gt_packed; what trt_vcf_block_parse_packed "
+                              "emits from VCF text), expanded on the device" if packed else
+                              "cyvcf2 layout: int16 [L][S][3] (trt_block_set_gt)"),
             "host_blocks": "{} pinned blocks of {} loci = {} distinct loci ({:.1f} GB) of the workload resident in host memory, "
                            "streamed {} blocks per step through two ping-pong contexts".format(
                                n_host, Lb, min(n_host * Lb, L), n_host * blk_bytes / 1e9, nblk)}

@@ -104,6 +104,15 @@ int trt_block_set_gt(trt_ctx* ctx, const int16_t* gt_host);
  * buffer must stay valid until the next trt_block_begin).  Used for device-generated blocks.     */
 int trt_block_set_gt_device(trt_ctx* ctx, const int16_t* gt_dev, size_t row_pitch_bytes);
 
+/* Compact transfer form of a DIPLOID GT block whose loci have at most 253 alleles: two bytes per call — allele index
+ * 0..252, 254 = ploidy pad (-2), 255 = no-call (-1) — and, optionally, one phase bit per call (phase_bits_host
+ * [L][ceil(S/8)], bit s & 7 of byte s >> 3; NULL = every call unphased) instead of cyvcf2's three int16.  The copy is a
+ * third of the size (PCIe bounds the host-buffer path); an expansion kernel rebuilds the native rows in HBM, so every
+ * other entry point is unchanged.  trt_vcf_block_parse_packed produces this form straight from the VCF text.           */
+int trt_block_set_gt_packed(trt_ctx* ctx, const uint8_t* gt2_host /*[L][S][2]*/, const uint8_t* phase_bits_host);
+/* the block's genotypes (a locus range) back in the packed form                                                        */
+int trt_block_get_gt_packed(trt_ctx* ctx, int64_t locus0, int64_t n, uint8_t* gt2_out_host, uint8_t* phase_bits_out_host);
+
 int trt_block_set_format_i32(trt_ctx* ctx, int field_id, const int32_t* v_host /*[L][S]*/);
 int trt_block_set_format_f32(trt_ctx* ctx, int field_id, const float* v_host /*[L][S][ncol]*/, int ncol);
 int trt_block_set_format_device(trt_ctx* ctx, int field_id, const void* v_dev, int ncol, int is_float);
@@ -374,6 +383,13 @@ int         trt_vcf_block_text(const trt_vcf_block* b, const char** text, const 
 int         trt_vcf_block_parse(const trt_vcf_block* b, int ploidy, int16_t* gt_out, int n_keys,
                                 const char* const* keys, const int32_t* key_is_float, void* const* key_out,
                                 uint8_t* present, int32_t* rec_ploidy, uint8_t* rec_status);
+
+/* The same pass with GT in the packed transfer form of trt_block_set_gt_packed: gt2_out uint8 [n][S][2] (allele 0..252,
+ * 254 = ploidy pad, 255 = no-call), phase_out (may be NULL) [n][ceil(S/8)] one bit per call.  rec_status 3 = the record
+ * does not fit (an allele index above 252, or a call with more than two haplotypes): parse the block in the plain form.  */
+int         trt_vcf_block_parse_packed(const trt_vcf_block* b, uint8_t* gt2_out, uint8_t* phase_out, int n_keys,
+                                       const char* const* keys, const int32_t* key_is_float, void* const* key_out,
+                                       uint8_t* present, int32_t* rec_ploidy, uint8_t* rec_status);
 
 /* raw text of the field at position field_index of the record's FORMAT column, for every kept
  * sample, as fixed-width NUL-padded byte strings [S][width] (String FORMAT keys: vcfrecord.format

@@ -451,3 +451,47 @@ def test_packed_length_genotype_tensor(ctx, monkeypatch, L, S):
             lg = np.where(gt >= 0, ref_lens[np.clip(gt, 0, len(lens) - 1)], gt.astype(float))
             got = np.where(packed[l] >= 0, uniq[np.clip(packed[l], 0, len(uniq) - 1)], packed[l].astype(float))
             assert np.array_equal(got, lg), l
+
+
+def test_packed_gt_transfer_form_round_trip_and_same_statistics(ctx):
+    """trt_block_set_gt_packed (2 bytes per call + phase bits across PCIe, expanded on the device) rebuilds exactly the
+    rows trt_block_set_gt uploads — pads, no-calls, half calls, unphased calls, S not a multiple of 8 — the packed
+    read-back equals numpy's packing, and the statistics are identical through both transfer paths."""
+    from trtools_b200 import synth
+    from trtools_b200.block import pack_gt, unpack_gt
+    for L, S, seed in ((37, 3001, 5), (5, 8, 6), (64, 4096, 7)):
+        sl = synth.make_loci(L, seed=seed)
+        calls = synth.fill_calls(sl, S)
+        gt = calls.gt.copy()
+        rng = np.random.default_rng(seed)
+        gt[rng.random((L, S)) < 0.05, 2] = 0                      # some unphased calls
+        hap = rng.random((L, S)) < 0.03
+        gt[hap, 1] = -2                                           # haploid calls (ploidy pad)
+        g2, ph = pack_gt(gt)
+        assert np.array_equal(unpack_gt(g2, ph), gt)
+        tables = synth.allele_tables(sl)
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt(gt)
+        ctx.block_set_alleles(*tables)
+        ctx._current_block = None
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        want = {k: v.copy() for k, v in ctx.locus_stats(False, None, 0.01).items()}
+        back2, backph = ctx.block_get_gt_packed(0, L, with_phase=True)
+        assert np.array_equal(back2, g2) and np.array_equal(backph, ph)
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt_packed(g2, ph)
+        ctx.block_set_alleles(*tables)
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        assert np.array_equal(ctx.block_get_gt(0, L), gt)
+        got = ctx.locus_stats(False, None, 0.01)
+        for k in want:
+            assert np.array_equal(want[k], got[k], equal_nan=True), k
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt_packed(g2)                               # no phase plane: every call reads unphased
+        ctx.block_set_alleles(*tables)
+        unph = gt.copy()
+        unph[:, :, 2] = 0
+        assert np.array_equal(ctx.block_get_gt(0, L), unph)
+    big = np.zeros((1, 16, 3), np.int16)
+    big[0, 3, 0] = 300
+    assert pack_gt(big) is None                                   # does not fit: callers use the int16 layout

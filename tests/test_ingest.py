@@ -396,6 +396,12 @@ class _RecordingCtx:
         self.calls["gt"] = np.array(gt)
         self.calls["gt_is_view"] = gt.base is not None
 
+    def block_set_gt_packed(self, gt2, phase=None):
+        from trtools_b200.block import unpack_gt
+        self.calls["gt"] = unpack_gt(np.array(gt2), None if phase is None else np.array(phase))
+        self.calls["gt_is_view"] = gt2.base is not None
+        self.calls["packed"] = True
+
     def block_set_alleles(self, *a):
         self.calls["alleles"] = a
 
@@ -710,3 +716,37 @@ def test_many_short_records_small_blocks_is_linear(tmp_path):
     dt = time.time() - t0
     assert count == n
     assert dt < 60, "reading {} short records took {:.1f} s".format(n, dt)
+
+
+def test_packed_parse_equals_packing_the_plain_parse(tmp_path):
+    """trt_vcf_block_parse_packed writes the transfer form of trt_block_set_gt_packed straight from the text: it must
+    equal numpy's packing of the plain int16 parse (phase bits included), and flag records that do not fit."""
+    from trtools_b200.block import pack_gt
+    for path in (os.path.join(DATA, "many_samples.vcf.gz"), os.path.join(DATA, "trio_chr21_hipstr.sorted.vcf.gz")):
+        outs = []
+        for packed in (True, False):
+            v = NativeVCF(path)
+            v._packed_gt = packed
+            v._native_block_loci = 200
+            recs = [r for _, r in zip(range(200), v)]
+            nblk = recs[0]._nblk
+            nblk.parse(())
+            outs.append(nblk)
+        p, q = outs
+        assert p.gt2 is not None and q.gt2 is None and q.gt is not None
+        ok = q.status == 0
+        assert np.array_equal(p.status == 0, ok)
+        g2, ph = pack_gt(q.gt[ok])
+        assert np.array_equal(p.gt2[ok], g2) and np.array_equal(p.phase[ok], ph)
+        assert np.array_equal(p.gt[ok], q.gt[ok])                 # materialised on demand
+        for i in np.nonzero(ok)[0][:20]:
+            assert np.array_equal(p.gt_of(int(i)), q.gt_of(int(i)))
+    # an allele index above 252 falls back to the plain form for the whole run
+    alts = ",".join("AC" * (k + 2) for k in range(260))
+    text = _vcf_text(["1\t100\t.\tAC\t%s\t.\t.\tSTART=100;END=101;PERIOD=2\tGT\t0|1\t255|3\t.\t259/0" % alts])
+    path = _write(tmp_path, "wide.vcf", text)
+    v = NativeVCF(path)
+    rec = next(iter(v))
+    assert rec._nblk.gt2 is None or not rec._nblk.parsed
+    assert rec.genotype.array().tolist() == [[0, 1, 1], [255, 3, 1], [-1, -2, 0], [259, 0, 0]]
+    assert rec._nblk.gt2 is None

@@ -114,22 +114,57 @@ def record_meta(vcftype: str, rec) -> RecordMeta:
     return m
 
 
+def pack_gt(gt: np.ndarray):
+    """cyvcf2-layout diploid GT int16 [..., S, 3] -> (uint8 [..., S, 2], phase bits uint8 [..., ceil(S/8)]) or None
+    when an allele index does not fit the packed transfer form (see include/trtools_b200.h trt_block_set_gt_packed)."""
+    a = gt[..., :2]
+    if gt.shape[-1] != 3 or a.size and (int(a.max()) > 252 or int(a.min()) < -2):
+        return None
+    g2 = np.where(a >= 0, a, 256 + a).astype(np.uint8)
+    ph = np.packbits(gt[..., 2] != 0, axis=-1, bitorder="little")
+    return g2, ph
+
+
+def unpack_gt(gt2: np.ndarray, phase_bits: Optional[np.ndarray] = None) -> np.ndarray:
+    """Inverse of :func:`pack_gt` -> int16 [..., S, 3]."""
+    S = gt2.shape[-2]
+    out = np.empty(gt2.shape[:-1] + (3,), np.int16)
+    v = gt2.astype(np.int16)
+    out[..., :2] = np.where(v >= 254, v - 256, v)
+    if phase_bits is None:
+        out[..., 2] = 0
+    else:
+        out[..., 2] = np.unpackbits(phase_bits, axis=-1, count=S, bitorder="little")
+    return out
+
+
 class Block:
     """L harmonized loci resident on the GPU + the host-side tables describing them."""
 
     def __init__(self, ctx: "_lib.Context", vcftype: str, metas: List[RecordMeta], gt: Optional[np.ndarray],
-                 fmt: Optional[Dict[str, np.ndarray]] = None):
+                 fmt: Optional[Dict[str, np.ndarray]] = None, gt_packed=None):
+        """``gt``: cyvcf2-layout int16 [L][S][P+1]; or ``gt_packed`` = (uint8 [L][S][2], phase bits or None), the packed
+        transfer form the block reader parses straight from the text (a third of the host->device bytes)."""
         self.ctx = ctx
         self.vcftype = vcftype
         self.metas = metas
         L = len(metas)
         self.L = L
-        self.has_samples = gt is not None
-        if gt is None:
-            gt = np.zeros((L, 0, 3), dtype=np.int16)
-        self.gt = np.ascontiguousarray(gt, dtype=np.int16)
-        self.S = self.gt.shape[1]
-        self.P = self.gt.shape[2] - 1
+        self.gt_packed = None
+        if gt_packed is not None:
+            g2, ph = gt_packed
+            self.gt_packed = (np.ascontiguousarray(g2, dtype=np.uint8), None if ph is None else np.ascontiguousarray(ph, dtype=np.uint8))
+            self.has_samples = True
+            self.gt = None
+            self.S = self.gt_packed[0].shape[1]
+            self.P = 2
+        else:
+            self.has_samples = gt is not None
+            if gt is None:
+                gt = np.zeros((L, 0, 3), dtype=np.int16)
+            self.gt = np.ascontiguousarray(gt, dtype=np.int16)
+            self.S = self.gt.shape[1]
+            self.P = self.gt.shape[2] - 1
         # ---- allele table ----------------------------------------------------------------------
         seq_parts: List[bytes] = []
         allele_off = [0]
@@ -167,7 +202,7 @@ class Block:
         self.motifs_in = b"".join(motifs) if any_motif else None
         # ---- upload + harmonize --------------------------------------------------------------
         ctx.block_begin(L, self.S, self.P, vcftype)
-        ctx.block_set_gt(self.gt)
+        self._upload_gt()
         ctx.block_set_alleles(self.seqs, self.allele_off, self.locus_off, self.pos, self.start, self.end,
                               self.period, self.given_len, self.motifs_in)
         self.fmt = fmt or {}
@@ -195,6 +230,12 @@ class Block:
     def ctx_stats(self, use_length, nalleles_thresh, group_masks):
         self._activate()
         return self.ctx.locus_stats(use_length, group_masks, nalleles_thresh)
+
+    def _upload_gt(self):
+        if self.gt_packed is not None:
+            self.ctx.block_set_gt_packed(*self.gt_packed)
+        else:
+            self.ctx.block_set_gt(self.gt)
 
     def _upload_fmt(self):
         """numeric FORMAT arrays -> device slots (fixed slots for the HipSTR/GangSTR fields, AUX otherwise)"""
@@ -230,7 +271,7 @@ class Block:
         """Make this block the context's current block again (another block may have replaced it)."""
         if getattr(self.ctx, "_current_block", None) is not self:
             self.ctx.block_begin(self.L, self.S, self.P, self.vcftype)
-            self.ctx.block_set_gt(self.gt)
+            self._upload_gt()
             self.ctx.block_set_alleles(self.seqs, self.allele_off, self.locus_off, self.pos, self.start, self.end,
                                        self.period, self.given_len, self.motifs_in)
             self._upload_fmt()
@@ -326,7 +367,7 @@ def _native_run(records):
         slot = r.native_slot() if hasattr(r, "native_slot") else None
         if slot is None or slot[0] is not nblk or slot[1] != i0 + j:
             return None
-    if nblk.S == 0 or int(nblk.rec_ploidy[i0:i0 + len(records)].max()) != nblk.gt.shape[2] - 1:
+    if nblk.S == 0 or int(nblk.rec_ploidy[i0:i0 + len(records)].max()) != nblk.ploidy:
         return None
     return nblk, i0
 
@@ -364,7 +405,10 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
                 stacked = _stack_format(records, key)
                 if stacked is not None:
                     fmt[key] = stacked
-        blk = Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
+        if nblk.gt2 is not None:            # parsed straight into the packed transfer form
+            blk = Block(ctx, vcftype, metas, None, fmt, gt_packed=(nblk.gt2[i0:i1], nblk.phase[i0:i1]))
+        else:
+            blk = Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
         blk._records = list(records)
         return blk
     gts = []

@@ -545,8 +545,10 @@ __global__ void __launch_bounds__(128) assoc_dosage_kernel(DosageAssocParams q) 
                 if (!(ok1 && ok2)) continue;
                 const float* r1 = q.ap1 + ap_base + (size_t)s * nalt;
                 const float* r2 = q.ap2 + ap_base + (size_t)s * nalt;
-                const float ref1 = fmaxf(0.0f, __fsub_rn(1.0f, np_sum_f32_assoc(r1, nalt)));
-                const float ref2 = fmaxf(0.0f, __fsub_rn(1.0f, np_sum_f32_assoc(r2, nalt)));
+                // np.maximum(0, 1 - sum) propagates NaN (a missing AP entry)
+                const float t1 = __fsub_rn(1.0f, np_sum_f32_assoc(r1, nalt)), t2 = __fsub_rn(1.0f, np_sum_f32_assoc(r2, nalt));
+                const float ref1 = (t1 != t1) ? t1 : fmaxf(0.0f, t1);
+                const float ref2 = (t2 != t2) ? t2 : fmaxf(0.0f, t2);
                 const double x1 = (h1 >= 0) ? p.allele_len[a0 + h1] : -2.0, x2 = (h2 >= 0) ? p.allele_len[a0 + h2] : -2.0;
                 const double xr1 = (h1 >= 0) ? la[h1] : -2.0, xr2 = (h2 >= 0) ? la[h2] : -2.0;
                 double y1 = 0.0, y2 = 0.0, g = 0.0;

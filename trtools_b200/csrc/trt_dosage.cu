@@ -57,6 +57,9 @@ __device__ float np_sum_f32(const float* a, int n) {
 }
 
 __device__ __forceinline__ void flag(int32_t* err, int code) { atomicMin(err, code); }
+// np.clip / np.maximum propagate NaN (a missing AP entry makes the sample's dosage NaN); fminf / fmaxf would drop it
+__device__ __forceinline__ float clip_f32(float x, float lo, float hi) { return (x != x) ? x : fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ double clip_f64(double x, double lo, double hi) { return (x != x) ? x : fmin(fmax(x, lo), hi); }
 
 __global__ void __launch_bounds__(256) dosage_kernel(DosParams p) {
     const float NaNf = __int_as_float(0x7fc00000);
@@ -105,10 +108,10 @@ __global__ void __launch_bounds__(256) dosage_kernel(DosParams p) {
                 }
                 if (neg) flag(&p.err[l], TRT_DE_AP_NEGATIVE);
                 if (nalt > 0) {
-                    d1 = fmin(fmax(d1, 0.0), max_alt);
-                    d2 = fmin(fmax(d2, 0.0), max_alt);
+                    d1 = clip_f64(d1, 0.0, max_alt);
+                    d2 = clip_f64(d2, 0.0, max_alt);
                 }
-                const float ref1 = fminf(fmaxf(__fsub_rn(1.0f, s1), 0.0f), 1.0f), ref2 = fminf(fmaxf(__fsub_rn(1.0f, s2), 0.0f), 1.0f);
+                const float ref1 = clip_f32(__fsub_rn(1.0f, s1), 0.0f, 1.0f), ref2 = clip_f32(__fsub_rn(1.0f, s2), 0.0f, 1.0f);
                 const float reflen = (float)len[0];
                 const float rd1 = __fmul_rn(ref1, reflen), rd2 = __fmul_rn(ref2, reflen);
                 unnorm = (float)(((d1 + d2) + (double)rd1) + (double)rd2);

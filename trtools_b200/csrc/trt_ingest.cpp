@@ -873,12 +873,17 @@ int trt_vcf_block_text(const trt_vcf_block* b, const char** text, const int64_t*
     return TRT_OK;
 }
 
+// gt2_out != NULL: the packed transfer form (trt_block_set_gt_packed) instead of gt_out — two bytes per call (allele
+// 0..252, 254 = ploidy pad, 255 = no-call) and one phase bit per call.  The record is parsed into a per-thread int16
+// row (cache-resident) and packed from there; a record with an allele index above 252 or more than two haplotypes
+// gets rec_status 3 and the caller parses the block in the plain form.
 static int vcf_block_parse_impl(const trt_vcf_block* b, int ploidy, int16_t* gt_out, int n_keys, const char* const* keys,
                                 const int32_t* key_is_float, void* const* key_out, uint8_t* present, int32_t* rec_ploidy,
-                                uint8_t* rec_status) {
+                                uint8_t* rec_status, uint8_t* gt2_out = nullptr, uint8_t* phase_out = nullptr) {
     if (!b || n_keys < 0 || n_keys > 32 || !rec_ploidy || !rec_status || (n_keys && (!keys || !key_out || !present)))
         return TRT_EINVAL;
     if (gt_out && ploidy < 1) return TRT_EINVAL;
+    if (gt2_out && (gt_out || ploidy != 2)) return TRT_EINVAL;
     std::vector<KeySpec> ks((size_t)n_keys);
     for (int k = 0; k < n_keys; ++k) {
         ks[k].name = keys[k];
@@ -902,9 +907,34 @@ static int vcf_block_parse_impl(const trt_vcf_block* b, int ploidy, int16_t* gt_
         const char* ls = t + b->line_off[i];
         const char* le = (const char*)memchr(ls, '\n', (size_t)(t + b->line_off[i + 1] - ls));
         if (le > ls && le[-1] == '\r') --le;
-        LineResult r = parse_line(ls, le, b->samp_off[i], b->keep, b->n_file_samples, ploidy, gt_out, ks, i, S, pres);
+        if (!gt2_out) {
+            LineResult r = parse_line(ls, le, b->samp_off[i], b->keep, b->n_file_samples, ploidy, gt_out, ks, i, S, pres);
+            rec_ploidy[i] = r.ploidy;
+            rec_status[i] = (uint8_t)r.status;
+            return;
+        }
+        static thread_local std::vector<int16_t> row;
+        row.resize((size_t)S * 3 + 8);
+        // parse_line addresses record i of a [n][S][3] array: hand it the row shifted back by i records
+        LineResult r = parse_line(ls, le, b->samp_off[i], b->keep, b->n_file_samples, 2, row.data() - (size_t)i * S * 3, ks, i, S, pres);
         rec_ploidy[i] = r.ploidy;
         rec_status[i] = (uint8_t)r.status;
+        if (r.status != 0) return;
+        if (r.ploidy > 2) { rec_status[i] = 3; return; }
+        uint8_t* o = gt2_out + (size_t)i * S * 2;
+        const size_t pbytes = (size_t)(S + 7) / 8;
+        uint8_t* ph = phase_out ? phase_out + (size_t)i * pbytes : nullptr;
+        if (ph) memset(ph, 0, pbytes);
+        const int16_t* g = row.data();
+        bool fits = true;
+        for (int64_t s = 0; s < S; ++s, g += 3) {
+            const int a0 = g[0], a1 = g[1];
+            fits = fits && a0 <= 252 && a1 <= 252 && a0 >= -2 && a1 >= -2;
+            o[2 * s] = (uint8_t)(a0 >= 0 ? a0 : 256 + a0);          // -1 -> 255, -2 -> 254
+            o[2 * s + 1] = (uint8_t)(a1 >= 0 ? a1 : 256 + a1);
+            if (ph && g[2]) ph[s >> 3] |= (uint8_t)(1u << (s & 7));
+        }
+        if (!fits) rec_status[i] = 3;
     });
     return TRT_OK;
 }
@@ -1066,6 +1096,18 @@ int trt_vcf_block_parse(const trt_vcf_block* b, int ploidy, int16_t* gt_out, int
     try {
         return vcf_block_parse_impl(b, ploidy, gt_out, n_keys, keys, key_is_float, key_out, present, rec_ploidy,
                                     rec_status);
+    } catch (const std::exception&) {
+        return TRT_ENOMEM;
+    }
+}
+
+int trt_vcf_block_parse_packed(const trt_vcf_block* b, uint8_t* gt2_out, uint8_t* phase_out, int n_keys,
+                               const char* const* keys, const int32_t* key_is_float, void* const* key_out, uint8_t* present,
+                               int32_t* rec_ploidy, uint8_t* rec_status) {
+    if (!gt2_out) return TRT_EINVAL;
+    try {
+        return vcf_block_parse_impl(b, 2, nullptr, n_keys, keys, key_is_float, key_out, present, rec_ploidy, rec_status,
+                                    gt2_out, phase_out);
     } catch (const std::exception&) {
         return TRT_ENOMEM;
     }

@@ -34,7 +34,7 @@ struct trt_ctx {
     const int16_t* d_gt = nullptr;        // native GT rows (owned: gt_buf, or external)
     const int16_t* d_gt_active = nullptr; // what stats read: d_gt, or the masked copy after call filters
     size_t  gt_active_pitch = 0;
-    DevBuf  gt_buf, gt_masked_buf;
+    DevBuf  gt_buf, gt_masked_buf, gt_packed_buf;
     bool    have_gt = false;
     const void* d_fmt[TRT_FMT_NFIELDS] = {nullptr};
     int     fmt_ncol[TRT_FMT_NFIELDS] = {0};

@@ -92,7 +92,9 @@ class _NativeBlock:
         self.line_off = np.ctypeslib.as_array((C.c_int64 * (n + 1)).from_address(off.value)).copy()
         self.fixed_len = np.ctypeslib.as_array((C.c_int64 * n).from_address(fixed.value)).copy()
         self.S = len(vcf.samples)
-        self.gt: Optional[np.ndarray] = None       # int16 [n][S][P+1]
+        self._gt: Optional[np.ndarray] = None      # int16 [n][S][P+1] (plain parse, or materialised from the packed form)
+        self.gt2: Optional[np.ndarray] = None      # packed transfer form: uint8 [n][S][2] ...
+        self.phase: Optional[np.ndarray] = None    # ... + phase bits uint8 [n][ceil(S/8)]
         self.rec_ploidy: Optional[np.ndarray] = None
         self.status: Optional[np.ndarray] = None
         self.fmt: Dict[str, np.ndarray] = {}       # key -> [n][S]
@@ -105,6 +107,23 @@ class _NativeBlock:
                 self.h = None
         except Exception:
             pass
+
+    @property
+    def parsed(self) -> bool:
+        return self.status is not None
+
+    @property
+    def ploidy(self) -> int:
+        return 2 if self.gt2 is not None else self._gt.shape[2] - 1
+
+    @property
+    def gt(self) -> Optional[np.ndarray]:
+        """cyvcf2-layout int16 [n][S][P+1] of the whole run (materialised on demand when the run was parsed into the
+        packed transfer form: the GPU path uploads the packed arrays and never asks for this)."""
+        if self._gt is None and self.gt2 is not None:
+            from .block import unpack_gt
+            self._gt = unpack_gt(self.gt2, self.phase)
+        return self._gt
 
     # ---- text ----------------------------------------------------------------------------------
     def prefix(self, i: int) -> str:
@@ -130,7 +149,7 @@ class _NativeBlock:
     def parse(self, keys: Sequence[str] = ()):
         """One C++ pass: GT (first time) + the numeric scalar keys not parsed yet."""
         todo = [k for k in dict.fromkeys(keys) if k not in self.fmt and self._native_key(k) is not None][:32]
-        want_gt = self.gt is None
+        want_gt = not self.parsed
         if not want_gt and not todo:
             return
         n, S = self.n, self.S
@@ -143,7 +162,21 @@ class _NativeBlock:
         rec_ploidy = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.uint8)
         P = 2
-        while True:
+        gt2 = phase = None
+        if want_gt and getattr(self.vcf, "_packed_gt", True) and hasattr(self.lib, "trt_vcf_block_parse_packed"):
+            # straight into the packed transfer form (2 bytes per call + a phase bit): what the GPU block uploads
+            gt2 = np.empty((n, S, 2), dtype=np.uint8)
+            phase = np.empty((n, (S + 7) // 8), dtype=np.uint8)
+            rc = self.lib.trt_vcf_block_parse_packed(
+                self.h, gt2.ctypes.data_as(C.c_void_p), phase.ctypes.data_as(C.c_void_p), nk,
+                C.cast(c_keys, C.c_void_p), C.cast(c_isf, C.c_void_p), C.cast(c_out, C.c_void_p),
+                present.ctypes.data_as(C.c_void_p), rec_ploidy.ctypes.data_as(C.c_void_p),
+                status.ctypes.data_as(C.c_void_p))
+            if rc != _lib.TRT_OK:
+                raise OSError("trt_vcf_block_parse_packed failed ({})".format(rc))
+            if (status == 3).any():          # an allele index above 252 or a polyploid call: plain int16 parse below
+                gt2 = phase = None
+        while gt2 is None:
             gt = np.empty((n, S, P + 1), dtype=np.int16) if want_gt else None
             rc = self.lib.trt_vcf_block_parse(
                 self.h, P, None if gt is None else gt.ctypes.data_as(C.c_void_p), nk,
@@ -160,7 +193,10 @@ class _NativeBlock:
                 break
             P = pmax            # a call with more alleles than the array holds: size it and redo the pass
         if want_gt:
-            self.gt = gt
+            if gt2 is not None:
+                self.gt2, self.phase = gt2, phase
+            else:
+                self._gt = gt
             self.rec_ploidy = np.maximum(rec_ploidy, 1)
             self.status = status
         for j, k in enumerate(todo):
@@ -169,15 +205,20 @@ class _NativeBlock:
 
     def gt_of(self, i: int) -> Optional[np.ndarray]:
         """cyvcf2-layout GT of record i ([S][p+1], p = the record's ploidy) or None if flagged."""
-        if self.gt is None:
+        if not self.parsed:
             self.parse(self.vcf._prefetch)
         if self.status[i] != 0:
             return None
-        P = self.gt.shape[2] - 1
+        if self.gt2 is not None and self._gt is None:
+            from .block import unpack_gt
+            g = unpack_gt(self.gt2[i], self.phase[i])
+        else:
+            g = self.gt[i]
+        P = g.shape[1] - 1
         p = int(self.rec_ploidy[i])
         if p == P:
-            return self.gt[i]
-        return np.concatenate([self.gt[i, :, :p], self.gt[i, :, P:]], axis=1)
+            return g
+        return np.concatenate([g[:, :p], g[:, P:]], axis=1)
 
     def numeric(self, key: str, i: int) -> Optional[np.ndarray]:
         """[S][1] array of a numeric scalar FORMAT key of record i, or None (not handled natively)."""
@@ -259,7 +300,7 @@ class NativeVariant(_compat.Variant):
         if key not in self.FORMAT:
             return None
         blk = self._nblk
-        if blk.gt is None:
+        if not blk.parsed:
             blk.parse(self._vcf._prefetch)
         if blk.status[self._nidx] != 0:
             return None
@@ -281,7 +322,7 @@ class NativeVariant(_compat.Variant):
         """(block, index) if this record's GT is still the block's own parse, else None."""
         if self._gt_arr is not None and not self._gt_native:
             return None
-        if self._nblk.gt is None:
+        if not self._nblk.parsed:
             self._nblk.parse(self._vcf._prefetch)
         if self._nblk.status[self._nidx] != 0 or 'GT' not in self.FORMAT:
             return None
@@ -393,7 +434,7 @@ class NativeVCF(_compat.TextVCF):
                 raise ValueError("malformed VCF line")
             if self._sample_idx is not None:
                 # a sample subset of a ragged record fails in the text reader's constructor: same here
-                if blk.gt is None:
+                if not blk.parsed:
                     blk.parse(self._prefetch)
                 if blk.status[i] == 2:
                     var = _compat.Variant(blk.line(i), self)
