@@ -327,6 +327,51 @@ typedef struct {
 int trt_assoc_dosage_ols(trt_ctx* ctx, const int32_t* cls /*[nA]*/, const double* len_round /*[nA]*/,
                          const double* len_around /*[nA]*/, trt_assoc_dosage_out* out);
 
+/* ---- reductions of the qcSTR / compareSTR consumers --------------------------------------------
+ * qcSTR's record loop trtools/qcSTR/qcSTR.py:523-570 over the block: calls per sample (a call = not every haplotype
+ * '.', :532-535), calls per locus (chrom_calls), and the quality-field sums behind the quality plots (:536-556; a
+ * no-call or missing quality reads 0, or is skipped with ignore_no_call).  sample_mask (may be NULL): [S] bytes.
+ * The per-sample arrays are ADDED to (they persist across blocks).                                                     */
+typedef struct {
+    int64_t* sample_calls;     /* [S]                                                                                    */
+    int64_t* locus_calls;      /* [L]                                                                                    */
+    double*  sample_quality;   /* [S] sum of the quality field over the loci (NULL when quality_field < 0)               */
+    double*  locus_quality;    /* [L] mean quality over the selected samples (NaN when nothing is averaged)              */
+} trt_qc_out;
+int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host, int quality_field /* TRT_FMT_* or -1 */, int ignore_no_call,
+                  trt_qc_out* out);
+
+/* compareSTR.UpdateComparisonResults trtools/compareSTR/compareSTR.py:508-643 for the block (call set 1, resident) against
+ * a second call set of the SAME loci: gt2 in cyvcf2 layout [L][S2][P+1], the shared samples as index pairs, and per allele
+ * of set 2 its repeat-unit length and the set-1 sequence class it equals (trt_get_harmonized seq_class of that allele) or
+ * a negative id of its own.  reflen[l] = len(record1.ref_allele) / period.  Per locus: samples called in both sets,
+ * sequence / length concordant calls (haplotypes compared as unordered pairs when the calls are unphased or
+ * ignore_phasing is set), the sums of d1, d2, d1^2, d1 d2, d2^2 with d = sum over haplotypes of (length - reflen), and a
+ * status (1: a sample's ploidy differs between the sets, 2: mixed phasedness — the reference raises ValueError).         */
+typedef struct {
+    const int16_t* gt2;
+    int64_t        S2;
+    const int32_t* idx1;        /* [n_shared] sample index in set 1 ...                                                  */
+    const int32_t* idx2;        /* ... and the same sample's index in set 2                                               */
+    int64_t        n_shared;
+    const int32_t* locus_off2;  /* [L+1] allele ranges of set 2                                                           */
+    const int32_t* seq_id2;     /* [nA2]                                                                                  */
+    const double*  len2;        /* [nA2]                                                                                  */
+    const double*  reflen;      /* [L]                                                                                    */
+    int32_t        ignore_phasing;
+} trt_compare_in;
+typedef struct {
+    int64_t* numcalls;          /* [L]                                                                                    */
+    int64_t* conc_seq;          /* [L]                                                                                    */
+    int64_t* conc_len;          /* [L]                                                                                    */
+    double*  len_sums;          /* [L][5]                                                                                 */
+    int32_t* status;            /* [L]                                                                                    */
+    int64_t* sample_numcalls;   /* [n_shared] ADDED to                                                                    */
+    int64_t* sample_conc_seq;   /* [n_shared] ADDED to                                                                    */
+    int64_t* sample_conc_len;   /* [n_shared] ADDED to                                                                    */
+} trt_compare_out;
+int trt_compare(trt_ctx* ctx, const trt_compare_in* in, trt_compare_out* out);
+
 /* ---- synthetic blocks (bench / parity at sizes that do not fit through PCIe) ------------------
  * Device twin of trtools_b200/synth.py::fill_calls — bit-identical arrays.                        */
 int trt_synth_fill(trt_ctx* ctx, uint64_t seed, int64_t locus_offset, int64_t n_loci, int64_t n_samples,

@@ -332,6 +332,8 @@ def main():
         section_edge()
     if want("dosage"):
         section_dosage()
+    if want("reduce"):
+        section_reduce()
 
 
 def section_many():
@@ -538,6 +540,75 @@ def section_dosage():
     extra["assoc_dosage_subset"] = associatr_dosage_loci(good, [traits], non_major_cutoff=20, sample_mask=mask)
     save_loci(os.path.join(HERE, "dosage_synth.npz"), sloci, extra=extra, info_keys=INFO_KEYS)
     print("dosage fixtures", len(loci), len(sloci))
+
+
+def section_reduce():
+    # ---- 8. qcSTR / compareSTR reductions ---------------------------------------------------------
+    import trtools.compareSTR.compareSTR as rcmp
+    import trtools.utils.mergeutils as rmerge  # noqa: F401  (imported by compareSTR; keeps the shims honest)
+    # qcSTR: the record loop of qcSTR.main (qcSTR.py:523-570) on the first 150 records of many_samples.vcf.gz
+    many = os.path.join(DATA, "many_samples.vcf.gz")
+    vcf = cyvcf2.VCF(many)
+    rng = np.random.default_rng(5)
+    sample_index = rng.random(len(vcf.samples)) < 0.7
+    out = {"sample_index": sample_index.tolist(), "runs": {}}
+    recs = [rec for _, rec in zip(range(150), vcf)]
+    for ignore in (False, True):
+        sample_calls = np.zeros(int(sample_index.sum()))
+        per_sample_total_qual = np.zeros(int(sample_index.sum()))
+        locus_calls, per_locus = [], []
+        for rec in recs:
+            tr = trh.HarmonizeRecord("hipstr", rec)
+            idx_gts = tr.GetGenotypeIndicies()[sample_index, :-1]
+            nocall = np.full((1, idx_gts.shape[1]), -1)
+            calls = ~np.all(idx_gts == nocall, axis=1)
+            sample_calls += calls
+            locus_calls.append(int(np.sum(calls)))
+            q = tr.GetQualityScores()[sample_index, :]
+            q[~calls] = np.nan
+            if not ignore:
+                q[np.isnan(q)] = 0
+                per_sample_total_qual += q.reshape(-1)
+                per_locus.append(f(np.mean(q)))
+            else:
+                qi = ~np.isnan(q)
+                per_sample_total_qual[qi.reshape(-1)] += q[qi].reshape(-1)
+                per_locus.append(f(np.mean(q[qi])))
+        out["runs"]["ignore" if ignore else "zero"] = dict(sample_calls=sample_calls.tolist(), locus_calls=locus_calls,
+                                                            per_sample_total_qual=[f(x) for x in per_sample_total_qual],
+                                                            per_locus=per_locus)
+    # compareSTR: the unmodified UpdateComparisonResults on the reference's own pair of GangSTR call sets
+    CS = os.path.join(SV, "compareSTR_vcfs")
+    f1 = copy_data(os.path.join(CS, "test_gangstr1.vcf.gz"))
+    f2 = copy_data(os.path.join(CS, "test_gangstr2.vcf.gz"))
+    v1, v2 = cyvcf2.VCF(f1), cyvcf2.VCF(f2)
+    shared = [s for s in v1.samples if s in v2.samples]
+    idxs = [np.array([v1.samples.index(s) for s in shared]), np.array([v2.samples.index(s) for s in shared])]
+    r2 = {(r.CHROM, r.POS): r for r in v2}
+    pairs = []
+    for r in v1:
+        if (r.CHROM, r.POS) in r2:
+            pairs.append((r, r2[(r.CHROM, r.POS)]))
+    cmp_out = {"shared": shared, "n_pairs": len(pairs), "positions": [[p[0].CHROM, int(p[0].POS)] for p in pairs], "runs": {}}
+    for ignore_phasing in (False, True):
+        overall = {"ALL": rcmp.NewOverallPeriod([], [])}
+        locus = {"chrom": [], "start": [], "numcalls": [], "metric-conc-seq": [], "metric-conc-len": []}
+        sample = {"numcalls": np.zeros(len(shared)), "conc-seq-count": np.zeros(len(shared)), "conc-len-count": np.zeros(len(shared))}
+        errors = []
+        for a, b in pairs:
+            t1, t2 = trh.HarmonizeRecord("gangstr", a), trh.HarmonizeRecord("gangstr", b)
+            try:
+                rcmp.UpdateComparisonResults(t1, t2, idxs, ignore_phasing, False, [], [], 0, overall, locus, sample, None)
+            except ValueError as e:
+                errors.append([a.CHROM, int(a.POS), str(e)])
+        cmp_out["runs"]["ignore_phasing" if ignore_phasing else "phased"] = dict(
+            overall={k: f(v) for k, v in overall["ALL"]["ALL"].items()},
+            locus={k: [f(x) if not isinstance(x, str) else x for x in v] for k, v in locus.items()},
+            sample={k: v.tolist() for k, v in sample.items()}, errors=errors)
+    out["compare"] = cmp_out
+    with open(os.path.join(HERE, "reductions.json"), "w") as fh:
+        json.dump(out, fh)
+    print("reductions", len(recs), cmp_out["n_pairs"], {k: len(v["errors"]) for k, v in cmp_out["runs"].items()})
 
 
 def associatr_dosage_loci(loci, trait_arrays, non_major_cutoff=20, sample_mask=None):

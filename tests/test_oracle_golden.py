@@ -333,3 +333,70 @@ def test_oracle_assoc_dosage_rows_match_reference(golden_dir, key, cutoff, use_m
         if w[5] != "nan":
             for c in (6, 7, 8):
                 assert abs(float(g[c]) - float(w[c])) <= 1e-9 * abs(float(w[c])), (i, c)
+
+
+# ---- qcSTR / compareSTR reductions ---------------------------------------------------------------
+def _records(path, vcftype, limit=None):
+    from oracle.records import locus_from_variant
+    from trtools_b200.cyvcf2_compat import TextVCF
+    v = TextVCF(path)
+    out = []
+    for i, rec in enumerate(v):
+        if limit is not None and i >= limit:
+            break
+        out.append(locus_from_variant(rec, vcftype, numeric_fmt={"Q", "DP"}))
+    return out, v.samples
+
+
+def test_oracle_qc_reductions_match_reference(golden_dir, data_dir):
+    from oracle import reduce as ored
+    want = json.load(open(os.path.join(golden_dir, "reductions.json")))
+    loci, _ = _records(os.path.join(data_dir, "many_samples.vcf.gz"), "hipstr", 150)
+    idx = np.array(want["sample_index"], dtype=bool)
+    for key, ignore in (("zero", False), ("ignore", True)):
+        got = ored.qc_reduce(loci, idx, "Q", ignore)
+        w = want["runs"][key]
+        assert got["sample_calls"].tolist() == w["sample_calls"]
+        assert got["locus_calls"] == w["locus_calls"]
+        assert_close_list(got["per_sample_total_qual"].tolist(), w["per_sample_total_qual"], "per-sample quality " + key, rel=1e-12)
+        assert_close_list(got["per_locus"], w["per_locus"], "per-locus quality " + key, rel=1e-7)
+
+
+@pytest.mark.parametrize("key,ignore_phasing", [("phased", False), ("ignore_phasing", True)])
+def test_oracle_compare_reductions_match_reference(golden_dir, data_dir, key, ignore_phasing):
+    from oracle import reduce as ored
+    want = json.load(open(os.path.join(golden_dir, "reductions.json")))["compare"]
+    l1, s1 = _records(os.path.join(data_dir, "test_gangstr1.vcf.gz"), "gangstr")
+    l2, s2 = _records(os.path.join(data_dir, "test_gangstr2.vcf.gz"), "gangstr")
+    by_pos = {(l.chrom, l.pos): l for l in l2}
+    shared = want["shared"]
+    idxs = [np.array([s1.index(s) for s in shared]), np.array([s2.index(s) for s in shared])]
+    w = want["runs"][key]
+    sample = {k: np.zeros(len(shared)) for k in ("numcalls", "conc-seq-count", "conc-len-count")}
+    tot = np.zeros(5)
+    n_seq = n_len = n_calls = 0
+    rows = []
+    for a in l1:
+        b = by_pos.get((a.chrom, a.pos))
+        if b is None:
+            continue
+        r = ored.compare_locus(a, otrh.harmonize(a), b, otrh.harmonize(b), idxs, ignore_phasing)
+        if r is None:
+            continue
+        rows.append((r["numcalls"], float(np.sum(r["conc_seq"])) / r["numcalls"], float(np.sum(r["conc_len"])) / r["numcalls"]))
+        sample["numcalls"] += r["both"]
+        sample["conc-seq-count"][r["both"]] += r["conc_seq"]
+        sample["conc-len-count"][r["both"]] += r["conc_len"]
+        tot += r["sums"]
+        n_calls += r["numcalls"]
+        n_seq += int(np.sum(r["conc_seq"]))
+        n_len += int(np.sum(r["conc_len"]))
+    assert [x[0] for x in rows] == [int(x) for x in w["locus"]["numcalls"]]
+    assert_close_list([x[1] for x in rows], w["locus"]["metric-conc-seq"], "conc-seq", rel=1e-12)
+    assert_close_list([x[2] for x in rows], w["locus"]["metric-conc-len"], "conc-len", rel=1e-12)
+    for k in sample:
+        assert sample[k].tolist() == w["sample"][k], k
+    o = w["overall"]
+    assert (n_calls, n_seq, n_len) == (int(o["numcalls"]), int(o["conc_seq_count"]), int(o["conc_len_count"]))
+    assert_close_list(tot.tolist(), [o["total_len_1"], o["total_len_2"], o["total_len_11"], o["total_len_12"], o["total_len_22"]],
+                      "length sums", rel=1e-9)

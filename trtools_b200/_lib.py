@@ -34,7 +34,7 @@ EXPORTS = [
     "trt_block_set_format_f32", "trt_block_set_format_device", "trt_block_set_alleles",
     "trt_harmonize", "trt_get_harmonized", "trt_pack_length_genotypes", "trt_get_packed_gt",
     "trt_locus_stats", "trt_genotype_counts", "trt_call_filters", "trt_locus_filters", "trt_assoc_set_design", "trt_assoc_ols",
-    "trt_block_set_ap", "trt_dosages", "trt_assoc_dosage_ols",
+    "trt_block_set_ap", "trt_dosages", "trt_assoc_dosage_ols", "trt_qc_reduce", "trt_compare",
     "trt_synth_fill", "trt_block_get_gt", "trt_block_get_format",
     "trt_dist_unique_id", "trt_dist_init", "trt_dist_allgather_f64", "trt_dist_allreduce_sum_i64",
     "trt_dist_allreduce_sum_f64", "trt_dist_allreduce_max_f64", "trt_dist_barrier", "trt_dist_gather_region",
@@ -100,6 +100,23 @@ class AssocDosageOut(C.Structure):
                 ("std_g", C.c_void_p), ("ncovars_code", C.c_void_p), ("class_stats", C.c_void_p), ("length_stats", C.c_void_p)]
 
 
+class QcOut(C.Structure):
+    _fields_ = [("sample_calls", C.c_void_p), ("locus_calls", C.c_void_p), ("sample_quality", C.c_void_p),
+                ("locus_quality", C.c_void_p)]
+
+
+class CompareIn(C.Structure):
+    _fields_ = [("gt2", C.c_void_p), ("S2", C.c_int64), ("idx1", C.c_void_p), ("idx2", C.c_void_p), ("n_shared", C.c_int64),
+                ("locus_off2", C.c_void_p), ("seq_id2", C.c_void_p), ("len2", C.c_void_p), ("reflen", C.c_void_p),
+                ("ignore_phasing", C.c_int32)]
+
+
+class CompareOut(C.Structure):
+    _fields_ = [("numcalls", C.c_void_p), ("conc_seq", C.c_void_p), ("conc_len", C.c_void_p), ("len_sums", C.c_void_p),
+                ("status", C.c_void_p), ("sample_numcalls", C.c_void_p), ("sample_conc_seq", C.c_void_p),
+                ("sample_conc_len", C.c_void_p)]
+
+
 DOSAGE_TYPES = {"bestguess": 0, "beagleap": 1, "bestguess_norm": 2, "beagleap_norm": 3}
 DE_OK, DE_NO_AP, DE_AP_SUM, DE_AP_NEGATIVE, DE_NORM_RANGE = range(5)
 
@@ -153,6 +170,8 @@ def load():
         "trt_block_set_ap": (i32, [vp, vp, vp, vp]),
         "trt_dosages": (i32, [vp, i32, vp, vp]),
         "trt_assoc_dosage_ols": (i32, [vp, vp, vp, vp, C.POINTER(AssocDosageOut)]),
+        "trt_qc_reduce": (i32, [vp, vp, i32, i32, C.POINTER(QcOut)]),
+        "trt_compare": (i32, [vp, C.POINTER(CompareIn), C.POINTER(CompareOut)]),
         "trt_synth_fill": (i32, [vp, u64, i64, i64, i64, vp, u32, u32, i32]),
         "trt_block_get_gt": (i32, [vp, i64, i64, vp]),
         "trt_block_get_format": (i32, [vp, i32, i64, i64, vp]),
@@ -481,6 +500,38 @@ class Context:
                    length_stats=np.empty((L, 5)))
         out = AssocDosageOut(**{k: _ptr(v) for k, v in res.items()})
         self.check(self.lib.trt_assoc_dosage_ols(self.h, _ptr(c), _ptr(lr), _ptr(la), C.byref(out)))
+        return res
+
+    def qc_reduce(self, sample_calls: np.ndarray, sample_quality: Optional[np.ndarray], sample_mask: Optional[np.ndarray],
+                  quality_field: int = -1, ignore_no_call: bool = False) -> dict:
+        """qcSTR's per-block reductions (trt_qc_reduce).  ``sample_calls`` int64 [S] and ``sample_quality`` float64 [S]
+        are accumulated in place over the whole sample axis (entries outside ``sample_mask`` stay untouched)."""
+        assert sample_calls.dtype == np.int64 and sample_calls.shape == (self.S,)
+        m = None if sample_mask is None else _c(sample_mask, np.uint8)
+        res = dict(locus_calls=np.empty(self.L, np.int64), locus_quality=np.empty(self.L, np.float64))
+        out = QcOut(sample_calls=_ptr(sample_calls), locus_calls=_ptr(res["locus_calls"]),
+                    sample_quality=_ptr(sample_quality) if quality_field >= 0 else None,
+                    locus_quality=_ptr(res["locus_quality"]) if quality_field >= 0 else None)
+        self.check(self.lib.trt_qc_reduce(self.h, _ptr(m), int(quality_field), 1 if ignore_no_call else 0, C.byref(out)))
+        return res
+
+    def compare(self, gt2: np.ndarray, idx1, idx2, locus_off2, seq_id2, len2, reflen, ignore_phasing: bool,
+                sample_numcalls: np.ndarray, sample_conc_seq: np.ndarray, sample_conc_len: np.ndarray) -> dict:
+        """compareSTR.UpdateComparisonResults for the current block against a second call set (trt_compare)."""
+        g2 = _c(gt2, np.int16)
+        assert g2.ndim == 3 and g2.shape[0] == self.L and g2.shape[2] == self.P + 1, (g2.shape, self.L, self.P)
+        i1, i2 = _c(idx1, np.int32), _c(idx2, np.int32)
+        lo2, sid, l2, rl = _c(locus_off2, np.int32), _c(seq_id2, np.int32), _c(len2, np.float64), _c(reflen, np.float64)
+        n = len(i1)
+        for a in (sample_numcalls, sample_conc_seq, sample_conc_len):
+            assert a.dtype == np.int64 and a.shape == (n,)
+        res = dict(numcalls=np.empty(self.L, np.int64), conc_seq=np.empty(self.L, np.int64), conc_len=np.empty(self.L, np.int64),
+                   len_sums=np.empty((self.L, 5)), status=np.empty(self.L, np.int32))
+        cin = CompareIn(gt2=_ptr(g2), S2=g2.shape[1], idx1=_ptr(i1), idx2=_ptr(i2), n_shared=n, locus_off2=_ptr(lo2),
+                        seq_id2=_ptr(sid), len2=_ptr(l2), reflen=_ptr(rl), ignore_phasing=1 if ignore_phasing else 0)
+        out = CompareOut(sample_numcalls=_ptr(sample_numcalls), sample_conc_seq=_ptr(sample_conc_seq),
+                         sample_conc_len=_ptr(sample_conc_len), **{k: _ptr(v) for k, v in res.items()})
+        self.check(self.lib.trt_compare(self.h, C.byref(cin), C.byref(out)))
         return res
 
     def synth_fill(self, seed, locus_offset, cum_freq, miss_thresh, half_thresh, with_format=True):

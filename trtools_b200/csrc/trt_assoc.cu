@@ -487,24 +487,27 @@ struct DosageAssocParams {
 };
 
 __device__ float np_sum_f32_assoc(const float* a, int n) {
-    // np.sum over the contiguous last axis of a float32 array: first element + pairwise_sum of the rest
-    if (n <= 0) return 0.0f;
-    const float* b = a + 1;
-    const int m = n - 1;
-    float res;
-    if (m < 8) {
-        res = 0.0f;
-        for (int i = 0; i < m; i++) res = __fadd_rn(res, b[i]);
-    } else {
-        float r[8];
-        for (int j = 0; j < 8; j++) r[j] = b[j];
-        int i = 8;
-        for (; i < m - (m % 8); i += 8)
-            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], b[i + j]);
-        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < m; i++) res = __fadd_rn(res, b[i]);
+    // np.sum over the contiguous last axis of a float32 array = numpy's pairwise_sum of the row
+    // (numpy/_core/src/umath/loops_utils.h.src): plain left-to-right loop below 8 elements, eight partial sums
+    // combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) up to 128, halves split at a multiple of 8 above
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
     }
-    return __fadd_rn(a[0], res);
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], a[i + j]);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_sum_f32_assoc(a, n2), np_sum_f32_assoc(a + n2, n - n2));
 }
 
 template <int KP>
@@ -540,7 +543,8 @@ __global__ void __launch_bounds__(128) assoc_dosage_kernel(DosageAssocParams q) 
                 if (s >= p.S) continue;
                 const int r = p.row_of_sample[s];
                 if (r < 0) continue;
-                const int h1 = row[s * 3], h2 = row[s * 3 + 1];
+                // (a block of single-haplotype records — in practice records whose every call is a lone '.' — reads a pad)
+                const int h1 = row[s * (p.P + 1)], h2 = (p.P >= 2) ? row[s * (p.P + 1) + 1] : -2;
                 const bool ok1 = (h1 >= 0 && h1 < A) || h1 == -2, ok2 = (h2 >= 0 && h2 < A) || h2 == -2;
                 if (!(ok1 && ok2)) continue;
                 const float* r1 = q.ap1 + ap_base + (size_t)s * nalt;
@@ -815,7 +819,7 @@ int trt_assoc_dosage_ols(trt_ctx* ctx, const int32_t* cls, const double* len_rou
         return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_dosage_ols: needs a block with GT and trt_harmonize");
     if (!ctx->have_design) return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_dosage_ols: call trt_assoc_set_design first");
     if (!ctx->have_ap) return trt_set_error(ctx, TRT_ESTATE, "trt_assoc_dosage_ols: call trt_block_set_ap first");
-    if (ctx->P != 2) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_dosage_ols: Beagle AP1/AP2 dosages are diploid");
+    if (ctx->P > 2) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_dosage_ols: Beagle AP1/AP2 dosages are diploid (block ploidy %d)", ctx->P);
     if (!out || !cls || !len_round || !len_around) return trt_set_error(ctx, TRT_EINVAL, "trt_assoc_dosage_ols: NULL argument");
     TRT_CUDA(cudaSetDevice(ctx->device));
     const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA, n = ctx->n_design;

@@ -276,8 +276,11 @@ __global__ void assoc_reduce_mom_kernel(const double* __restrict__ part, int nse
 // rows (z = (c_1 .. c_{K-1}, y)) is tiled into 4 x 4 register blocks of its upper triangle: a lane owns one block of
 // one sample group, so a z-row staged in shared memory costs 4 LDS.128 for 16 DFMAs, and G = 32 / blocks samples
 // are processed by the warp at once (K = 12: 6 blocks, 5 samples in flight).  Groups are summed by shuffles per locus.
+#ifndef TRT_DD_MINBLOCKS
+#define TRT_DD_MINBLOCKS 2
+#endif
 template <int NB>
-__global__ void __launch_bounds__(256, 2) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
+__global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
     constexpr int kBlocks = NB * (NB + 1) / 2;
     constexpr int kG = 32 / kBlocks;             // samples processed concurrently by a warp
     // z-rows staged per round trip to L2: a 32-chunk window holds ~15 uncalled samples at 2 % missingness, so ~20 slots
@@ -498,7 +501,7 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
         TRT_KERNEL_CHECK();
     }
     {
-        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)sms * 8));
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)sms * 4 * TRT_DD_MINBLOCKS));
         if (K <= 4) assoc_downdate_mask_kernel<1><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
         else if (K <= 8) assoc_downdate_mask_kernel<2><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
         else if (K <= 12) assoc_downdate_mask_kernel<3><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);

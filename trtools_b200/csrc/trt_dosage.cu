@@ -34,26 +34,28 @@ struct DosParams {
     int32_t* err;              // [L], pre-set to INT_MAX; the smallest code wins (the reference's check order)
 };
 
-// np.sum over the contiguous last axis of a float32 array: first element + pairwise_sum of the rest
-// (numpy/_core/src/umath/loops_utils.h.src: plain loop below 8 elements, eight partial sums up to 128)
 __device__ float np_sum_f32(const float* a, int n) {
-    if (n <= 0) return 0.0f;
-    const float* b = a + 1;
-    const int m = n - 1;
-    float res;
-    if (m < 8) {
-        res = 0.0f;
-        for (int i = 0; i < m; i++) res = __fadd_rn(res, b[i]);
-    } else {
-        float r[8];
-        for (int j = 0; j < 8; j++) r[j] = b[j];
-        int i = 8;
-        for (; i < m - (m % 8); i += 8)
-            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], b[i + j]);
-        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < m; i++) res = __fadd_rn(res, b[i]);
+    // np.sum over the contiguous last axis of a float32 array = numpy's pairwise_sum of the row
+    // (numpy/_core/src/umath/loops_utils.h.src): plain left-to-right loop below 8 elements, eight partial sums
+    // combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) up to 128, halves split at a multiple of 8 above
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
     }
-    return __fadd_rn(a[0], res);
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], a[i + j]);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_sum_f32(a, n2), np_sum_f32(a + n2, n - n2));
 }
 
 __device__ __forceinline__ void flag(int32_t* err, int code) { atomicMin(err, code); }

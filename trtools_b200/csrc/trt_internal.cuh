@@ -62,6 +62,7 @@ struct trt_ctx {
 
     // Beagle allele probabilities (FORMAT AP1 / AP2) and the dosage tensor (trt_dosage.cu)
     DevBuf  ap1, ap2, has_ap, dosage, dosage_err, dos_meta, dos_out;
+    DevBuf  reduce_buf;              // scratch of the qcSTR / compareSTR reductions (trt_reduce.cu)
     bool    have_ap = false;
 
     // stats scratch (device)

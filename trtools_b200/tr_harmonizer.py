@@ -418,9 +418,6 @@ class TRRecord:
             common.WARNING(msg)
             return np.array([np.nan] * n)
 
-        beagle = dosagetype in (TRDosageTypes.beagleap, TRDosageTypes.beagleap_norm)
-        if beagle and self._blk.P != 2:
-            return fail("{}:{} Beagle AP1/AP2 dosages need diploid genotypes".format(self.chrom, self.pos))
         values, codes = self._blk.dosages(dosagetype.value)
         code = int(codes[self._l])
         if code == _lib.DE_NO_AP:
