@@ -338,8 +338,11 @@ typedef struct {
     double*  sample_quality;   /* [S] sum of the quality field over the loci (NULL when quality_field < 0)               */
     double*  locus_quality;    /* [L] mean quality over the selected samples (NaN when nothing is averaged)              */
 } trt_qc_out;
-int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host, int quality_field /* TRT_FMT_* or -1 */, int ignore_no_call,
-                  trt_qc_out* out);
+int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host,
+                  const int32_t* rec_ploidy_host /* [L] GT columns of each record's own cyvcf2 array, or NULL = block ploidy:
+                                                    a '.' of a record narrower than the block is [-1, -2] in the block but
+                                                    [-1] to the reference's np.all(idx_gts == -1) */,
+                  int quality_field /* TRT_FMT_* or -1 */, int ignore_no_call, trt_qc_out* out);
 
 /* compareSTR.UpdateComparisonResults trtools/compareSTR/compareSTR.py:508-643 for the block (call set 1, resident) against
  * a second call set of the SAME loci: gt2 in cyvcf2 layout [L][S2][P+1], the shared samples as index pairs, and per allele

@@ -138,7 +138,7 @@ def test_assoc_dosage_kernel_vs_reference_and_oracle_on_synthetic(golden_dir, ct
     meta = associaTR.dosage_classes(blk)
     res = ctx.assoc_dosage_ols(*meta)
     buf = io.StringIO()
-    associaTR._write_dosage_block(buf, blk, res, meta, design.pheno_std, cutoff)
+    associaTR._write_dosage_block(buf, blk, res, meta, design.pheno_std, cutoff, np.asarray(design.sample_filter, dtype=bool))
     want_lines = extra[key].splitlines()[1:]
     got_lines = buf.getvalue().splitlines()
     assert len(got_lines) == len(want_lines) == len(good)

@@ -247,6 +247,43 @@ def test_stats_vs_oracle_on_synthetic(ctx, L, S):
                     assert_close(st[stat][g, j], want[stat][g], what + " " + stat, abs_tol=1e-300)
 
 
+@pytest.mark.parametrize("L,S,G", [(48, 10000, 5), (40, 2055, 3), (12, 40000, 4), (150, 4100, 7)])
+def test_sample_groups_share_scan_passes(ctx, L, S, G):
+    """statSTR --samples with several files: the scan counts up to three sample groups per read of the genotypes.
+    Overlapping, full and empty groups against the oracle, and against one-group-at-a-time runs of the same block."""
+    from oracle import stats as ostats, trh as otrh
+    from oracle.records import synth_to_loci, LocusAsVariant
+    from trtools_b200 import synth, block
+    from trtools_b200.statSTR import _locus_keys, _afreq_string
+    sl = synth.make_loci(L, seed=S + G)
+    calls = synth.fill_calls(sl, S)
+    loci = synth_to_loci(sl, calls, with_fmt=False)
+    blk = block.build_block(ctx, "hipstr", [LocusAsVariant(l) for l in loci])
+    rng = np.random.default_rng(S * 7 + G)
+    gm = np.stack([(rng.random(S) < p).astype(np.uint8) for p in np.linspace(0.15, 0.9, G)])
+    gm[1] = 1                                  # everyone
+    if G > 3:
+        gm[3] = 0                              # nobody
+    st = blk.stats(True, 0.01, gm)
+    for g in range(G):
+        alone = blk.stats(True, 0.01, gm[g:g + 1])
+        for key in ("ac", "n_called", "nalleles", "het", "hwep", "mean", "var", "mode", "entropy", "thresh"):
+            a, b = np.asarray(st[key][g]), np.asarray(alone[key][0])
+            assert np.array_equal(a, b, equal_nan=True), (key, g)
+    groups = [gm[g].astype(bool) for g in range(G)]
+    for j in range(0, L, max(1, L // 6)):
+        h = otrh.harmonize(loci[j])
+        want = ostats.locus_stats(h, loci[j].gt, ostats.STAT_ORDER, groups, uselength=True)
+        keys = _locus_keys(blk, j, True)
+        sl_ = blk.allele_slice(j)
+        for g in range(G):
+            what = "L{} S{} locus {} g {}".format(L, S, j, g)
+            assert _afreq_string(keys, st["ac"][g, sl_], True) == want["acount"][g], what
+            assert int(st["n_called"][g, j]) == want["numcalled"][g], what
+            for stat in ("thresh", "hwep", "het", "entropy", "mean", "mode", "var"):
+                assert_close(st[stat][g, j], want[stat][g], what + " " + stat, abs_tol=1e-300)
+
+
 def test_many_alleles_and_odd_shapes(ctx):
     """Loci beyond the fast path's allele budget (generic kernel), haploid and triploid blocks."""
     from oracle import stats as ostats, trh as otrh

@@ -81,7 +81,7 @@ def test_synthetic_vcf_text_end_to_end(tmp_path):
     recs = list(v)
     blk = _block.build_block(ctx, "hipstr", recs, ("DP", "DFLANKINDEL", "Q"))
     assert np.array_equal(blk.gt, calls.gt)
-    assert blk.gt.base is not None                      # the reader's slab itself
+    assert blk.gt_packed is not None and blk.gt_packed[0].base is not None     # the reader's packed slab itself
     st = blk.stats(False)
     # the same block from the generator's arrays, through the record-free upload path
     metas = [_block.record_meta("hipstr", r) for r in recs]

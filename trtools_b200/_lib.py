@@ -170,7 +170,7 @@ def load():
         "trt_block_set_ap": (i32, [vp, vp, vp, vp]),
         "trt_dosages": (i32, [vp, i32, vp, vp]),
         "trt_assoc_dosage_ols": (i32, [vp, vp, vp, vp, C.POINTER(AssocDosageOut)]),
-        "trt_qc_reduce": (i32, [vp, vp, i32, i32, C.POINTER(QcOut)]),
+        "trt_qc_reduce": (i32, [vp, vp, vp, i32, i32, C.POINTER(QcOut)]),
         "trt_compare": (i32, [vp, C.POINTER(CompareIn), C.POINTER(CompareOut)]),
         "trt_synth_fill": (i32, [vp, u64, i64, i64, i64, vp, u32, u32, i32]),
         "trt_block_get_gt": (i32, [vp, i64, i64, vp]),
@@ -503,7 +503,7 @@ class Context:
         return res
 
     def qc_reduce(self, sample_calls: np.ndarray, sample_quality: Optional[np.ndarray], sample_mask: Optional[np.ndarray],
-                  quality_field: int = -1, ignore_no_call: bool = False) -> dict:
+                  quality_field: int = -1, ignore_no_call: bool = False, rec_ploidy: Optional[np.ndarray] = None) -> dict:
         """qcSTR's per-block reductions (trt_qc_reduce).  ``sample_calls`` int64 [S] and ``sample_quality`` float64 [S]
         are accumulated in place over the whole sample axis (entries outside ``sample_mask`` stay untouched)."""
         assert sample_calls.dtype == np.int64 and sample_calls.shape == (self.S,)
@@ -512,7 +512,9 @@ class Context:
         out = QcOut(sample_calls=_ptr(sample_calls), locus_calls=_ptr(res["locus_calls"]),
                     sample_quality=_ptr(sample_quality) if quality_field >= 0 else None,
                     locus_quality=_ptr(res["locus_quality"]) if quality_field >= 0 else None)
-        self.check(self.lib.trt_qc_reduce(self.h, _ptr(m), int(quality_field), 1 if ignore_no_call else 0, C.byref(out)))
+        rp = None if rec_ploidy is None else _c(rec_ploidy, np.int32)
+        assert rp is None or rp.shape == (self.L,)
+        self.check(self.lib.trt_qc_reduce(self.h, _ptr(m), _ptr(rp), int(quality_field), 1 if ignore_no_call else 0, C.byref(out)))
         return res
 
     def compare(self, gt2: np.ndarray, idx1, idx2, locus_off2, seq_id2, len2, reflen, ignore_phasing: bool,

@@ -161,7 +161,7 @@ def _r2(n, sx, sxx, sy, syy, sxy):
         return np.float64(min(max(r, -1.0), 1.0)) ** 2
 
 
-def _write_dosage_block(outfile, blk, res, meta, pheno_std, non_major_cutoff):
+def _write_dosage_block(outfile, blk, res, meta, pheno_std, non_major_cutoff, sample_filter):
     """TSV rows of one GPU block with --beagle-dosages (reference associaTR.py:252-304, lafg.py:175-238)."""
     cls, len_round, _ = meta
     lafg = load_and_filter_genotypes
@@ -183,6 +183,10 @@ def _write_dosage_block(outfile, blk, res, meta, pheno_std, non_major_cutoff):
                 r2[key] = _r2(2 * n, cs[c, 2], cs[c, 2], cs[c, 0], cs[c, 1], cs[c, 3])
         ls = res["length_stats"][l]
         length_r2 = _r2(2 * n, ls[0], ls[1], ls[2], ls[3], ls[4])
+        if n > 0 and any(cs[j, 2] == 2 * n for j in reps):          # every best guess the same length: see lafg
+            tr = trh.TRRecord._from_block(blk, l, blk._records[l])
+            curr = sample_filter & tr.GetCalledSamples()
+            length_r2 = lafg.flat_locus_length_r2(tr, curr, lafg.dosage_arrays(tr, curr, [float(x) for x in lr]))
         m = blk.metas[l]
         motif = blk.motif(l)
         details = [motif, str(len(motif)), str(round(float(blk.h["allele_len"][sl.start]), lafg.allele_len_precision)),
@@ -237,7 +241,7 @@ def perform_gwas_helper(outfile, all_samples, get_genotype_iter, phenotype_name,
             blk.ensure_ap()
             meta = dosage_classes(blk)
             res = ctx.assoc_dosage_ols(*meta)
-            write = lambda f: _write_dosage_block(f, blk, res, meta, pheno_std, source.non_major_cutoff)
+            write = lambda f: _write_dosage_block(f, blk, res, meta, pheno_std, source.non_major_cutoff, sample_filter)
         else:
             res = ctx.assoc_ols(source.non_major_cutoff)
             write = lambda f: _write_block(f, blk, res, pheno_std, source.non_major_cutoff)

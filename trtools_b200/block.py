@@ -141,6 +141,13 @@ def unpack_gt(gt2: np.ndarray, phase_bits: Optional[np.ndarray] = None) -> np.nd
 class Block:
     """L harmonized loci resident on the GPU + the host-side tables describing them."""
 
+    @property
+    def gt(self) -> np.ndarray:
+        """cyvcf2-layout int16 [L][S][P+1] on the host (expanded on first use when the block was built packed)."""
+        if self._gt is None:
+            self._gt = unpack_gt(*self.gt_packed)
+        return self._gt
+
     def __init__(self, ctx: "_lib.Context", vcftype: str, metas: List[RecordMeta], gt: Optional[np.ndarray],
                  fmt: Optional[Dict[str, np.ndarray]] = None, gt_packed=None):
         """``gt``: cyvcf2-layout int16 [L][S][P+1]; or ``gt_packed`` = (uint8 [L][S][2], phase bits or None), the packed
@@ -155,16 +162,17 @@ class Block:
             g2, ph = gt_packed
             self.gt_packed = (np.ascontiguousarray(g2, dtype=np.uint8), None if ph is None else np.ascontiguousarray(ph, dtype=np.uint8))
             self.has_samples = True
-            self.gt = None
+            self._gt = None
             self.S = self.gt_packed[0].shape[1]
             self.P = 2
         else:
             self.has_samples = gt is not None
             if gt is None:
                 gt = np.zeros((L, 0, 3), dtype=np.int16)
-            self.gt = np.ascontiguousarray(gt, dtype=np.int16)
-            self.S = self.gt.shape[1]
-            self.P = self.gt.shape[2] - 1
+            self._gt = np.ascontiguousarray(gt, dtype=np.int16)
+            self.S = self._gt.shape[1]
+            self.P = self._gt.shape[2] - 1
+        self.rec_ploidy = None       # int32 [L]: GT columns of each record's own array (None: all as wide as the block)
         # ---- allele table ----------------------------------------------------------------------
         seq_parts: List[bytes] = []
         allele_off = [0]
@@ -235,7 +243,7 @@ class Block:
         if self.gt_packed is not None:
             self.ctx.block_set_gt_packed(*self.gt_packed)
         else:
-            self.ctx.block_set_gt(self.gt)
+            self.ctx.block_set_gt(self._gt)
 
     def _upload_fmt(self):
         """numeric FORMAT arrays -> device slots (fixed slots for the HipSTR/GangSTR fields, AUX otherwise)"""
@@ -410,6 +418,7 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
         else:
             blk = Block(ctx, vcftype, metas, nblk.gt[i0:i1], fmt)
         blk._records = list(records)
+        blk.rec_ploidy = np.ascontiguousarray(nblk.rec_ploidy[i0:i1], dtype=np.int32)
         return blk
     gts = []
     has_samples = True
@@ -435,4 +444,6 @@ def build_block(ctx, vcftype: str, records: Sequence[Any], fmt_keys: Sequence[st
             fmt[key] = stacked
     blk = Block(ctx, vcftype, metas, gt, fmt)
     blk._records = list(records)
+    if gts and gt is not None:
+        blk.rec_ploidy = np.array([g.shape[1] - 1 for g in gts], dtype=np.int32)
     return blk

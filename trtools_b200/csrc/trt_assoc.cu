@@ -703,7 +703,7 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
     if (L > 0) {
         ctx->want_ac_part = true;
         const bool all_samples = (n == S);
-        int rc = trt_run_scan(ctx, all_samples ? nullptr : (const uint8_t*)ctx->group_masks.p, 0, 1);
+        int rc = trt_run_scan(ctx, all_samples ? nullptr : (const uint8_t*)ctx->group_masks.p, 1);
         ctx->want_ac_part = false;
         if (rc != TRT_OK) return rc;
         AssocParams ap;

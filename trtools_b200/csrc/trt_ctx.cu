@@ -185,7 +185,7 @@ void trt_destroy(trt_ctx* ctx) {
                       &ctx->start, &ctx->end, &ctx->period, &ctx->given_len, &ctx->motif_in, &ctx->allele_len, &ctx->trim_off,
                       &ctx->trim_len, &ctx->len_class, &ctx->seq_class, &ctx->len_order, &ctx->seq_order, &ctx->hrun,
                       &ctx->hflags, &ctx->motif, &ctx->motif_off, &ctx->packed, &ctx->ac, &ctx->ac_part, &ctx->lc, &ctx->group_masks,
-                      &ctx->stat_f64, &ctx->stat_i32, &ctx->work_counter, &ctx->scan_lists, &ctx->ap1, &ctx->ap2, &ctx->has_ap, &ctx->dosage,
+                      &ctx->stat_f64, &ctx->stat_i32, &ctx->work_counter, &ctx->scan_lists, &ctx->scan_gbits, &ctx->ap1, &ctx->ap2, &ctx->has_ap, &ctx->dosage,
                       &ctx->dosage_err, &ctx->dos_meta, &ctx->dos_out, &ctx->reduce_buf, &ctx->cf_specs, &ctx->call_mask, &ctx->trig,
                       &ctx->samp_counts, &ctx->samp_dp, &ctx->misc, &ctx->covars, &ctx->outcome, &ctx->sample_index,
                       &ctx->design_row_of_sample, &ctx->assoc_acc, &ctx->assoc_out, &ctx->assoc_tot, &ctx->assoc_zt, &ctx->assoc_fast_tiles,

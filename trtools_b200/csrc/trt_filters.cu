@@ -925,7 +925,7 @@ int trt_locus_filters(trt_ctx* ctx, const trt_locus_filter_spec* specs, int n_sp
     TRT_CUDA(cudaMemsetAsync(ctx->lc.p, 0, (size_t)L * TRT_LC_N * 8 + 16, ctx->stream));
     if (L > 0) {
         TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
-        TRT_TRY(trt_run_scan(ctx, nullptr, 0, 1));
+        TRT_TRY(trt_run_scan(ctx, nullptr, 1));
         TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
         TRT_TRY(trt_run_epilogue(ctx, use_length, 0.01, 1));
         const double* f = (const double*)ctx->stat_f64.p;

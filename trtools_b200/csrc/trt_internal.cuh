@@ -68,6 +68,7 @@ struct trt_ctx {
     // stats scratch (device)
     DevBuf  ac, ac_part, lc, group_masks, stat_f64, stat_i32, work_counter;
     DevBuf  scan_lists;              // per-tier locus lists of the current block (trt_scan.cu)
+    DevBuf  scan_gbits;              // one byte per sample: membership bits of the sample groups of one scan pass
     bool    scan_lists_valid = false;
     int     scan_tier_off[8] = {0};   // list offsets per tier (+ end)
     int     scan_n_tier[8] = {0}, scan_max_in_tier[8] = {0}, scan_rows_in_tier[8] = {0}, scan_lists_fast = -1;

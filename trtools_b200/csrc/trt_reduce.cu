@@ -27,6 +27,7 @@ struct QcParams {
     const float* q;             // [L][S][ncol] or null
     int ncol;
     int ignore_no_call;
+    const int32_t* rec_ploidy;       // [L] GT columns of the record itself (cyvcf2's array width - 1), or null: P
     unsigned long long* sample_calls;   // [S]
     double* sample_quality;             // [S]
     unsigned long long* locus_calls;    // [L]
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(256) qc_reduce_kernel(QcParams p) {
         if (in) {
             const int16_t* g = (const int16_t*)((const char*)p.gt + (size_t)l * p.pitch) + s * (p.P + 1);
             bool all_missing = true;
-            for (int h = 0; h < p.P; h++) all_missing = all_missing && (g[h] == -1);
+            const int width = p.rec_ploidy ? p.rec_ploidy[l] : p.P;      // block columns past the record's own are pads
+            for (int h = 0; h < width; h++) all_missing = all_missing && (g[h] == -1);
             call = !all_missing;
             if (p.q) {
                 float x = p.q[((size_t)l * p.S + s) * p.ncol];
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(256) compare_conc_kernel(CmpParams p) {
 
 extern "C" {
 
-int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host, int quality_field, int ignore_no_call, trt_qc_out* out) {
+int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host, const int32_t* rec_ploidy_host, int quality_field,
+                  int ignore_no_call, trt_qc_out* out) {
     if (!ctx || !ctx->block_open || !ctx->have_gt) return trt_set_error(ctx, TRT_ESTATE, "trt_qc_reduce: needs a block with GT");
     if (!out) return trt_set_error(ctx, TRT_EINVAL, "trt_qc_reduce: out is NULL");
     if (quality_field >= TRT_FMT_NFIELDS || (quality_field >= 0 && (!ctx->d_fmt[quality_field] || !ctx->fmt_is_float[quality_field])))
@@ -227,7 +230,8 @@ int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host, int quality_fie
     const int64_t L = ctx->L, S = ctx->S;
     // scratch: [S] sample calls (u64) | [S] sample quality (f64) | [L] locus calls | [L] quality sums | [L] quality counts
     const size_t bytes = ((size_t)2 * S + (size_t)3 * L) * 8 + 64;
-    TRT_TRY(trt_ensure(ctx, ctx->reduce_buf, bytes + (size_t)S + 16));
+    const size_t mask_bytes = ((size_t)S + 15) & ~(size_t)15;
+    TRT_TRY(trt_ensure(ctx, ctx->reduce_buf, bytes + mask_bytes + (size_t)L * 4 + 16));
     char* base = (char*)ctx->reduce_buf.p;
     TRT_CUDA(cudaMemsetAsync(base, 0, bytes, ctx->stream));
     QcParams p;
@@ -239,6 +243,16 @@ int trt_qc_reduce(trt_ctx* ctx, const uint8_t* sample_mask_host, int quality_fie
         uint8_t* dm = (uint8_t*)(base + bytes);
         if (S) TRT_CUDA(cudaMemcpyAsync(dm, sample_mask_host, (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
         p.mask = dm;
+    }
+    p.rec_ploidy = nullptr;
+    if (rec_ploidy_host && L) {
+        for (int64_t l = 0; l < L; l++)
+            if (rec_ploidy_host[l] < 1 || rec_ploidy_host[l] > ctx->P)
+                return trt_set_error(ctx, TRT_EINVAL, "trt_qc_reduce: rec_ploidy[%lld] = %d outside 1..%d", (long long)l,
+                                     rec_ploidy_host[l], ctx->P);
+        int32_t* dp = (int32_t*)(base + bytes + mask_bytes);
+        TRT_CUDA(cudaMemcpyAsync(dp, rec_ploidy_host, (size_t)L * 4, cudaMemcpyHostToDevice, ctx->stream));
+        p.rec_ploidy = dp;
     }
     p.q = quality_field >= 0 ? (const float*)ctx->d_fmt[quality_field] : nullptr;
     p.ncol = quality_field >= 0 ? ctx->fmt_ncol[quality_field] : 1;

@@ -137,12 +137,14 @@ template <> struct CellTraits<uint8_t> {
     }
 };
 
-struct __align__(16) PairHeader {
+constexpr int kPMaxSampleGroups = 3;           // sample groups (statSTR --samples) counted in ONE pass over the GT rows
+template <int NGH>
+struct __align__(16) PairHeaderT {
     uint64_t full[kPMaxStages];
     uint64_t empty[kPMaxStages];
-    uint64_t part_free[2];                              // the epilogue warp has consumed partial[parity]
-    unsigned int partial[2][kPMaxGroups][kPMaxBins];    // per-group sums, double buffered by locus parity
-    unsigned int T[kPMaxBins];                          // the epilogue warp's CTA-wide pair table
+    uint64_t part_free[2];                                   // the epilogue warp has consumed partial[parity]
+    unsigned int partial[2][NGH][kPMaxGroups][kPMaxBins];    // per-fold-group sums of each sample group, double buffered by locus parity
+    unsigned int T[kPMaxBins];                               // the epilogue warp's CTA-wide pair table
 };
 
 // bin of an UNORDERED digit pair (genotypes are unphased for every statistic): tri(hi, lo), lo <= hi
@@ -177,8 +179,14 @@ __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.
 // A digit of a haplotype: pad(-2) -> 0, no-call(-1) -> 1, allele a -> a+2, anything else -> D-1 ("bad").  Both digits of
 // a call come from ONE add-and-min on the packed int16 pair (VIADDMNMX.U16x2) and the bin from ONE dot product
 // (IDP.2A: d0*D + d1) while D^2 <= kSquareRows rows; wider loci use UNORDERED pairs (D(D+1)/2 rows).
-template <bool MASKED, typename CELL>
+// NG = 0: every sample counts.  NG = 1..3: that many SAMPLE GROUPS (statSTR --samples, associaTR's design membership)
+// are counted in this one pass: p.gbits holds one byte per sample whose bit (p.group0 + g) says "in group g", every
+// group has its own table, and a call bumps the tables of the groups its sample belongs to — the GT rows are read once
+// however many groups there are (the reference re-derives its counts per group, statSTR.py:520-542).
+template <int NG, typename CELL>
 __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, int tier, int max_rows, int stages) {
+    constexpr int NGH = NG > 0 ? NG : 1;
+    typedef PairHeaderT<NGH> PairHeader;
     using CT = CellTraits<CELL>;
     constexpr int kGW = CT::kGroupWarps;                  // warps per fold group
     constexpr int kGT = kGW * 32;                         // threads per fold group
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
         mbar_fence_init();
     }
     {
-        const int words = (max_rows + 1) * kRowWords;
+        const int words = NGH * (max_rows + 1) * kRowWords;
         for (int i = tid; i < words; i += kPThreads) ((uint32_t*)table)[i] = 0u;
     }
     __syncthreads();
@@ -253,55 +261,59 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
             named_sync(1 + parity, kPT + 32);            // the fold groups' partials of this locus are complete
             const int nb = (int)(D * (D + 1u) / 2u);
             unsigned int* T = hdr->T;
-            long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
-            for (int b0 = 0; b0 < nb; b0 += 32) {
-                const int b = min(b0 + lane, nb - 1);
-                unsigned hi = (unsigned)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
-                while (tri(hi + 1u, 0u) <= (unsigned)b) hi++;
-                while (tri(hi, 0u) > (unsigned)b) hi--;
-                const unsigned lo = (unsigned)b - tri(hi, 0u);
-                unsigned t = 0;
+            for (int sg = 0; sg < NGH; sg++) {
+                long long n_full = 0, n_non = 0, n_pad = 0, h_idx = 0, h_len = 0, h_seq = 0, n_bad = 0;
+                for (int b0 = 0; b0 < nb; b0 += 32) {
+                    const int b = min(b0 + lane, nb - 1);
+                    unsigned hi = (unsigned)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+                    while (tri(hi + 1u, 0u) <= (unsigned)b) hi++;
+                    while (tri(hi, 0u) > (unsigned)b) hi--;
+                    const unsigned lo = (unsigned)b - tri(hi, 0u);
+                    unsigned t = 0;
 #pragma unroll
-                for (int g = 0; g < kGroups; g++) {
-                    const unsigned int* pp = hdr->partial[parity][g];
-                    if (sq) t += pp[hi * D + lo] + ((lo != hi) ? pp[lo * D + hi] : 0u);
-                    else t += pp[b];
+                    for (int g = 0; g < kGroups; g++) {
+                        const unsigned int* pp = hdr->partial[parity][sg][g];
+                        if (sq) t += pp[hi * D + lo] + ((lo != hi) ? pp[lo * D + hi] : 0u);
+                        else t += pp[b];
+                    }
+                    if (b0 + lane < nb) T[b] = t;
+                    const int cl_lo = __shfl_sync(0xffffffffu, cl, lo), cl_hi = __shfl_sync(0xffffffffu, cl, hi);
+                    const int cq_lo = __shfl_sync(0xffffffffu, cq, lo), cq_hi = __shfl_sync(0xffffffffu, cq, hi);
+                    const long long n = (b0 + lane < nb) ? (long long)t : 0;
+                    const bool bad = (hi == Dm1);                        // lo <= hi
+                    const bool m1 = (lo == 1u) | (hi == 1u) | bad;
+                    const bool vlo = (lo >= 2u) & (lo < Dm1), vhi = (hi >= 2u) & (hi < Dm1);
+                    if (bad) n_bad += n;
+                    if (vlo | vhi) n_non += n;
+                    if (!m1) {
+                        n_full += n;
+                        if (lo == 0u) n_pad += n;
+                        if (lo == hi) h_idx += n;
+                        if (cl_lo == cl_hi) h_len += n;
+                        if (cq_lo == cq_hi) h_seq += n;
+                    }
                 }
-                if (b0 + lane < nb) T[b] = t;
-                const int cl_lo = __shfl_sync(0xffffffffu, cl, lo), cl_hi = __shfl_sync(0xffffffffu, cl, hi);
-                const int cq_lo = __shfl_sync(0xffffffffu, cq, lo), cq_hi = __shfl_sync(0xffffffffu, cq, hi);
-                const long long n = (b0 + lane < nb) ? (long long)t : 0;
-                const bool bad = (hi == Dm1);                        // lo <= hi
-                const bool m1 = (lo == 1u) | (hi == 1u) | bad;
-                const bool vlo = (lo >= 2u) & (lo < Dm1), vhi = (hi >= 2u) & (hi < Dm1);
-                if (bad) n_bad += n;
-                if (vlo | vhi) n_non += n;
-                if (!m1) {
-                    n_full += n;
-                    if (lo == 0u) n_pad += n;
-                    if (lo == hi) h_idx += n;
-                    if (cl_lo == cl_hi) h_len += n;
-                    if (cq_lo == cq_hi) h_seq += n;
+                __syncwarp();
+                if (sg == NGH - 1 && lane == 0) mbar_arrive(&hdr->part_free[parity]);   // partial[parity] may be refilled (locus + 2)
+                n_full = warp_sum_ll(n_full); n_non = warp_sum_ll(n_non); n_pad = warp_sum_ll(n_pad);
+                h_idx = warp_sum_ll(h_idx); h_len = warp_sum_ll(h_len); h_seq = warp_sum_ll(h_seq);
+                n_bad = warp_sum_ll(n_bad);
+                const size_t og = (size_t)(p.group0 + sg);
+                if (lane == 0) {
+                    long long* o = p.lc + og * p.lc_stride + l * TRT_LC_N;
+                    o[TRT_LC_NFULL] = n_full; o[TRT_LC_NNONSTRICT] = n_non; o[TRT_LC_NPAD] = n_pad;
+                    o[TRT_LC_HOM_IDX] = h_idx; o[TRT_LC_HOM_LEN] = h_len; o[TRT_LC_HOM_SEQ] = h_seq;
+                    o[6] = n_bad; o[7] = 0;
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hdr->part_free[parity]);     // partial[parity] may be refilled (locus + 2)
-            n_full = warp_sum_ll(n_full); n_non = warp_sum_ll(n_non); n_pad = warp_sum_ll(n_pad);
-            h_idx = warp_sum_ll(h_idx); h_len = warp_sum_ll(h_len); h_seq = warp_sum_ll(h_seq);
-            n_bad = warp_sum_ll(n_bad);
-            if (lane == 0) {
-                long long* o = p.lc + l * TRT_LC_N;
-                o[TRT_LC_NFULL] = n_full; o[TRT_LC_NNONSTRICT] = n_non; o[TRT_LC_NPAD] = n_pad;
-                o[TRT_LC_HOM_IDX] = h_idx; o[TRT_LC_HOM_LEN] = h_len; o[TRT_LC_HOM_SEQ] = h_seq;
-                o[6] = n_bad; o[7] = 0;
-            }
-            for (int a = lane; a < A; a += 32) {
-                const unsigned d = (unsigned)a + 2u;
-                unsigned cnt = 2u * T[tri(d, d)];
-                for (unsigned e = 0; e < d; e++) cnt += T[tri(d, e)];
-                for (unsigned e = d + 1u; e < D; e++) cnt += T[tri(e, d)];
-                p.ac[a0 + a] = (int)cnt;
-                if (p.ac_part) p.ac_part[a0 + a] = (int)(T[tri(d, 1u)] + T[tri(Dm1, d)]);   // partner '.' or invalid
+                for (int a = lane; a < A; a += 32) {
+                    const unsigned d = (unsigned)a + 2u;
+                    unsigned cnt = 2u * T[tri(d, d)];
+                    for (unsigned e = 0; e < d; e++) cnt += T[tri(d, e)];
+                    for (unsigned e = d + 1u; e < D; e++) cnt += T[tri(e, d)];
+                    p.ac[og * p.ac_stride + a0 + a] = (int)cnt;
+                    if (p.ac_part) p.ac_part[og * p.ac_stride + a0 + a] = (int)(T[tri(d, 1u)] + T[tri(Dm1, d)]);   // partner '.' or invalid
+                }
+                __syncwarp();
             }
             __syncwarp();
             parity ^= 1;
@@ -312,6 +324,7 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
     // ===== consumers =====
     const int group = warp / kGW, gwarp = warp % kGW;
     CELL* my = table + CT::cell_index(warp, lane);
+    const size_t gstride = (size_t)(max_rows + 1) * kPT;      // cells per sample group's table
     int stage = 0;
     uint32_t phase = 0;
     int parity = 0;
@@ -366,17 +379,27 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
                 const bool returned = __all_sync(0xffffffffu, any != 0xffffffffu);
                 if (lane == 0 && returned) mbar_arrive(&hdr->empty[stage_used]);
             }
-            if (MASKED || c >= nfull) {
+            if (c >= nfull) {
                 const int left = (int)min((int64_t)kPChunkCalls, p.S - (int64_t)c * kPChunkCalls) - s_rel0;   // live calls of this thread
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    bool live = j < left;
-                    if (MASKED) live = live && p.mask[live ? (int64_t)c * kPChunkCalls + s_rel0 + j : 0] != 0;
-                    idx[j] = live ? idx[j] : trash;
+                for (int j = 0; j < 8; j++) idx[j] = (j < left) ? idx[j] : trash;
+            }
+            if (NG == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) bump2<CELL>(my, idx[j], idx[j + 1]);
+            } else {
+                // membership bytes of this thread's 8 samples (zero beyond S), one 64-bit load from the L1/L2-resident array
+                const uint64_t mb = *reinterpret_cast<const uint64_t*>(p.gbits + (size_t)c * kPChunkCalls + s_rel0) >> p.group0;
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    CELL* mine = my + (size_t)g * gstride;
+                    unsigned ig[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) ig[j] = ((mb >> (8 * j + g)) & 1ull) ? idx[j] : trash;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) bump2<CELL>(mine, ig[j], ig[j + 1]);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) bump2<CELL>(my, idx[j], idx[j + 1]);
         }
 
         // ---- each fold GROUP reduces and zeroes its own 128-byte slice of every row (group-local barrier only) ------
@@ -384,20 +407,23 @@ __global__ void __launch_bounds__(kPThreads, 1) scan_pairs_kernel(ScanParams p, 
         named_sync(3 + group, kGT);
         // partial[parity] was last used two loci ago: wait until the epilogue warp has consumed it
         if (n_locus >= 2u) mbar_wait(&hdr->part_free[parity], ((n_locus >> 1) - 1u) & 1u);
-        unsigned int* part = hdr->partial[parity][group];
-        for (int b = gwarp * 32 + lane; b < nrows; b += kGT) {
-            // this group's cells of row b = 128 B = 8 x 16 B; lanes own different rows (same bank offset), so each
-            // rotates its 16-byte slot: the 8 lanes of a quarter-warp hit 8 different bank groups (conflict-free)
-            uint4* rowp = (uint4*)((uint32_t*)table + (size_t)b * kRowWords + group * 32);
-            unsigned sum = 0;
+        for (int sg = 0; sg < NGH; sg++) {
+            unsigned int* part = hdr->partial[parity][sg][group];
+            uint32_t* tab = (uint32_t*)(table + (size_t)sg * gstride);
+            for (int b = gwarp * 32 + lane; b < nrows; b += kGT) {
+                // this group's cells of row b = 128 B = 8 x 16 B; lanes own different rows (same bank offset), so each
+                // rotates its 16-byte slot: the 8 lanes of a quarter-warp hit 8 different bank groups (conflict-free)
+                uint4* rowp = (uint4*)(tab + (size_t)b * kRowWords + group * 32);
+                unsigned sum = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int kk = (k + lane) & 7;
-                const uint4 x = rowp[kk];
-                rowp[kk] = make_uint4(0u, 0u, 0u, 0u);
-                sum += CT::sum4(x);
+                for (int k = 0; k < 8; k++) {
+                    const int kk = (k + lane) & 7;
+                    const uint4 x = rowp[kk];
+                    rowp[kk] = make_uint4(0u, 0u, 0u, 0u);
+                    sum += CT::sum4(x);
+                }
+                part[b] = sum;
             }
-            part[b] = sum;
         }
         // the words just folded/zeroed hold every group warp's cells: none may start the next locus earlier
         named_sync(3 + group, kGT);
@@ -561,12 +587,22 @@ int set_smem(trt_ctx* ctx, K kernel, size_t smem) {
     return TRT_OK;
 }
 
+__global__ void group_bits_kernel(const uint8_t* __restrict__ masks, int64_t S, int64_t S_pad, int g0, int ng, uint8_t* __restrict__ bits) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S_pad) return;
+    unsigned b = 0;
+    if (s < S)
+        for (int g = 0; g < ng; g++) b |= (masks[(size_t)(g0 + g) * S + s] != 0 ? 1u : 0u) << g;
+    bits[s] = (uint8_t)b;
+}
+
 }  // namespace
 
-// run the scan (all tiers) for one group mask; results into ctx->ac / ctx->lc at group g
-int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
-    (void)G;
+// The GT scan of the block for G sample groups.  Pair-table tiers: up to kPMaxSampleGroups groups per pass over the GT
+// rows (as many as leave the TMA ring three stages of shared memory); wide / generic tiers: one launch per group.
+int trt_run_scan(trt_ctx* ctx, const uint8_t* d_masks, int G) {
     const int64_t L = ctx->L, S = ctx->S, nA = ctx->nA;
+    if (G < 1 || (G > 1 && !d_masks)) return trt_set_error(ctx, TRT_EINVAL, "scan: %d groups need their masks", G);
     ScanParams sp;
     sp.gt = ctx->d_gt_active;
     sp.pitch = ctx->gt_active_pitch;
@@ -579,10 +615,14 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     sp.len_rank = (const int32_t*)ctx->stat_i32.p;
     sp.seq_rank = (const int32_t*)ctx->stat_i32.p + nA;
     sp.hflags = (const int32_t*)ctx->hflags.p;
-    sp.mask = d_mask;
-    sp.ac = (int32_t*)ctx->ac.p + (size_t)g * nA;
-    sp.ac_part = ctx->want_ac_part ? (int32_t*)ctx->ac_part.p + (size_t)g * nA : nullptr;
-    sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
+    sp.mask = nullptr;
+    sp.gbits = nullptr;
+    sp.group0 = 0;
+    sp.ac_stride = (size_t)nA;
+    sp.lc_stride = (size_t)L * TRT_LC_N;
+    sp.ac = (int32_t*)ctx->ac.p;
+    sp.ac_part = ctx->want_ac_part ? (int32_t*)ctx->ac_part.p : nullptr;
+    sp.lc = (long long*)ctx->lc.p;
     const bool fast = (ctx->P == 2 && S >= kMinFastSamples);
     sp.fast_enabled = fast ? 1 : 0;
     sp.list = nullptr;
@@ -623,50 +663,90 @@ int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G) {
     const size_t row_bytes_gt = (((size_t)S * 6 + 15) & ~size_t(15));
     const int nchunks_p = (int)((row_bytes_gt + kPChunkBytes - 1) / kPChunkBytes);
     const bool cells8 = nchunks_p <= kPMaxChunks8 && !getenv("TRT_SCAN_CELLS16");
+    const bool masked = d_masks != nullptr;
+    const int64_t S_pad = (int64_t)nchunks_p * kPChunkCalls + 8;
+    if (masked && (n_tier[TIER_PAIRS_A] || n_tier[TIER_PAIRS_B])) TRT_TRY(trt_ensure(ctx, ctx->scan_gbits, (size_t)S_pad + 16));
     for (int t = TIER_PAIRS_A; t <= TIER_PAIRS_B; t++) {
         if (!n_tier[t]) continue;
         sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[t];
         sp.n_list = n_tier[t];
         const int rows = rows_in_tier[t];
-        const size_t table = (size_t)(rows + 1) * kPT * (cells8 ? 1 : 2);
-        int stages = (int)((smem_limit - sizeof(PairHeader) - table - 256) / kPChunkBytes);
-        stages = std::max(kPMinStages, std::min(kPMaxStages, stages));
-        if (const char* e = getenv("TRT_SCAN_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
-        const size_t smem = (size_t)stages * kPChunkBytes + sizeof(PairHeader) + table;
-        if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
+        const size_t table1 = (size_t)(rows + 1) * kPT * (cells8 ? 1 : 2);
+        auto stages_for = [&](int ngh) {
+            const size_t hdr = ngh == 1 ? sizeof(PairHeaderT<1>) : (ngh == 2 ? sizeof(PairHeaderT<2>) : sizeof(PairHeaderT<3>));
+            const long long left = (long long)smem_limit - (long long)hdr - (long long)table1 * ngh - 256;
+            return std::make_pair((int)std::min<long long>(kPMaxStages, left / kPChunkBytes), hdr);
+        };
+        // sample groups per pass: as many (<= 3) as leave the ring its minimum depth
+        int per_pass = 1;
+        if (masked)
+            for (int n = std::min(G, kPMaxSampleGroups); n >= 1; n--)
+                if (stages_for(n).first >= kPMinStages) { per_pass = n; break; }
         const int grid = std::min(grid_persist, n_tier[t]);
-#define LAUNCH_PAIRS(M, C)                                                                        \
+        for (int g0 = 0; g0 < G; g0 += per_pass) {
+            const int ng = masked ? std::min(per_pass, G - g0) : 0;
+            const int ngh = std::max(ng, 1);
+            auto sh = stages_for(ngh);
+            int stages = std::max(kPMinStages, sh.first);
+            if (const char* e = getenv("TRT_SCAN_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
+            const size_t smem = (size_t)stages * kPChunkBytes + sh.second + table1 * ngh;
+            if (smem > smem_limit) return trt_set_error(ctx, TRT_ENOMEM, "scan: %zu B of shared memory needed, %zu available", smem, smem_limit);
+            if (masked) {
+                // bit g of byte s = "sample s is in group g0 + g" for this pass' groups
+                group_bits_kernel<<<(unsigned)((S_pad + 255) / 256), 256, 0, ctx->stream>>>(d_masks, S, S_pad, g0, ng, (uint8_t*)ctx->scan_gbits.p);
+                TRT_KERNEL_CHECK();
+                sp.gbits = (const uint8_t*)ctx->scan_gbits.p;
+            }
+            sp.group0 = 0;                                   // bits of this pass start at 0 ...
+            sp.ac = (int32_t*)ctx->ac.p + (size_t)g0 * nA;   // ... and its outputs at group g0
+            sp.ac_part = ctx->want_ac_part ? (int32_t*)ctx->ac_part.p + (size_t)g0 * nA : nullptr;
+            sp.lc = (long long*)ctx->lc.p + (size_t)g0 * L * TRT_LC_N;
+#define LAUNCH_PAIRS(N, C)                                                                        \
     do {                                                                                          \
-        TRT_TRY(set_smem(ctx, scan_pairs_kernel<M, C>, smem));                                    \
-        scan_pairs_kernel<M, C><<<grid, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);     \
+        TRT_TRY(set_smem(ctx, scan_pairs_kernel<N, C>, smem));                                    \
+        scan_pairs_kernel<N, C><<<grid, kPThreads, smem, ctx->stream>>>(sp, t, rows, stages);     \
     } while (0)
-        if (d_mask) {
-            if (cells8) LAUNCH_PAIRS(true, uint8_t); else LAUNCH_PAIRS(true, uint16_t);
-        } else {
-            if (cells8) LAUNCH_PAIRS(false, uint8_t); else LAUNCH_PAIRS(false, uint16_t);
-        }
+#define LAUNCH_NG(N)                                                               \
+    do {                                                                           \
+        if (cells8) LAUNCH_PAIRS(N, uint8_t); else LAUNCH_PAIRS(N, uint16_t);      \
+    } while (0)
+            switch (ng) {
+                case 0: LAUNCH_NG(0); break;
+                case 1: LAUNCH_NG(1); break;
+                case 2: LAUNCH_NG(2); break;
+                default: LAUNCH_NG(3); break;
+            }
+#undef LAUNCH_NG
 #undef LAUNCH_PAIRS
-        TRT_KERNEL_CHECK();
-    }
-    if (n_tier[TIER_WIDE]) {
-        sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[TIER_WIDE];
-        sp.n_list = n_tier[TIER_WIDE];
-        const int amax = max_in_tier[TIER_WIDE];
-        const size_t smem = (size_t)kWStages * kWChunkBytes + sizeof(WideHeader) + (size_t)amax * kWT * 2;
-        if (d_mask) {
-            TRT_TRY(set_smem(ctx, scan_wide_kernel<true>, smem));
-            scan_wide_kernel<true><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
-        } else {
-            TRT_TRY(set_smem(ctx, scan_wide_kernel<false>, smem));
-            scan_wide_kernel<false><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
+            TRT_KERNEL_CHECK();
         }
-        TRT_KERNEL_CHECK();
     }
-    if (n_tier[TIER_GENERIC]) {
-        const int warps_per_block = 8;
-        const int64_t blocks = std::min<int64_t>((L + warps_per_block - 1) / warps_per_block, (int64_t)ctx->sm_count * 8);
-        scan_generic_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, ctx->stream>>>(sp);
-        TRT_KERNEL_CHECK();
+    // wide / generic tiers: one launch per group under its byte mask
+    for (int g = 0; g < G; g++) {
+        sp.mask = masked ? d_masks + (size_t)g * S : nullptr;
+        sp.ac = (int32_t*)ctx->ac.p + (size_t)g * nA;
+        sp.ac_part = ctx->want_ac_part ? (int32_t*)ctx->ac_part.p + (size_t)g * nA : nullptr;
+        sp.lc = (long long*)ctx->lc.p + (size_t)g * L * TRT_LC_N;
+        if (n_tier[TIER_WIDE]) {
+            sp.list = (const int32_t*)ctx->scan_lists.p + ctx->scan_tier_off[TIER_WIDE];
+            sp.n_list = n_tier[TIER_WIDE];
+            const int amax = max_in_tier[TIER_WIDE];
+            const size_t smem = (size_t)kWStages * kWChunkBytes + sizeof(WideHeader) + (size_t)amax * kWT * 2;
+            if (masked) {
+                TRT_TRY(set_smem(ctx, scan_wide_kernel<true>, smem));
+                scan_wide_kernel<true><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
+            } else {
+                TRT_TRY(set_smem(ctx, scan_wide_kernel<false>, smem));
+                scan_wide_kernel<false><<<std::min(grid_persist, n_tier[TIER_WIDE]), kWThreads, smem, ctx->stream>>>(sp, amax);
+            }
+            TRT_KERNEL_CHECK();
+        }
+        if (n_tier[TIER_GENERIC]) {
+            const int warps_per_block = 8;
+            const int64_t blocks = std::min<int64_t>((L + warps_per_block - 1) / warps_per_block, (int64_t)ctx->sm_count * 8);
+            scan_generic_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, ctx->stream>>>(sp);
+            TRT_KERNEL_CHECK();
+        }
     }
     return TRT_OK;
 }

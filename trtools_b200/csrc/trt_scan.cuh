@@ -13,8 +13,12 @@ struct ScanParams {
     const int32_t* len_rank;
     const int32_t* seq_rank;
     const int32_t* hflags;
-    const uint8_t* mask;   // [S] bytes or null
-    int32_t* ac;           // [nA]
+    const uint8_t* mask;   // [S] bytes or null: the ONE group the wide / generic tiers count in this launch
+    const uint8_t* gbits;  // pair tiers: one byte per sample (zero padded to whole chunks), bit g = "in sample group g"
+    int group0;            // pair tiers: first group of this launch (bit and output index)
+    size_t ac_stride;      // pair tiers: elements between the groups' ac[] / ac_part[] ...
+    size_t lc_stride;      // ... and lc[] blocks
+    int32_t* ac;           // [nA] (pair tiers: group 0's)
     int32_t* ac_part;      // optional [nA], zero-initialised: alleles carried by PARTIALLY called samples (a/.)
     long long* lc;         // [L][TRT_LC_N]
     int fast_enabled;      // the TMA tiers are in use (diploid, enough samples)
@@ -40,6 +44,8 @@ __host__ __device__ __forceinline__ int pairs_rows(int A) {
     return pairs_square(A) ? D * D : D * (D + 1) / 2;
 }
 
-int trt_run_scan(trt_ctx* ctx, const uint8_t* d_mask, int g, int G);
+// the GT scan of every sample group of the block: d_masks = [G][S] device bytes (0/1), or null with G = 1 for all
+// samples; results into ctx->ac [G][nA] (+ ctx->ac_part when ctx->want_ac_part) and ctx->lc [G][L][TRT_LC_N]
+int trt_run_scan(trt_ctx* ctx, const uint8_t* d_masks, int G);
 int trt_prepare_ranks(trt_ctx* ctx);
 int trt_run_epilogue(trt_ctx* ctx, int use_length, double nalleles_thresh, int G);

@@ -441,10 +441,8 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
     TRT_CUDA(cudaMemsetAsync(ctx->lc.p, 0, (size_t)G * L * TRT_LC_N * 8 + 16, ctx->stream));
     if (L > 0) {
         TRT_CUDA(cudaEventRecord(ctx->ev_s0, ctx->stream));
-        for (int g = 0; g < G; g++) {
-            const uint8_t* m = group_masks ? (const uint8_t*)ctx->group_masks.p + (size_t)g * S : nullptr;
-            TRT_TRY(trt_run_scan(ctx, m, g, G));
-        }
+        // every sample group in as few passes over the GT rows as shared memory allows (up to three groups per pass)
+        TRT_TRY(trt_run_scan(ctx, group_masks ? (const uint8_t*)ctx->group_masks.p : nullptr, G));
         TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
         TRT_TRY(trt_run_epilogue(ctx, use_length, nalleles_thresh, G));
     }

@@ -133,6 +133,30 @@ def load_trs(vcf_fname: str, samples: Union[np.ndarray, slice], region: Optional
                called_samples_filter, reason, locus_details)
 
 
+def dosage_arrays(trrecord, curr, len_alleles):
+    """Per-length haplotype dosages [n][2] of the samples ``curr`` from AP1 / AP2 (reference lafg.py:175-186)."""
+    n_samples = int(np.sum(curr))
+    gts = {_len: np.zeros((n_samples, 2)) for _len in np.unique(len_alleles)}
+    for p in (1, 2):
+        ap = trrecord.format['AP{}'.format(p)]
+        gts[len_alleles[0]][:, (p - 1)] += np.maximum(0, 1 - np.sum(ap[curr, :], axis=1))
+        for i in range(ap.shape[1]):
+            gts[len_alleles[i + 1]][:, (p - 1)] += ap[curr, i]
+    return gts
+
+
+def flat_locus_length_r2(trrecord, curr, gts):
+    """``r2_length_dosages_vs_best_guess_lengths`` of a locus whose best-guess lengths are all equal.  There the
+    reference's np.corrcoef (lafg.py:208-213) divides rounding residue by rounding residue — the mean of n copies of
+    a length need not be that length — so the printed value (nan, 0.0 or 1.0) is a property of numpy's summation and
+    not of the moments the device accumulates.  Such loci are filtered ('Only one called allele'); their one detail
+    column is computed here with the reference's own expression."""
+    best_guesses = trrecord.GetLengthGenotypes()[curr, :-1]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.corrcoef(best_guesses.flatten(),
+                           np.add.reduce([len_ * dosages for len_, dosages in gts.items()]).flatten())[0, 1] ** 2
+
+
 def _dosage_locus(trrecord, samples, non_major_cutoff):
     """One locus of the ``beagle_dosages`` branch (reference lafg.py:160-259) for the generator protocol.  The dict of
     per-length haplotype dosages is what the consumer regresses on, so it is built here from the record's AP fields;
@@ -149,12 +173,7 @@ def _dosage_locus(trrecord, samples, non_major_cutoff):
         design_idx = np.nonzero(samples)[0].astype(np.int32)
     n_samples = int(np.sum(curr))
     len_alleles = [round(x, allele_len_precision) for x in [trrecord.ref_allele_length] + trrecord.alt_allele_lengths]
-    gts = {_len: np.zeros((n_samples, 2)) for _len in np.unique(len_alleles)}
-    for p in (1, 2):
-        ap = trrecord.format['AP{}'.format(p)]
-        gts[len_alleles[0]][:, (p - 1)] += np.maximum(0, 1 - np.sum(ap[curr, :], axis=1))
-        for i in range(ap.shape[1]):
-            gts[len_alleles[i + 1]][:, (p - 1)] += ap[curr, i]
+    gts = dosage_arrays(trrecord, curr, len_alleles)
     cache = blk.__dict__.setdefault("_dosage_stats", {})
     key = design_idx.tobytes()
     if key not in cache:
@@ -179,6 +198,8 @@ def _dosage_locus(trrecord, samples, non_major_cutoff):
             r2[float(lr[j])] = _assoc._r2(2 * n_samples, cs[c, 2], cs[c, 2], cs[c, 0], cs[c, 1], cs[c, 3])
     ls = res["length_stats"][l]
     length_r2 = _assoc._r2(2 * n_samples, ls[0], ls[1], ls[2], ls[3], ls[4])
+    if n_samples > 0 and any(cs[j, 2] == 2 * n_samples for j in range(len(lr))):
+        length_r2 = flat_locus_length_r2(trrecord, curr, gts)
     locus_details = [trrecord.motif, str(len(trrecord.motif)), str(round(trrecord.ref_allele_length, allele_len_precision)),
                      dict_str({k: '{:.2g}'.format(v) for k, v in allele_frequency.items()}),
                      dict_str(round_vals(r2, r2_precision)), str(round(length_r2, r2_precision))]

@@ -29,7 +29,7 @@ def qc_block(blk: "_block.Block", sample_index: Optional[np.ndarray], sample_cal
         if quality_key not in blk.fmt_slot:
             raise KeyError("quality field {} is not in the block".format(quality_key))
         slot = blk.fmt_slot[quality_key]
-    res = blk.ctx.qc_reduce(sample_calls, per_sample_total_qual, mask, slot, ignore_no_call)
+    res = blk.ctx.qc_reduce(sample_calls, per_sample_total_qual, mask, slot, ignore_no_call, blk.rec_ploidy)
     st = blk.ctx.locus_stats(True, None if mask is None else mask[None, :], 0.01, want=("ac",))
     res["allele_counts"] = st["ac"][0]
     return res
@@ -61,7 +61,7 @@ def compare_blocks(blk1: "_block.Block", blk2: "_block.Block", sample_idxs: Sequ
             seq_id2[s2.start + j] = first[seq] if seq in first else -1 - own.setdefault(seq, len(own))
         motif = blk1.motif(l)
         reflen[l] = len(a1[0]) / len(motif)
-    gt2 = blk2.gt if blk2.gt is not None else _block.unpack_gt(*blk2.gt_packed)
+    gt2 = blk2.gt
     blk1._activate()
     res = blk1.ctx.compare(gt2, sample_idxs[0], sample_idxs[1], blk2.locus_off, seq_id2, blk2.h["allele_len"], reflen,
                            ignore_phasing, sample_results["numcalls"], sample_results["conc-seq-count"],
