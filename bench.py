@@ -62,31 +62,90 @@ def workload_config(L, S, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread in this process (a sample
+    every few milliseconds; the timed region of the default run is tens of milliseconds), nvidia-smi as the fallback.
+    ``start`` is called before the barrier that opens the timed region, so starting it cannot skew the ranks."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, interval_s=0.004):
         self.device_index = device_index
+        self.interval_s = interval_s
         self.proc = None
         self.lines = []
+        self.samples = []          # (t, sm_mhz, reason bits)
+        self.sm_max = None
+        self.nvml = None
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device_index])
+            except (ValueError, IndexError):
+                pass
+        return self.device_index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.perf_counter(), sm, bits))
+            except Exception:
+                pass
+            self._stop.wait(self.interval_s)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1.0)
+            nv = self.nvml
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            inside = [x for x in self.samples if self.t0 is None or (self.t0 <= x[0] <= (self.t1 or x[0]))]
+            used = inside if inside else self.samples       # a region shorter than one poll: the samples around it
+            reasons = sorted({n for _, _, bits in used for n, m in names if bits & m})
+            return {"sm_mhz": float(np.median([x[1] for x in used])) if used else None, "sm_max_mhz": self.sm_max,
+                    "reasons": reasons, "samples": len(used), "samples_in_timed_region": len(inside), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -109,7 +168,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -351,12 +410,13 @@ def run_gpu(args):
         comm.gather_region(tdist.REGION_ALLELE_COUNTS, 0, 4 * nA, sizes[:, 1], 0, None if gathered is None else gathered[1], wait=False)
         return None                                                     # ... and travel to rank 0 under the next step
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                     # before the warm-up: nothing but the barrier precedes the clock
     for _ in range(max(args.warmup, 0)):
         step()
-    sampler = ClockSampler(local_rank)
     scan_ms = []
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launch_count()
     t_wall0 = time.perf_counter()
     ctx.stopwatch_start()
@@ -369,6 +429,7 @@ def run_gpu(args):
     ms = ctx.stopwatch_stop()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
+    sampler.mark_end()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
     # the device stopwatch only spans this rank's stream; use the larger of device and wall time, then the max over ranks
@@ -701,14 +762,16 @@ def run_assoc_stream(args):
             ctx.assoc_ols(20.0, want=())
         if comm is not None:
             comm.gather_region(tdist.REGION_ASSOC, 0, n0 * row_bytes, counts_of(0) * row_bytes, 0, recv[0], wait=True)
-    if comm is not None:
-        comm.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if comm is not None:
+        comm.barrier()
+    sampler.mark_begin()
     launches0 = ctx.launch_count()
     t0 = time.perf_counter()
     hot_ms, gen_ms, scan_ms = run(True)
     wall_s = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = ctx.launch_count() - launches0
     hot = tdist.max_over_ranks(comm, hot_ms)

@@ -211,3 +211,81 @@ def test_assoc_tile_fast_path_matches_generic_kernels_and_oracle(ctx, monkeypatc
         assert_close(fast["r2"][i], row.r2, "r2 locus %d" % i, rel=1e-6, abs_tol=1e-12)
         n_ok += 1
     assert n_ok > 5
+
+
+@pytest.mark.parametrize("n_cov,S,L,use_subset", [(10, 3001, 700, False), (3, 2048, 500, True), (14, 2500, 193, False),
+                                                   (1, 70001, 260, True), (0, 300, 50, False)])
+def test_assoc_tensor_path_matches_fp64_paths_and_oracle(ctx, monkeypatch, n_cov, S, L, use_subset):
+    """The integer tensor-core path (trt_assoc_mma.cu: u8 x s8 mma.sync, exact int32 sums of 7 base-256 digits per design
+    column) against the FP64 tile path and the generic kernels on the same block, and against the oracle's pinv OLS.
+    The block mixes loci the integer form cannot hold — a 131-bp allele beside 1-bp steps (spread > 127 units), haploid
+    calls ([a, -2] pads among the called samples), a locus with 16 alleles — with ragged sizes: S not a multiple of 32,
+    L not a multiple of the 192-locus tile, more than one sample segment (S = 70001), K from 2 to 16."""
+    from oracle import assoc as oassoc, trh as otrh
+    from oracle.records import synth_to_loci
+    from trtools_b200 import _lib, synth
+    sl = synth.make_loci(L, seed=1000 + L, max_alleles=16)
+    special = {}
+    if L > 40:
+        a = 7                                             # spread: a long allele next to single-bp steps
+        sl.alts[a] = [sl.ref[a] + "T", sl.ref[a] + "T" * 131] + list(sl.alts[a][2:])
+        special[a] = "spread"
+        b = 21                                            # > 14 alleles: generic kernels
+        sl.alts[b] = [sl.ref[b] + "ACGT"[k % 4] * (k + 1) for k in range(15)]
+        sl.n_alleles[b] = 16
+        sl.cum_freq[b] = (np.arange(1, 17, dtype=np.float64) / 16 * 2 ** 32 - 1).astype(np.uint32)
+        special[b] = "wide"
+    sl.n_alleles[:] = [1 + len(x) for x in sl.alts]
+    calls = synth.fill_calls(sl, S)
+    if L > 40:
+        c = 33                                            # haploid calls among the called samples
+        calls.gt[c, ::7, 1] = -2
+        calls.gt[c, ::7, 0] = np.maximum(calls.gt[c, ::7, 0], 0)
+        special[c] = "pads"
+    rng = np.random.default_rng(S + L)
+    traits = rng.standard_normal((S, 1 + n_cov))
+    g0 = calls.gt[0, :, :2].astype(float).sum(axis=1)
+    traits[:, 0] += 0.05 * g0
+    if n_cov:
+        traits[:, 1] *= 1e4                               # column scales far apart
+        traits[:, -1] = traits[:, -1] * 1e-3 + 5.0
+    mask = (rng.random(S) < 0.7) if use_subset else None
+    design = oassoc.prepare_design([traits], S, mask)
+    idx = np.nonzero(design.sample_filter)[0].astype(np.int32)
+
+    def run():
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt(calls.gt)
+        ctx.block_set_alleles(*synth.allele_tables(sl))
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        ctx.assoc_set_design(design.covars, design.outcome, idx)
+        return ctx.assoc_ols(5)
+
+    mma = run()
+    monkeypatch.setenv("TRT_ASSOC_NO_MMA", "1")
+    fp64 = run()
+    monkeypatch.setenv("TRT_ASSOC_GENERIC", "1")
+    gen = run()
+    monkeypatch.delenv("TRT_ASSOC_GENERIC")
+    monkeypatch.delenv("TRT_ASSOC_NO_MMA")
+    for other, name in ((fp64, "fp64 tiles"), (gen, "generic")):
+        assert np.array_equal(mma["filter_code"], other["filter_code"]), name
+        assert np.array_equal(mma["n_tested"], other["n_tested"]), name
+        assert np.array_equal(mma["ac_len"], other["ac_len"]), name
+        for k in ("p", "coef", "se", "r2", "std_g"):
+            for i in range(L):
+                assert_close(mma[k][i], other[k][i], "{} {} locus {} {}".format(name, k, i, special.get(i, "")), rel=2e-7,
+                             abs_tol=1e-300 if k == "p" else 1e-13)
+    loci = synth_to_loci(sl, calls, with_fmt=False)
+    n_ok = 0
+    for i in sorted(set(list(range(0, L, max(1, L // 8))) + list(special))):
+        if int(mma["filter_code"][i]) != _lib.AF_OK:
+            continue
+        h = otrh.harmonize(loci[i])
+        row = oassoc.regress_locus(oassoc.load_locus(loci[i], h, design.sample_filter.copy(), 5), design)
+        assert_close(mma["p"][i], row.p, "p locus %d" % i, abs_tol=1e-300)
+        assert_close(mma["coef"][i] * design.pheno_std, row.coef, "coef locus %d" % i, rel=1e-6, abs_tol=1e-12)
+        assert_close(mma["se"][i] * design.pheno_std, row.se, "se locus %d" % i)
+        assert_close(mma["r2"][i], row.r2, "r2 locus %d" % i, rel=1e-6, abs_tol=1e-12)
+        n_ok += 1
+    assert n_ok > 3

@@ -655,9 +655,10 @@ int trt_assoc_set_design(trt_ctx* ctx, const double* covars, const double* outco
     design_totals_kernel<<<ne, 256, 0, ctx->stream>>>((const double*)ctx->covars.p, (const double*)ctx->outcome.p,
                                                                  n_design, K, (double*)ctx->assoc_tot.p);
     TRT_KERNEL_CHECK();
-    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->n_design = n_design;
     ctx->K = K;
+    if (K <= kAssocFastMaxK) TRT_TRY(trt_assoc_mma_design(ctx));
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_design = true;
     ctx->design_checked_S = -1;
     return TRT_OK;
@@ -738,7 +739,14 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
                 ap.list = (const int32_t*)ctx->assoc_fast_tiles.p;
                 ap.n_list = (int64_t)generic_list.size();
             }
-            TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, ap.mom, ap.dd));
+            // integer-form loci on the tensor cores (trt_assoc_mma.cu); what does not fit that form, through the FP64 tiles
+            if (trt_assoc_mma_supported(ctx)) {
+                int n_fp64 = 0;
+                TRT_TRY(trt_assoc_mma(ctx, ap.row_of_sample, ap.mom, ap.dd, &n_fp64));
+                if (n_fp64 > 0) TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, ap.mom, ap.dd, (const uint8_t*)ctx->assoc_flags.p));
+            } else {
+                TRT_TRY(trt_assoc_fast(ctx, ap.row_of_sample, ap.mom, ap.dd, nullptr));
+            }
         }
         const int64_t n_gen = ap.list ? ap.n_list : L;
         const int64_t ntiles = (n_gen + kTileLoci - 1) / kTileLoci;

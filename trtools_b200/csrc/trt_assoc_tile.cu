@@ -56,7 +56,15 @@ struct TileParams {
                                     // word per (locus, chunk), the down-date kernel reads a locus' window as ONE 128-byte line
     int nwin;                       // ceil(nchunks / 32)
     int stages;
+    const uint8_t* flags;           // per locus path flag (null: every locus with <= kAssocFastMaxAlleles alleles is ours)
+    int want;                       // ... the flag value of the loci to process
+    int mask_tile_loci, mask_bits;  // geometry of `masks` for the down-date kernel: loci per tile, samples per word
 };
+
+__device__ __forceinline__ bool tile_owns(const TileParams& p, int64_t l) {
+    if (p.locus_off[l + 1] - p.locus_off[l] > kAssocFastMaxAlleles) return false;       // generic-path locus
+    return !p.flags || p.flags[l] == p.want;
+}
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
     asm volatile(
@@ -137,7 +145,8 @@ __global__ void __launch_bounds__(kTThreads, 1) assoc_tile_kernel(const __grid_c
                 a0 = p.locus_off[l];
                 A = p.locus_off[l + 1] - a0;
             }
-            valid[h] = (l < p.L) && A <= kAssocFastMaxAlleles;      // wider loci go through the generic kernels
+            valid[h] = (l < p.L) && A <= kAssocFastMaxAlleles &&     // wider loci go through the generic kernels,
+                       (!p.flags || p.flags[l] == p.want);            // integer-form loci through the tensor path
             if (!valid[h]) A = 0;
             if (A > 0) ref = p.allele_len[a0];
             D[h] = (unsigned)A + 2u;
@@ -262,11 +271,11 @@ __global__ void assoc_ztable_kernel(const double* __restrict__ covars, const dou
 }
 
 __global__ void assoc_reduce_mom_kernel(const double* __restrict__ part, int nseg, int64_t n, double* __restrict__ mom,
-                                        const int32_t* __restrict__ locus_off, int nacc) {
+                                        TileParams p, int nacc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t l = i / nacc;
-    if (locus_off[l + 1] - locus_off[l] > kAssocFastMaxAlleles) return;   // generic-path locus
+    if (!tile_owns(p, l)) return;
     double s = 0.0;
     for (int g = 0; g < nseg; g++) s += part[(size_t)g * n + i];   // fixed order: bit-reproducible
     mom[i] = s;
@@ -286,8 +295,8 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
     // z-rows staged per round trip to L2: a 32-chunk window holds ~15 uncalled samples at 2 % missingness, so ~20 slots
     // cover a window in one trip
     constexpr int kBatch = (kG >= 16) ? kG : ((20 + kG - 1) / kG) * kG;
-    constexpr int kZS = 18;                      // staged row pitch in doubles (144 B: odd multiple of 16 B)
-    __shared__ uint16_t lst_all[8][32 * kTChunk];   // uncalled samples of a 32-chunk window, relative to its first sample
+    constexpr int kZS = 4 * NB + 2;              // staged row pitch in doubles (an odd multiple of 16 B; 144 B for NB = 4)
+    __shared__ uint16_t lst_all[8][32 * 32];        // uncalled samples of a 32-word window, relative to its first sample
     __shared__ __align__(16) double zs_all[8][kBatch][kZS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint16_t* lst = lst_all[wib];
@@ -304,10 +313,11 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
     __syncwarp();
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; l < p.L; l += nwarps) {
-        if (p.locus_off[l + 1] - p.locus_off[l] > kAssocFastMaxAlleles) continue;   // generic-path locus
-        const int64_t tile = l / kTLoci;
-        const int tl = (int)(l % kTLoci);
-        const uint32_t* mrow = p.masks + ((size_t)tile * p.nwin * kTLoci + tl) * 32 + lane;   // + window * kTLoci * 32
+        if (!tile_owns(p, l)) continue;
+        const int tloci = p.mask_tile_loci, wbits = p.mask_bits;
+        const int64_t tile = l / tloci;
+        const int tl = (int)(l % tloci);
+        const uint32_t* mrow = p.masks + ((size_t)tile * p.nwin * tloci + tl) * 32 + lane;   // + window * tloci * 32
         double acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
             uint32_t m = m_next;
             {   // the next window's masks are requested now: their latency hides under this window's work
                 const int cn = cb + 32 + lane;
-                m_next = (cn < p.nchunks) ? mrow[(size_t)((cb >> 5) + 1) * kTLoci * 32] : 0u;
+                m_next = (cn < p.nchunks) ? mrow[(size_t)((cb >> 5) + 1) * tloci * 32] : 0u;
             }
             const int cnt = __popc(m);
             int off = cnt;
@@ -333,10 +343,10 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
             while (m) {
                 const int b = __ffs((int)m) - 1;
                 m &= m - 1;
-                lst[off++] = (uint16_t)(lane * kTChunk + b);
+                lst[off++] = (uint16_t)(lane * wbits + b);
             }
             __syncwarp();
-            const int64_t s_base = (int64_t)cb * kTChunk;
+            const int64_t s_base = (int64_t)cb * wbits;
             for (int e0 = 0; e0 < total; e0 += kBatch) {
                 // stage up to kBatch z-rows: lanes (2 rows per load round) fetch z = (c_1 .. c_{K-1}, y) from
                 // zt rows [y, c_1 .. c_{K-1}, ..]
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
 #pragma unroll
                 for (int r = 0; r < (kBatch + 1) / 2; r++) {
                     const int slot = 2 * r + sub;
-                    if (slot < kBatch) zs[slot][col] = zv[r];      // rows past `total` become zero rows
+                    if (slot < kBatch && col < kZS) zs[slot][col] = zv[r];      // rows past `total` become zero rows
                 }
                 __syncwarp();
 #pragma unroll
@@ -392,10 +402,6 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -426,11 +432,48 @@ int launch_tile(trt_ctx* ctx, const CUtensorMap& tmap, TileParams& tp, int grid)
 
 }  // namespace
 
+EncodeTiledFn trt_tmap_encode_fn() { return encode_fn(); }
+
 int trt_assoc_fast_zw(int K) { return (K + 2) & ~1; }
+
+int trt_assoc_downdate(trt_ctx* ctx, const int32_t* d_row_of_sample, const uint32_t* masks, int n_tiles, int nwords, int nwin,
+                       int tile_loci, int bits, const uint8_t* flags, int want, double* dd) {
+    const int64_t L = ctx->L, S = ctx->S;
+    const int K = ctx->K, ZW = trt_assoc_fast_zw(K);
+    if (L == 0) return TRT_OK;
+    const int64_t S_pad = (int64_t)nwords * bits;
+    TRT_TRY(trt_ensure(ctx, ctx->assoc_zt, (size_t)S_pad * ZW * 8 + 64));
+    {
+        const int64_t n = S_pad * ZW;
+        assoc_ztable_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            (const double*)ctx->covars.p, (const double*)ctx->outcome.p, d_row_of_sample, S, S_pad, K, ZW, (double*)ctx->assoc_zt.p);
+        TRT_KERNEL_CHECK();
+    }
+    TileParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.L = L; tp.S = S;
+    tp.locus_off = (const int32_t*)ctx->locus_off.p;
+    tp.n_tiles = n_tiles;
+    tp.nchunks = nwords;
+    tp.nwin = nwin;
+    tp.zt = (const double*)ctx->assoc_zt.p;
+    tp.masks = const_cast<uint32_t*>(masks);
+    tp.flags = flags;
+    tp.want = want;
+    tp.mask_tile_loci = tile_loci;
+    tp.mask_bits = bits;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)ctx->sm_count * 4 * TRT_DD_MINBLOCKS));
+    if (K <= 4) assoc_downdate_mask_kernel<1><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+    else if (K <= 8) assoc_downdate_mask_kernel<2><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+    else if (K <= 12) assoc_downdate_mask_kernel<3><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+    else assoc_downdate_mask_kernel<4><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+    TRT_KERNEL_CHECK();
+    return TRT_OK;
+}
 
 // Moments (into mom [L][K+3]) and down-dates (into dd [L][K(K+1)/2]) of every locus with at most
 // kAssocFastMaxAlleles alleles; the others are left to the generic kernels.
-int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, double* dd) {
+int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, double* dd, const uint8_t* flags) {
     const int64_t L = ctx->L, S = ctx->S;
     const int K = ctx->K, nacc = K + 3, ZW = trt_assoc_fast_zw(K);
     if (L == 0) return TRT_OK;
@@ -487,6 +530,10 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     tp.mom_part = (double*)ctx->assoc_mom_part.p;
     tp.masks = (uint32_t*)ctx->assoc_masks.p;
     tp.stages = 0;
+    tp.flags = flags;
+    tp.want = 2;
+    tp.mask_tile_loci = kTLoci;
+    tp.mask_bits = kTChunk;
     const int grid = (int)std::min<int64_t>((int64_t)n_tiles * nseg, sms);
     switch (K) {
 #define CASE(KK) case KK: TRT_TRY(launch_tile<KK>(ctx, tmap, tp, grid)); break;
@@ -497,16 +544,10 @@ int trt_assoc_fast(trt_ctx* ctx, const int32_t* d_row_of_sample, double* mom, do
     {
         const int64_t n = L * nacc;
         assoc_reduce_mom_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-            (const double*)ctx->assoc_mom_part.p, nseg, n, mom, tp.locus_off, nacc);
+            (const double*)ctx->assoc_mom_part.p, nseg, n, mom, tp, nacc);
         TRT_KERNEL_CHECK();
     }
-    {
-        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)sms * 4 * TRT_DD_MINBLOCKS));
-        if (K <= 4) assoc_downdate_mask_kernel<1><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-        else if (K <= 8) assoc_downdate_mask_kernel<2><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-        else if (K <= 12) assoc_downdate_mask_kernel<3><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-        else assoc_downdate_mask_kernel<4><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-        TRT_KERNEL_CHECK();
-    }
+    // the z-rows table built above covers nchunks * kTChunk samples: the down-date call rebuilds the same table
+    TRT_TRY(trt_assoc_downdate(ctx, d_row_of_sample, tp.masks, n_tiles, nchunks, nwin, kTLoci, kTChunk, flags, 2, dd));
     return TRT_OK;
 }

@@ -189,7 +189,8 @@ void trt_destroy(trt_ctx* ctx) {
                       &ctx->dosage_err, &ctx->dos_meta, &ctx->dos_out, &ctx->reduce_buf, &ctx->cf_specs, &ctx->call_mask, &ctx->trig,
                       &ctx->samp_counts, &ctx->samp_dp, &ctx->misc, &ctx->covars, &ctx->outcome, &ctx->sample_index,
                       &ctx->design_row_of_sample, &ctx->assoc_acc, &ctx->assoc_out, &ctx->assoc_tot, &ctx->assoc_zt, &ctx->assoc_fast_tiles,
-                      &ctx->assoc_tile_fast, &ctx->assoc_masks, &ctx->assoc_mom_part, &ctx->dist_send,
+                      &ctx->assoc_tile_fast, &ctx->assoc_masks, &ctx->assoc_mom_part, &ctx->assoc_flags, &ctx->assoc_mma_tab, &ctx->assoc_xd,
+                      &ctx->assoc_mma_part, &ctx->assoc_mma_masks, &ctx->assoc_colscale, &ctx->dist_send,
                       &ctx->dist_recv};
     for (DevBuf* b : bufs) trt_free_buf(*b);
     for (int i = 0; i < TRT_FMT_NFIELDS; i++) trt_free_buf(ctx->fmt_buf[i]);

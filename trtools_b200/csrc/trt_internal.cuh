@@ -78,6 +78,7 @@ struct trt_ctx {
     // associaTR
     DevBuf  covars, outcome, sample_index, design_row_of_sample, assoc_acc, assoc_out, assoc_tot;
     DevBuf  assoc_zt, assoc_fast_tiles, assoc_tile_fast, assoc_masks, assoc_mom_part;   // fast path (trt_assoc_tile.cu)
+    DevBuf  assoc_flags, assoc_mma_tab, assoc_xd, assoc_mma_part, assoc_mma_masks, assoc_colscale;   // tensor path (trt_assoc_mma.cu)
     int64_t n_design = 0;
     int     K = 0;
     bool    have_design = false;
