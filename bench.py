@@ -520,8 +520,9 @@ def run_gpu(args):
         ms_a, k_a = timed(assoc_step, max(2, min(args.steps, 5)), 2)
         assoc_res = {k: v.copy() for k, v in assoc_step.res.items()}
         tools["associaTR"] = {"value": world * L / (ms_a / 1000.0), "unit": "loci/s", "ms_per_step": ms_a,
-                              "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; FP64 moments "
-                                          "(thread-per-locus TMA tiles) + mask down-dates + solve, results to host",
+                              "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; allele counts (GT scan) + "
+                                          "exact integer cross moments on the tensor cores (u8 x s8 mma.sync, 7 base-256 digits per "
+                                          "design column) + mask down-dates + FP64 solve, results to host",
                               "kernel_ms": k_a, "algorithmic_bytes_per_call": 6,
                               "roofline_frac": (6.0 * L * S / (k_a / 1000.0) / 1e9) / peak if k_a > 0 else None}
         cf_specs = [(L_.CF_RATIO_GT, L_.FMT_DFLANKINDEL, 0.15), (L_.CF_MIN, L_.FMT_DP, 20)]

@@ -282,35 +282,30 @@ __global__ void assoc_reduce_mom_kernel(const double* __restrict__ part, int nse
 }
 
 // exact down-dates from the uncalled-sample masks: warp per locus.  The K x K matrix sum z z' over the uncalled design
-// rows (z = (c_1 .. c_{K-1}, y)) is tiled into 4 x 4 register blocks of its upper triangle: a lane owns one block of
-// one sample group, so a z-row staged in shared memory costs 4 LDS.128 for 16 DFMAs, and G = 32 / blocks samples
-// are processed by the warp at once (K = 12: 6 blocks, 5 samples in flight).  Groups are summed by shuffles per locus.
-#ifndef TRT_DD_MINBLOCKS
-#define TRT_DD_MINBLOCKS 2
-#endif
-template <int NB>
-__global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
-    constexpr int kBlocks = NB * (NB + 1) / 2;
-    constexpr int kG = 32 / kBlocks;             // samples processed concurrently by a warp
-    // z-rows staged per round trip to L2: a 32-chunk window holds ~15 uncalled samples at 2 % missingness, so ~20 slots
-    // cover a window in one trip
-    constexpr int kBatch = (kG >= 16) ? kG : ((20 + kG - 1) / kG) * kG;
-    constexpr int kZS = 4 * NB + 2;              // staged row pitch in doubles (an odd multiple of 16 B; 144 B for NB = 4)
-    __shared__ uint16_t lst_all[8][32 * 32];        // uncalled samples of a 32-word window, relative to its first sample
-    __shared__ __align__(16) double zs_all[8][kBatch][kZS];
+// rows (z = (c_1 .. c_{K-1}, y)) is a Gram matrix, accumulated four samples at a time by FP64 mma.sync.m8n8k4: lane
+// (g, t) holds z_t[g] (and z_t[g + 8] when K > 8) of the group's four samples — the A fragment of a column block and,
+// the same numbers, the B fragment — loaded straight from the z-row table in L2 (eight lanes read 64 consecutive bytes of
+// one row), so there is no staging, and the accumulators of a locus are the C fragments: nothing to reduce at the end.
+// NB8 = column blocks of 8: K <= 8 -> 1 MMA per group, K <= 16 -> 3 (blocks 00, 01, 11).
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int NB8>
+__global__ void __launch_bounds__(256) assoc_downdate_mask_kernel(TileParams p, int K, int ZW, double* __restrict__ dd) {
+    constexpr int kU = 4;                           // sample groups per round trip to L2 (16 samples)
+    constexpr int kRound = 4 * kU;
+    __shared__ uint32_t lst_all[8][32 * 32 + kRound];   // pending uncalled samples of the locus (absolute sample indices)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint16_t* lst = lst_all[wib];
-    double(*zs)[kZS] = zs_all[wib];
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t* lst = lst_all[wib];
     const int ne = K * (K + 1) / 2;
-    // this lane's block (bi <= bj) and sample group
-    const int grp = lane / kBlocks, blk = lane % kBlocks;
-    int bi = 0, rem = blk;
-    while (rem >= NB - bi) { rem -= NB - bi; bi++; }
-    const int bj = bi + rem;
-    const bool worker = grp < kG;
-    // zero the staging rows once: columns >= K stay zero for the whole kernel
-    for (int i = lane; i < kBatch * kZS; i += 32) (&zs[0][0])[i] = 0.0;
-    __syncwarp();
+    // column j of the Gram matrix (order c_1 .. c_{K-1}, y) sits at index j + 1 (or 0 for y) of a z-row [y, c_1 .. c_{K-1}, ind];
+    // lanes whose column does not exist read column 0 and drop it
+    const int src_lo = (g < K - 1) ? g + 1 : (g == K - 1 ? 0 : -1);
+    const int src_hi = (g + 8 < K - 1) ? g + 9 : (g + 8 == K - 1 ? 0 : -1);
+    const double* zlo = p.zt + (src_lo >= 0 ? src_lo : 0);
+    const double* zhi = p.zt + (src_hi >= 0 ? src_hi : 0);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; l < p.L; l += nwarps) {
         if (!tile_owns(p, l)) continue;
@@ -318,11 +313,33 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
         const int64_t tile = l / tloci;
         const int tl = (int)(l % tloci);
         const uint32_t* mrow = p.masks + ((size_t)tile * p.nwin * tloci + tl) * 32 + lane;   // + window * tloci * 32
-        double acc[4][4];
+        double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+        // one round: 16 listed samples (fewer only when the locus is flushed) -> 4 groups of 4 -> up to 12 MMAs
+        auto round = [&](int pos, int n) {
+            double lo[kU], hi[kU];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+            for (int u = 0; u < kU; u++) {
+                const int e = 4 * u + t;
+                const unsigned row = lst[pos + min(e, n - 1)] * (unsigned)ZW;        // always a listed sample
+                const double vlo = zlo[row];
+                lo[u] = (e < n && src_lo >= 0) ? vlo : 0.0;
+                if (NB8 > 1) {
+                    const double vhi = zhi[row];
+                    hi[u] = (e < n && src_hi >= 0) ? vhi : 0.0;
+                }
+            }
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+            for (int u = 0; u < kU; u++) {
+                if (4 * u < n) {                    // warp-uniform; false only in the flush round
+                    dmma884(c00, lo[u], lo[u]);
+                    if (NB8 > 1) {
+                        dmma884(c01, lo[u], hi[u]);
+                        dmma884(c11, hi[u], hi[u]);
+                    }
+                }
+            }
+        };
+        int pending = 0;                            // listed samples not yet accumulated (< kRound between windows)
         uint32_t m_next = (lane < p.nchunks) ? mrow[0] : 0u;
         for (int cb = 0; cb < p.nchunks; cb += 32) {
             uint32_t m = m_next;
@@ -334,71 +351,43 @@ __global__ void __launch_bounds__(256, TRT_DD_MINBLOCKS) assoc_downdate_mask_ker
             int off = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, off, o);
-                if (lane >= o) off += t;
+                const int v = __shfl_up_sync(0xffffffffu, off, o);
+                if (lane >= o) off += v;
             }
             const int total = __shfl_sync(0xffffffffu, off, 31);
             if (total == 0) continue;
-            off -= cnt;
+            off += pending - cnt;
+            const uint32_t s0 = (uint32_t)(cb + lane) * (uint32_t)wbits;
             while (m) {
                 const int b = __ffs((int)m) - 1;
                 m &= m - 1;
-                lst[off++] = (uint16_t)(lane * wbits + b);
+                lst[off++] = s0 + (uint32_t)b;
             }
             __syncwarp();
-            const int64_t s_base = (int64_t)cb * wbits;
-            for (int e0 = 0; e0 < total; e0 += kBatch) {
-                // stage up to kBatch z-rows: lanes (2 rows per load round) fetch z = (c_1 .. c_{K-1}, y) from
-                // zt rows [y, c_1 .. c_{K-1}, ..]
-                const int sub = lane >> 4, col = lane & 15;
-                const int zsrc = (col < K - 1) ? col + 1 : 0;
-                double zv[(kBatch + 1) / 2];
+            const int have = pending + total;
+            int pos = 0;
+            for (; pos + kRound <= have; pos += kRound) round(pos, kRound);
+            pending = have - pos;
+            // the remainder moves to the front of the list for the next window
+            uint32_t carry = 0;
+            if (lane < pending) carry = lst[pos + lane];
+            __syncwarp();
+            if (lane < pending) lst[lane] = carry;
+            __syncwarp();
+        }
+        if (pending > 0) round(0, pending);
+        __syncwarp();
+        // C fragments: rows g, columns 2 t and 2 t + 1 of each block
 #pragma unroll
-                for (int r = 0; r < (kBatch + 1) / 2; r++) {
-                    const int slot = 2 * r + sub, e = e0 + slot;
-                    zv[r] = 0.0;
-                    if (slot < kBatch && e < total && col < K) zv[r] = p.zt[(size_t)(s_base + lst[e]) * ZW + zsrc];
-                }
-#pragma unroll
-                for (int r = 0; r < (kBatch + 1) / 2; r++) {
-                    const int slot = 2 * r + sub;
-                    if (slot < kBatch && col < kZS) zs[slot][col] = zv[r];      // rows past `total` become zero rows
-                }
-                __syncwarp();
-#pragma unroll
-                for (int r0 = 0; r0 < kBatch; r0 += kG) {
-                    const int slot = r0 + grp;
-                    if (worker && slot < kBatch) {
-                        const double2* za2 = (const double2*)&zs[slot][4 * bi];
-                        const double2* zb2 = (const double2*)&zs[slot][4 * bj];
-                        const double2 a01 = za2[0], a23 = za2[1], b01 = zb2[0], b23 = zb2[1];
-                        const double za[4] = {a01.x, a01.y, a23.x, a23.y}, zb[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) acc[i][j] = fma(za[i], zb[j], acc[i][j]);
-                    }
-                }
-                __syncwarp();
+        for (int i = 0; i < 2; i++) {
+            const int ca = 2 * t + i;
+            if (g <= ca && ca < K) dd[l * ne + (g * K - g * (g - 1) / 2 + (ca - g))] = c00[i];
+            if (NB8 > 1) {
+                const int cb2 = 8 + ca, gb = 8 + g;
+                if (cb2 < K) dd[l * ne + (g * K - g * (g - 1) / 2 + (cb2 - g))] = c01[i];
+                if (gb <= cb2 && cb2 < K) dd[l * ne + (gb * K - gb * (gb - 1) / 2 + (cb2 - gb))] = c11[i];
             }
         }
-        // sum the sample groups into group 0, then write the block's entries of the upper triangle
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                double v = worker ? acc[i][j] : 0.0;
-                double tot = v;
-#pragma unroll
-                for (int g = 1; g < kG; g++) {
-                    const double o = __shfl_sync(0xffffffffu, v, (lane + g * kBlocks) & 31);
-                    tot += o;
-                }
-                if (grp == 0) {
-                    const int ra = 4 * bi + i, rb = 4 * bj + j;
-                    if (ra <= rb && rb < K) dd[l * ne + (ra * K - ra * (ra - 1) / 2 + (rb - ra))] = tot;
-                }
-            }
     }
 }
 
@@ -462,11 +451,9 @@ int trt_assoc_downdate(trt_ctx* ctx, const int32_t* d_row_of_sample, const uint3
     tp.want = want;
     tp.mask_tile_loci = tile_loci;
     tp.mask_bits = bits;
-    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)ctx->sm_count * 4 * TRT_DD_MINBLOCKS));
-    if (K <= 4) assoc_downdate_mask_kernel<1><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-    else if (K <= 8) assoc_downdate_mask_kernel<2><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-    else if (K <= 12) assoc_downdate_mask_kernel<3><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
-    else assoc_downdate_mask_kernel<4><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L + 7) / 8, (int64_t)ctx->sm_count * 8));
+    if (K <= 8) assoc_downdate_mask_kernel<1><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
+    else assoc_downdate_mask_kernel<2><<<blocks, 256, 0, ctx->stream>>>(tp, K, ZW, dd);
     TRT_KERNEL_CHECK();
     return TRT_OK;
 }
