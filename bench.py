@@ -434,6 +434,7 @@ def run_gpu(args):
     clocks = sampler.stop()
     # the device stopwatch only spans this rank's stream; use the larger of device and wall time, then the max over ranks
     step_ms = max(ms, wall_ms) / args.steps
+    per_rank_us = None if comm is None else comm.allgather_i64([int(ms / args.steps * 1000), int(wall_ms / args.steps * 1000)]).tolist()
     step_ms = tdist.max_over_ranks(comm, step_ms)
     value = world * L / (step_ms / 1000.0)
     if comm is not None:
@@ -472,7 +473,11 @@ def run_gpu(args):
         ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=False)
         ctx.block_set_alleles(*tables)
 
-    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True)
+    fits_nibble = int(np.max(loci.n_alleles)) <= 14
+    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True, nibble=fits_nibble)
+    if fits_nibble:
+        regen()
+        e2e["packed_2_bytes"] = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True)
     regen()
     e2e["cyvcf2_layout"] = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=False)
 
@@ -500,6 +505,8 @@ def run_gpu(args):
             dev = ctx.stopwatch_stop()
             wall = (time.perf_counter() - t0) * 1000.0
             ms_ = max(dev, wall) / steps
+            if comm is not None:            # microseconds per step of every rank (device, wall): which rank sets the max, and why
+                timed.per_rank = comm.allgather_i64([int(dev / steps * 1000), int(wall / steps * 1000)]).tolist()
             return tdist.max_over_ranks(comm, ms_), float(np.mean(scan))
 
         def pack_step():
@@ -517,13 +524,15 @@ def run_gpu(args):
         def assoc_step():
             assoc_step.res = ctx.assoc_ols(20.0, pinned=True)
 
+        timed.per_rank = None
         ms_a, k_a = timed(assoc_step, max(2, min(args.steps, 5)), 2)
+        assoc_per_rank = timed.per_rank
         assoc_res = {k: v.copy() for k, v in assoc_step.res.items()}
         tools["associaTR"] = {"value": world * L / (ms_a / 1000.0), "unit": "loci/s", "ms_per_step": ms_a,
                               "workload": "trait ~ TR length + 10 covariates (K=12), non-major cutoff 20; allele counts (GT scan) + "
                                           "exact integer cross moments on the tensor cores (u8 x s8 mma.sync, 7 base-256 digits per "
                                           "design column) + mask down-dates + FP64 solve, results to host",
-                              "kernel_ms": k_a, "algorithmic_bytes_per_call": 6,
+                              "kernel_ms": k_a, "algorithmic_bytes_per_call": 6, "per_rank_us_device_wall": assoc_per_rank,
                               "roofline_frac": (6.0 * L * S / (k_a / 1000.0) / 1e9) / peak if k_a > 0 else None}
         cf_specs = [(L_.CF_RATIO_GT, L_.FMT_DFLANKINDEL, 0.15), (L_.CF_MIN, L_.FMT_DP, 20)]
         counts = np.zeros((2, S), np.int64)
@@ -572,7 +581,7 @@ def run_gpu(args):
             "device": {"name": info["name"], "sm_count": info["sm_count"], "numa_bound_cpus": numa_cpus},
             "gather": None if comm is None else "per-locus rows (10 x 8 B x L + int32 allele counts) of every rank gathered on rank 0 "
                       "with ncclSend/ncclRecv from device buffers on the context stream (trt_dist_gather_region), host copy on a side stream",
-            "timing": {"device_ms_total": ms, "wall_ms_total": wall_ms},
+            "timing": {"device_ms_total": ms, "wall_ms_total": wall_ms, "per_rank_us_per_step_device_wall": per_rank_us},
         }
         emit(out)
     if comm is not None:
@@ -580,16 +589,17 @@ def run_gpu(args):
         comm.close()
 
 
-def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True):
+def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True, nibble=False):
     """The statSTR pass through the C-ABI with HOST buffers: pinned host blocks of the workload's genotypes ->
     trt_block_set_gt_packed / trt_block_set_gt (H2D) -> kernels -> D2H of the statistics.  The host blocks hold DISTINCT
     loci of the workload (copied out of the device-generated block before the clock starts), as many as fit the pinned
     budget; when the budget is smaller than the workload the resident blocks are streamed round-robin (every copy is a
-    real H2D).  ``packed``: uint8 [L][S][2] blocks (what trt_vcf_block_parse_packed emits) instead of int16 [L][S][3]."""
+    real H2D).  ``packed``: uint8 [L][S][2] blocks (what trt_vcf_block_parse_packed emits) instead of int16 [L][S][3];
+    ``nibble``: uint8 [L][S] blocks (trt_vcf_block_parse_nibble; every locus of the workload has <= 14 alleles)."""
     from trtools_b200 import _lib, synth, dist as tdist
     Lb = min(L, args.e2e_block)
     nblk = (L + Lb - 1) // Lb
-    blk_bytes = Lb * S * (2 if packed else 6)
+    blk_bytes = Lb * S * (1 if nibble else (2 if packed else 6))
     try:
         import psutil
         avail = psutil.virtual_memory().available
@@ -601,7 +611,10 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
     host_blocks = []
     for b in range(n_host):
         n = min(Lb, L - b * Lb)
-        if packed:
+        if nibble:
+            hb = ctx.pinned_empty((Lb, S), np.uint8)
+            ctx.check(ctx.lib.trt_block_get_gt_nibble(ctx.h, b * Lb, n, hb.ctypes.data, None))
+        elif packed:
             hb = ctx.pinned_empty((Lb, S, 2), np.uint8)
             ctx.check(ctx.lib.trt_block_get_gt_packed(ctx.h, b * Lb, n, hb.ctypes.data, None))
         else:
@@ -628,8 +641,10 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
             n = blk_tables[b][2].shape[0] - 1
             hb = host_blocks[b % n_host]
             c.block_begin(n, S, 2, "hipstr")
-            if packed:
-                c.block_set_gt_packed(hb[:n])                 # asynchronous copy from the pinned block + expansion kernel
+            if nibble:
+                c.block_set_gt_nibble(hb[:n])                 # asynchronous copy from the pinned block + expansion kernel
+            elif packed:
+                c.block_set_gt_packed(hb[:n])
             else:
                 c.block_set_gt(hb[:n])
             c.block_set_alleles(*blk_tables[b])
@@ -654,7 +669,10 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
     ctxs[1].close()
     return {"value": world * L / (e2e_ms / 1000.0), "unit": "loci/s", "h2d_bytes_per_step": int(counters["h2d"]),
             "d2h_bytes_per_step": int(counters["d2h"]), "ms_per_step": e2e_ms,
-            "transfer_form": ("packed: uint8 [L][S][2] allele codes (trt_block_set_gt_packed; what trt_vcf_block_parse_packed "
+            "transfer_form": ("nibble: uint8 [L][S], two 4-bit allele codes per call (trt_block_set_gt_nibble; what "
+                              "trt_vcf_block_parse_nibble emits from VCF text when no locus has more than 14 alleles), expanded on "
+                              "the device" if nibble else
+                              "packed: uint8 [L][S][2] allele codes (trt_block_set_gt_packed; what trt_vcf_block_parse_packed "
                               "emits from VCF text), expanded on the device" if packed else
                               "cyvcf2 layout: int16 [L][S][3] (trt_block_set_gt)"),
             "host_blocks": "{} pinned blocks of {} loci = {} distinct loci ({:.1f} GB) of the workload resident in host memory, "

@@ -112,6 +112,11 @@ int trt_block_set_gt_device(trt_ctx* ctx, const int16_t* gt_dev, size_t row_pitc
 int trt_block_set_gt_packed(trt_ctx* ctx, const uint8_t* gt2_host /*[L][S][2]*/, const uint8_t* phase_bits_host);
 /* the block's genotypes (a locus range) back in the packed form                                                        */
 int trt_block_get_gt_packed(trt_ctx* ctx, int64_t locus0, int64_t n, uint8_t* gt2_out_host, uint8_t* phase_bits_out_host);
+/* Nibble transfer form for DIPLOID blocks whose loci have at most 14 alleles (nearly every TR locus): ONE byte per call,
+ * first haplotype in the low nibble, second in the high nibble; 0..13 allele index, 14 = ploidy pad (-2), 15 = no-call
+ * (-1); phase bits as above.  A sixth of cyvcf2's bytes across PCIe.  trt_vcf_block_parse_nibble produces it from text. */
+int trt_block_set_gt_nibble(trt_ctx* ctx, const uint8_t* g4_host /*[L][S]*/, const uint8_t* phase_bits_host);
+int trt_block_get_gt_nibble(trt_ctx* ctx, int64_t locus0, int64_t n, uint8_t* g4_out_host, uint8_t* phase_bits_out_host);
 
 int trt_block_set_format_i32(trt_ctx* ctx, int field_id, const int32_t* v_host /*[L][S]*/);
 int trt_block_set_format_f32(trt_ctx* ctx, int field_id, const float* v_host /*[L][S][ncol]*/, int ncol);
@@ -436,6 +441,11 @@ int         trt_vcf_block_parse(const trt_vcf_block* b, int ploidy, int16_t* gt_
  * 254 = ploidy pad, 255 = no-call), phase_out (may be NULL) [n][ceil(S/8)] one bit per call.  rec_status 3 = the record
  * does not fit (an allele index above 252, or a call with more than two haplotypes): parse the block in the plain form.  */
 int         trt_vcf_block_parse_packed(const trt_vcf_block* b, uint8_t* gt2_out, uint8_t* phase_out, int n_keys,
+                                       const char* const* keys, const int32_t* key_is_float, void* const* key_out,
+                                       uint8_t* present, int32_t* rec_ploidy, uint8_t* rec_status);
+/* the same into the nibble form (trt_block_set_gt_nibble): g4_out [n][S]; rec_status 3 = the record has an allele index
+ * above 13 or more than two haplotypes (parse the block with trt_vcf_block_parse_packed instead)                        */
+int         trt_vcf_block_parse_nibble(const trt_vcf_block* b, uint8_t* g4_out, uint8_t* phase_out, int n_keys,
                                        const char* const* keys, const int32_t* key_is_float, void* const* key_out,
                                        uint8_t* present, int32_t* rec_ploidy, uint8_t* rec_status);
 

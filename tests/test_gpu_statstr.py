@@ -529,6 +529,23 @@ def test_packed_gt_transfer_form_round_trip_and_same_statistics(ctx):
         unph = gt.copy()
         unph[:, :, 2] = 0
         assert np.array_equal(ctx.block_get_gt(0, L), unph)
+        # the nibble form (one byte per call; the synthetic loci have <= 14 alleles)
+        from trtools_b200.block import pack_gt4, unpack_gt4
+        g4, ph4 = pack_gt4(gt)
+        assert np.array_equal(unpack_gt4(g4, ph4), gt) and np.array_equal(ph4, ph)
+        ctx.block_begin(L, S, 2, "hipstr")
+        ctx.block_set_gt_nibble(g4, ph4)
+        ctx.block_set_alleles(*tables)
+        ctx.check(ctx.lib.trt_harmonize(ctx.h))
+        assert np.array_equal(ctx.block_get_gt(0, L), gt)
+        back4, backph4 = ctx.block_get_gt_nibble(0, L, with_phase=True)
+        assert np.array_equal(back4, g4) and np.array_equal(backph4, ph4)
+        got = ctx.locus_stats(False, None, 0.01)
+        for k in want:
+            assert np.array_equal(want[k], got[k], equal_nan=True), k
     big = np.zeros((1, 16, 3), np.int16)
     big[0, 3, 0] = 300
     assert pack_gt(big) is None                                   # does not fit: callers use the int16 layout
+    big[0, 3, 0] = 14
+    from trtools_b200.block import pack_gt4
+    assert pack_gt4(big) is None and pack_gt(big) is not None     # 14 fits two bytes, not a nibble

@@ -402,6 +402,12 @@ class _RecordingCtx:
         self.calls["gt_is_view"] = gt2.base is not None
         self.calls["packed"] = True
 
+    def block_set_gt_nibble(self, g4, phase=None):
+        from trtools_b200.block import unpack_gt4
+        self.calls["gt"] = unpack_gt4(np.array(g4), None if phase is None else np.array(phase))
+        self.calls["gt_is_view"] = g4.base is not None
+        self.calls["packed"] = True
+
     def block_set_alleles(self, *a):
         self.calls["alleles"] = a
 
@@ -721,19 +727,20 @@ def test_many_short_records_small_blocks_is_linear(tmp_path):
 def test_packed_parse_equals_packing_the_plain_parse(tmp_path):
     """trt_vcf_block_parse_packed writes the transfer form of trt_block_set_gt_packed straight from the text: it must
     equal numpy's packing of the plain int16 parse (phase bits included), and flag records that do not fit."""
-    from trtools_b200.block import pack_gt
+    from trtools_b200.block import pack_gt, pack_gt4
     for path in (os.path.join(DATA, "many_samples.vcf.gz"), os.path.join(DATA, "trio_chr21_hipstr.sorted.vcf.gz")):
         outs = []
-        for packed in (True, False):
+        for packed, nibble in ((True, True), (True, False), (False, False)):
             v = NativeVCF(path)
             v._packed_gt = packed
+            v._nibble_gt = nibble
             v._native_block_loci = 200
             recs = [r for _, r in zip(range(200), v)]
             nblk = recs[0]._nblk
             nblk.parse(())
             outs.append(nblk)
-        p, q = outs
-        assert p.gt2 is not None and q.gt2 is None and q.gt is not None
+        n4, p, q = outs
+        assert p.gt2 is not None and p.gt2.ndim == 3 and q.gt2 is None and q.gt is not None
         ok = q.status == 0
         assert np.array_equal(p.status == 0, ok)
         g2, ph = pack_gt(q.gt[ok])
@@ -741,6 +748,16 @@ def test_packed_parse_equals_packing_the_plain_parse(tmp_path):
         assert np.array_equal(p.gt[ok], q.gt[ok])                 # materialised on demand
         for i in np.nonzero(ok)[0][:20]:
             assert np.array_equal(p.gt_of(int(i)), q.gt_of(int(i)))
+        # the nibble form (one byte per call) when no allele index of the run exceeds 13, else the two-byte form
+        fits = pack_gt4(q.gt[ok])
+        if fits is not None and (q.rec_ploidy[ok] <= 2).all():
+            assert n4.gt2 is not None and n4.gt2.ndim == 2
+            assert np.array_equal(n4.gt2[ok], fits[0]) and np.array_equal(n4.phase[ok], fits[1])
+            assert np.array_equal(n4.gt[ok], q.gt[ok])
+            for i in np.nonzero(ok)[0][:20]:
+                assert np.array_equal(n4.gt_of(int(i)), q.gt_of(int(i)))
+        else:
+            assert n4.gt2 is not None and n4.gt2.ndim == 3 and np.array_equal(n4.gt2[ok], g2)
     # an allele index above 252 falls back to the plain form for the whole run
     alts = ",".join("AC" * (k + 2) for k in range(260))
     text = _vcf_text(["1\t100\t.\tAC\t%s\t.\t.\tSTART=100;END=101;PERIOD=2\tGT\t0|1\t255|3\t.\t259/0" % alts])
@@ -750,3 +767,10 @@ def test_packed_parse_equals_packing_the_plain_parse(tmp_path):
     assert rec._nblk.gt2 is None or not rec._nblk.parsed
     assert rec.genotype.array().tolist() == [[0, 1, 1], [255, 3, 1], [-1, -2, 0], [259, 0, 0]]
     assert rec._nblk.gt2 is None
+    # an allele index of 14 .. 252: the nibble form does not fit, the two-byte form does
+    alts = ",".join("AC" * (k + 2) for k in range(20))
+    text = _vcf_text(["1\t100\t.\tAC\t%s\t.\t.\tSTART=100;END=101;PERIOD=2\tGT\t0|1\t14|3\t.\t13/0" % alts])
+    path = _write(tmp_path, "mid.vcf", text)
+    rec = next(iter(NativeVCF(path)))
+    assert rec.genotype.array().tolist() == [[0, 1, 1], [14, 3, 1], [-1, -2, 0], [13, 0, 0]]
+    assert rec._nblk.gt2 is not None and rec._nblk.gt2.ndim == 3

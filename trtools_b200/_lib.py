@@ -30,7 +30,7 @@ EXPORTS = [
     "trt_device_count", "trt_init", "trt_destroy", "trt_last_error", "trt_device_info", "trt_synchronize",
     "trt_host_alloc", "trt_host_free", "trt_launch_count", "trt_last_kernel_ms", "trt_last_scan_ms",
     "trt_stopwatch_start", "trt_stopwatch_stop",
-    "trt_block_begin", "trt_block_set_gt", "trt_block_set_gt_packed", "trt_block_get_gt_packed", "trt_block_set_gt_device", "trt_block_set_format_i32",
+    "trt_block_begin", "trt_block_set_gt", "trt_block_set_gt_packed", "trt_block_get_gt_packed", "trt_block_set_gt_nibble", "trt_block_get_gt_nibble", "trt_block_set_gt_device", "trt_block_set_format_i32",
     "trt_block_set_format_f32", "trt_block_set_format_device", "trt_block_set_alleles",
     "trt_harmonize", "trt_get_harmonized", "trt_pack_length_genotypes", "trt_get_packed_gt",
     "trt_locus_stats", "trt_genotype_counts", "trt_call_filters", "trt_locus_filters", "trt_assoc_set_design", "trt_assoc_ols",
@@ -40,7 +40,7 @@ EXPORTS = [
     "trt_dist_allreduce_sum_f64", "trt_dist_allreduce_max_f64", "trt_dist_barrier", "trt_dist_gather_region",
     "trt_dist_gather_host", "trt_dist_wait", "trt_dist_finalize",
     "trt_vcf_open", "trt_vcf_close", "trt_vcf_last_error", "trt_vcf_header", "trt_vcf_n_samples",
-    "trt_vcf_set_samples", "trt_vcf_seek", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse", "trt_vcf_block_parse_packed", "trt_vcf_block_field", "trt_vcf_join_samples",
+    "trt_vcf_set_samples", "trt_vcf_seek", "trt_vcf_read_block", "trt_vcf_block_free", "trt_vcf_block_text", "trt_vcf_block_parse", "trt_vcf_block_parse_packed", "trt_vcf_block_parse_nibble", "trt_vcf_block_field", "trt_vcf_join_samples",
 ]
 
 
@@ -152,6 +152,8 @@ def load():
         "trt_block_set_gt": (i32, [vp, vp]),
         "trt_block_set_gt_packed": (i32, [vp, vp, vp]),
         "trt_block_get_gt_packed": (i32, [vp, i64, i64, vp, vp]),
+        "trt_block_set_gt_nibble": (i32, [vp, vp, vp]),
+        "trt_block_get_gt_nibble": (i32, [vp, i64, i64, vp, vp]),
         "trt_block_set_gt_device": (i32, [vp, vp, sz]),
         "trt_block_set_format_i32": (i32, [vp, i32, vp]),
         "trt_block_set_format_f32": (i32, [vp, i32, vp, i32]),
@@ -198,6 +200,7 @@ def load():
         "trt_vcf_block_text": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "trt_vcf_block_parse": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
         "trt_vcf_block_parse_packed": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "trt_vcf_block_parse_nibble": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
         "trt_vcf_block_field": (i32, [vp, i64, i32, C.c_int32, vp, vp]),
         "trt_vcf_join_samples": (i64, [i64, i32, vp, vp, vp, vp, i64]),
     }
@@ -337,6 +340,23 @@ class Context:
             ph = _c(phase_bits, np.uint8)
             assert ph.shape == (self.L, (self.S + 7) // 8)
         self.check(self.lib.trt_block_set_gt_packed(self.h, _ptr(g), _ptr(ph)))
+
+    def block_set_gt_nibble(self, g4: np.ndarray, phase_bits: Optional[np.ndarray] = None):
+        """Nibble transfer form: uint8 [L][S], first haplotype in the low nibble (allele 0..13, 14 pad, 15 no-call) +
+        optional phase bits; a sixth of the bytes of ``block_set_gt`` across PCIe, expanded on the device."""
+        g = _c(g4, np.uint8)
+        assert g.shape == (self.L, self.S) and self.P == 2, (g.shape, (self.L, self.S), self.P)
+        ph = None
+        if phase_bits is not None:
+            ph = _c(phase_bits, np.uint8)
+            assert ph.shape == (self.L, (self.S + 7) // 8)
+        self.check(self.lib.trt_block_set_gt_nibble(self.h, _ptr(g), _ptr(ph)))
+
+    def block_get_gt_nibble(self, locus0, n, out: Optional[np.ndarray] = None, with_phase: bool = False):
+        g = np.empty((n, self.S), np.uint8) if out is None else out
+        ph = np.empty((n, (self.S + 7) // 8), np.uint8) if with_phase else None
+        self.check(self.lib.trt_block_get_gt_nibble(self.h, int(locus0), int(n), _ptr(g), _ptr(ph)))
+        return (g, ph) if with_phase else g
 
     def block_get_gt_packed(self, locus0, n, out: Optional[np.ndarray] = None, with_phase: bool = False):
         g = np.empty((n, self.S, 2), np.uint8) if out is None else out

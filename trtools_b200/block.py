@@ -125,6 +125,36 @@ def pack_gt(gt: np.ndarray):
     return g2, ph
 
 
+def pack_gt4(gt: np.ndarray):
+    """cyvcf2-layout diploid GT int16 [..., S, 3] -> (uint8 [..., S] nibble pairs, phase bits) or None when an allele
+    index is above 13 (see include/trtools_b200.h trt_block_set_gt_nibble)."""
+    a = gt[..., :2]
+    if gt.shape[-1] != 3 or a.size and (int(a.max()) > 13 or int(a.min()) < -2):
+        return None
+    g4 = ((a[..., 0] & 15) | ((a[..., 1] & 15) << 4)).astype(np.uint8)
+    ph = np.packbits(gt[..., 2] != 0, axis=-1, bitorder="little")
+    return g4, ph
+
+
+def unpack_gt4(g4: np.ndarray, phase_bits: Optional[np.ndarray] = None) -> np.ndarray:
+    """Inverse of :func:`pack_gt4` -> int16 [..., S, 3]."""
+    S = g4.shape[-1]
+    out = np.empty(g4.shape + (3,), np.int16)
+    lo, hi = (g4 & 15).astype(np.int16), (g4 >> 4).astype(np.int16)
+    out[..., 0] = np.where(lo >= 14, lo - 16, lo)
+    out[..., 1] = np.where(hi >= 14, hi - 16, hi)
+    if phase_bits is None:
+        out[..., 2] = 0
+    else:
+        out[..., 2] = np.unpackbits(phase_bits, axis=-1, count=S, bitorder="little")
+    return out
+
+
+def unpack_any(g: np.ndarray, phase_bits: Optional[np.ndarray] = None) -> np.ndarray:
+    """Either transfer form of a block ([L][S][2] two-byte or [L][S] nibble) -> int16 [L][S][3]."""
+    return unpack_gt(g, phase_bits) if g.ndim == 3 else unpack_gt4(g, phase_bits)
+
+
 def unpack_gt(gt2: np.ndarray, phase_bits: Optional[np.ndarray] = None) -> np.ndarray:
     """Inverse of :func:`pack_gt` -> int16 [..., S, 3]."""
     S = gt2.shape[-2]
@@ -145,13 +175,14 @@ class Block:
     def gt(self) -> np.ndarray:
         """cyvcf2-layout int16 [L][S][P+1] on the host (expanded on first use when the block was built packed)."""
         if self._gt is None:
-            self._gt = unpack_gt(*self.gt_packed)
+            self._gt = unpack_any(*self.gt_packed)
         return self._gt
 
     def __init__(self, ctx: "_lib.Context", vcftype: str, metas: List[RecordMeta], gt: Optional[np.ndarray],
                  fmt: Optional[Dict[str, np.ndarray]] = None, gt_packed=None):
-        """``gt``: cyvcf2-layout int16 [L][S][P+1]; or ``gt_packed`` = (uint8 [L][S][2], phase bits or None), the packed
-        transfer form the block reader parses straight from the text (a third of the host->device bytes)."""
+        """``gt``: cyvcf2-layout int16 [L][S][P+1]; or ``gt_packed`` = (uint8 [L][S][2] or nibble pairs uint8 [L][S],
+        phase bits or None), the transfer forms the block reader parses straight from the text (a third / a sixth of
+        the host->device bytes)."""
         self.ctx = ctx
         self.vcftype = vcftype
         self.metas = metas
@@ -240,7 +271,9 @@ class Block:
         return self.ctx.locus_stats(use_length, group_masks, nalleles_thresh)
 
     def _upload_gt(self):
-        if self.gt_packed is not None:
+        if self.gt_packed is not None and self.gt_packed[0].ndim == 2:
+            self.ctx.block_set_gt_nibble(*self.gt_packed)
+        elif self.gt_packed is not None:
             self.ctx.block_set_gt_packed(*self.gt_packed)
         else:
             self.ctx.block_set_gt(self._gt)

@@ -84,6 +84,12 @@ struct AssocParams {
     double* dd;                     // [L][K(K+1)/2] outer products of the uncalled design rows
     const int32_t* list;            // loci handled by the generic kernels (null: all L loci)
     int64_t n_list;
+    // a short list is spread over the SMs by cutting the sample axis into segments (grid.y): partial sums go to
+    // part [nseg][n_list][K+3 | K(K+1)/2] and are added up in segment order by assoc_generic_reduce_kernel
+    int nseg;
+    int64_t seg_len;                // multiple of 256
+    double* mom_part;
+    double* dd_part;
 };
 
 // summed length genotype of one call; returns false if the sample is not (strictly) called
@@ -127,7 +133,8 @@ __global__ void __launch_bounds__(kMomThreads) assoc_moments_kernel(AssocParams 
         double acc0[KP + 3], acc1[KP + 3];
 #pragma unroll
         for (int k = 0; k < KP + 3; k++) { acc0[k] = 0.0; acc1[k] = 0.0; }
-        for (int64_t base = 0; base < p.S; base += 256) {
+        const int64_t s_begin = (int64_t)blockIdx.y * p.seg_len, s_end = min(p.S, s_begin + p.seg_len);
+        for (int64_t base = s_begin; base < s_end; base += 256) {
             __syncthreads();
             {   // stage the chunk's z-vectors (zeros for samples outside the design)
                 const int64_t s = base + tid;
@@ -167,8 +174,15 @@ __global__ void __launch_bounds__(kMomThreads) assoc_moments_kernel(AssocParams 
             if (k < nacc) {
                 const double a = warp_sum_d(acc0[k]), b = warp_sum_d(acc1[k]);
                 if (lane == 0) {
-                    if (q[0] < p.L) p.mom[q[0] * nacc + k] = a;
-                    if (q[1] < p.L) p.mom[q[1] * nacc + k] = b;
+                    if (p.nseg > 1) {
+                        const int64_t i0 = tile * kTileLoci + warp * 2;
+                        double* o = p.mom_part + ((size_t)blockIdx.y * n_loci + i0) * nacc + k;
+                        if (q[0] < p.L) o[0] = a;
+                        if (q[1] < p.L) o[nacc] = b;
+                    } else {
+                        if (q[0] < p.L) p.mom[q[0] * nacc + k] = a;
+                        if (q[1] < p.L) p.mom[q[1] * nacc + k] = b;
+                    }
                 }
             }
         }
@@ -197,7 +211,9 @@ __global__ void __launch_bounds__(256) assoc_downdate_kernel(AssocParams p) {
         eb[r] = a + rem;
     }
     const int64_t n_loci = p.list ? p.n_list : p.L;
-    for (int64_t li = warp; li < n_loci; li += nwarps) {
+    for (int64_t wi = warp; wi < n_loci * p.nseg; wi += nwarps) {
+        const int64_t li = wi % n_loci;
+        const int seg = (int)(wi / n_loci);
         const int64_t l = p.list ? (int64_t)p.list[li] : li;
         const int a0 = p.locus_off[l];
         const int A = p.locus_off[l + 1] - a0;
@@ -205,11 +221,12 @@ __global__ void __launch_bounds__(256) assoc_downdate_kernel(AssocParams p) {
         double acc[kR];
 #pragma unroll
         for (int r = 0; r < kR; r++) acc[r] = 0.0;
-        for (int64_t sb = 0; sb < p.S; sb += 32) {
+        const int64_t s_begin = (int64_t)seg * p.seg_len, s_end = min(p.S, s_begin + p.seg_len);
+        for (int64_t sb = s_begin; sb < s_end; sb += 32) {
             const int64_t s = sb + lane;
             int r_row = -1;
             bool uncalled = false;
-            if (s < p.S) {
+            if (s < s_end) {
                 r_row = p.row_of_sample[s];
                 if (r_row >= 0) {
                     const int16_t* g = row + s * (p.P + 1);
@@ -243,8 +260,28 @@ __global__ void __launch_bounds__(256) assoc_downdate_kernel(AssocParams p) {
 #pragma unroll
         for (int r = 0; r < kR; r++) {
             const int e = lane + 32 * r;
-            if (e < ne) p.dd[l * ne + e] = acc[r];
+            if (e < ne) {
+                if (p.nseg > 1) p.dd_part[((size_t)seg * n_loci + li) * ne + e] = acc[r];
+                else p.dd[l * ne + e] = acc[r];
+            }
         }
+    }
+}
+
+__global__ void assoc_generic_reduce_kernel(AssocParams p, int nacc, int ne) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = nacc + ne;
+    if (i >= p.n_list * w) return;
+    const int64_t li = i / w;
+    const int k = (int)(i % w);
+    const int64_t l = p.list[li];
+    double v = 0.0;
+    if (k < nacc) {
+        for (int sg = 0; sg < p.nseg; sg++) v += p.mom_part[((size_t)sg * p.n_list + li) * nacc + k];
+        p.mom[l * nacc + k] = v;
+    } else {
+        for (int sg = 0; sg < p.nseg; sg++) v += p.dd_part[((size_t)sg * p.n_list + li) * ne + (k - nacc)];
+        p.dd[l * ne + (k - nacc)] = v;
     }
 }
 
@@ -752,15 +789,37 @@ int trt_assoc_ols(trt_ctx* ctx, double non_major_cutoff, trt_assoc_out* out) {
         const int64_t ntiles = (n_gen + kTileLoci - 1) / kTileLoci;
         const size_t smem = (size_t)K * 256 * 8;
         const unsigned mgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
-        const int64_t wblocks = std::max<int64_t>(1, std::min<int64_t>((n_gen + 7) / 8, (int64_t)ctx->sm_count * 8));
+        // a handful of listed loci would otherwise sit on a handful of CTAs for the whole sample axis
+        ap.nseg = 1;
+        ap.seg_len = (S + 255) & ~int64_t(255);
+        ap.mom_part = ap.dd_part = nullptr;
+        if (ap.list && need_generic && ntiles < (int64_t)ctx->sm_count * 2 && S >= 4096) {
+            int nseg = (int)std::min<int64_t>(((int64_t)ctx->sm_count * 4 + ntiles - 1) / ntiles, S / 2048);
+            nseg = std::max(1, std::min(nseg, 4096));
+            const int64_t seg_len = (((S + nseg - 1) / nseg) + 255) & ~int64_t(255);
+            nseg = (int)((S + seg_len - 1) / seg_len);
+            if (nseg > 1) {
+                TRT_TRY(trt_ensure(ctx, ctx->assoc_tile_fast, (size_t)nseg * n_gen * (nacc + ne) * 8 + 64));
+                ap.nseg = nseg;
+                ap.seg_len = seg_len;
+                ap.mom_part = (double*)ctx->assoc_tile_fast.p;
+                ap.dd_part = ap.mom_part + (size_t)nseg * n_gen * nacc;
+            }
+        }
+        const int64_t wblocks = std::max<int64_t>(1, std::min<int64_t>((n_gen * ap.nseg + 7) / 8, (int64_t)ctx->sm_count * 8));
 #define LAUNCH_MOMENTS(KP)                                                                                              \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
             TRT_CUDA(cudaFuncSetAttribute(assoc_moments_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        assoc_moments_kernel<KP><<<mgrid, kMomThreads, smem, ctx->stream>>>(ap);                                        \
+        assoc_moments_kernel<KP><<<dim3(mgrid, (unsigned)ap.nseg), kMomThreads, smem, ctx->stream>>>(ap);               \
         TRT_KERNEL_CHECK();                                                                                             \
         assoc_downdate_kernel<KP><<<(unsigned)wblocks, 256, 0, ctx->stream>>>(ap);                                      \
         TRT_KERNEL_CHECK();                                                                                             \
+        if (ap.nseg > 1) {                                                                                              \
+            const int64_t nred = n_gen * (nacc + ne);                                                                   \
+            assoc_generic_reduce_kernel<<<(unsigned)((nred + 255) / 256), 256, 0, ctx->stream>>>(ap, nacc, ne);         \
+            TRT_KERNEL_CHECK();                                                                                         \
+        }                                                                                                               \
     } while (0)
         if (!need_generic) {
         } else if (K <= 8) LAUNCH_MOMENTS(8);
@@ -897,6 +956,9 @@ int trt_assoc_dosage_ols(trt_ctx* ctx, const int32_t* cls, const double* len_rou
         ap.dd = ap.mom + (size_t)L * nacc;
         ap.list = nullptr;
         ap.n_list = 0;
+        ap.nseg = 1;
+        ap.seg_len = (S + 255) & ~int64_t(255);
+        ap.mom_part = ap.dd_part = nullptr;
         q.ap1 = (const float*)ctx->ap1.p;
         q.ap2 = (const float*)ctx->ap2.p;
         q.cls = d_cls;

@@ -114,6 +114,61 @@ __global__ void __launch_bounds__(256) gt_pack_kernel(const int16_t* __restrict_
     }
 }
 
+// nibble transfer form (alleles <= 13): one byte per call, first haplotype in the low nibble; 14 = ploidy pad, 15 = no call
+__global__ void __launch_bounds__(256) gt_expand4_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ phase,
+                                                         int64_t L, int64_t S, int16_t* __restrict__ gt, size_t pitch) {
+    const int64_t groups = (S + 7) / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L * groups; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = i / groups, gidx = i % groups;
+        const int64_t s0 = gidx * 8;
+        const uint8_t* src = packed + (size_t)l * S + s0;
+        const unsigned ph = phase ? phase[(size_t)l * groups + gidx] : 0u;
+        int16_t* dst = (int16_t*)((char*)gt + (size_t)l * pitch) + s0 * 3;
+        unsigned long long v = 0;
+        const int nvalid = (int)min((int64_t)8, S - s0);
+        if (nvalid == 8 && (((size_t)l * S + s0) & 7) == 0) v = *reinterpret_cast<const unsigned long long*>(src);
+        else for (int j = 0; j < nvalid; j++) v |= (unsigned long long)src[j] << (8 * j);
+        int16_t h[24];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned b = (unsigned)(v >> (8 * j)) & 0xffu, a0 = b & 15u, a1 = b >> 4;
+            h[3 * j] = (int16_t)(a0 >= 14u ? (int)a0 - 16 : (int)a0);
+            h[3 * j + 1] = (int16_t)(a1 >= 14u ? (int)a1 - 16 : (int)a1);
+            h[3 * j + 2] = (int16_t)((ph >> j) & 1u);
+        }
+        if (nvalid == 8) {
+            uint32_t o[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) o[k] = (uint32_t)(uint16_t)h[2 * k] | ((uint32_t)(uint16_t)h[2 * k + 1] << 16);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);         // rows are 16-byte multiples and s0 * 6 = gidx * 48
+            d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        } else {
+            for (int j = 0; j < 3 * nvalid; j++) dst[j] = h[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gt_pack4_kernel(const int16_t* __restrict__ gt, size_t pitch, int64_t l0, int64_t n, int64_t S,
+                                                       uint8_t* __restrict__ packed, uint8_t* __restrict__ phase, int* __restrict__ bad) {
+    const int64_t groups = (S + 7) / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * groups; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = i / groups, gidx = i % groups;
+        const int64_t s0 = gidx * 8;
+        const int16_t* src = (const int16_t*)((const char*)gt + (size_t)(l0 + l) * pitch) + s0 * 3;
+        uint8_t* dst = packed + (size_t)l * S + s0;
+        unsigned ph = 0;
+        for (int j = 0; j < 8 && s0 + j < S; j++) {
+            const int a = src[3 * j], b = src[3 * j + 1];
+            if (a > 13 || b > 13 || a < -2 || b < -2) *bad = 1;
+            dst[j] = (uint8_t)((a & 15) | ((b & 15) << 4));          // -1 -> 15, -2 -> 14
+            ph |= (src[3 * j + 2] ? 1u : 0u) << j;
+        }
+        if (phase) phase[(size_t)l * groups + gidx] = (uint8_t)ph;
+    }
+}
+
 template <typename T>
 static int upload(trt_ctx* ctx, DevBuf& b, const T* host, size_t n) {
     TRT_TRY(trt_ensure(ctx, b, n * sizeof(T) + 16));
@@ -178,9 +233,16 @@ void trt_destroy(trt_ctx* ctx) {
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
         cudaEventDestroy(ctx->ev_gathered);
-        for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_copied[i]);
+        for (int i = 0; i < 5; i++) {
+            cudaEventDestroy(ctx->ev_copied[i]);
+            cudaEventDestroy(ctx->ev_staged[i]);
+            cudaEventDestroy(ctx->ev_sent[i]);
+        }
     }
-    for (int i = 0; i < 5; i++) trt_free_buf(ctx->dist_recv_r[i]);
+    for (int i = 0; i < 5; i++) {
+        trt_free_buf(ctx->dist_recv_r[i]);
+        trt_free_buf(ctx->dist_stage_r[i]);
+    }
     DevBuf* bufs[] = {&ctx->gt_buf, &ctx->gt_masked_buf, &ctx->gt_packed_buf, &ctx->seqs, &ctx->allele_off, &ctx->locus_off, &ctx->pos,
                       &ctx->start, &ctx->end, &ctx->period, &ctx->given_len, &ctx->motif_in, &ctx->allele_len, &ctx->trim_off,
                       &ctx->trim_len, &ctx->len_class, &ctx->seq_class, &ctx->len_order, &ctx->seq_order, &ctx->hrun,
@@ -368,6 +430,66 @@ int trt_block_get_gt_packed(trt_ctx* ctx, int64_t locus0, int64_t n, uint8_t* gt
     TRT_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     TRT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (bad) return trt_set_error(ctx, TRT_EINVAL, "trt_block_get_gt_packed: an allele index above 252 does not fit the packed form");
+    return TRT_OK;
+}
+
+int trt_block_set_gt_nibble(trt_ctx* ctx, const uint8_t* g4_host, const uint8_t* phase_bits_host) {
+    if (!ctx || !ctx->block_open) return trt_set_error(ctx, TRT_ESTATE, "trt_block_set_gt_nibble: no open block");
+    if (ctx->P != 2) return trt_set_error(ctx, TRT_EINVAL, "trt_block_set_gt_nibble: the nibble form is diploid (block ploidy %d)", ctx->P);
+    if (!g4_host && ctx->L * ctx->S > 0) return trt_set_error(ctx, TRT_EINVAL, "trt_block_set_gt_nibble: NULL array");
+    const int64_t L = ctx->L, S = ctx->S;
+    const size_t row = gt_row_bytes(ctx);
+    size_t pitch = (row + 15) & ~size_t(15);
+    if (pitch == 0) pitch = 16;
+    const size_t pbytes = (size_t)(S + 7) / 8;
+    TRT_TRY(trt_ensure(ctx, ctx->gt_buf, pitch * (size_t)L + 16));
+    TRT_TRY(trt_ensure(ctx, ctx->gt_packed_buf, (size_t)L * S + (size_t)L * pbytes + 64));
+    uint8_t* d_packed = (uint8_t*)ctx->gt_packed_buf.p;
+    uint8_t* d_phase = d_packed + (((size_t)L * S + 15) & ~size_t(15));
+    if (L > 0 && S > 0) {
+        if (pitch != row) TRT_CUDA(cudaMemsetAsync(ctx->gt_buf.p, 0xFE, pitch * (size_t)L, ctx->stream));   // keep the pad bytes defined
+        TRT_CUDA(cudaMemcpyAsync(d_packed, g4_host, (size_t)L * S, cudaMemcpyHostToDevice, ctx->stream));
+        if (phase_bits_host)
+            TRT_CUDA(cudaMemcpyAsync(d_phase, phase_bits_host, (size_t)L * pbytes, cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t work = L * ((S + 7) / 8);
+        const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 32);
+        gt_expand4_kernel<<<blocks, 256, 0, ctx->stream>>>(d_packed, phase_bits_host ? d_phase : nullptr, L, S, (int16_t*)ctx->gt_buf.p, pitch);
+        TRT_KERNEL_CHECK();
+    }
+    ctx->d_gt = (const int16_t*)ctx->gt_buf.p;
+    ctx->gt_pitch = pitch;
+    ctx->d_gt_active = ctx->d_gt;
+    ctx->gt_active_pitch = pitch;
+    ctx->have_gt = true;
+    ctx->have_packed = false;
+    return TRT_OK;
+}
+
+int trt_block_get_gt_nibble(trt_ctx* ctx, int64_t locus0, int64_t n, uint8_t* g4_out_host, uint8_t* phase_bits_out_host) {
+    if (!ctx || !ctx->have_gt) return trt_set_error(ctx, TRT_ESTATE, "trt_block_get_gt_nibble: no GT in the block");
+    if (ctx->P != 2) return trt_set_error(ctx, TRT_EINVAL, "trt_block_get_gt_nibble: the nibble form is diploid");
+    if (locus0 < 0 || n < 0 || locus0 + n > ctx->L || (n && !g4_out_host)) return trt_set_error(ctx, TRT_EINVAL, "trt_block_get_gt_nibble: range");
+    const int64_t S = ctx->S;
+    const size_t pbytes = (size_t)(S + 7) / 8;
+    TRT_TRY(trt_ensure(ctx, ctx->gt_packed_buf, (size_t)n * S + (size_t)n * pbytes + 64 + 16));
+    uint8_t* d_packed = (uint8_t*)ctx->gt_packed_buf.p;
+    uint8_t* d_phase = d_packed + (((size_t)n * S + 15) & ~size_t(15));
+    int* d_bad = (int*)(d_phase + (((size_t)n * pbytes + 15) & ~size_t(15)));
+    int bad = 0;
+    TRT_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    if (n > 0 && S > 0) {
+        const int64_t work = n * ((S + 7) / 8);
+        const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 32);
+        gt_pack4_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_gt_active, ctx->gt_active_pitch, locus0, n, S, d_packed,
+                                                          phase_bits_out_host ? d_phase : nullptr, d_bad);
+        TRT_KERNEL_CHECK();
+        TRT_CUDA(cudaMemcpyAsync(g4_out_host, d_packed, (size_t)n * S, cudaMemcpyDeviceToHost, ctx->stream));
+        if (phase_bits_out_host)
+            TRT_CUDA(cudaMemcpyAsync(phase_bits_out_host, d_phase, (size_t)n * pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRT_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) return trt_set_error(ctx, TRT_EINVAL, "trt_block_get_gt_nibble: an allele index above 13 does not fit the nibble form");
     return TRT_OK;
 }
 

@@ -1,6 +1,7 @@
 // Multi-GPU plumbing: loci shard by contiguous ranges (no data-path collective); NCCL only gathers
 // the fixed-width per-locus result rows and sums the dumpSTR per-sample counters.
 #include <nccl.h>
+#include <stdlib.h>
 
 #include "trt_internal.cuh"
 
@@ -34,6 +35,7 @@ int trt_dist_init(trt_ctx* ctx, int rank, int world, const void* unique_id_128_b
     return TRT_OK;
 }
 
+static int join_side_stream(trt_ctx* ctx);
 static int need_comm(trt_ctx* ctx) {
     if (!ctx || !ctx->nccl_comm) return trt_set_error(ctx, TRT_ESTATE, "trt_dist_*: call trt_dist_init first");
     return TRT_OK;
@@ -43,6 +45,7 @@ int trt_dist_allgather_f64(trt_ctx* ctx, const double* send_host, int64_t count,
     TRT_TRY(need_comm(ctx));
     TRT_TRY(trt_ensure(ctx, ctx->dist_send, (size_t)count * 8 + 16));
     TRT_TRY(trt_ensure(ctx, ctx->dist_recv, (size_t)count * 8 * ctx->world + 16));
+    TRT_TRY(join_side_stream(ctx));
     TRT_CUDA(cudaMemcpyAsync(ctx->dist_send.p, send_host, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
     TRT_NCCL(ncclAllGather(ctx->dist_send.p, ctx->dist_recv.p, (size_t)count, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     TRT_CUDA(cudaMemcpyAsync(recv_host, ctx->dist_recv.p, (size_t)count * 8 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
@@ -53,6 +56,7 @@ int trt_dist_allgather_f64(trt_ctx* ctx, const double* send_host, int64_t count,
 static int allreduce(trt_ctx* ctx, void* inout_host, int64_t count, ncclDataType_t dt) {
     TRT_TRY(need_comm(ctx));
     TRT_TRY(trt_ensure(ctx, ctx->dist_send, (size_t)count * 8 + 16));
+    TRT_TRY(join_side_stream(ctx));
     TRT_CUDA(cudaMemcpyAsync(ctx->dist_send.p, inout_host, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
     TRT_NCCL(ncclAllReduce(ctx->dist_send.p, ctx->dist_send.p, (size_t)count, dt, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     TRT_CUDA(cudaMemcpyAsync(inout_host, ctx->dist_send.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -66,6 +70,7 @@ int trt_dist_allreduce_sum_f64(trt_ctx* ctx, double* inout_host, int64_t count) 
 int trt_dist_allreduce_max_f64(trt_ctx* ctx, double* inout_host, int64_t count) {
     TRT_TRY(need_comm(ctx));
     TRT_TRY(trt_ensure(ctx, ctx->dist_send, (size_t)count * 8 + 16));
+    TRT_TRY(join_side_stream(ctx));
     TRT_CUDA(cudaMemcpyAsync(ctx->dist_send.p, inout_host, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
     TRT_NCCL(ncclAllReduce(ctx->dist_send.p, ctx->dist_send.p, (size_t)count, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     TRT_CUDA(cudaMemcpyAsync(inout_host, ctx->dist_send.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -78,19 +83,35 @@ int trt_dist_barrier(trt_ctx* ctx) {
     return trt_dist_allreduce_sum_i64(ctx, &one, 1);
 }
 
-// side stream + event for the device->host copy of a gathered table (so the next step's kernels overlap it)
+// Side stream for the gathers: the rows of a step travel (NCCL) and reach the host (D2H) while the next step's kernels
+// run on the context stream.  The context stream only pays a device-to-device copy of its rows into a staging buffer.
 static int ensure_copy_stream(trt_ctx* ctx) {
     if (!ctx->copy_stream) {
         TRT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_gathered, cudaEventDisableTiming));
-        for (int i = 0; i < 5; i++) TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        for (int i = 0; i < 5; i++) {
+            TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_staged[i], cudaEventDisableTiming));
+            TRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_sent[i], cudaEventDisableTiming));
+        }
     }
     return TRT_OK;
 }
 
-// rank -> dst gather of `nbytes` device bytes per rank (ragged: nbytes_per_rank) on the context stream; on dst the
-// gathered bytes land in ctx->dist_recv in rank order and, when host_out is given, are copied to the host on the side
-// stream.  Nothing blocks the host unless `async` is 0.
+// NCCL operations of one communicator must be issued in one order: before a collective goes onto the context stream,
+// that stream waits for everything the side stream still has in flight
+static int join_side_stream(trt_ctx* ctx) {
+    if (ctx->copy_stream) {
+        TRT_CUDA(cudaEventRecord(ctx->ev_gathered, ctx->copy_stream));
+        TRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_gathered, 0));
+    }
+    return TRT_OK;
+}
+
+// rank -> dst gather of `nbytes` device bytes per rank (ragged: nbytes_per_rank).  Context stream: rows -> staging buffer
+// of the slot.  Side stream: grouped ncclSend / ncclRecv from the staging buffers; on dst the gathered bytes land in the
+// slot's receive buffer in rank order and, when host_out is given, are copied to the host.  Nothing blocks the host
+// unless `async` is 0.
 static int gather_device(trt_ctx* ctx, int slot, const void* send_dev, int64_t nbytes, const int64_t* nbytes_per_rank, int dst,
                          void* host_out, int async) {
     TRT_TRY(need_comm(ctx));
@@ -100,42 +121,61 @@ static int gather_device(trt_ctx* ctx, int slot, const void* send_dev, int64_t n
     TRT_TRY(ensure_copy_stream(ctx));
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     DevBuf& recv = ctx->dist_recv_r[slot];
+    DevBuf& stage = ctx->dist_stage_r[slot];
     int64_t total = 0;
     for (int r = 0; r < ctx->world; r++) total += nbytes_per_rank[r];
-    if (ctx->rank == dst) {
-        // the previous gather's host copy must have left dist_recv before it is overwritten
+    if ((size_t)nbytes + 16 > stage.cap || (ctx->rank == dst && (size_t)total + 16 > recv.cap)) {
+        TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));          // growing a buffer the side stream may still use
+        TRT_TRY(trt_ensure(ctx, stage, (size_t)nbytes + 16));
+        if (ctx->rank == dst) TRT_TRY(trt_ensure(ctx, recv, (size_t)total + 16));
+    }
+    // TRT_DIST_MAIN_STREAM=1: the exchange itself stays on the context stream (only the host copy overlaps the next step)
+    static const bool side = !getenv("TRT_DIST_MAIN_STREAM");
+    cudaStream_t xs = side ? ctx->copy_stream : ctx->stream;
+    const void* src = send_dev;
+    if (side) {
+        // context stream: the previous send from this staging buffer must be over, then stage the rows
+        TRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sent[slot], 0));
+        if (nbytes > 0) TRT_CUDA(cudaMemcpyAsync(stage.p, send_dev, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        TRT_CUDA(cudaEventRecord(ctx->ev_staged[slot], ctx->stream));
+        // side stream: exchange (stream order already puts this behind the previous gather's host copy of the same buffer)
+        TRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_staged[slot], 0));
+        src = stage.p;
+    } else if (ctx->rank == dst) {
+        // the previous gather's host copy must have left the receive buffer before it is overwritten
         TRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
-        if ((size_t)total + 16 > recv.cap) {
-            TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-            TRT_TRY(trt_ensure(ctx, recv, (size_t)total + 16));
-        }
     }
     TRT_NCCL(ncclGroupStart());
     if (ctx->rank == dst) {
         int64_t off = 0;
         for (int r = 0; r < ctx->world; r++) {
             if (r != dst && nbytes_per_rank[r] > 0)
-                TRT_NCCL(ncclRecv((char*)recv.p + off, (size_t)nbytes_per_rank[r], ncclChar, r, comm, ctx->stream));
+                TRT_NCCL(ncclRecv((char*)recv.p + off, (size_t)nbytes_per_rank[r], ncclChar, r, comm, xs));
             off += nbytes_per_rank[r];
         }
     } else if (nbytes > 0) {
-        TRT_NCCL(ncclSend(send_dev, (size_t)nbytes, ncclChar, dst, comm, ctx->stream));
+        TRT_NCCL(ncclSend(src, (size_t)nbytes, ncclChar, dst, comm, xs));
     }
     TRT_NCCL(ncclGroupEnd());
     if (ctx->rank == dst) {
         int64_t off = 0;
         for (int r = 0; r < dst; r++) off += nbytes_per_rank[r];
-        if (nbytes > 0)
-            TRT_CUDA(cudaMemcpyAsync((char*)recv.p + off, send_dev, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (nbytes > 0) TRT_CUDA(cudaMemcpyAsync((char*)recv.p + off, src, (size_t)nbytes, cudaMemcpyDeviceToDevice, xs));
+    }
+    if (side) {
+        TRT_CUDA(cudaEventRecord(ctx->ev_sent[slot], ctx->copy_stream));
+    } else if (ctx->rank == dst) {
         TRT_CUDA(cudaEventRecord(ctx->ev_gathered, ctx->stream));
         TRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gathered, 0));
+    }
+    if (ctx->rank == dst) {
         if (host_out && total > 0)
             TRT_CUDA(cudaMemcpyAsync(host_out, recv.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->copy_stream));
         TRT_CUDA(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
     }
     if (!async) {
         TRT_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->rank == dst) TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        TRT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     }
     return TRT_OK;
 }

@@ -879,7 +879,8 @@ int trt_vcf_block_text(const trt_vcf_block* b, const char** text, const int64_t*
 // gets rec_status 3 and the caller parses the block in the plain form.
 static int vcf_block_parse_impl(const trt_vcf_block* b, int ploidy, int16_t* gt_out, int n_keys, const char* const* keys,
                                 const int32_t* key_is_float, void* const* key_out, uint8_t* present, int32_t* rec_ploidy,
-                                uint8_t* rec_status, uint8_t* gt2_out = nullptr, uint8_t* phase_out = nullptr) {
+                                uint8_t* rec_status, uint8_t* gt2_out = nullptr, uint8_t* phase_out = nullptr,
+                                bool nibble = false) {
     if (!b || n_keys < 0 || n_keys > 32 || !rec_ploidy || !rec_status || (n_keys && (!keys || !key_out || !present)))
         return TRT_EINVAL;
     if (gt_out && ploidy < 1) return TRT_EINVAL;
@@ -921,12 +922,23 @@ static int vcf_block_parse_impl(const trt_vcf_block* b, int ploidy, int16_t* gt_
         rec_status[i] = (uint8_t)r.status;
         if (r.status != 0) return;
         if (r.ploidy > 2) { rec_status[i] = 3; return; }
-        uint8_t* o = gt2_out + (size_t)i * S * 2;
         const size_t pbytes = (size_t)(S + 7) / 8;
         uint8_t* ph = phase_out ? phase_out + (size_t)i * pbytes : nullptr;
         if (ph) memset(ph, 0, pbytes);
         const int16_t* g = row.data();
         bool fits = true;
+        if (nibble) {                       // one byte per call: low nibble first haplotype; -1 -> 15, -2 -> 14
+            uint8_t* o4 = gt2_out + (size_t)i * S;
+            for (int64_t s = 0; s < S; ++s, g += 3) {
+                const int a0 = g[0], a1 = g[1];
+                fits = fits && a0 <= 13 && a1 <= 13 && a0 >= -2 && a1 >= -2;
+                o4[s] = (uint8_t)((a0 & 15) | ((a1 & 15) << 4));
+                if (ph && g[2]) ph[s >> 3] |= (uint8_t)(1u << (s & 7));
+            }
+            if (!fits) rec_status[i] = 3;
+            return;
+        }
+        uint8_t* o = gt2_out + (size_t)i * S * 2;
         for (int64_t s = 0; s < S; ++s, g += 3) {
             const int a0 = g[0], a1 = g[1];
             fits = fits && a0 <= 252 && a1 <= 252 && a0 >= -2 && a1 >= -2;
@@ -1108,6 +1120,18 @@ int trt_vcf_block_parse_packed(const trt_vcf_block* b, uint8_t* gt2_out, uint8_t
     try {
         return vcf_block_parse_impl(b, 2, nullptr, n_keys, keys, key_is_float, key_out, present, rec_ploidy, rec_status,
                                     gt2_out, phase_out);
+    } catch (const std::exception&) {
+        return TRT_ENOMEM;
+    }
+}
+
+int trt_vcf_block_parse_nibble(const trt_vcf_block* b, uint8_t* g4_out, uint8_t* phase_out, int n_keys,
+                               const char* const* keys, const int32_t* key_is_float, void* const* key_out, uint8_t* present,
+                               int32_t* rec_ploidy, uint8_t* rec_status) {
+    if (!g4_out) return TRT_EINVAL;
+    try {
+        return vcf_block_parse_impl(b, 2, nullptr, n_keys, keys, key_is_float, key_out, present, rec_ploidy, rec_status,
+                                    g4_out, phase_out, true);
     } catch (const std::exception&) {
         return TRT_ENOMEM;
     }

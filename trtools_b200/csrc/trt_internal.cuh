@@ -89,8 +89,10 @@ struct trt_ctx {
     int     rank = 0, world = 1;
     DevBuf  dist_send, dist_recv;
     DevBuf  dist_recv_r[5];                 // receive buffer per result region (+ one for host-payload gathers)
+    DevBuf  dist_stage_r[5];                // the rank's own rows of a gather, staged for the side stream
     cudaStream_t copy_stream = nullptr;     // device->host copies of gathered tables (overlap the next step's kernels)
     cudaEvent_t  ev_gathered = nullptr, ev_copied[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t  ev_staged[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_sent[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 int  trt_set_error(trt_ctx* ctx, int code, const char* fmt, ...);

@@ -9,12 +9,17 @@
 // utils.GetHardyWeinbergBinomialTest trtools/utils/utils.py:328-333).
 //
 // Three tiers, all HBM-bandwidth bound by design (no data reuse; DRAM traffic = algorithmic bytes):
-//   scan_pairs_kernel  (diploid, A <= 14 alleles): persistent CTAs, one locus at a time.  A producer
-//       warp streams the row through a 3-stage shared-memory ring with 1-D bulk TMA copies
-//       (cp.async.bulk + mbarrier tx bytes).  8 consumer warps read 2 x 48 B per thread (conflict-free
-//       LDS.128) and do ONE thread-private shared-memory increment per CALL into a genotype-pair table
-//       [(A+3)^2][256 threads]; every statistic is derived from the reduced pair table, so there is no
-//       per-call flag logic at all (~13 instructions per call; the roofline allows ~33).
+//   scan_pairs_kernel<NG, CELL>  (diploid, A <= 14 alleles): persistent CTAs, one locus at a time (several short loci per
+//       CTA pass when S is small).  576 threads: a producer warp streams the row through an up-to-8-stage shared-memory
+//       ring of 4096-call chunks with 1-D bulk TMA copies (cp.async.bulk + mbarrier tx bytes); 16 consumer warps read
+//       48 B = 8 calls per thread (conflict-free LDS.128), turn each call into a bin of the unordered genotype-pair
+//       table with packed 16-bit arithmetic (VIADDMNMX.U16x2 clamp + IDP.2A index) and do ONE thread-private
+//       shared-memory increment per call — 8-bit cells [(A+2)(A+3)/2][512] folded every <= 31 chunks (16-bit cells as the
+//       fallback); an epilogue warp turns the previous locus' reduced pair table into allele counts and the TRT_LC_*
+//       counters while the consumers already stream the next locus (named barriers, no CTA-wide barrier in the loop).
+//       Every statistic is derived from the pair table, so there is no per-call flag logic at all.
+//       NG > 0: up to three sample groups (statSTR --samples f1,f2,..) are counted in the SAME pass — one membership
+//       byte per sample (bit per group), a table per group.
 //   scan_wide_kernel   (diploid, A <= 96): same TMA ring, thread-private per-haplotype 16-bit counters.
 //   scan_generic_kernel: warp per locus; any ploidy, any allele count, tiny sample counts.
 #include <stdlib.h>

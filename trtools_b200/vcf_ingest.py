@@ -93,7 +93,7 @@ class _NativeBlock:
         self.fixed_len = np.ctypeslib.as_array((C.c_int64 * n).from_address(fixed.value)).copy()
         self.S = len(vcf.samples)
         self._gt: Optional[np.ndarray] = None      # int16 [n][S][P+1] (plain parse, or materialised from the packed form)
-        self.gt2: Optional[np.ndarray] = None      # packed transfer form: uint8 [n][S][2] ...
+        self.gt2: Optional[np.ndarray] = None      # transfer form: nibble pairs uint8 [n][S] or two-byte uint8 [n][S][2] ...
         self.phase: Optional[np.ndarray] = None    # ... + phase bits uint8 [n][ceil(S/8)]
         self.rec_ploidy: Optional[np.ndarray] = None
         self.status: Optional[np.ndarray] = None
@@ -121,8 +121,8 @@ class _NativeBlock:
         """cyvcf2-layout int16 [n][S][P+1] of the whole run (materialised on demand when the run was parsed into the
         packed transfer form: the GPU path uploads the packed arrays and never asks for this)."""
         if self._gt is None and self.gt2 is not None:
-            from .block import unpack_gt
-            self._gt = unpack_gt(self.gt2, self.phase)
+            from .block import unpack_any
+            self._gt = unpack_any(self.gt2, self.phase)
         return self._gt
 
     # ---- text ----------------------------------------------------------------------------------
@@ -163,7 +163,21 @@ class _NativeBlock:
         status = np.zeros(n, dtype=np.uint8)
         P = 2
         gt2 = phase = None
-        if want_gt and getattr(self.vcf, "_packed_gt", True) and hasattr(self.lib, "trt_vcf_block_parse_packed"):
+        if want_gt and getattr(self.vcf, "_packed_gt", True) and getattr(self.vcf, "_nibble_gt", True) and \
+                hasattr(self.lib, "trt_vcf_block_parse_nibble"):
+            # one byte per call (alleles <= 13: nearly every TR locus) + a phase bit
+            gt2 = np.empty((n, S), dtype=np.uint8)
+            phase = np.empty((n, (S + 7) // 8), dtype=np.uint8)
+            rc = self.lib.trt_vcf_block_parse_nibble(
+                self.h, gt2.ctypes.data_as(C.c_void_p), phase.ctypes.data_as(C.c_void_p), nk,
+                C.cast(c_keys, C.c_void_p), C.cast(c_isf, C.c_void_p), C.cast(c_out, C.c_void_p),
+                present.ctypes.data_as(C.c_void_p), rec_ploidy.ctypes.data_as(C.c_void_p),
+                status.ctypes.data_as(C.c_void_p))
+            if rc != _lib.TRT_OK:
+                raise OSError("trt_vcf_block_parse_nibble failed ({})".format(rc))
+            if (status == 3).any():          # an allele index above 13 (or a polyploid call): the two-byte form below
+                gt2 = phase = None
+        if gt2 is None and want_gt and getattr(self.vcf, "_packed_gt", True) and hasattr(self.lib, "trt_vcf_block_parse_packed"):
             # straight into the packed transfer form (2 bytes per call + a phase bit): what the GPU block uploads
             gt2 = np.empty((n, S, 2), dtype=np.uint8)
             phase = np.empty((n, (S + 7) // 8), dtype=np.uint8)
@@ -210,8 +224,8 @@ class _NativeBlock:
         if self.status[i] != 0:
             return None
         if self.gt2 is not None and self._gt is None:
-            from .block import unpack_gt
-            g = unpack_gt(self.gt2[i], self.phase[i])
+            from .block import unpack_any
+            g = unpack_any(self.gt2[i][None], self.phase[i][None])[0]
         else:
             g = self.gt[i]
         P = g.shape[1] - 1
