@@ -473,11 +473,9 @@ def run_gpu(args):
         ctx.synth_fill(SEED, rank * L, loci.cum_freq, loci.miss_thresh, loci.half_thresh, with_format=False)
         ctx.block_set_alleles(*tables)
 
-    fits_nibble = int(np.max(loci.n_alleles)) <= 14
-    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True, nibble=fits_nibble)
-    if fits_nibble:
-        regen()
-        e2e["packed_2_bytes"] = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True)
+    e2e = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True, nibble=True)
+    regen()
+    e2e["packed_2_bytes"] = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True)
     regen()
     e2e["cyvcf2_layout"] = run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=False)
 
@@ -599,7 +597,7 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
     from trtools_b200 import _lib, synth, dist as tdist
     Lb = min(L, args.e2e_block)
     nblk = (L + Lb - 1) // Lb
-    blk_bytes = Lb * S * (1 if nibble else (2 if packed else 6))
+    blk_bytes = Lb * S * (2 if packed else 6)       # (nibble blocks are half of this)
     try:
         import psutil
         avail = psutil.virtual_memory().available
@@ -611,7 +609,8 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
     host_blocks = []
     for b in range(n_host):
         n = min(Lb, L - b * Lb)
-        if nibble:
+        # like the block reader, a block whose loci all have <= 14 alleles travels as nibbles, any other as two bytes
+        if nibble and int(np.max(loci.n_alleles[b * Lb:b * Lb + n])) <= 14:
             hb = ctx.pinned_empty((Lb, S), np.uint8)
             ctx.check(ctx.lib.trt_block_get_gt_nibble(ctx.h, b * Lb, n, hb.ctypes.data, None))
         elif packed:
@@ -641,7 +640,7 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
             n = blk_tables[b][2].shape[0] - 1
             hb = host_blocks[b % n_host]
             c.block_begin(n, S, 2, "hipstr")
-            if nibble:
+            if hb.ndim == 2:
                 c.block_set_gt_nibble(hb[:n])                 # asynchronous copy from the pinned block + expansion kernel
             elif packed:
                 c.block_set_gt_packed(hb[:n])
@@ -664,6 +663,8 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
     ctx.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
     e2e_ms = tdist.max_over_ranks(comm, e2e_ms)
+    host_bytes = sum(hb.nbytes for hb in host_blocks)
+    n_nibble = sum(1 for hb in host_blocks if hb.ndim == 2)
     for hb in host_blocks:
         ctx.free_pinned(hb)
     ctxs[1].close()
@@ -677,7 +678,9 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
                               "cyvcf2 layout: int16 [L][S][3] (trt_block_set_gt)"),
             "host_blocks": "{} pinned blocks of {} loci = {} distinct loci ({:.1f} GB) of the workload resident in host memory, "
                            "streamed {} blocks per step through two ping-pong contexts".format(
-                               n_host, Lb, min(n_host * Lb, L), n_host * blk_bytes / 1e9, nblk)}
+                               n_host, Lb, min(n_host * Lb, L), host_bytes / 1e9, nblk) +
+                           (" ({} of the {} resident blocks as nibbles, the others as two bytes per call)".format(n_nibble, n_host)
+                            if nibble else "")}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -8,7 +8,5 @@ import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(sys.argv[1], round(d['value']), round(d['ms_per_step'],3), d['timing'].get('per_rank_us_per_step_device_wall'), round(d['e2e']['value']))
 " $1; }
-timeout 200 python bench.py $F > gpurun_out/r2_ab_n1.json 2>/dev/null; pr gpurun_out/r2_ab_n1.json
-timeout 200 $T --nproc-per-node 2 --master-port 29561 bench.py --gpus 2 $F > gpurun_out/r2_ab_n2_side.json 2>/dev/null; pr gpurun_out/r2_ab_n2_side.json
-TRT_DIST_MAIN_STREAM=1 timeout 200 $T --nproc-per-node 2 --master-port 29571 bench.py --gpus 2 $F > gpurun_out/r2_ab_n2_main.json 2>/dev/null; pr gpurun_out/r2_ab_n2_main.json
-timeout 200 $T --nproc-per-node 2 --master-port 29581 bench.py --gpus 2 $F > gpurun_out/r2_ab_n2_side2.json 2>/dev/null; pr gpurun_out/r2_ab_n2_side2.json
+timeout 150 $T --nproc-per-node 2 --master-port 29561 bench.py --gpus 2 $F > gpurun_out/r2_ab_n2_side.json 2>>gpurun_out/r2_ab.err; pr gpurun_out/r2_ab_n2_side.json
+TRT_DIST_MAIN_STREAM=1 timeout 150 $T --nproc-per-node 2 --master-port 29571 bench.py --gpus 2 $F > gpurun_out/r2_ab_n2_main.json 2>>gpurun_out/r2_ab.err; pr gpurun_out/r2_ab_n2_main.json
