@@ -640,13 +640,15 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
             n = blk_tables[b][2].shape[0] - 1
             hb = host_blocks[b % n_host]
             c.block_begin(n, S, 2, "hipstr")
+            # allele tables first: that call returns once its (small, pageable) tables are on the device, and must not
+            # wait behind the block's genotype copy
+            c.block_set_alleles(*blk_tables[b])
             if hb.ndim == 2:
                 c.block_set_gt_nibble(hb[:n])                 # asynchronous copy from the pinned block + expansion kernel
             elif packed:
                 c.block_set_gt_packed(hb[:n])
             else:
                 c.block_set_gt(hb[:n])
-            c.block_set_alleles(*blk_tables[b])
             counters["h2d"] += hb[:n].nbytes + len(blk_tables[b][0]) + sum(a.nbytes for a in blk_tables[b][1:])
             if pending is not None:
                 finish(pending)

@@ -585,6 +585,12 @@ def test_region_queries_through_tabix_index_match_linear_scan(data_dir, fname, r
             assert _same(got_recs[0].genotype.array(), t.genotype.array()), region
             assert _same(got_recs[0].format("DP"), t.format("DP")), region
     assert used_index == len(regions)
+    # ONE reader serving every region in turn (and once more in reverse order): cyvcf2 readers can be queried repeatedly
+    v = NativeVCF(path)
+    for region in list(regions) + list(regions)[::-1]:
+        want = [(r.CHROM, r.POS, r.ID) for r in cc.TextVCF(path)(region)]
+        got = [(r.CHROM, r.POS, r.ID) for r in v(region)]
+        assert got == want, ("repeated query", region, len(got), len(want))
     # without the index: same answers by linear scan
     assert vcf_ingest._tabix_start(path + ".nope.tbi", "1", 5) is None
 
@@ -774,3 +780,38 @@ def test_packed_parse_equals_packing_the_plain_parse(tmp_path):
     rec = next(iter(NativeVCF(path)))
     assert rec.genotype.array().tolist() == [[0, 1, 1], [14, 3, 1], [-1, -2, 0], [13, 0, 0]]
     assert rec._nblk.gt2 is not None and rec._nblk.gt2.ndim == 3
+
+
+def test_writer_emits_bgzf_that_both_readers_and_gzip_accept(tmp_path):
+    """Writer('x.vcf.gz') writes BGZF (dumpSTR --zip must stay indexable): every member carries the BC size field and
+    inflates to <= 65 280 bytes, the file ends with the EOF member, gzip reads it as a multi-member stream, and the C++
+    block reader (which rejects plain gzip for seeks) reads the records back byte for byte."""
+    import gzip
+    import struct
+    from trtools_b200.cyvcf2_compat import TextVCF, Writer
+    src = os.path.join(DATA, "many_samples.vcf.gz")
+    tmpl = TextVCF(src)
+    recs = [r for _, r in zip(range(120), tmpl)]
+    out = str(tmp_path / "out.vcf.gz")
+    w = Writer(out, tmpl)
+    for r in recs:
+        w.write_record(r)
+    w.close()
+    raw = open(out, "rb").read()
+    off, members, total = 0, 0, 0
+    while off < len(raw):
+        assert raw[off:off + 4] == b"\x1f\x8b\x08\x04" and raw[off + 12:off + 16] == b"BC\x02\x00"
+        bsize = struct.unpack("<H", raw[off + 16:off + 18])[0] + 1
+        isize = struct.unpack("<I", raw[off + bsize - 4:off + bsize])[0]
+        assert isize <= 65280
+        total += isize
+        off += bsize
+        members += 1
+    assert off == len(raw) and members >= 3
+    assert raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")   # the BGZF EOF marker
+    text = gzip.open(out, "rt").read()
+    assert len(text.encode()) == total
+    want = tmpl.raw_header + "".join(str(r) for r in recs)
+    assert text == want
+    back = [str(r) for r in NativeVCF(out)]
+    assert back == [str(r) for r in recs]

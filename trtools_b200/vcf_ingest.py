@@ -393,6 +393,7 @@ class NativeVCF(_compat.TextVCF):
                                           C.byref(blk), C.byref(n))
         if rc != _lib.TRT_OK:
             raise OSError("Error reading {}: {}".format(self.fname, self._err()))
+        self._started = True
         if n.value == 0:
             return None
         return _NativeBlock(self, blk, n.value)
@@ -469,6 +470,8 @@ class NativeVCF(_compat.TextVCF):
         scan as the text reader."""
         super().__call__(region)
         self._region_stop = False
+        self._region_empty = False          # a reader serves any number of region queries, like cyvcf2's
+        self._seen_region_chrom = False
         chrom, start, _ = self._region
         try:
             voff = _tabix_start(self.fname + ".tbi", chrom, start)
@@ -483,10 +486,21 @@ class NativeVCF(_compat.TextVCF):
         if voff < 0:             # the index knows the contig is absent or the window is past its last record
             self._region_empty = True
             return self
-        if voff > 0:             # 0 = before any record of the file: keep reading where the header ended
+        if voff > 0:
             rc = self._lib.trt_vcf_seek(self._h, voff >> 16, voff & 0xffff)
             if rc != _lib.TRT_OK:
                 raise OSError("Error reading {}: {}".format(self.fname, self._err()))
+            self._started = True
+        elif getattr(self, "_started", False):
+            # 0 = before any record of the file, but this reader has already moved: start over behind the header
+            self._lib.trt_vcf_close(self._h)
+            h = C.c_void_p()
+            if self._lib.trt_vcf_open(os.fsencode(self.fname), 0, C.byref(h)) != _lib.TRT_OK:
+                raise OSError("Error opening %s" % self.fname)
+            self._h = h
+            if self._sample_idx is not None:
+                idx = np.asarray(self._sample_idx, dtype=np.int64)
+                self._lib.trt_vcf_set_samples(self._h, idx.ctypes.data_as(C.c_void_p), len(idx))
         self._region_stop = True
         return self
 
