@@ -815,3 +815,77 @@ def test_writer_emits_bgzf_that_both_readers_and_gzip_accept(tmp_path):
     assert text == want
     back = [str(r) for r in NativeVCF(out)]
     assert back == [str(r) for r in recs]
+
+
+def _parse_tbi(path):
+    data = gzip.open(path, "rb").read()
+    assert data[:4] == b"TBI\x01"
+    n_ref, fmt, cs, cb, ce, meta, skip, l_nm = struct.unpack_from("<8i", data, 4)
+    names = data[36:36 + l_nm].split(b"\x00")[:n_ref]
+    o, refs = 36 + l_nm, []
+    for _ in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", data, o)
+        o += 4
+        bins = {}
+        for _ in range(n_bin):
+            b, nc = struct.unpack_from("<Ii", data, o)
+            o += 8
+            bins[b] = [struct.unpack_from("<QQ", data, o + 16 * i) for i in range(nc)]
+            o += 16 * nc
+        (n_intv,) = struct.unpack_from("<i", data, o)
+        o += 4
+        refs.append((bins, list(struct.unpack_from("<%dQ" % n_intv, data, o))))
+        o += 8 * n_intv
+    return (fmt, cs, cb, ce, meta, skip), names, refs
+
+
+def test_native_tabix_index_writer(tmp_path, data_dir):
+    """tabix_index.write_tbi (dumpSTR --zip without the tabix binary): header, contig names and the whole linear index
+    equal the reference's own tabix-made .tbi files; every chunk of the real index lies inside a chunk of ours at the
+    same or a parent bin (htslib additionally merges small bins into their parents); and a file written by Writer,
+    indexed here, serves region queries through the index exactly like a linear scan."""
+    from trtools_b200.cyvcf2_compat import TextVCF, Writer
+    from trtools_b200.tabix_index import write_tbi
+    n_checked = 0
+    for fname in sorted(os.listdir(data_dir)):
+        path = os.path.join(data_dir, fname)
+        if not fname.endswith(".vcf.gz") or not os.path.isfile(path + ".tbi"):
+            continue
+        mine = write_tbi(path, str(tmp_path / (fname + ".tbi")))
+        a, b = _parse_tbi(path + ".tbi"), _parse_tbi(mine)
+        assert a[0] == b[0] and a[1] == b[1], fname
+        for (bins_a, lin_a), (bins_b, lin_b) in zip(a[2], b[2]):
+            assert lin_a == lin_b, fname
+            ours = sorted(c for cs in bins_b.values() for c in cs)
+            for bin_id, chunks in bins_a.items():
+                if bin_id == 37450:                         # htslib's pseudo-bin with mapped/unmapped counts
+                    continue
+                for cb, ce in chunks:
+                    assert any(ob <= cb and ce <= oe for ob, oe in _merged(ours)), (fname, bin_id)
+        n_checked += 1
+    assert n_checked >= 2
+    # Writer -> BGZF -> our index -> region queries
+    src = os.path.join(data_dir, "many_samples.vcf.gz")
+    tmpl = TextVCF(src)
+    out = str(tmp_path / "written.vcf.gz")
+    w = Writer(out, tmpl)
+    for r in tmpl:
+        w.write_record(r)
+    w.close()
+    write_tbi(out)
+    v = NativeVCF(out)
+    for region in ("1:1-20000", "1:164000-230000", "1:3000000-3100000", "1:900000", "2:1-100"):
+        want = [(r.CHROM, r.POS) for r in TextVCF(src)(region)]
+        got = [(r.CHROM, r.POS) for r in v(region)]
+        assert got == want, region
+        assert v._region_stop or v._region_empty, region      # served through the index, not by a linear scan
+
+
+def _merged(chunks):
+    out = []
+    for b, e in chunks:
+        if out and b <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], e)
+        else:
+            out.append([b, e])
+    return out

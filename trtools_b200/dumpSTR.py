@@ -708,9 +708,13 @@ def main(args):
     WriteSampLog(sample_info, invcf.samples, args.out + ".samplog.tab")
     WriteLocLog(loc_info, args.out + ".loclog.tab")
     if args.zip:
-        proc = sp.run(["tabix", args.out + suffix])
-        if proc.returncode != 0:
-            common.WARNING("Tabix failed with returncode " + str(proc.returncode))
+        # reference dumpSTR.py:1347-1352 shells out to `tabix`; the index is written natively here (same linear index,
+        # same header; see tabix_index.py), so --zip does not depend on the binary being installed
+        try:
+            from .tabix_index import write_tbi
+            write_tbi(args.out + suffix)
+        except Exception as e:
+            common.WARNING("Tabix failed with returncode 1 ({})".format(e))
             return 1
     return 0
 
