@@ -889,3 +889,27 @@ def _merged(chunks):
         else:
             out.append([b, e])
     return out
+
+
+def test_ragged_float_vectors_end_like_htslib_and_reserialise_unchanged(tmp_path):
+    """A Number=. Float FORMAT field with rows of different lengths: the padding is BCF's float vector-end marker (a NaN,
+    so 'missing' tests still hold), not a missing value — after a write-back of ANOTHER field re-serialises the record,
+    '1.5' must not become '1.5,.' (the loop writer, the vectorised writer and the C++ serialiser all skip the marker)."""
+    header = HEADER + '##FORMAT=<ID=XF,Number=.,Type=Float,Description="ragged float vector">\n'
+    cols = ["0/1:5:1.5", "0/0:6:2,3", "1/1:7:.", "0|2:8:.,4"]
+    for n_copies in (1, 40):               # 4 samples: the loop writer; 160 samples: the vectorised / C++ writers
+        samples = tuple("S%d" % i for i in range(4 * n_copies))
+        text = _vcf_text([_rec(100, "GT:DP:XF", cols * n_copies)], samples=samples, header=header)
+        path = _write(tmp_path, "ragged%d.vcf" % n_copies, text)
+        for reader in (cc.TextVCF, NativeVCF):
+            rec = next(iter(reader(path)))
+            xf = rec.format("XF")
+            assert xf.shape == (4 * n_copies, 2) and xf.dtype == np.float32
+            assert xf[0, 0] == 1.5 and np.isnan(xf[0, 1]) and cc.is_float_vector_end(xf)[0].tolist() == [False, True]
+            assert cc.is_float_vector_end(xf)[2].tolist() == [False, True] and np.isnan(xf[2, 0])     # '.' then the end marker
+            assert not cc.is_float_vector_end(xf)[3].any() and np.isnan(xf[3, 0]) and xf[3, 1] == 4
+            dp = rec.format("DP").copy()
+            dp[0] = 9
+            rec.set_format("DP", dp)        # forces every decoded field to be re-serialised
+            got = str(rec).rstrip("\n").split("\t")[9:]
+            assert got[0] == "0/1:9:1.5" and got[1:4] == ["0/0:6:2,3", "1/1:7:.", "0|2:8:.,4"], (reader.__name__, got[:4])

@@ -1067,14 +1067,31 @@ int64_t trt_vcf_join_samples(int64_t n_samples, int n_fields, const int32_t* kin
                 }
                 case 3:
                 case 4: {
+                    int printed = 0;
                     for (int j = 0; j < nc; ++j) {
-                        double x = kind[f] == 3 ? (double)((const float*)data[f])[(size_t)s * nc + j]
-                                                : ((const double*)data[f])[(size_t)s * nc + j];
-                        if (j) putc_(',');
+                        double x;
+                        bool vector_end;                  // BCF's float vector-end NaN (payload 2): a ragged row's padding
+                        if (kind[f] == 3) {
+                            uint32_t u;
+                            memcpy(&u, (const float*)data[f] + (size_t)s * nc + j, 4);
+                            vector_end = (u & 0x7F800000u) == 0x7F800000u && (u & 0x003FFFFFu) == 2u;
+                            float fl;
+                            memcpy(&fl, &u, 4);
+                            x = (double)fl;
+                        } else {
+                            uint64_t u;
+                            memcpy(&u, (const double*)data[f] + (size_t)s * nc + j, 8);
+                            vector_end = (u & 0x7FF0000000000000ull) == 0x7FF0000000000000ull &&
+                                         (u & 0x0007FFFFFFFFFFFFull) == (2ull << 29);
+                            memcpy(&x, &u, 8);
+                        }
+                        if (vector_end) continue;
+                        if (printed) putc_(',');
                         if (std::isnan(x)) putc_('.');
                         else put(num, (size_t)snprintf(num, sizeof num, "%g", x));
+                        ++printed;
                     }
-                    if (nc == 0) putc_('.');
+                    if (!printed) putc_('.');
                     break;
                 }
                 default:

@@ -34,6 +34,22 @@ import numpy as np
 INT32_MISSING = -2147483648
 _VEC_MIN_SAMPLES = 64      # below this many samples the per-sample loop is as fast as the np.char path
 INT32_VECTOR_END = -2147483647
+# BCF's float vector-end marker (a NaN with payload 2; np.isnan is true for it, so "missing" logic is unchanged).  Copies
+# keep the bits; float32 <-> float64 conversions may set the quiet bit, hence the payload test below.
+FLOAT_VECTOR_END = np.array([0x7F800002], dtype=np.uint32).view(np.float32)[0]
+
+
+def is_float_vector_end(a: np.ndarray) -> np.ndarray:
+    """Boolean mask of BCF float vector-end entries of a float32 / float64 array."""
+    a = np.asarray(a)
+    if a.dtype == np.float32:
+        u = a.view(np.uint32)
+        return ((u & np.uint32(0x7F800000)) == np.uint32(0x7F800000)) & ((u & np.uint32(0x003FFFFF)) == np.uint32(2))
+    if a.dtype == np.float64:
+        u = a.view(np.uint64)
+        return ((u & np.uint64(0x7FF0000000000000)) == np.uint64(0x7FF0000000000000)) & \
+               ((u & np.uint64(0x0007FFFFFFFFFFFF)) == np.uint64(2 << 29))
+    return np.zeros(a.shape, bool)
 
 _header_kv = re.compile(r'([A-Za-z0-9_]+)=("(?:[^"\\]|\\.)*"|[^,]*)')
 
@@ -329,11 +345,10 @@ class Variant:
                     for j, x in enumerate(p):
                         out[i, j] = INT32_MISSING if x in ('.', '') else int(x)
             else:
-                out = np.full((len(raw), ncol), np.nan, dtype=np.float32)
+                out = np.full((len(raw), ncol), FLOAT_VECTOR_END, dtype=np.float32)      # ragged rows end like htslib's
                 for i, p in enumerate(parts):
                     for j, x in enumerate(p):
-                        if x not in ('.', ''):
-                            out[i, j] = np.float32(x)
+                        out[i, j] = np.nan if x in ('.', '') else np.float32(x)
         self._fmt_cache[key] = out
         return out
 
@@ -382,7 +397,7 @@ class Variant:
         if col.dtype.kind == 'f':
             nan = np.isnan(col)
             txt = np.char.mod('%g', np.where(nan, 0, col).astype(col.dtype))
-            return np.where(nan, '.', txt), np.zeros(col.shape, bool)
+            return np.where(nan, '.', txt), is_float_vector_end(np.ascontiguousarray(col))
         if col.dtype.kind == 'U':
             return col, np.zeros(col.shape, bool)
         return None, None
@@ -457,8 +472,9 @@ class Variant:
                 else:
                     vals = []
                     for row in data:
-                        items = [self._fmt_scalar(x) for x in row
-                                 if not (isinstance(x, np.integer) and x == INT32_VECTOR_END)]
+                        ve = is_float_vector_end(np.ascontiguousarray(row)) if row.dtype.kind == 'f' else None
+                        items = [self._fmt_scalar(x) for j, x in enumerate(row)
+                                 if not (isinstance(x, np.integer) and x == INT32_VECTOR_END) and not (ve is not None and ve[j])]
                         vals.append(','.join(items) if items else '.')
                     per_field.append(vals)
             else:
