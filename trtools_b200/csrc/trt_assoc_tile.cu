@@ -1,4 +1,6 @@
-// K4 fast path — associaTR moments with one THREAD per locus.
+// K4 FP64 tile path — associaTR moments with one THREAD per locus.  Since round 2 this is the FALLBACK of the tensor path
+// (trt_assoc_mma.cu) for loci outside its integer form (flags[l] == 2); this file also holds the down-date kernel and the
+// z-row table both paths share.
 //
 // The per-locus regression needs, over the called design samples of the locus (associaTR.py:246-291 in the
 // reference tree), n, sum g, sum g^2, g.y and g.c_k for every covariate column: a skinny FP64 contraction
@@ -16,8 +18,8 @@
 //     never a bank conflict whatever alleles the lanes carry);
 //   * the accumulators live in registers for the whole segment, so there is no cross-thread reduction at all.
 // Uncalled design samples (the rows whose outer products must be removed from C'C, C'y, y'y for this locus)
-// are emitted as one 24-bit mask per (locus, chunk); assoc_downdate_mask_kernel turns the masks into the exact
-// down-dates without reading GT again.
+// are emitted as one 24-bit mask per (locus, chunk) (32-bit words from the tensor path); assoc_downdate_mask_kernel turns
+// the masks into the exact down-dates without reading GT again (FP64 mma.sync Gram updates).
 //
 // Algorithmic traffic: 6 B/call of GT once (+ 0.2 B/call of masks written and read back).
 #include <cuda.h>
