@@ -51,6 +51,20 @@ void trt_timer_end(trt_ctx* ctx) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms;
+    ctx->timer_pending = false;
+}
+// the same without blocking the host: the elapsed time is read when somebody asks for it (trt_last_kernel_ms)
+void trt_timer_end_async(trt_ctx* ctx) {
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    ctx->timer_pending = true;
+}
+static void timer_resolve(trt_ctx* ctx) {
+    if (!ctx->timer_pending) return;
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms;
+    ctx->timer_pending = false;
 }
 
 // ---- packed GT transfer form <-> native cyvcf2 rows ---------------------------------------------------------------
@@ -302,7 +316,11 @@ int trt_host_free(trt_ctx* ctx, void* p) {
 }
 
 int64_t trt_launch_count(const trt_ctx* ctx) { return ctx ? ctx->launches : 0; }
-double trt_last_kernel_ms(const trt_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
+double trt_last_kernel_ms(const trt_ctx* ctx) {
+    if (!ctx) return 0.0;
+    timer_resolve(const_cast<trt_ctx*>(ctx));
+    return ctx->last_ms;
+}
 double trt_last_scan_ms(const trt_ctx* ctx) { return ctx ? ctx->last_scan_ms : 0.0; }
 int trt_stopwatch_start(trt_ctx* ctx) {
     if (!ctx) return TRT_EINVAL;
@@ -576,6 +594,13 @@ int trt_block_set_alleles(trt_ctx* ctx, const char* seqs, const int64_t* allele_
         std::vector<double> nanv((size_t)nA, __builtin_nan(""));
         TRT_TRY(upload(ctx, ctx->given_len, nanv.data(), (size_t)nA));
         TRT_CUDA(cudaStreamSynchronize(ctx->stream));  // nanv goes out of scope
+    }
+    {   // motif offsets = exclusive prefix sum of max(period, 0) (the harmonize kernel's output layout)
+        std::vector<int64_t> moff((size_t)L + 1, 0);
+        for (int64_t l = 0; l < L; l++) moff[l + 1] = moff[l] + (period[l] > 0 ? period[l] : 0);
+        ctx->motif_bytes = moff[L];
+        TRT_TRY(upload(ctx, ctx->motif_off, moff.data(), (size_t)L + 1));
+        TRT_CUDA(cudaStreamSynchronize(ctx->stream));  // moff goes out of scope
     }
     ctx->have_motif_in = false;
     if (motifs) {

@@ -131,8 +131,11 @@ __device__ int rot_cmp(const char* s, int p, int r1, int r2) {
 // GS lanes cooperate on one locus (GS = 32: warp per locus; GS = 8: four loci per warp — most loci have only a
 // handful of alleles, so a full warp per locus leaves 80% of the lanes idle).  `lane` is the lane within the group
 // and every shuffle / vote / barrier below is restricted to the group's lanes.
+constexpr int kMaxKeys = 128;     // k-mer keys kept per locus in shared memory (longer repeats recompute them)
+
 template <int GS>
 __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
+    __shared__ unsigned long long skeys[128 / GS][kMaxKeys];
     const int lane = threadIdx.x % GS;
     const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) / GS * GS));
     const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
@@ -277,10 +280,20 @@ __global__ void __launch_bounds__(128) harmonize_kernel(HarmParams P) {
                 // reaches the final maximum count (see oracle/trh.py::infer_repeat_sequence)
                 int best_c = 0, best_i = 0x7fffffff;
                 const unsigned long long kmask = period >= 8 ? ~0ull : ((1ull << (8 * period)) - 1ull);
+                // k-mers of <= 8 bases as upper-cased 64-bit keys (one unaligned 8-byte read each), computed once per
+                // k-mer into the locus' shared-memory slot when they fit: the pair loop below then compares keys only
+                const bool keyed = period <= 8 && K <= kMaxKeys;
+                unsigned long long* keys = skeys[threadIdx.x / GS];
+                if (keyed) {
+                    for (int i = lane; i < K; i += GS) keys[i] = load8_up(seq + (size_t)i * period) & kmask;
+                    __syncwarp(gmask);
+                }
                 for (int i = lane; i < K; i += GS) {
                     int c = 0;
-                    if (period <= 8) {
-                        // k-mers as 64-bit keys: one unaligned 8-byte read each
+                    if (keyed) {
+                        const unsigned long long ki = keys[i];
+                        for (int j = 0; j <= i; j++) c += (keys[j] == ki);
+                    } else if (period <= 8) {
                         const unsigned long long ki = load8_up(seq + (size_t)i * period) & kmask;
                         for (int j = 0; j <= i; j++) c += ((load8_up(seq + (size_t)j * period) & kmask) == ki);
                     } else
@@ -441,13 +454,7 @@ int trt_harmonize(trt_ctx* ctx) {
         return trt_set_error(ctx, TRT_ESTATE, "trt_harmonize: call trt_block_begin and trt_block_set_alleles first");
     TRT_CUDA(cudaSetDevice(ctx->device));
     const int64_t L = ctx->L, nA = ctx->nA;
-    // motif offsets = exclusive prefix sum of max(period,0)
-    std::vector<int64_t> moff((size_t)L + 1, 0);
-    for (int64_t l = 0; l < L; l++) moff[l + 1] = moff[l] + (ctx->h_period[l] > 0 ? ctx->h_period[l] : 0);
-    ctx->motif_bytes = moff[L];
-    TRT_TRY(trt_ensure(ctx, ctx->motif_off, (size_t)(L + 1) * 8));
-    TRT_CUDA(cudaMemcpyAsync(ctx->motif_off.p, moff.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    // (motif offsets = exclusive prefix sum of max(period, 0): uploaded with the allele tables, trt_block_set_alleles)
     TRT_TRY(trt_ensure(ctx, ctx->motif, (size_t)ctx->motif_bytes + 16));
     TRT_TRY(trt_ensure(ctx, ctx->allele_len, (size_t)nA * 8));
     TRT_TRY(trt_ensure(ctx, ctx->trim_off, (size_t)nA * 4));
@@ -492,9 +499,9 @@ int trt_harmonize(trt_ctx* ctx) {
             harmonize_kernel<32><<<(unsigned)((L + per - 1) / per), 128, 0, ctx->stream>>>(P);
         }
         TRT_KERNEL_CHECK();
-        trt_timer_end(ctx);
+        trt_timer_end_async(ctx);
     }
-    TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    // no host synchronisation: every consumer of the tables is a later operation on the context's stream
     ctx->harmonized = true;
     ctx->have_packed = false;
     return TRT_OK;

@@ -24,6 +24,7 @@ struct trt_ctx {
     std::string err;
     int64_t launches = 0;
     double last_ms = 0.0;
+    bool   timer_pending = false;   // trt_timer_end_async: ev1 recorded, elapsed time not read yet
 
     // ---- block state ----------------------------------------------------------------
     bool    block_open = false;
@@ -100,6 +101,7 @@ int  trt_ensure(trt_ctx* ctx, DevBuf& b, size_t bytes);
 void trt_free_buf(DevBuf& b);
 void trt_timer_begin(trt_ctx* ctx);
 void trt_timer_end(trt_ctx* ctx);
+void trt_timer_end_async(trt_ctx* ctx);
 
 #define TRT_CUDA(call)                                                                          \
     do {                                                                                        \

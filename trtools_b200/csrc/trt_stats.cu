@@ -446,13 +446,7 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
         TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
         TRT_TRY(trt_run_epilogue(ctx, use_length, nalleles_thresh, G));
     }
-    trt_timer_end(ctx);
-    ctx->last_scan_ms = 0.0;
-    if (L > 0) {
-        float ms = 0.f;
-        TRT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1));
-        ctx->last_scan_ms = ms;
-    }
+    trt_timer_end_async(ctx);       // the copies below queue up behind the epilogue: one host synchronisation per call
     // ---- results to the caller's host buffers --------------------------------------------------
     const double* f = (const double*)ctx->stat_f64.p;
 #define D2H(dst, src, bytes) \
@@ -474,6 +468,12 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
     if (n_out) TRT_CUDA(cudaMemcpyAsync(&bad, f + 12 * n_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
 #undef D2H
     TRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->last_scan_ms = 0.0;
+    if (L > 0) {
+        float ms = 0.f;
+        TRT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1));
+        ctx->last_scan_ms = ms;
+    }
     if (bad && getenv("TRT_DEBUG_BAD")) {
         // diagnostics: which loci report out-of-range genotype entries, and what the scan counted for them
         std::vector<long long> lcv(n_out * TRT_LC_N);
