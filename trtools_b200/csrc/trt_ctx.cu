@@ -68,46 +68,7 @@ static void timer_resolve(trt_ctx* ctx) {
 }
 
 // ---- packed GT transfer form <-> native cyvcf2 rows ---------------------------------------------------------------
-// 8 calls per thread: 16 packed bytes (+ one phase byte) <-> 48 bytes of int16 triples, 16-byte accesses on both sides
-__global__ void __launch_bounds__(256) gt_expand_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ phase,
-                                                        int64_t L, int64_t S, int16_t* __restrict__ gt, size_t pitch) {
-    const int64_t groups = (S + 7) / 8;
-    const int64_t pbytes = groups;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L * groups; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t l = i / groups, gidx = i % groups;
-        const int64_t s0 = gidx * 8;
-        const uint8_t* src = packed + ((size_t)l * S + s0) * 2;
-        const unsigned ph = phase ? phase[(size_t)l * pbytes + gidx] : 0u;
-        int16_t* dst = (int16_t*)((char*)gt + (size_t)l * pitch) + s0 * 3;
-        if (s0 + 8 <= S && (((size_t)l * S + s0) * 2) % 16 == 0) {
-            const uint4 v = *reinterpret_cast<const uint4*>(src);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t o[12];
-            int16_t h[24];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const unsigned a = (w[j >> 1] >> (16 * (j & 1))) & 0xffu, b = (w[j >> 1] >> (16 * (j & 1) + 8)) & 0xffu;
-                h[3 * j] = (int16_t)(a >= 254u ? (int)a - 256 : (int)a);
-                h[3 * j + 1] = (int16_t)(b >= 254u ? (int)b - 256 : (int)b);
-                h[3 * j + 2] = (int16_t)((ph >> j) & 1u);
-            }
-#pragma unroll
-            for (int k = 0; k < 12; k++) o[k] = (uint32_t)(uint16_t)h[2 * k] | ((uint32_t)(uint16_t)h[2 * k + 1] << 16);
-            uint4* d4 = reinterpret_cast<uint4*>(dst);         // rows are 16-byte multiples and s0 * 6 = gidx * 48
-            d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        } else {
-            for (int j = 0; j < 8 && s0 + j < S; j++) {
-                const unsigned a = src[2 * j], b = src[2 * j + 1];
-                dst[3 * j] = (int16_t)(a >= 254u ? (int)a - 256 : (int)a);
-                dst[3 * j + 1] = (int16_t)(b >= 254u ? (int)b - 256 : (int)b);
-                dst[3 * j + 2] = (int16_t)((ph >> j) & 1u);
-            }
-        }
-    }
-}
-
+// packing side: 8 calls per thread, 48 bytes of int16 triples -> 16 packed bytes (+ one phase byte)
 __global__ void __launch_bounds__(256) gt_pack_kernel(const int16_t* __restrict__ gt, size_t pitch, int64_t l0, int64_t n, int64_t S,
                                                       uint8_t* __restrict__ packed, uint8_t* __restrict__ phase, int* __restrict__ bad) {
     const int64_t groups = (S + 7) / 8;
@@ -128,42 +89,83 @@ __global__ void __launch_bounds__(256) gt_pack_kernel(const int16_t* __restrict_
     }
 }
 
-// nibble transfer form (alleles <= 13): one byte per call, first haplotype in the low nibble; 14 = ploidy pad, 15 = no call
-__global__ void __launch_bounds__(256) gt_expand4_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ phase,
-                                                         int64_t L, int64_t S, int16_t* __restrict__ gt, size_t pitch) {
+// Both transfer forms -> native rows, one 2048-call tile of one locus per block iteration: a thread decodes 8 calls into
+// 48 bytes of shared memory (48-byte stride: conflict-free 16-byte stores), then the block writes the 12 KB tile with
+// fully coalesced 16-byte stores (a thread-per-8-calls kernel storing straight to global memory strides its 16-byte
+// stores by 48 bytes and reached 2.5-3.4 TB/s; the rows are written once, this is the kernel's whole cost).
+template <bool NIBBLE>
+__global__ void __launch_bounds__(256) gt_expand_tile_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ phase,
+                                                             int64_t L, int64_t S, int16_t* __restrict__ gt, size_t pitch) {
+    __shared__ uint4 tile[768];
+    const int tid = threadIdx.x;
+    const int64_t tiles_per_row = (S + 2047) / 2048;
     const int64_t groups = (S + 7) / 8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L * groups; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t l = i / groups, gidx = i % groups;
-        const int64_t s0 = gidx * 8;
-        const uint8_t* src = packed + (size_t)l * S + s0;
-        const unsigned ph = phase ? phase[(size_t)l * groups + gidx] : 0u;
-        int16_t* dst = (int16_t*)((char*)gt + (size_t)l * pitch) + s0 * 3;
-        unsigned long long v = 0;
-        const int nvalid = (int)min((int64_t)8, S - s0);
-        if (nvalid == 8 && (((size_t)l * S + s0) & 7) == 0) v = *reinterpret_cast<const unsigned long long*>(src);
-        else for (int j = 0; j < nvalid; j++) v |= (unsigned long long)src[j] << (8 * j);
-        int16_t h[24];
+    for (int64_t t = blockIdx.x; t < L * tiles_per_row; t += gridDim.x) {
+        const int64_t l = t / tiles_per_row;
+        const int64_t c0 = (t % tiles_per_row) * 2048;
+        const int64_t s0 = c0 + (int64_t)tid * 8;
+        const int nvalid = (int)max((int64_t)0, min((int64_t)8, S - s0));
+        uint32_t o[12];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const unsigned b = (unsigned)(v >> (8 * j)) & 0xffu, a0 = b & 15u, a1 = b >> 4;
-            h[3 * j] = (int16_t)(a0 >= 14u ? (int)a0 - 16 : (int)a0);
-            h[3 * j + 1] = (int16_t)(a1 >= 14u ? (int)a1 - 16 : (int)a1);
-            h[3 * j + 2] = (int16_t)((ph >> j) & 1u);
-        }
-        if (nvalid == 8) {
-            uint32_t o[12];
+        for (int k = 0; k < 12; k++) o[k] = 0xFEFEFEFEu;                // beyond the row: the pad pattern
+        if (nvalid > 0) {
+            const unsigned ph = phase ? phase[(size_t)l * groups + (s0 >> 3)] : 0u;
+            int16_t h[24];
+            if (NIBBLE) {
+                const uint8_t* src = packed + (size_t)l * S + s0;
+                unsigned long long v = 0;
+                if (nvalid == 8 && (((size_t)l * S + s0) & 7) == 0) v = *reinterpret_cast<const unsigned long long*>(src);
+                else for (int j = 0; j < nvalid; j++) v |= (unsigned long long)src[j] << (8 * j);
 #pragma unroll
-            for (int k = 0; k < 12; k++) o[k] = (uint32_t)(uint16_t)h[2 * k] | ((uint32_t)(uint16_t)h[2 * k + 1] << 16);
-            uint4* d4 = reinterpret_cast<uint4*>(dst);         // rows are 16-byte multiples and s0 * 6 = gidx * 48
-            d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        } else {
-            for (int j = 0; j < 3 * nvalid; j++) dst[j] = h[j];
+                for (int j = 0; j < 8; j++) {
+                    const unsigned b = (unsigned)(v >> (8 * j)) & 0xffu, a0 = b & 15u, a1 = b >> 4;
+                    h[3 * j] = (int16_t)(a0 >= 14u ? (int)a0 - 16 : (int)a0);
+                    h[3 * j + 1] = (int16_t)(a1 >= 14u ? (int)a1 - 16 : (int)a1);
+                    h[3 * j + 2] = (int16_t)((ph >> j) & 1u);
+                }
+            } else {
+                const uint8_t* src = packed + ((size_t)l * S + s0) * 2;
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                if (nvalid == 8 && ((((size_t)l * S + s0) * 2) & 15) == 0) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src);
+                    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                } else {
+                    for (int j = 0; j < 2 * nvalid; j++) w[j >> 2] |= (uint32_t)src[j] << (8 * (j & 3));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned a = (w[j >> 1] >> (16 * (j & 1))) & 0xffu, b = (w[j >> 1] >> (16 * (j & 1) + 8)) & 0xffu;
+                    h[3 * j] = (int16_t)(a >= 254u ? (int)a - 256 : (int)a);
+                    h[3 * j + 1] = (int16_t)(b >= 254u ? (int)b - 256 : (int)b);
+                    h[3 * j + 2] = (int16_t)((ph >> j) & 1u);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (2 * k < 3 * nvalid) {
+                    const uint32_t lo = (uint16_t)h[2 * k];
+                    const uint32_t hi = (2 * k + 1 < 3 * nvalid) ? (uint32_t)(uint16_t)h[2 * k + 1] : 0xFEFEu;
+                    o[k] = lo | (hi << 16);
+                }
         }
+        tile[3 * tid] = make_uint4(o[0], o[1], o[2], o[3]);
+        tile[3 * tid + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        tile[3 * tid + 2] = make_uint4(o[8], o[9], o[10], o[11]);
+        __syncthreads();
+        const int64_t row_vecs = (int64_t)(pitch / 16);                  // the row incl. its pad, in 16-byte units
+        const int64_t v0 = c0 * 6 / 16;                                  // c0 is a multiple of 2048: 768 vectors per tile
+        uint4* dst = reinterpret_cast<uint4*>((char*)gt + (size_t)l * pitch) + v0;
+        const int n_vec = (int)min((int64_t)768, row_vecs - v0);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i = k * 256 + tid;
+            if (i < n_vec) dst[i] = tile[i];
+        }
+        __syncthreads();
     }
 }
 
+// nibble transfer form (alleles <= 13): one byte per call, first haplotype in the low nibble; 14 = ploidy pad, 15 = no call
 __global__ void __launch_bounds__(256) gt_pack4_kernel(const int16_t* __restrict__ gt, size_t pitch, int64_t l0, int64_t n, int64_t S,
                                                        uint8_t* __restrict__ packed, uint8_t* __restrict__ phase, int* __restrict__ bad) {
     const int64_t groups = (S + 7) / 8;
@@ -409,9 +411,10 @@ int trt_block_set_gt_packed(trt_ctx* ctx, const uint8_t* gt2_host, const uint8_t
         TRT_CUDA(cudaMemcpyAsync(d_packed, gt2_host, (size_t)L * S * 2, cudaMemcpyHostToDevice, ctx->stream));
         if (phase_bits_host)
             TRT_CUDA(cudaMemcpyAsync(d_phase, phase_bits_host, (size_t)L * pbytes, cudaMemcpyHostToDevice, ctx->stream));
-        const int64_t work = L * ((S + 7) / 8);
-        const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 32);
-        gt_expand_kernel<<<blocks, 256, 0, ctx->stream>>>(d_packed, phase_bits_host ? d_phase : nullptr, L, S, (int16_t*)ctx->gt_buf.p, pitch);
+        const int64_t work = L * ((S + 2047) / 2048);
+        const unsigned blocks = (unsigned)std::min<int64_t>(work, (int64_t)ctx->sm_count * 16);
+        gt_expand_tile_kernel<false><<<blocks, 256, 0, ctx->stream>>>(d_packed, phase_bits_host ? d_phase : nullptr, L, S,
+                                                                      (int16_t*)ctx->gt_buf.p, pitch);
         TRT_KERNEL_CHECK();
     }
     ctx->d_gt = (const int16_t*)ctx->gt_buf.p;
@@ -469,9 +472,10 @@ int trt_block_set_gt_nibble(trt_ctx* ctx, const uint8_t* g4_host, const uint8_t*
         TRT_CUDA(cudaMemcpyAsync(d_packed, g4_host, (size_t)L * S, cudaMemcpyHostToDevice, ctx->stream));
         if (phase_bits_host)
             TRT_CUDA(cudaMemcpyAsync(d_phase, phase_bits_host, (size_t)L * pbytes, cudaMemcpyHostToDevice, ctx->stream));
-        const int64_t work = L * ((S + 7) / 8);
-        const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 32);
-        gt_expand4_kernel<<<blocks, 256, 0, ctx->stream>>>(d_packed, phase_bits_host ? d_phase : nullptr, L, S, (int16_t*)ctx->gt_buf.p, pitch);
+        const int64_t work = L * ((S + 2047) / 2048);
+        const unsigned blocks = (unsigned)std::min<int64_t>(work, (int64_t)ctx->sm_count * 16);
+        gt_expand_tile_kernel<true><<<blocks, 256, 0, ctx->stream>>>(d_packed, phase_bits_host ? d_phase : nullptr, L, S,
+                                                                     (int16_t*)ctx->gt_buf.p, pitch);
         TRT_KERNEL_CHECK();
     }
     ctx->d_gt = (const int16_t*)ctx->gt_buf.p;
