@@ -597,7 +597,9 @@ def run_e2e(args, ctx, comm, loci, L, S, local_rank, world, barrier, packed=True
     real H2D).  ``packed``: uint8 [L][S][2] blocks (what trt_vcf_block_parse_packed emits) instead of int16 [L][S][3];
     ``nibble``: uint8 [L][S] blocks (trt_vcf_block_parse_nibble; every locus of the workload has <= 14 alleles)."""
     from trtools_b200 import _lib, synth, dist as tdist
-    Lb = min(L, args.e2e_block)
+    # the same pinned bytes per block in every form: 4096 loci of cyvcf2 layout = 8192 two-byte = 16384 nibble loci (the
+    # per-block fixed cost — table uploads, launches, result copies — is amortised over the loci of the block)
+    Lb = min(L, args.e2e_block * (4 if nibble else (2 if packed else 1)))
     nblk = (L + Lb - 1) // Lb
     blk_bytes = Lb * S * (2 if packed else 6)       # (nibble blocks are half of this)
     try:
