@@ -477,9 +477,11 @@ int trt_dist_barrier(trt_ctx* ctx);
 /* Gather of per-locus result rows on rank dst, DEVICE buffers on both sides (no host bounce): every rank sends
  * `nbytes` bytes starting `offset_bytes` into one of its device-resident result regions (the outputs of its most
  * recent trt_locus_stats / trt_assoc_ols / trt_locus_filters call, which may be made with NULL host pointers);
- * dst receives them in rank order (ragged sizes: nbytes_per_rank[world]) over NCCL on the context stream and copies the
- * gathered table to host_out (pinned memory from trt_host_alloc for full speed) on a side stream, so the next block's
- * kernels overlap the copy.  async != 0: returns without blocking the host; trt_dist_wait completes it.
+ * the context stream only copies the rows into a staging buffer; the exchange (grouped ncclSend / ncclRecv, ragged
+ * sizes: nbytes_per_rank[world], rank order on dst) and dst's copy of the gathered table to host_out (pinned memory
+ * from trt_host_alloc for full speed) run on a side stream, so the next block's kernels overlap both
+ * (TRT_DIST_MAIN_STREAM=1 in the environment keeps the exchange on the context stream).  async != 0: returns without
+ * blocking the host; trt_dist_wait completes it.
  * Region layouts (n = G*L rows of the call):
  *   TRT_REGION_STATS          12 arrays of n 8-byte values: thresh, het, entropy, mean, mode, var, hwep (f64),
  *                             nalleles (i32, first 4n bytes of its 8n slot), n_hom, n_called, n_called_nonstrict,
