@@ -251,13 +251,17 @@ void trt_destroy(trt_ctx* ctx) {
         cudaEventDestroy(ctx->ev_gathered);
         for (int i = 0; i < 5; i++) {
             cudaEventDestroy(ctx->ev_copied[i]);
-            cudaEventDestroy(ctx->ev_staged[i]);
-            cudaEventDestroy(ctx->ev_sent[i]);
+            for (int b = 0; b < 2; b++) {
+                cudaEventDestroy(ctx->ev_staged[i][b]);
+                cudaEventDestroy(ctx->ev_sent[i][b]);
+            }
         }
+        cudaEventDestroy(ctx->ev_after_scan);
     }
     for (int i = 0; i < 5; i++) {
         trt_free_buf(ctx->dist_recv_r[i]);
-        trt_free_buf(ctx->dist_stage_r[i]);
+        trt_free_buf(ctx->dist_stage_r[i][0]);
+        trt_free_buf(ctx->dist_stage_r[i][1]);
     }
     DevBuf* bufs[] = {&ctx->gt_buf, &ctx->gt_masked_buf, &ctx->gt_packed_buf, &ctx->seqs, &ctx->allele_off, &ctx->locus_off, &ctx->pos,
                       &ctx->start, &ctx->end, &ctx->period, &ctx->given_len, &ctx->motif_in, &ctx->allele_len, &ctx->trim_off,

@@ -14,6 +14,15 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// a gather whose rows are staged but whose exchange has not been issued yet (trt_dist.cu)
+struct trt_pending_gather {
+    int slot = 0, buf = 0;
+    int64_t nbytes = 0;
+    std::vector<int64_t> per_rank;
+    int dst = 0;
+    void* host_out = nullptr;
+};
+
 struct trt_ctx {
     int device = -1;
     int sm_count = 0;
@@ -90,10 +99,14 @@ struct trt_ctx {
     int     rank = 0, world = 1;
     DevBuf  dist_send, dist_recv;
     DevBuf  dist_recv_r[5];                 // receive buffer per result region (+ one for host-payload gathers)
-    DevBuf  dist_stage_r[5];                // the rank's own rows of a gather, staged for the side stream
+    DevBuf  dist_stage_r[5][2];             // the rank's own rows of a gather, staged for the side stream (two per slot, alternating)
+    int     dist_seq[5] = {0, 0, 0, 0, 0};  // gathers made per slot (parity picks the staging buffer)
     cudaStream_t copy_stream = nullptr;     // device->host copies of gathered tables (overlap the next step's kernels)
     cudaEvent_t  ev_gathered = nullptr, ev_copied[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t  ev_staged[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_sent[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t  ev_staged[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t  ev_sent[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t  ev_after_scan = nullptr;
+    std::vector<trt_pending_gather> dist_pending;
 };
 
 int  trt_set_error(trt_ctx* ctx, int code, const char* fmt, ...);
@@ -102,6 +115,7 @@ void trt_free_buf(DevBuf& b);
 void trt_timer_begin(trt_ctx* ctx);
 void trt_timer_end(trt_ctx* ctx);
 void trt_timer_end_async(trt_ctx* ctx);
+int  trt_dist_flush_after_scan(trt_ctx* ctx);     // trt_dist.cu: deferred gathers start behind the scan just queued
 
 #define TRT_CUDA(call)                                                                          \
     do {                                                                                        \

@@ -444,6 +444,7 @@ extern "C" int trt_locus_stats(trt_ctx* ctx, int use_length, const uint8_t* grou
         // every sample group in as few passes over the GT rows as shared memory allows (up to three groups per pass)
         TRT_TRY(trt_run_scan(ctx, group_masks ? (const uint8_t*)ctx->group_masks.p : nullptr, G));
         TRT_CUDA(cudaEventRecord(ctx->ev_s1, ctx->stream));
+        TRT_TRY(trt_dist_flush_after_scan(ctx));     // multi-GPU: the previous step's rows travel from here on
         TRT_TRY(trt_run_epilogue(ctx, use_length, nalleles_thresh, G));
     }
     trt_timer_end_async(ctx);       // the copies below queue up behind the epilogue: one host synchronisation per call
