@@ -913,3 +913,22 @@ def test_ragged_float_vectors_end_like_htslib_and_reserialise_unchanged(tmp_path
             rec.set_format("DP", dp)        # forces every decoded field to be re-serialised
             got = str(rec).rstrip("\n").split("\t")[9:]
             assert got[0] == "0/1:9:1.5" and got[1:4] == ["0/0:6:2,3", "1/1:7:.", "0|2:8:.,4"], (reader.__name__, got[:4])
+
+
+def test_region_queries_through_csi_index_match_linear_scan(data_dir):
+    """vcf(region) with a .csi next to the file (the reference's example-files/test_sample1.vcf.gz and its bcftools-made
+    index, min_shift 14 / depth 6): htslib's min_off walk + overlapping-bin chunks give a start offset from which the
+    reader serves exactly the records of the text reader's linear scan, and empty regions are answered from the index."""
+    from trtools_b200 import vcf_ingest
+    path = os.path.join(data_dir, "csi_indexed_sample.vcf.gz")
+    assert os.path.isfile(path + ".csi") and not os.path.isfile(path + ".tbi")
+    v = NativeVCF(path)
+    for region in ("chr21:9483511-9490000", "chr21:20000000-20100000", "chr21:48000000", "chr21:1-100",
+                   "chr21:30000000-30000500", "chr22:1-100", "chr21:14000000-14500000", "chr21:9483522-9483522", "chr21"):
+        want = [(r.CHROM, r.POS, r.REF) for r in cc.TextVCF(path)(region)]
+        got = [(r.CHROM, r.POS, r.REF) for r in v(region)]
+        assert got == want, (region, len(got), len(want))
+        assert v._region_stop or v._region_empty, region
+    assert vcf_ingest._csi_start(path + ".csi", "chr21", 30000000, 30000500) == -1      # no chunk overlaps: nothing to read
+    assert vcf_ingest._csi_start(path + ".csi", "chrNope", 1) == -1
+    assert vcf_ingest._csi_start(path + ".nope.csi", "chr21", 1) is None

@@ -76,6 +76,79 @@ def _tabix_start(tbi_path: str, chrom: str, start: Optional[int]) -> Optional[in
     return None
 
 
+def _csi_start(csi_path: str, chrom: str, start: Optional[int], end: Optional[int] = None) -> Optional[int]:
+    """The same lower bound from a CSI index (``bcftools index`` / ``tabix -C``; needed for contigs beyond 512 Mb), the
+    way htslib's iterator finds it: ``min_off`` = ``loffset`` of the deepest existing bin at or left of the one holding
+    ``start`` (leaf bin of the position, then previous siblings, then the parent, up to bin 0); the answer is the
+    smallest chunk start among the bins overlapping the region whose chunk ends past ``min_off``.  Same return
+    convention as _tabix_start (-1: the index shows the region holds nothing)."""
+    import gzip
+    import struct
+    if not os.path.isfile(csi_path):
+        return None
+    with gzip.open(csi_path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"CSI\x01":
+        return None
+    min_shift, depth, l_aux = struct.unpack_from("<3i", data, 4)
+    if l_aux < 28:
+        return None                      # no tabix header in the auxiliary block: contig names unknown
+    fmt, _cs, _cb, _ce, _meta, _skip, l_nm = struct.unpack_from("<7i", data, 16)
+    if (fmt & 0xffff) != 2:
+        return None
+    names = data[44:44 + l_nm].split(b"\x00")
+    o = 16 + l_aux
+    (n_ref,) = struct.unpack_from("<i", data, o)
+    o += 4
+    names = names[:n_ref]
+    try:
+        tid = names.index(chrom.encode())
+    except ValueError:
+        return -1
+    for r in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", data, o)
+        o += 4
+        bins = {}
+        for _ in range(n_bin):
+            b, lo, n_chunk = struct.unpack_from("<IQi", data, o)
+            o += 16
+            if r == tid:
+                bins[b] = (lo, [struct.unpack_from("<QQ", data, o + 16 * i) for i in range(n_chunk)])
+            o += 16 * n_chunk
+        if r != tid:
+            continue
+        limit = ((1 << (3 * (depth + 1))) - 1) // 7          # first id past the real bins (pseudo-bins sit above)
+        real = {b: v for b, v in bins.items() if b < limit}
+        if not real:
+            return -1
+        span = 1 << (min_shift + 3 * depth)                  # positions the index can address
+        beg = max((start or 1) - 1, 0)
+        stop = min(end if end is not None else span, span)
+        if beg >= span or stop <= beg:
+            return -1
+        b = ((1 << (3 * depth)) - 1) // 7 + (beg >> min_shift)
+        while b:
+            if b in real:
+                break
+            first_sibling = (((b - 1) >> 3) << 3) + 1
+            b = b - 1 if b > first_sibling else (b - 1) >> 3
+        min_off = real[b][0] if b in real else 0
+        best = None
+        shift, t = min_shift + 3 * depth, 0
+        for level in range(depth + 1):
+            for bb in range(t + (beg >> shift), t + ((stop - 1) >> shift) + 1):
+                if bb in real:
+                    for cb, ce in real[bb][1]:
+                        if ce > min_off and (best is None or cb < best):
+                            best = cb
+            shift -= 3
+            t += 1 << (3 * level)
+        if best is None:
+            return -1
+        return int(max(best, min_off))
+    return None
+
+
 class _NativeBlock:
     """One run of records held by the C++ reader (``trt_vcf_block``) and its parsed arrays."""
 
@@ -475,6 +548,8 @@ class NativeVCF(_compat.TextVCF):
         chrom, start, _ = self._region
         try:
             voff = _tabix_start(self.fname + ".tbi", chrom, start)
+            if voff is None:
+                voff = _csi_start(self.fname + ".csi", chrom, start, self._region[2])
         except Exception:
             voff = None          # no / unreadable index: linear scan
         if voff is None:
