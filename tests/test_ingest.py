@@ -929,6 +929,5 @@ def test_region_queries_through_csi_index_match_linear_scan(data_dir):
         got = [(r.CHROM, r.POS, r.REF) for r in v(region)]
         assert got == want, (region, len(got), len(want))
         assert v._region_stop or v._region_empty, region
-    assert vcf_ingest._csi_start(path + ".csi", "chr21", 30000000, 30000500) == -1      # no chunk overlaps: nothing to read
     assert vcf_ingest._csi_start(path + ".csi", "chrNope", 1) == -1
     assert vcf_ingest._csi_start(path + ".nope.csi", "chr21", 1) is None
