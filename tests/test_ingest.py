@@ -931,3 +931,35 @@ def test_region_queries_through_csi_index_match_linear_scan(data_dir):
         assert v._region_stop or v._region_empty, region
     assert vcf_ingest._csi_start(path + ".csi", "chrNope", 1) == -1
     assert vcf_ingest._csi_start(path + ".nope.csi", "chr21", 1) is None
+
+
+def test_native_tabix_index_multi_contig_and_unsorted(tmp_path):
+    """Two contigs in one file: per-contig bins and linear index, region queries on both; an unsorted or interleaved
+    file is refused the way tabix refuses it."""
+    from trtools_b200.cyvcf2_compat import BgzfWriter, TextVCF
+    from trtools_b200.tabix_index import write_tbi
+    header = HEADER.replace("##contig=<ID=1,length=1000000>\n", "##contig=<ID=1,length=1000000>\n##contig=<ID=2,length=1000000>\n")
+
+    def rec(chrom, pos):
+        return _rec(pos, "GT:DP", ["0/1:5", "0/0:6", "1/1:7", "0|2:8"]).replace("1\t", chrom + "\t", 1)
+
+    recs = [rec("1", p) for p in (100, 20000, 40000, 700000)] + [rec("2", p) for p in (50, 16500, 900000)]
+    path = str(tmp_path / "two.vcf.gz")
+    w = BgzfWriter(path)
+    w.write(_vcf_text(recs, header=header).encode())
+    w.close()
+    write_tbi(path)
+    a = _parse_tbi(path + ".tbi")
+    assert a[1] == [b"1", b"2"] and len(a[2][0][1]) == (700000 >> 14) + 1 and len(a[2][1][1]) == (900000 >> 14) + 1
+    v = NativeVCF(path)
+    for region in ("1:1-30000", "1:600000", "2:1-17000", "2:800000-950000", "2:100-200", "3:1-10"):
+        want = [(r.CHROM, r.POS) for r in TextVCF(path)(region)]
+        got = [(r.CHROM, r.POS) for r in v(region)]
+        assert got == want, region
+    for bad in ([rec("1", 500), rec("1", 100)], [rec("1", 100), rec("2", 100), rec("1", 200)]):
+        p2 = str(tmp_path / "bad.vcf.gz")
+        w = BgzfWriter(p2)
+        w.write(_vcf_text(bad, header=header).encode())
+        w.close()
+        with pytest.raises(ValueError):
+            write_tbi(p2)

@@ -5,6 +5,7 @@ follows the tabix specification: per contig a binning index (UCSC bins, 14-bit m
 virtual offsets) and a linear index (smallest virtual offset of any record overlapping each 16 kb window), the whole
 thing BGZF-compressed.  ``vcf_ingest._tabix_start`` / ``trt_vcf_seek`` read it back for ``vcf(region)``.
 """
+import os
 import struct
 import zlib
 from typing import Dict, List, Tuple
@@ -30,54 +31,62 @@ def _reg2bin(beg: int, end: int) -> int:
     return 0
 
 
+def _bgzf_members(path: str):
+    """(compressed offset, inflated bytes) of every BGZF member, read one member at a time."""
+    with open(path, "rb") as f:
+        off = 0
+        while True:
+            head = f.read(12)
+            if not head:
+                return
+            if len(head) < 12 or head[:4] != b"\x1f\x8b\x08\x04":
+                raise OSError("{} is not BGZF".format(path))
+            xlen = struct.unpack_from("<H", head, 10)[0]
+            extra = f.read(xlen)
+            bsize, p = None, 0
+            while p + 4 <= len(extra):
+                si, slen = extra[p:p + 2], struct.unpack_from("<H", extra, p + 2)[0]
+                if si == b"BC" and slen == 2:
+                    bsize = struct.unpack_from("<H", extra, p + 4)[0] + 1
+                p += 4 + slen
+            if bsize is None:
+                raise OSError("{} is not BGZF (no BC field)".format(path))
+            body = f.read(bsize - 12 - xlen)
+            if len(body) != bsize - 12 - xlen:
+                raise OSError("{}: truncated BGZF member".format(path))
+            yield off, zlib.decompress(body[:-8], -15)
+            off += bsize
+
+
 def _bgzf_lines(path: str):
     """(virtual offset of the line's first byte, virtual offset just past its newline, line bytes) for every line."""
-    with open(path, "rb") as f:
-        raw = f.read()
-    members = []                       # (compressed offset, inflated bytes)
-    off = 0
-    while off < len(raw):
-        if raw[off:off + 4] != b"\x1f\x8b\x08\x04":
-            raise OSError("{} is not BGZF".format(path))
-        xlen = struct.unpack_from("<H", raw, off + 10)[0]
-        bsize, p = None, off + 12
-        while p < off + 12 + xlen:
-            si, slen = raw[p:p + 2], struct.unpack_from("<H", raw, p + 2)[0]
-            if si == b"BC":
-                bsize = struct.unpack_from("<H", raw, p + 4)[0] + 1
-            p += 4 + slen
-        if bsize is None:
-            raise OSError("{} is not BGZF (no BC field)".format(path))
-        data = zlib.decompress(raw[off + 12 + xlen:off + bsize - 8], -15)
-        members.append((off, data))
-        off += bsize
-    eof_voff = off << 16
-    pending = b""
-    start_voff = None
-    for i, (coff, data) in enumerate(members):
+    pending, start_voff = b"", None
+    held = None                         # a line that ended with its member: its end offset is the next member's start
+    for coff, data in _bgzf_members(path):
+        if held is not None:
+            yield held[0], coff << 16, held[1]
+            held = None
         pos = 0
-        while True:
+        while pos < len(data):
             nl = data.find(b"\n", pos)
             if nl < 0:
-                if pos < len(data):
-                    if not pending:
-                        start_voff = (coff << 16) | pos
-                    pending += data[pos:]
+                if not pending:
+                    start_voff = (coff << 16) | pos
+                pending += data[pos:]
                 break
             if pending:
-                line = pending + data[pos:nl]
-                beg = start_voff
-                pending = b""
+                line, beg, pending = pending + data[pos:nl], start_voff, b""
             else:
-                line = data[pos:nl]
-                beg = (coff << 16) | pos
+                line, beg = data[pos:nl], (coff << 16) | pos
             nxt = nl + 1
             if nxt < len(data):
-                end = (coff << 16) | nxt
-            else:                       # the next byte is the first of the following member (the EOF member after the last line)
-                end = (members[i + 1][0] << 16) if i + 1 < len(members) else eof_voff
-            yield beg, end, line
+                yield beg, (coff << 16) | nxt, line
+            else:
+                held = (beg, line)      # the next byte is the first of the following member
             pos = nxt
+    eof_voff = os.path.getsize(path) << 16
+    if held is not None:
+        yield held[0], eof_voff, held[1]
     if pending:
         yield start_voff, eof_voff, pending
 
